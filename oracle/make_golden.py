@@ -1,0 +1,134 @@
+"""TEST INFRASTRUCTURE ONLY.  Run in the build container (needs /root/reference):
+
+    python -m oracle.make_golden
+
+1. builds the UNMODIFIED reference Videoseal for each card via oracle/ref_import.py,
+2. loads the seeded synthetic checkpoint of oracle/restate.py::synth_state_dict into it
+   (`load_state_dict(strict=False)` exactly like utils/cfg.py:148-149),
+3. checks oracle/restate.py against the reference outputs on seeded inputs (pins the oracle),
+4. writes small fixtures to tests/golden/<card>.pt: full logits, strided samples + global
+   statistics of the image-sized outputs, so the fixtures stay small.
+"""
+import os
+import sys
+import time
+
+import torch
+import yaml
+
+from oracle import ref_import, restate
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+CARDS = ["videoseal_1.0", "pixelseal"]
+SEED = 1234
+
+
+def sample(t: torch.Tensor, stride: int = 8) -> torch.Tensor:
+    return t[..., ::stride, ::stride].contiguous().clone()
+
+
+def stats(t: torch.Tensor) -> dict:
+    t = t.double()
+    return {"mean": t.mean().item(), "absmean": t.abs().mean().item(), "std": t.std().item(),
+            "min": t.min().item(), "max": t.max().item()}
+
+
+def main():
+    torch.manual_seed(0)
+    torch.set_num_threads(8)
+    for card_name in CARDS:
+        t0 = time.time()
+        ref, cfg = ref_import.build_reference_model(card_name)
+        card = yaml.safe_load(open(os.path.join(ref_import.REF_ROOT, "videoseal/cards", card_name + ".yaml")))
+        spec = restate.spec_from_card(card)
+        sd = restate.synth_state_dict(spec, seed=SEED)
+        msg = ref.load_state_dict(sd, strict=False)
+        assert not msg.unexpected_keys, msg.unexpected_keys
+        missing = [k for k in msg.missing_keys if not k.startswith("attenuation.")]
+        assert not missing, missing
+        orc = restate.OracleModel(spec, sd)
+        out = {"card": card_name, "seed": SEED, "torch": torch.__version__, "spec": spec, "cases": {}}
+
+        g = torch.Generator().manual_seed(0)
+        # case A: image mode @ processing size, B=2
+        imgs = torch.rand(2, 3, 256, 256, generator=g)
+        msgs = torch.randint(0, 2, (2, spec["nbits"]), generator=g)
+        with torch.no_grad():
+            r = ref.embed(imgs, msgs, is_video=False)
+            d = ref.detect(r["imgs_w"], is_video=False)
+            o = orc.embed(imgs, msgs, is_video=False)
+            od = orc.detect(o["imgs_w"], is_video=False)
+            # raw network seams (embedder.py:151 / extractor.py:154)
+            x_e = ref.rgb2yuv(imgs)[:, 0:1] if ref.embedder.yuv else imgs
+            delta = ref.embedder(x_e, msgs)
+            hm = ref.attenuation.heatmaps(imgs)
+        errs = {
+            "imgs_w": (r["imgs_w"] - o["imgs_w"]).abs().max().item(),
+            "preds_w": (r["preds_w"] - o["preds_w"]).abs().max().item(),
+            "preds": (d["preds"] - od["preds"]).abs().max().item(),
+            "delta": (delta - orc.embedder(imgs, msgs)).abs().max().item(),
+            "hmaps": (hm - orc.heatmaps(imgs)).abs().max().item(),
+        }
+        print(card_name, "A", errs)
+        assert errs["imgs_w"] < 1e-5 and errs["preds"] < 1e-4 and errs["delta"] < 1e-4 and errs["hmaps"] < 1e-6, errs
+        out["cases"]["img256"] = {
+            "gen_seed": 0, "B": 2, "H": 256, "W": 256,
+            "imgs_w_s": sample(r["imgs_w"]), "preds_w_s": sample(r["preds_w"]), "delta_s": sample(delta),
+            "hmaps_s": sample(hm), "preds": d["preds"].clone(),
+            "imgs_w_stats": stats(r["imgs_w"]), "delta_stats": stats(delta),
+            "psnr": restate.psnr(r["imgs_w"], imgs), "oracle_vs_ref": errs,
+        }
+
+        # case B: image mode, non-square input needing AA-resize, B=1
+        g = torch.Generator().manual_seed(1)
+        imgs = torch.rand(1, 3, 384, 480, generator=g)
+        msgs = torch.randint(0, 2, (1, spec["nbits"]), generator=g)
+        with torch.no_grad():
+            r = ref.embed(imgs, msgs, is_video=False)
+            d = ref.detect(r["imgs_w"], is_video=False)
+            o = orc.embed(imgs, msgs, is_video=False)
+            od = orc.detect(o["imgs_w"], is_video=False)
+        errs = {"imgs_w": (r["imgs_w"] - o["imgs_w"]).abs().max().item(),
+                "preds_w": (r["preds_w"] - o["preds_w"]).abs().max().item(),
+                "preds": (d["preds"] - od["preds"]).abs().max().item()}
+        print(card_name, "B", errs)
+        assert errs["imgs_w"] < 1e-5 and errs["preds"] < 1e-4, errs
+        out["cases"]["img384x480"] = {
+            "gen_seed": 1, "B": 1, "H": 384, "W": 480,
+            "imgs_w_s": sample(r["imgs_w"]), "preds_w_s": sample(r["preds_w"]), "preds": d["preds"].clone(),
+            "imgs_w_stats": stats(r["imgs_w"]), "oracle_vs_ref": errs,
+        }
+
+        # case C: video mode, 10 frames @ 320x288 (ragged tail: 10 is not a multiple of step_size),
+        # small chunk so the chunk loop runs more than once
+        g = torch.Generator().manual_seed(2)
+        vid = torch.rand(10, 3, 320, 288, generator=g)
+        msgs = torch.randint(0, 2, (1, spec["nbits"]), generator=g)
+        ref.chunk_size, orc.chunk_size = 2, 2
+        ref.step_size, orc.step_size = 4, 4
+        with torch.no_grad():
+            r = ref.embed(vid, msgs, is_video=True)
+            d = ref.detect(r["imgs_w"], is_video=True)
+            o = orc.embed(vid, msgs, is_video=True)
+            od = orc.detect(o["imgs_w"], is_video=True)
+            em = ref.extract_message(r["imgs_w"])
+            oem = orc.extract_message(o["imgs_w"])
+        errs = {"imgs_w": (r["imgs_w"] - o["imgs_w"]).abs().max().item(),
+                "preds": (d["preds"] - od["preds"]).abs().max().item(),
+                "extract_equal": bool((em == oem).all())}
+        print(card_name, "C", errs)
+        assert errs["imgs_w"] < 1e-5 and errs["preds"] < 1e-4 and errs["extract_equal"], errs
+        out["cases"]["vid10"] = {
+            "gen_seed": 2, "F": 10, "H": 320, "W": 288, "chunk_size": 2, "step_size": 4,
+            "imgs_w_s": sample(r["imgs_w"]), "preds": d["preds"].clone(), "extract": em.clone(),
+            "imgs_w_stats": stats(r["imgs_w"]), "oracle_vs_ref": errs,
+        }
+        path = os.path.join(ROOT, "tests", "golden", card_name + ".pt")
+        torch.save(out, path)
+        print(card_name, "->", path, os.path.getsize(path) // 1024, "KiB", f"{time.time()-t0:.1f}s")
+
+
+if __name__ == "__main__":
+    if not ref_import.available():
+        sys.exit("needs the reference tree at " + ref_import.REF_ROOT)
+    main()
