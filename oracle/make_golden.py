@@ -47,7 +47,7 @@ def main():
         missing = [k for k in msg.missing_keys if not k.startswith("attenuation.")]
         assert not missing, missing
         orc = restate.OracleModel(spec, sd)
-        out = {"card": card_name, "seed": SEED, "torch": torch.__version__, "spec": spec, "cases": {}}
+        out = {"card": card_name, "seed": SEED, "torch": str(torch.__version__), "spec": spec, "cases": {}}
 
         g = torch.Generator().manual_seed(0)
         # case A: image mode @ processing size, B=2
