@@ -1,0 +1,68 @@
+"""CPU-side checks: the C-ABI library builds/loads and exports every symbol include/vsb200.h declares; the host logic
+(card parsing, API surface) works and fails loudly without a GPU."""
+import re
+import os
+
+import pytest
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_exports_match_header(built_lib):
+    hdr = open(os.path.join(ROOT, "include", "vsb200.h")).read()
+    declared = set(re.findall(r"\b(vsb_[a-z_0-9]+)\s*\(", hdr))
+    declared -= {"vsb_model", "vsb_model_desc", "vsb_conv_test", "vsb_status", "vsb_video_mode", "vsb_flags"}
+    assert declared, "no declarations parsed"
+    for sym in sorted(declared):
+        assert hasattr(built_lib, sym), f"libvsb200.so does not export {sym}"
+    from videoseal_b200 import _lib
+    assert set(_lib.EXPORTS) == declared
+
+
+def test_desc_struct_layout_matches_header():
+    from videoseal_b200 import _lib
+    import ctypes as C
+    # 4 + 3 + 6 + 4 + 8 + 1 + 2 = 28 int32 fields in vsb_model_desc
+    assert C.sizeof(_lib.ModelDesc) == 28 * 4
+
+
+@pytest.mark.parametrize("card", ["videoseal_1.0", "pixelseal", "chunkyseal"])
+def test_card_parsing_matches_oracle_spec(card):
+    from tests.util import load_card
+    from oracle import restate
+    from videoseal_b200 import cfg
+    c = load_card(card)
+    a, b = cfg.spec_from_card(c), restate.spec_from_card(c)
+    assert a["nbits"] == b["nbits"] and a["hidden"] == b["hidden"] and a["img_size"] == b["img_size"]
+    assert a["unet"]["z"] == [b["unet"]["z_channels"] * m for m in b["unet"]["mults"]]
+    assert a["convnext"]["dims"] == b["convnext"]["dims"] and a["convnext"]["depths"] == b["convnext"]["depths"]
+    assert a["yuv"] == b["yuv"] and a["step_size"] == b["step_size"] and a["chunk_size"] == b["chunk_size"]
+
+
+def test_load_and_fail_loudly_without_gpu(built_lib):
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import videoseal_b200
+    from tests.util import synthetic_card_on_disk
+    cpath, spec, _ = synthetic_card_on_disk("videoseal_1.0", tiny={"num_blocks": 1, "depths": [1, 1, 1, 1]})
+    model = videoseal_b200.load(cpath).eval()
+    assert model.get_random_msg(3).shape == (3, spec["nbits"])
+    assert model.blender.scaling_w == pytest.approx(0.2) and model.step_size == 4 and model.chunk_size == 32
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model.embed(torch.rand(1, 3, 256, 256), is_video=False)
+    with pytest.raises(RuntimeError, match="no CPU fallback"):
+        model.detect(torch.rand(1, 3, 256, 256))
+
+
+def test_unsupported_card_features_raise_at_load():
+    from tests.util import load_card
+    from videoseal_b200 import cfg
+    c = load_card("videoseal_1.0")
+    c["args"]["blending_method"] = "multiplicative"
+    with pytest.raises(NotImplementedError):
+        cfg.spec_from_card(c)
+    c = load_card("videoseal_1.0")
+    c["extractor"]["model"] = "sam_small"
+    with pytest.raises(NotImplementedError):
+        cfg.spec_from_card(c)

@@ -1,0 +1,67 @@
+"""Pins the CPU oracle (oracle/restate.py) against the golden fixtures generated from the UNMODIFIED reference modules
+(oracle/make_golden.py, run in the build container).  Bit-level agreement was observed at generation time (max |diff| = 0);
+here a 1e-5 / 1e-4 tolerance absorbs CPU-kernel differences between machines."""
+import os
+
+import pytest
+import torch
+
+from oracle import restate
+from tests.util import load_card, SEED
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _sample(t, stride=8):
+    return t[..., ::stride, ::stride]
+
+
+@pytest.mark.parametrize("card", ["videoseal_1.0", "pixelseal"])
+def test_oracle_matches_reference_golden(card):
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", f"{card}.pt"))
+    spec = restate.spec_from_card(load_card(card))
+    assert gold["seed"] == SEED
+    sd = restate.synth_state_dict(spec, seed=gold["seed"])
+    orc = restate.OracleModel(spec, sd)
+    with torch.no_grad():
+        c = gold["cases"]["img256"]
+        g = torch.Generator().manual_seed(c["gen_seed"])
+        imgs = torch.rand(c["B"], 3, c["H"], c["W"], generator=g)
+        msgs = torch.randint(0, 2, (c["B"], spec["nbits"]), generator=g)
+        o = orc.embed(imgs, msgs, is_video=False)
+        d = orc.detect(o["imgs_w"], is_video=False)
+        assert (_sample(o["imgs_w"]) - c["imgs_w_s"]).abs().max() < 1e-5
+        assert (_sample(o["preds_w"]) - c["preds_w_s"]).abs().max() < 1e-5
+        assert (_sample(orc.heatmaps(imgs)) - c["hmaps_s"]).abs().max() < 1e-6
+        assert (d["preds"] - c["preds"]).abs().max() < 1e-4
+        assert abs(o["imgs_w"].double().mean().item() - c["imgs_w_stats"]["mean"]) < 1e-6
+        assert (restate.psnr(o["imgs_w"], imgs) - c["psnr"]).abs().max() < 1e-3
+
+        c = gold["cases"]["img384x480"]
+        g = torch.Generator().manual_seed(c["gen_seed"])
+        imgs = torch.rand(c["B"], 3, c["H"], c["W"], generator=g)
+        msgs = torch.randint(0, 2, (c["B"], spec["nbits"]), generator=g)
+        o = orc.embed(imgs, msgs, is_video=False)
+        d = orc.detect(o["imgs_w"], is_video=False)
+        assert (_sample(o["imgs_w"]) - c["imgs_w_s"]).abs().max() < 1e-5
+        assert (d["preds"] - c["preds"]).abs().max() < 1e-4
+
+        c = gold["cases"]["vid10"]
+        g = torch.Generator().manual_seed(c["gen_seed"])
+        vid = torch.rand(c["F"], 3, c["H"], c["W"], generator=g)
+        msgs = torch.randint(0, 2, (1, spec["nbits"]), generator=g)
+        orc.chunk_size, orc.step_size = c["chunk_size"], c["step_size"]
+        o = orc.embed(vid, msgs, is_video=True)
+        d = orc.detect(o["imgs_w"], is_video=True)
+        assert (_sample(o["imgs_w"]) - c["imgs_w_s"]).abs().max() < 1e-5
+        assert (d["preds"] - c["preds"]).abs().max() < 1e-4
+        assert (orc.extract_message(o["imgs_w"]) == c["extract"]).all()
+
+
+def test_video_mode_and_metrics_restatements():
+    p = torch.arange(3, dtype=torch.float32).view(3, 1, 1, 1) + 1
+    assert restate.apply_video_mode(p, 10, 4, "repeat").flatten().tolist() == [1, 1, 1, 1, 2, 2, 2, 2, 3, 3]
+    assert restate.apply_video_mode(p, 10, 4, "alternate").flatten().tolist() == [1, 0, 0, 0, 2, 0, 0, 0, 3, 0]
+    preds = torch.tensor([[0.0, 1.0, -1.0, 2.0]])
+    assert restate.bit_accuracy(preds, torch.tensor([[1, 0, 0]])).item() == pytest.approx(2 / 3)

@@ -1,0 +1,533 @@
+// K1/K2: implicit-GEMM convolution / linear layer on the 5th-gen tensor cores (tcgen05.mma,
+// accumulators in TMEM), persistent and warp-specialised:
+//
+//   warp 0      : TMA producer (weights always; activations too when LOADER == LD_TMA)
+//   warp 1      : single-thread tcgen05.mma issuer
+//   warp 2      : TMEM allocator
+//   warps 4..7  : epilogue (TMEM -> registers -> fused bias/BN-fold/act/residual/LN/tanh/GRN-stats -> HBM)
+//   warps 8..11 : (gather loaders only) build the im2col-free A tile in swizzled shared memory from
+//                 NHWC activations: strided / reflect-padded convs, fused bilinear x2 + reflect-pad +
+//                 virtual skip-concat (UBlock), GRN per-(sample,k) scaling (ConvNeXt pwconv2).
+//
+// GEMM view: D[M = output pixels, N = C_out] = A[M, K = taps*C_in] * W[N, K]^T, fp16 operands,
+// fp32 accumulation.  BLOCK_M = 128 (one UMMA M=128 atom, cta_group::1), BLOCK_N <= 256, two TMEM
+// accumulator stages so the epilogue of tile i overlaps the main loop of tile i+1.
+//
+// Replaces: nn.Conv2d / nn.Linear + BatchNorm2d(eval) + ReLU / LayerNorm / GELU / GRN / tanh call sites of
+// videoseal/modules/unet.py:17-197, modules/common.py:45-52,150-169, modules/convnext.py:41-57,
+// modules/pixel_decoder.py:44-55 (see DESIGN.md for the per-layer mapping).
+#pragma once
+#include "ptx.cuh"
+
+namespace vsb {
+
+enum : int { LD_TMA = 0, LD_GATHER_CONV = 1, LD_GATHER_UPS = 2, LD_GATHER_SCALE = 3 };
+enum : int { EPI_AFFINE = 0, EPI_LN = 1 };
+enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
+
+constexpr int kBlockM = 128;
+constexpr int kMaxStages = 8;
+constexpr int kTmemCols = 512;
+constexpr int kAccStride = 256;  // TMEM columns between the two accumulator stages
+
+struct ConvGemmParams {
+  // ---- GEMM view
+  int M, N, num_kb, kblk, block_n, n_tiles, m_tiles, num_tiles, stages;
+  uint32_t a_stage_bytes, b_stage_bytes, stage_bytes, idesc;
+  // ---- A via TMA
+  int a_is_conv;  // 0: 2D map (K, M)   1: 4D map (C, W, H, B) with zero-fill halo
+  int H, W, tile_w, tile_h, tiles_x, tiles_per_img, R, S, pad, c_blocks;
+  // ---- A via gather (NHWC fp16 sources; K order = (r, s, c) with c over the virtual concat [src0 | src1])
+  const __half* src0;
+  const __half* src1;
+  int C0, C1, ld0, ld1, IH, IW, OH, OW, stride, pad_mode /*0 zero, 1 reflect*/, Ktot;
+  const float* a_scale;  // LD_GATHER_SCALE: [num_samples, ld_scale] fp32
+  int rows_per_sample, ld_scale;
+  // ---- epilogue
+  int epi, act;
+  const float* bias;     // [N] or null
+  const __half* resid16; int ld_res16;   // added AFTER the activation (ResnetBlock: act(norm(conv)) + res)
+  const float* resid32;  int ld_res32;
+  __half* out16; int ld_out16;
+  float* out32;  int ld_out32;
+  const float* ln_w; const float* ln_b; float ln_eps;     // EPI_LN (requires n_tiles == 1)
+  const float* outc_w; const float* outc_b; float* delta; int n_out, hw, outc_tanh;  // fused 1x1 outc (+tanh)
+  float* grn_stats;      // [num_samples, N] sum of squares of the epilogue output (GRN), or null
+};
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+__device__ __forceinline__ int reflect_idx(int i, int n) {
+  if (i < 0) i = -i;
+  if (i >= n) i = 2 * n - 2 - i;
+  return i;
+}
+
+__device__ __forceinline__ uint4 lerp4_h8(uint4 a, uint4 b, uint4 c, uint4 d, float wa, float wb, float wc, float wd) {
+  const __half2* pa = reinterpret_cast<const __half2*>(&a);
+  const __half2* pb = reinterpret_cast<const __half2*>(&b);
+  const __half2* pc = reinterpret_cast<const __half2*>(&c);
+  const __half2* pd = reinterpret_cast<const __half2*>(&d);
+  uint4 o;
+  __half2* po = reinterpret_cast<__half2*>(&o);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    float2 fa = __half22float2(pa[i]), fb = __half22float2(pb[i]), fc = __half22float2(pc[i]), fd = __half22float2(pd[i]);
+    float2 r;
+    r.x = wa * fa.x + wb * fb.x + wc * fc.x + wd * fd.x;
+    r.y = wa * fa.y + wb * fb.y + wc * fc.y + wd * fd.y;
+    po[i] = __float22half2_rn(r);
+  }
+  return o;
+}
+
+template <int LOADER>
+__global__ void __launch_bounds__(LOADER == LD_TMA ? 256 : 384, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                 const __grid_constant__ ConvGemmParams p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve-up: [0,1024) barriers + tmem pointer; then `stages` x (A tile | B tile), 1024-aligned
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
+  uint64_t* empty_bar = full_bar + kMaxStages;
+  uint64_t* tfull_bar = empty_bar + kMaxStages;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+  uint8_t* tiles = smem + 1024;
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  constexpr uint32_t kNumGather = 128;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], LOADER == LD_TMA ? 1u : 1u + kNumGather);
+      mbar_init(&empty_bar[s], 1u);
+    }
+    for (int s = 0; s < 2; ++s) {
+      mbar_init(&tfull_bar[s], 1u);
+      mbar_init(&tempty_bar[s], 128u);
+    }
+    fence_barrier_init();
+    if (LOADER == LD_TMA) tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_ptr_smem, kTmemCols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr_smem;
+  const uint32_t row_bytes = (uint32_t)p.kblk * 2u;
+
+  if (warp == 0) {
+    // ===================================================================== TMA producer
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+        int cb = 0, cx = 0, cy = 0;
+        if (LOADER == LD_TMA && p.a_is_conv) {
+          cb = m_tile / p.tiles_per_img;
+          const int rem = m_tile - cb * p.tiles_per_img;
+          const int ty = rem / p.tiles_x;
+          cy = ty * p.tile_h;
+          cx = (rem - ty * p.tiles_x) * p.tile_w;
+        }
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sa = tiles + (size_t)stage * p.stage_bytes;
+          uint8_t* sb = sa + p.a_stage_bytes;
+          if (LOADER == LD_TMA) {
+            mbar_arrive_expect_tx(&full_bar[stage], p.a_stage_bytes + p.b_stage_bytes);
+            if (p.a_is_conv) {
+              const int tap = kb / p.c_blocks, cblk = kb - tap * p.c_blocks;
+              const int r = tap / p.S, s = tap - r * p.S;
+              tma_load_4d(&tmA, &full_bar[stage], sa, cblk * p.kblk, cx + s - p.pad, cy + r - p.pad, cb);
+            } else {
+              tma_load_2d(&tmA, &full_bar[stage], sa, kb * p.kblk, m_tile * kBlockM);
+            }
+          } else {
+            mbar_arrive_expect_tx(&full_bar[stage], p.b_stage_bytes);
+          }
+          tma_load_2d(&tmB, &full_bar[stage], sb, kb * p.kblk, n_tile * p.block_n);
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================================================================== MMA issuer
+    if (elect_one()) {
+      int stage = 0;
+      uint32_t phase = 0;
+      int as = 0;
+      uint32_t aphase = 0;
+      const int nmma = p.kblk >> 4;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        mbar_wait(&tempty_bar[as], aphase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * kAccStride);
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(tiles + (size_t)stage * p.stage_bytes);
+          const uint64_t adesc = make_smem_desc(sa, row_bytes);
+          const uint64_t bdesc = make_smem_desc(sa + p.a_stage_bytes, row_bytes);
+          for (int j = 0; j < nmma; ++j) {
+            // advance 16 K-elements = 32 bytes inside the swizzled row: +2 in the (addr >> 4) field
+            umma_f16_ss(d_tmem, adesc + (uint64_t)(2 * j), bdesc + (uint64_t)(2 * j), p.idesc, (uint32_t)((kb | j) != 0));
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+        umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+        as ^= 1;
+        if (as == 0) aphase ^= 1u;
+      }
+    }
+  } else if (warp >= 4 && warp < 8) {
+    // ===================================================================== epilogue
+    const int ew = warp - 4;  // == warp % 4 -> TMEM lane quadrant this warp may access
+    const int row = ew * 32 + lane;
+    int as = 0;
+    uint32_t aphase = 0;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+      const int n0 = n_tile * p.block_n;
+      long m;
+      bool mvalid;
+      if (LOADER == LD_TMA && p.a_is_conv) {
+        const int b = m_tile / p.tiles_per_img;
+        const int rem = m_tile - b * p.tiles_per_img;
+        const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
+        const int ry = row / p.tile_w, rx = row - ry * p.tile_w;
+        m = ((long)b * p.H + (ty * p.tile_h + ry)) * p.W + (tx * p.tile_w + rx);
+        mvalid = true;
+      } else {
+        m = (long)m_tile * kBlockM + row;
+        mvalid = m < p.M;
+      }
+      mbar_wait(&tfull_bar[as], aphase);
+      tc_fence_after();
+      const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * kAccStride);
+
+      if (p.epi == EPI_LN) {
+        // channels-first LayerNorm over the full C_out row (biased variance), then activation
+        const int N = p.N;
+        float sum = 0.f;
+        for (int c = 0; c < p.block_n; c += 16) {
+          float v[16];
+          tmem_ld16(trow + c, v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) sum += (c + j < N) ? v[j] : 0.f;
+        }
+        const float mean = sum / (float)N;
+        float var = 0.f;
+        for (int c = 0; c < p.block_n; c += 16) {
+          float v[16];
+          tmem_ld16(trow + c, v);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const float d = v[j] - mean;
+            var += (c + j < N) ? d * d : 0.f;
+          }
+        }
+        const float rstd = 1.0f / sqrtf(var / (float)N + p.ln_eps);
+        for (int c = 0; c < p.block_n; c += 16) {
+          float v[16];
+          tmem_ld16(trow + c, v);
+          if (c >= N) continue;
+          __align__(16) __half h[16];
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            const int n = c + j;
+            float y = 0.f;
+            if (n < N) {
+              y = (v[j] - mean) * rstd * p.ln_w[n] + p.ln_b[n];
+              if (p.act == ACT_RELU) y = fmaxf(y, 0.f);
+              else if (p.act == ACT_GELU) y = gelu_erf(y);
+            }
+            h[j] = __float2half_rn(y);
+          }
+          if (mvalid) {
+            __half* o = p.out16 + m * p.ld_out16 + c;
+            if (c + 16 <= N) {
+              reinterpret_cast<uint4*>(o)[0] = reinterpret_cast<const uint4*>(h)[0];
+              reinterpret_cast<uint4*>(o)[1] = reinterpret_cast<const uint4*>(h)[1];
+            } else {
+              for (int j = 0; j < 16 && c + j < N; ++j) o[j] = h[j];
+            }
+          }
+        }
+      } else {
+        float dot[3] = {0.f, 0.f, 0.f};
+        const bool grn_uniform =
+            p.grn_stats != nullptr &&
+            ((long)m_tile * kBlockM + ew * 32) / p.rows_per_sample == ((long)m_tile * kBlockM + ew * 32 + 31) / p.rows_per_sample &&
+            ((long)m_tile * kBlockM + ew * 32 + 31) < p.M;
+        for (int c = 0; c < p.block_n; c += 16) {
+          float v[16];
+          tmem_ld16(trow + c, v);
+          const int n = n0 + c;
+          if (n >= p.N) continue;  // uniform across the warp
+          const bool full = (n + 16 <= p.N);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) {
+            float x = v[j];
+            if (p.bias != nullptr && (full || n + j < p.N)) x += __ldg(p.bias + n + j);
+            if (p.act == ACT_RELU) x = fmaxf(x, 0.f);
+            else if (p.act == ACT_GELU) x = gelu_erf(x);
+            v[j] = x;
+          }
+          if (mvalid) {
+            if (p.resid16 != nullptr) {
+              const __half* r = p.resid16 + m * p.ld_res16 + n;
+              if (full) {
+                __align__(16) __half h[16];
+                reinterpret_cast<uint4*>(h)[0] = __ldg(reinterpret_cast<const uint4*>(r));
+                reinterpret_cast<uint4*>(h)[1] = __ldg(reinterpret_cast<const uint4*>(r) + 1);
+#pragma unroll
+                for (int j = 0; j < 16; ++j) v[j] += __half2float(h[j]);
+              } else {
+                for (int j = 0; j < 16; ++j) if (n + j < p.N) v[j] += __half2float(r[j]);
+              }
+            }
+            if (p.resid32 != nullptr) {
+              const float* r = p.resid32 + m * p.ld_res32 + n;
+              if (full) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  const float4 t = __ldg(reinterpret_cast<const float4*>(r) + q);
+                  v[4 * q + 0] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+                }
+              } else {
+                for (int j = 0; j < 16; ++j) if (n + j < p.N) v[j] += r[j];
+              }
+            }
+          }
+          if (p.outc_w != nullptr) {
+            for (int o = 0; o < p.n_out; ++o) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j)
+                if (full || n + j < p.N) dot[o] += v[j] * __ldg(p.outc_w + o * p.N + n + j);
+            }
+          }
+          if (mvalid) {
+            if (p.out16 != nullptr) {
+              __half* o = p.out16 + m * p.ld_out16 + n;
+              if (full) {
+                __align__(16) __half h[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) h[j] = __float2half_rn(fminf(fmaxf(v[j], -65504.f), 65504.f));
+                reinterpret_cast<uint4*>(o)[0] = reinterpret_cast<const uint4*>(h)[0];
+                reinterpret_cast<uint4*>(o)[1] = reinterpret_cast<const uint4*>(h)[1];
+              } else {
+                for (int j = 0; j < 16; ++j)
+                  if (n + j < p.N) o[j] = __float2half_rn(fminf(fmaxf(v[j], -65504.f), 65504.f));
+              }
+            }
+            if (p.out32 != nullptr) {
+              float* o = p.out32 + m * p.ld_out32 + n;
+              if (full) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                  reinterpret_cast<float4*>(o)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+              } else {
+                for (int j = 0; j < 16; ++j) if (n + j < p.N) o[j] = v[j];
+              }
+            }
+          }
+          if (p.grn_stats != nullptr) {
+            // column sums of squares over this warp's 32 rows (GRN: ||x||_2 over H,W per (sample, channel))
+            float q[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) q[j] = (mvalid && (full || n + j < p.N)) ? v[j] * v[j] : 0.f;
+            if (grn_uniform) {
+              // halving butterfly: after xor 16,8,4,2 each lane holds one column summed over 16 rows
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float send = (lane & 16) ? q[i] : q[i + 8];
+                const float keep = (lane & 16) ? q[i + 8] : q[i];
+                q[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float send = (lane & 8) ? q[i] : q[i + 4];
+                const float keep = (lane & 8) ? q[i + 4] : q[i];
+                q[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+              }
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                const float send = (lane & 4) ? q[i] : q[i + 2];
+                const float keep = (lane & 4) ? q[i + 2] : q[i];
+                q[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+              }
+              {
+                const float send = (lane & 2) ? q[0] : q[1];
+                const float keep = (lane & 2) ? q[1] : q[0];
+                q[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+              }
+              q[0] += __shfl_xor_sync(0xffffffffu, q[0], 1);
+              const int col = (lane >> 1) & 15;
+              if ((lane & 1) == 0 && n + col < p.N) {
+                const long sample = ((long)m_tile * kBlockM + ew * 32) / p.rows_per_sample;
+                atomicAdd(p.grn_stats + sample * p.N + n + col, q[0]);
+              }
+            } else if (mvalid) {
+              const long sample = m / p.rows_per_sample;
+              for (int j = 0; j < 16; ++j)
+                if (n + j < p.N) atomicAdd(p.grn_stats + sample * p.N + n + j, q[j]);
+            }
+          }
+        }
+        if (p.outc_w != nullptr && mvalid) {
+          const long b = m / p.hw, pix = m - b * p.hw;
+          for (int o = 0; o < p.n_out; ++o) {
+            float d = dot[o] + p.outc_b[o];
+            if (p.outc_tanh) d = tanhf(d);
+            p.delta[(b * p.n_out + o) * p.hw + pix] = d;
+          }
+        }
+      }
+      tc_fence_before();
+      mbar_arrive(&tempty_bar[as]);
+      as ^= 1;
+      if (as == 0) aphase ^= 1u;
+    }
+  } else if (LOADER != LD_TMA && warp >= 8) {
+    // ===================================================================== gather producers (A tile)
+    const int gt = threadIdx.x - 256;  // 0..127
+    const int j = gt & 7;              // 16-byte chunk (8 fp16 K-elements) within the 128-byte swizzled row
+    const int rg = gt >> 3;            // rows rg + 16*i
+    int stage = 0;
+    uint32_t phase = 0;
+    const int Ct = p.C0 + p.C1;
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      const int m_tile = tile / p.n_tiles;
+      int pb[8], py[8], px[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        const long m = (long)m_tile * kBlockM + rg + 16 * i;
+        if (m < p.M) {
+          if (LOADER == LD_GATHER_SCALE) {
+            pb[i] = (int)(m / p.rows_per_sample);
+            py[i] = 0;
+            px[i] = (int)m;
+          } else {
+            const int ox = (int)(m % p.OW);
+            const long t = m / p.OW;
+            px[i] = ox;
+            py[i] = (int)(t % p.OH);
+            pb[i] = (int)(t / p.OH);
+          }
+        } else {
+          pb[i] = -1; py[i] = 0; px[i] = 0;
+        }
+      }
+      for (int kb = 0; kb < p.num_kb; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        uint8_t* sa = tiles + (size_t)stage * p.stage_bytes;
+        const int k = kb * 64 + j * 8;
+        const bool kvalid = k < p.Ktot;
+        if (LOADER == LD_GATHER_SCALE) {
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            uint4 val = make_uint4(0, 0, 0, 0);
+            if (kvalid && pb[i] >= 0) {
+              const uint4 g = __ldg(reinterpret_cast<const uint4*>(p.src0 + (long)px[i] * p.ld0 + k));
+              const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.a_scale + (long)pb[i] * p.ld_scale + k));
+              const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.a_scale + (long)pb[i] * p.ld_scale + k) + 1);
+              const __half2* ph = reinterpret_cast<const __half2*>(&g);
+              __half2* po = reinterpret_cast<__half2*>(&val);
+              float2 f;
+              f = __half22float2(ph[0]); f.x *= s0.x; f.y *= s0.y; po[0] = __float22half2_rn(f);
+              f = __half22float2(ph[1]); f.x *= s0.z; f.y *= s0.w; po[1] = __float22half2_rn(f);
+              f = __half22float2(ph[2]); f.x *= s1.x; f.y *= s1.y; po[2] = __float22half2_rn(f);
+              f = __half22float2(ph[3]); f.x *= s1.z; f.y *= s1.w; po[3] = __float22half2_rn(f);
+            }
+            const int r = rg + 16 * i;
+            *reinterpret_cast<uint4*>(sa + r * 128 + ((j ^ (r & 7)) << 4)) = val;
+          }
+        } else {
+          const int tap = kvalid ? k / Ct : 0;
+          const int c = k - tap * Ct;
+          const int tr = tap / p.S, ts = tap - tr * p.S;
+          const __half* src = (c < p.C0) ? p.src0 : p.src1;
+          const int ld = (c < p.C0) ? p.ld0 : p.ld1;
+          const int cc = (c < p.C0) ? c : c - p.C0;
+          if (LOADER == LD_GATHER_CONV) {
+            uint4 val[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              val[i] = make_uint4(0, 0, 0, 0);
+              if (kvalid && pb[i] >= 0) {
+                int iy = py[i] * p.stride + tr - p.pad;
+                int ix = px[i] * p.stride + ts - p.pad;
+                bool ok = true;
+                if (p.pad_mode == 1) {
+                  iy = reflect_idx(iy, p.IH);
+                  ix = reflect_idx(ix, p.IW);
+                } else {
+                  ok = (iy >= 0) && (iy < p.IH) && (ix >= 0) && (ix < p.IW);
+                }
+                if (ok) val[i] = __ldg(reinterpret_cast<const uint4*>(src + (((long)pb[i] * p.IH + iy) * p.IW + ix) * ld + cc));
+              }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              const int r = rg + 16 * i;
+              *reinterpret_cast<uint4*>(sa + r * 128 + ((j ^ (r & 7)) << 4)) = val[i];
+            }
+          } else {  // LD_GATHER_UPS: conv3x3(valid) o reflect-pad(1) o bilinear-x2(align_corners=False) of the IHxIW source
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+              uint4 val[4];
+#pragma unroll
+              for (int ii = 0; ii < 4; ++ii) {
+                const int i = half * 4 + ii;
+                val[ii] = make_uint4(0, 0, 0, 0);
+                if (kvalid && pb[i] >= 0) {
+                  const int uy = reflect_idx(py[i] + tr - 1, 2 * p.IH);
+                  const int ux = reflect_idx(px[i] + ts - 1, 2 * p.IW);
+                  const int iy = uy >> 1, ix = ux >> 1;
+                  int ya, yb, xa, xb;
+                  float wya, wxa;
+                  if (uy & 1) { ya = iy; yb = min(iy + 1, p.IH - 1); wya = 0.75f; }
+                  else        { ya = max(iy - 1, 0); yb = iy; wya = 0.25f; }
+                  if (ux & 1) { xa = ix; xb = min(ix + 1, p.IW - 1); wxa = 0.75f; }
+                  else        { xa = max(ix - 1, 0); xb = ix; wxa = 0.25f; }
+                  const __half* base = src + (long)pb[i] * p.IH * p.IW * ld + cc;
+                  const uint4 v00 = __ldg(reinterpret_cast<const uint4*>(base + ((long)ya * p.IW + xa) * ld));
+                  const uint4 v01 = __ldg(reinterpret_cast<const uint4*>(base + ((long)ya * p.IW + xb) * ld));
+                  const uint4 v10 = __ldg(reinterpret_cast<const uint4*>(base + ((long)yb * p.IW + xa) * ld));
+                  const uint4 v11 = __ldg(reinterpret_cast<const uint4*>(base + ((long)yb * p.IW + xb) * ld));
+                  val[ii] = lerp4_h8(v00, v01, v10, v11, wya * wxa, wya * (1.f - wxa), (1.f - wya) * wxa, (1.f - wya) * (1.f - wxa));
+                }
+              }
+#pragma unroll
+              for (int ii = 0; ii < 4; ++ii) {
+                const int r = rg + 16 * (half * 4 + ii);
+                *reinterpret_cast<uint4*>(sa + r * 128 + ((j ^ (r & 7)) << 4)) = val[ii];
+              }
+            }
+          }
+        }
+        fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+        mbar_arrive(&full_bar[stage]);
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, kTmemCols);
+  }
+}
+
+}  // namespace vsb

@@ -1,0 +1,205 @@
+// Host-side construction + launch of conv_gemm_kernel instances (tensor maps, tiling, smem budget).
+#pragma once
+#include <cstdio>
+#include <cstring>
+#include <stdexcept>
+#include <string>
+
+#include "conv_gemm.cuh"
+
+namespace vsb {
+
+struct Error : std::runtime_error {
+  using std::runtime_error::runtime_error;
+};
+
+#define VSB_CHECK(cond, msg)                                                                      \
+  do {                                                                                            \
+    if (!(cond)) throw ::vsb::Error(std::string(msg) + " [" #cond "] at " __FILE__ ":" + std::to_string(__LINE__)); \
+  } while (0)
+
+#define VSB_CUDA(expr)                                                                            \
+  do {                                                                                            \
+    cudaError_t _e = (expr);                                                                      \
+    if (_e != cudaSuccess)                                                                        \
+      throw ::vsb::Error(std::string("CUDA error ") + cudaGetErrorString(_e) + " in " #expr " at " __FILE__ ":" + std::to_string(__LINE__)); \
+  } while (0)
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled get_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    VSB_CUDA(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q));
+    VSB_CHECK(p != nullptr && q == cudaDriverEntryPointSuccess, "cuTensorMapEncodeTiled not available");
+    fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+inline CUtensorMapSwizzle swizzle_for(int kblk) {
+  return kblk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kblk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+// fp16 tensor map, dims innermost-first; strides (bytes) for dims 1..rank-1
+inline void encode_map(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
+                       const uint32_t* box, int kblk) {
+  cuuint64_t gd[5], gs[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
+  for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
+  VSB_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base must be 16B aligned");
+  for (int i = 0; i + 1 < rank; ++i) VSB_CHECK(gs[i] % 16 == 0, "TMA strides must be multiples of 16B");
+  CUresult r = get_encode_fn()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(kblk), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  VSB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
+}
+
+struct ConvGemmOp {
+  int loader = LD_TMA;
+  ConvGemmParams p;
+  CUtensorMap tmA, tmB;
+  int grid = 0, threads = 0;
+  size_t smem = 0;
+  const char* name = "";
+  ConvGemmOp() { memset(&p, 0, sizeof(p)); memset(&tmA, 0, sizeof(tmA)); memset(&tmB, 0, sizeof(tmB)); }
+};
+
+inline int pick_block_n(int N) {
+  const int n16 = (N + 15) / 16 * 16;
+  if (n16 <= 256) return n16;
+  // prefer the largest tile in {256,...,128} (multiples of 16) that divides n16; else 256 with a ragged last tile
+  for (int bn = 256; bn >= 128; bn -= 16)
+    if (n16 % bn == 0) return bn;
+  return 256;
+}
+
+// Common finalisation: weights map, tiling, stage count, smem, grid.
+// W: [N, Kw] fp16 row-major (K-major), Kw >= num_kb*kblk need not hold (TMA zero-fills out-of-bounds K).
+inline void finalize_op(ConvGemmOp& op, const __half* W, int N, int Kw, int ldw, int num_sms, int block_n_override = 0) {
+  ConvGemmParams& p = op.p;
+  p.N = N;
+  p.block_n = block_n_override ? block_n_override : pick_block_n(N);
+  VSB_CHECK(p.block_n % 16 == 0 && p.block_n >= 16 && p.block_n <= 256, "bad block_n");
+  p.n_tiles = (N + p.block_n - 1) / p.block_n;
+  p.num_tiles = p.m_tiles * p.n_tiles;
+  p.a_stage_bytes = (uint32_t)(kBlockM * p.kblk * 2);
+  p.b_stage_bytes = (uint32_t)(p.block_n * p.kblk * 2);
+  p.stage_bytes = p.a_stage_bytes + ((p.b_stage_bytes + 1023u) & ~1023u);
+  VSB_CHECK(p.a_stage_bytes % 1024 == 0, "A stage must be 1024B aligned");
+  const size_t budget = 220 * 1024;
+  int stages = (int)(budget / p.stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  VSB_CHECK(stages >= 2, "not enough shared memory for 2 stages");
+  p.stages = stages;
+  op.smem = 1024 /*align slack*/ + 1024 /*barriers*/ + (size_t)stages * p.stage_bytes;
+  // instruction descriptor (kind::f16): D=f32 (bit 4), A=B=f16 (0), K-major both, N>>3 at bit 17, M>>4 at bit 24
+  p.idesc = (1u << 4) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
+  if (p.epi == EPI_LN) VSB_CHECK(p.n_tiles == 1, "LN epilogue needs the full row in one tile");
+  // weights: dims (K, N)
+  uint64_t dims[2] = {(uint64_t)Kw, (uint64_t)N};
+  uint64_t strides[1] = {(uint64_t)ldw * 2};
+  uint32_t box[2] = {(uint32_t)p.kblk, (uint32_t)p.block_n};
+  encode_map(&op.tmB, W, 2, dims, strides, box, p.kblk);
+  op.grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
+  op.threads = op.loader == LD_TMA ? 256 : 384;
+}
+
+// A = NHWC fp16 activation [B, H, W, C] (pixel pitch ld elements); conv RxS stride 1, zero padding `pad`
+// (R = S = 1, pad = 0 for 1x1).  Weights [N][R*S*C] with K order (r, s, c).
+inline void setup_tma_conv(ConvGemmOp& op, const __half* src, int B, int H, int W, int C, int ld, int R, int S, int pad) {
+  ConvGemmParams& p = op.p;
+  op.loader = LD_TMA;
+  p.a_is_conv = 1;
+  p.kblk = C >= 64 ? 64 : C;
+  VSB_CHECK(p.kblk == 64 || p.kblk == 32 || p.kblk == 16, "TMA conv: C must be 16, 32 or a multiple of 64");
+  VSB_CHECK(C % p.kblk == 0, "TMA conv: C must be a multiple of the K block");
+  p.c_blocks = C / p.kblk;
+  p.R = R; p.S = S; p.pad = pad;
+  p.H = H; p.W = W;
+  p.tile_w = W < kBlockM ? W : kBlockM;
+  p.tile_h = kBlockM / p.tile_w;
+  VSB_CHECK(p.tile_w * p.tile_h == kBlockM && W % p.tile_w == 0 && H % p.tile_h == 0, "TMA conv: map size must tile by 128 pixels");
+  p.tiles_x = W / p.tile_w;
+  p.tiles_per_img = p.tiles_x * (H / p.tile_h);
+  p.m_tiles = B * p.tiles_per_img;
+  p.M = B * H * W;
+  p.num_kb = R * S * p.c_blocks;
+  uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+  uint64_t strides[3] = {(uint64_t)ld * 2, (uint64_t)W * ld * 2, (uint64_t)H * W * ld * 2};
+  uint32_t box[4] = {(uint32_t)p.kblk, (uint32_t)p.tile_w, (uint32_t)p.tile_h, 1u};
+  encode_map(&op.tmA, src, 4, dims, strides, box, p.kblk);
+}
+
+// A = [M, K] fp16 row-major (row pitch ld elements)
+inline void setup_tma_gemm(ConvGemmOp& op, const __half* A, long M, int K, int ld) {
+  ConvGemmParams& p = op.p;
+  op.loader = LD_TMA;
+  p.a_is_conv = 0;
+  p.kblk = K >= 64 ? 64 : K;
+  VSB_CHECK(p.kblk == 64 || p.kblk == 32 || p.kblk == 16, "TMA gemm: K must be 16, 32 or >= 64");
+  p.M = (int)M;
+  p.m_tiles = (int)((M + kBlockM - 1) / kBlockM);
+  p.num_kb = (K + p.kblk - 1) / p.kblk;
+  uint64_t dims[2] = {(uint64_t)K, (uint64_t)M};
+  uint64_t strides[1] = {(uint64_t)ld * 2};
+  uint32_t box[2] = {(uint32_t)p.kblk, (uint32_t)kBlockM};
+  encode_map(&op.tmA, A, 2, dims, strides, box, p.kblk);
+}
+
+// generic gathered conv: out[b,oy,ox,:] over taps (r,s) of the virtual concat [src0 (C0 ch) | src1 (C1 ch)]
+inline void setup_gather_conv(ConvGemmOp& op, int loader, const __half* src0, int C0, int ld0, const __half* src1, int C1, int ld1,
+                              int B, int IH, int IW, int OH, int OW, int R, int S, int stride, int pad, int pad_mode) {
+  ConvGemmParams& p = op.p;
+  op.loader = loader;
+  p.kblk = 64;
+  p.src0 = src0; p.src1 = src1; p.C0 = C0; p.C1 = C1; p.ld0 = ld0; p.ld1 = ld1;
+  VSB_CHECK(C0 % 8 == 0 && C1 % 8 == 0 && ld0 % 8 == 0 && (C1 == 0 || ld1 % 8 == 0), "gather conv: channels must be multiples of 8");
+  p.IH = IH; p.IW = IW; p.OH = OH; p.OW = OW; p.R = R; p.S = S; p.stride = stride; p.pad = pad; p.pad_mode = pad_mode;
+  p.Ktot = R * S * (C0 + C1);
+  p.M = B * OH * OW;
+  p.m_tiles = (p.M + kBlockM - 1) / kBlockM;
+  p.num_kb = (p.Ktot + 63) / 64;
+}
+
+// A[m, k] = G[m, k] * scale[m / rows_per_sample, k]   (ConvNeXt pwconv2 with the GRN factor folded in)
+inline void setup_gather_scale(ConvGemmOp& op, const __half* G, long M, int K, int ld, const float* scale, int ld_scale, int rows_per_sample) {
+  ConvGemmParams& p = op.p;
+  op.loader = LD_GATHER_SCALE;
+  p.kblk = 64;
+  p.src0 = G; p.ld0 = ld; p.C0 = K; p.C1 = 0;
+  VSB_CHECK(K % 8 == 0 && ld % 8 == 0 && ld_scale % 4 == 0, "gather scale: K must be a multiple of 8");
+  p.Ktot = K;
+  p.a_scale = scale; p.ld_scale = ld_scale; p.rows_per_sample = rows_per_sample;
+  p.M = (int)M;
+  p.m_tiles = (int)((M + kBlockM - 1) / kBlockM);
+  p.num_kb = (K + 63) / 64;
+}
+
+template <int LOADER>
+inline void launch_one(const ConvGemmOp& op, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    VSB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<LOADER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+  conv_gemm_kernel<LOADER><<<op.grid, op.threads, op.smem, st>>>(op.tmA, op.tmB, op.p);
+}
+
+inline void launch(const ConvGemmOp& op, cudaStream_t st) {
+  switch (op.loader) {
+    case LD_TMA: launch_one<LD_TMA>(op, st); break;
+    case LD_GATHER_CONV: launch_one<LD_GATHER_CONV>(op, st); break;
+    case LD_GATHER_UPS: launch_one<LD_GATHER_UPS>(op, st); break;
+    case LD_GATHER_SCALE: launch_one<LD_GATHER_SCALE>(op, st); break;
+    default: throw Error("bad loader");
+  }
+  VSB_CUDA(cudaGetLastError());
+}
+
+}  // namespace vsb

@@ -1,0 +1,807 @@
+// Model assembly: weight folding/packing (host), per-batch execution plans (device buffers + launch lists),
+// and the embed / detect drivers behind the C ABI.
+#pragma once
+#include <cmath>
+#include <functional>
+#include <map>
+#include <memory>
+#include <string>
+#include <vector>
+
+#include "../../include/vsb200.h"
+#include "conv_gemm_host.cuh"
+#include "pointwise.cuh"
+
+namespace vsb {
+
+static int64_t g_launches = 0;
+
+struct HostTensor {
+  std::vector<float> data;
+  std::vector<int64_t> shape;
+  int64_t numel() const { int64_t n = 1; for (auto s : shape) n *= s; return n; }
+};
+
+// device allocations owned by one object, freed together
+struct DevicePool {
+  std::vector<void*> ptrs;
+  size_t bytes = 0;
+  void* alloc(size_t n) {
+    void* p = nullptr;
+    n = (n + 255) & ~size_t(255);
+    if (n == 0) n = 256;
+    VSB_CUDA(cudaMalloc(&p, n));
+    ptrs.push_back(p);
+    bytes += n;
+    return p;
+  }
+  template <class T> T* alloc_n(size_t n) { return reinterpret_cast<T*>(alloc(n * sizeof(T))); }
+  template <class T> T* upload(const std::vector<T>& v) {
+    T* p = alloc_n<T>(v.size());
+    VSB_CUDA(cudaMemcpy(p, v.data(), v.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return p;
+  }
+  ~DevicePool() { for (void* p : ptrs) cudaFree(p); }
+};
+
+struct ConvW {          // packed conv / linear weights: fp16 [N][K] (K order r,s,c) + fp32 bias
+  __half* w = nullptr;
+  float* bias = nullptr;
+  int N = 0, K = 0;
+};
+
+struct DebugTensor { const void* ptr; int dtype; /*0 f32, 1 f16*/ int64_t shape[4]; int64_t ld; };
+
+struct Step {
+  std::function<void(cudaStream_t)> fn;
+  int launches = 1;
+};
+
+struct Plan {
+  DevicePool pool;
+  std::vector<Step> steps;
+  std::map<std::string, DebugTensor> dbg;
+  // embed plan I/O
+  const float* in_imgs = nullptr;  // set per call (pointer slot read by the first kernel's lambda)
+  long in_frame_stride = 0;
+  const uint8_t* in_msgs = nullptr;
+  int in_msg_stride = 0;
+  float* x_res = nullptr;   // [B,3,S,S] resized RGB when the input is not at processing size
+  float* delta = nullptr;   // [B,CD,S,S]
+  float* logits = nullptr;  // [B,1+K]
+  void run(cudaStream_t st) {
+    for (auto& s : steps) { s.fn(st); g_launches += s.launches; }
+  }
+};
+
+// ATen-compatible separable resample tables (host) ------------------------------------------------
+struct ResampleHost {
+  std::vector<int> start, cnt;
+  std::vector<float> w;
+  int maxt = 0;
+};
+
+// aten/src/ATen/native/cpu/UpSampleKernel.cpp (_compute_indices_weights_aa, bilinear filter) for antialias=True;
+// plain half-pixel bilinear (align_corners=False) otherwise.  Upscaling with antialias=True degenerates to plain bilinear.
+inline ResampleHost make_resample(int in, int out, bool antialias) {
+  ResampleHost t;
+  const double scale = (double)in / (double)out;
+  if (antialias && scale > 1.0) {
+    const double support = scale;  // interp_size/2 * scale with interp_size = 2
+    t.maxt = (int)std::ceil(support) * 2 + 1;
+    t.start.resize(out); t.cnt.resize(out); t.w.assign((size_t)out * t.maxt, 0.f);
+    for (int i = 0; i < out; ++i) {
+      const double center = scale * (i + 0.5);
+      const double invscale = 1.0 / scale;
+      int xmin = (int)(center - support + 0.5); if (xmin < 0) xmin = 0;
+      int xmax = (int)(center + support + 0.5); if (xmax > in) xmax = in;
+      const int n = xmax - xmin;
+      double total = 0.0;
+      std::vector<double> ww(n);
+      for (int j = 0; j < n; ++j) {
+        double x = (j + xmin - center + 0.5) * invscale;
+        if (x < 0) x = -x;
+        ww[j] = x < 1.0 ? 1.0 - x : 0.0;
+        total += ww[j];
+      }
+      t.start[i] = xmin; t.cnt[i] = n;
+      for (int j = 0; j < n; ++j) t.w[(size_t)i * t.maxt + j] = (float)(total != 0.0 ? ww[j] / total : 0.0);
+    }
+  } else {
+    t.maxt = 2;
+    t.start.resize(out); t.cnt.resize(out); t.w.assign((size_t)out * 2, 0.f);
+    for (int i = 0; i < out; ++i) {
+      // area_pixel_compute_source_index(scale, dst, align_corners=false, cubic=false)
+      float src = (float)scale * (i + 0.5f) - 0.5f;
+      if (src < 0.f) src = 0.f;
+      int x0 = (int)src; if (x0 > in - 1) x0 = in - 1;
+      const int x1 = x0 + ((x0 < in - 1) ? 1 : 0);
+      const float l1 = src - (float)x0, l0 = 1.f - l1;
+      t.start[i] = x0;
+      if (x1 == x0) { t.cnt[i] = 1; t.w[(size_t)i * 2] = 1.f; }
+      else { t.cnt[i] = 2; t.w[(size_t)i * 2] = l0; t.w[(size_t)i * 2 + 1] = l1; }
+    }
+  }
+  return t;
+}
+
+struct ResampleDev {
+  DevicePool pool;
+  ResampleTab tab;
+  ResampleDev(int ih, int iw, int oh, int ow, bool aa) {
+    ResampleHost y = make_resample(ih, oh, aa), x = make_resample(iw, ow, aa);
+    tab.ystart = pool.upload(y.start); tab.ycnt = pool.upload(y.cnt); tab.yw = pool.upload(y.w); tab.maxt_y = y.maxt;
+    tab.xstart = pool.upload(x.start); tab.xcnt = pool.upload(x.cnt); tab.xw = pool.upload(x.w); tab.maxt_x = x.maxt;
+  }
+};
+
+class Model {
+ public:
+  vsb_model_desc d;
+  std::map<std::string, HostTensor> sd;
+  bool finalized = false;
+  int device = -1, num_sms = 0;
+  DevicePool wpool;
+  static constexpr int kMaxBatch = 64;
+
+  // ---- packed weights
+  struct ResBlockW { ConvW c1, c2, res; };
+  float *first_w1 = nullptr, *first_b1 = nullptr, *first_wr = nullptr, *first_br = nullptr;  // inc (CUDA-core layer)
+  ConvW inc_c2;
+  std::vector<ConvW> down_conv;
+  std::vector<ResBlockW> down_rb, bott_rb, up_rb;
+  std::vector<ConvW> up_conv;
+  std::vector<float*> up_lnw, up_lnb;
+  float *outc_w = nullptr, *outc_b = nullptr;
+  float* msg_table = nullptr;
+  // extractor
+  float *stem_w = nullptr, *stem_b = nullptr, *stem_lnw = nullptr, *stem_lnb = nullptr;
+  struct DsW { float* lnw; float* lnb; ConvW conv; };
+  std::vector<DsW> ds;
+  struct CnBlockW { float* dww; float* dwb; float* lnw; float* lnb; ConvW pw1; float* gamma; ConvW pw2; };
+  std::vector<std::vector<CnBlockW>> cn;
+  ConvW head_conv;
+  float *head_lnw = nullptr, *head_lnb = nullptr, *head_lw = nullptr, *head_lb = nullptr;
+
+  std::map<int, std::unique_ptr<Plan>> embed_plans, detect_plans;
+  std::map<uint64_t, std::unique_ptr<ResampleDev>> resamplers;
+  Plan* last_plan = nullptr;
+
+  explicit Model(const vsb_model_desc& desc) : d(desc) {}
+
+  const HostTensor& get(const std::string& k) const {
+    auto it = sd.find(k);
+    if (it == sd.end()) throw Error("missing checkpoint tensor: " + k);
+    return it->second;
+  }
+
+  // ---------------------------------------------------------------- packing helpers
+  static std::vector<__half> to_half(const std::vector<float>& v) {
+    std::vector<__half> h(v.size());
+    for (size_t i = 0; i < v.size(); ++i) h[i] = __float2half_rn(v[i]);
+    return h;
+  }
+  // conv weight [N][C][R][S] (+ per-output-channel scale, + per-input-channel scale) -> [N][R][S][C]
+  ConvW pack_conv(const std::string& wkey, const std::vector<float>* out_scale, const std::vector<float>& bias,
+                  const std::vector<float>* in_scale = nullptr) {
+    const HostTensor& w = get(wkey);
+    VSB_CHECK(w.shape.size() == 4 || w.shape.size() == 2, "conv weight rank");
+    const int N = (int)w.shape[0], C = (int)w.shape[1];
+    const int R = w.shape.size() == 4 ? (int)w.shape[2] : 1, S = w.shape.size() == 4 ? (int)w.shape[3] : 1;
+    std::vector<float> p((size_t)N * R * S * C);
+    for (int n = 0; n < N; ++n)
+      for (int c = 0; c < C; ++c)
+        for (int r = 0; r < R; ++r)
+          for (int s = 0; s < S; ++s) {
+            float v = w.data[(((size_t)n * C + c) * R + r) * S + s];
+            if (out_scale) v *= (*out_scale)[n];
+            if (in_scale) v *= (*in_scale)[c];
+            p[(((size_t)n * R + r) * S + s) * C + c] = v;
+          }
+    ConvW cw;
+    cw.N = N; cw.K = R * S * C;
+    cw.w = wpool.upload(to_half(p));
+    cw.bias = bias.empty() ? nullptr : wpool.upload(bias);
+    return cw;
+  }
+  // eval-mode BatchNorm2d folded into the preceding bias-free conv: w' = w*g/sqrt(var+eps), b' = beta - mean*g/sqrt(var+eps)
+  void bn_fold(const std::string& bn, std::vector<float>& scale, std::vector<float>& bias) const {
+    const HostTensor &g = get(bn + ".weight"), &b = get(bn + ".bias"), &mu = get(bn + ".running_mean"), &var = get(bn + ".running_var");
+    const size_t n = g.data.size();
+    scale.resize(n); bias.resize(n);
+    for (size_t i = 0; i < n; ++i) {
+      const float s = g.data[i] / std::sqrt(var.data[i] + 1e-5f);
+      scale[i] = s;
+      bias[i] = b.data[i] - mu.data[i] * s;
+    }
+  }
+  ResBlockW pack_resblock(const std::string& key) {
+    ResBlockW rb;
+    std::vector<float> s, b;
+    bn_fold(key + ".double_conv.1", s, b);
+    rb.c1 = pack_conv(key + ".double_conv.0.weight", &s, b);
+    bn_fold(key + ".double_conv.4", s, b);
+    rb.c2 = pack_conv(key + ".double_conv.3.weight", &s, b);
+    rb.res = pack_conv(key + ".res_conv.weight", nullptr, get(key + ".res_conv.bias").data);
+    return rb;
+  }
+
+  void finalize(int dev) {
+    VSB_CHECK(!finalized, "already finalized");
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) throw Error("no CUDA device: libvsb200 has no CPU fallback");
+    VSB_CUDA(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    VSB_CUDA(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major != 10) throw Error("libvsb200 is built for sm_100a only (found sm_" + std::to_string(prop.major) + std::to_string(prop.minor) + ")");
+    device = dev;
+    num_sms = prop.multiProcessorCount;
+    if (d.unet_act != 0 || d.unet_norm != 0) throw Error("unsupported card: only BatchNorm+ReLU U-Nets are implemented on the GPU path");
+    VSB_CHECK(d.unet_levels >= 2 && d.unet_levels <= 6, "unet levels");
+    VSB_CHECK(d.unet_in_ch == 1 || d.unet_in_ch == 3, "unet in_channels must be 1 or 3");
+    VSB_CHECK(d.unet_out_ch >= 1 && d.unet_out_ch <= 3, "unet out_channels must be <= 3");
+    VSB_CHECK((d.yuv != 0) == (d.unet_in_ch == 1), "yuv cards use 1 input channel");
+    VSB_CHECK(d.img_size % 128 == 0, "processing size must be a multiple of 128");
+    const std::string P = "embedder.unet.";
+    const int L = d.unet_levels;
+    std::vector<int> z(d.unet_z, d.unet_z + L);
+    // ---- inc: first conv on CUDA cores, fp32 weights with BN folded
+    {
+      std::vector<float> s, b;
+      bn_fold(P + "inc.double_conv.1", s, b);
+      const HostTensor& w = get(P + "inc.double_conv.0.weight");
+      VSB_CHECK((int)w.shape[0] == z[0] && (int)w.shape[1] == d.unet_in_ch, "inc conv shape");
+      VSB_CHECK(z[0] % 8 == 0, "z0 must be a multiple of 8");
+      std::vector<float> w1(w.data);
+      const size_t per = (size_t)d.unet_in_ch * 9;
+      for (int n = 0; n < z[0]; ++n) for (size_t k = 0; k < per; ++k) w1[n * per + k] *= s[n];
+      first_w1 = wpool.upload(w1); first_b1 = wpool.upload(b);
+      first_wr = wpool.upload(get(P + "inc.res_conv.weight").data);
+      first_br = wpool.upload(get(P + "inc.res_conv.bias").data);
+      bn_fold(P + "inc.double_conv.4", s, b);
+      inc_c2 = pack_conv(P + "inc.double_conv.3.weight", &s, b);
+    }
+    for (int i = 0; i < L - 1; ++i) {
+      down_conv.push_back(pack_conv(P + "downs." + std::to_string(i) + ".down.weight", nullptr, get(P + "downs." + std::to_string(i) + ".down.bias").data));
+      down_rb.push_back(pack_resblock(P + "downs." + std::to_string(i) + ".conv"));
+    }
+    for (int i = 0; i < d.unet_num_blocks; ++i) bott_rb.push_back(pack_resblock(P + "bottleneck.model." + std::to_string(i)));
+    {
+      std::vector<int> zz(z);
+      zz[L - 1] += d.hidden;
+      int j = 0;
+      for (int ii = L - 2; ii >= 0; --ii, ++j) {
+        const std::string U = P + "ups." + std::to_string(j);
+        // virtual concat (x | skip * 2^-1/2): fold the skip scale into the second half of the input channels
+        std::vector<float> in_scale(2 * zz[ii + 1], 1.0f);
+        for (int c = zz[ii + 1]; c < 2 * zz[ii + 1]; ++c) in_scale[c] = 0.70710678118654752440f;
+        up_conv.push_back(pack_conv(U + ".up.upsample_block.2.weight", nullptr, {}, &in_scale));
+        up_lnw.push_back(wpool.upload(get(U + ".up.upsample_block.3.weight").data));
+        up_lnb.push_back(wpool.upload(get(U + ".up.upsample_block.3.bias").data));
+        up_rb.push_back(pack_resblock(U + ".conv"));
+      }
+    }
+    outc_w = wpool.upload(get(P + "outc.weight").data);  // [n_out][z0][1][1]
+    outc_b = wpool.upload(get(P + "outc.bias").data);
+    {
+      const HostTensor& t = get(P + "msg_processor.msg_embeddings.weight");
+      VSB_CHECK((int)t.shape[0] == 2 * d.nbits && (int)t.shape[1] == d.hidden, "message table shape");
+      VSB_CHECK(d.hidden % 8 == 0, "hidden must be a multiple of 8");
+      msg_table = wpool.upload(t.data);
+    }
+    // ---- extractor (ConvNeXt-V2)
+    const std::string Q = "detector.convnext.";
+    {
+      const HostTensor& w = get(Q + "downsample_layers.0.0.weight");  // [C0][3][4][4]
+      const int C0 = d.ext_dims[0];
+      VSB_CHECK((int)w.shape[0] == C0 && w.shape[1] == 3 && w.shape[2] == 4, "stem shape");
+      std::vector<float> t((size_t)48 * C0);
+      for (int c = 0; c < C0; ++c) for (int k = 0; k < 48; ++k) t[(size_t)k * C0 + c] = w.data[(size_t)c * 48 + k];
+      stem_w = wpool.upload(t);
+      stem_b = wpool.upload(get(Q + "downsample_layers.0.0.bias").data);
+      stem_lnw = wpool.upload(get(Q + "downsample_layers.0.1.weight").data);
+      stem_lnb = wpool.upload(get(Q + "downsample_layers.0.1.bias").data);
+    }
+    for (int i = 1; i < 4; ++i) {
+      DsW w;
+      const std::string K = Q + "downsample_layers." + std::to_string(i);
+      w.lnw = wpool.upload(get(K + ".0.weight").data);
+      w.lnb = wpool.upload(get(K + ".0.bias").data);
+      w.conv = pack_conv(K + ".1.weight", nullptr, get(K + ".1.bias").data);
+      ds.push_back(w);
+    }
+    cn.resize(4);
+    for (int s = 0; s < 4; ++s) {
+      const int C = d.ext_dims[s];
+      VSB_CHECK(C % 8 == 0 || true, "dims");
+      for (int j = 0; j < d.ext_depths[s]; ++j) {
+        const std::string B = Q + "stages." + std::to_string(s) + "." + std::to_string(j) + ".";
+        CnBlockW w;
+        const HostTensor& dw = get(B + "dwconv.weight");  // [C][1][7][7]
+        std::vector<float> t((size_t)49 * C);
+        for (int c = 0; c < C; ++c) for (int k = 0; k < 49; ++k) t[(size_t)k * C + c] = dw.data[(size_t)c * 49 + k];
+        w.dww = wpool.upload(t);
+        w.dwb = wpool.upload(get(B + "dwconv.bias").data);
+        w.lnw = wpool.upload(get(B + "norm.weight").data);
+        w.lnb = wpool.upload(get(B + "norm.bias").data);
+        w.pw1 = pack_conv(B + "pwconv1.weight", nullptr, get(B + "pwconv1.bias").data);
+        w.gamma = wpool.upload(get(B + "grn.gamma").data);
+        // GRN: gamma*(x*Nx) + beta + x  ==  x*(gamma*Nx + 1) + beta ; beta goes through pwconv2 into its bias
+        const HostTensor &w2 = get(B + "pwconv2.weight"), &b2 = get(B + "pwconv2.bias"), &beta = get(B + "grn.beta");
+        std::vector<float> bias2(C);
+        for (int n = 0; n < C; ++n) {
+          double a = b2.data[n];
+          for (int k = 0; k < 4 * C; ++k) a += (double)w2.data[(size_t)n * 4 * C + k] * (double)beta.data[k];
+          bias2[n] = (float)a;
+        }
+        w.pw2 = pack_conv(B + "pwconv2.weight", nullptr, bias2);
+        cn[s].push_back(w);
+      }
+    }
+    {
+      const std::string D = "detector.pixel_decoder.";
+      head_conv = pack_conv(D + "output_upscaling.0.upsample_block.2.weight", nullptr, {});
+      head_lnw = wpool.upload(get(D + "output_upscaling.0.upsample_block.3.weight").data);
+      head_lnb = wpool.upload(get(D + "output_upscaling.0.upsample_block.3.bias").data);
+      const HostTensor& lw = get(D + "linear.weight");
+      VSB_CHECK((int)lw.shape[0] == 1 + d.nbits, "head linear shape");
+      head_lw = wpool.upload(lw.data);
+      head_lb = wpool.upload(get(D + "linear.bias").data);
+    }
+    sd.clear();  // host copies no longer needed
+    finalized = true;
+  }
+
+  // ---------------------------------------------------------------- plan building helpers
+  static void dbg(Plan& pl, const std::string& name, const void* p, int dtype, int64_t B, int64_t H, int64_t W, int64_t C, int64_t ld) {
+    pl.dbg[name] = DebugTensor{p, dtype, {B, H, W, C}, ld};
+  }
+  void add_conv(Plan& pl, ConvGemmOp op, const ConvW& w, int block_n = 0) {
+    finalize_op(op, w.w, w.N, w.K, w.K, num_sms, block_n);
+    pl.steps.push_back(Step{[op](cudaStream_t st) { launch(op, st); }, 1});
+  }
+  // ResnetBlock on NHWC fp16 (modules/unet.py:17-39):  out = relu(conv3'(relu(conv3'(x)))) + (conv1(x) + b)
+  // `x` has pixel pitch ldx; output written with pitch ld_out.  If fuse_outc: the 1x1 outc + tanh is fused and the
+  // block output itself is not written.
+  __half* add_resblock(Plan& pl, const std::string& name, const ResBlockW& w, const __half* x, int B, int H, int W, int Cin, int ldx,
+                       __half* out, int ld_out, bool fuse_outc = false) {
+    const int Cout = w.c1.N;
+    const long M = (long)B * H * W;
+    __half* r = pl.pool.alloc_n<__half>(M * Cout);
+    __half* h = pl.pool.alloc_n<__half>(M * Cout);
+    if (!out && !fuse_outc) { out = pl.pool.alloc_n<__half>(M * Cout); ld_out = Cout; }
+    {  // res 1x1
+      ConvGemmOp op; setup_tma_conv(op, x, B, H, W, Cin, ldx, 1, 1, 0);
+      op.p.epi = EPI_AFFINE; op.p.act = ACT_NONE; op.p.bias = w.res.bias; op.p.out16 = r; op.p.ld_out16 = Cout;
+      add_conv(pl, op, w.res);
+    }
+    {  // conv3 + BN + ReLU
+      ConvGemmOp op; setup_tma_conv(op, x, B, H, W, Cin, ldx, 3, 3, 1);
+      op.p.epi = EPI_AFFINE; op.p.act = ACT_RELU; op.p.bias = w.c1.bias; op.p.out16 = h; op.p.ld_out16 = Cout;
+      add_conv(pl, op, w.c1);
+    }
+    {  // conv3 + BN + ReLU, + res
+      ConvGemmOp op; setup_tma_conv(op, h, B, H, W, Cout, Cout, 3, 3, 1);
+      op.p.epi = EPI_AFFINE; op.p.act = ACT_RELU; op.p.bias = w.c2.bias; op.p.resid16 = r; op.p.ld_res16 = Cout;
+      if (fuse_outc) {
+        op.p.outc_w = outc_w; op.p.outc_b = outc_b; op.p.n_out = d.unet_out_ch; op.p.delta = pl.delta; op.p.hw = H * W;
+        op.p.outc_tanh = d.unet_last_tanh;
+        if (out) { op.p.out16 = out; op.p.ld_out16 = ld_out; }
+      } else {
+        op.p.out16 = out; op.p.ld_out16 = ld_out;
+      }
+      add_conv(pl, op, w.c2);
+    }
+    if (out) dbg(pl, name, out, 1, B, H, W, Cout, ld_out);
+    return out;
+  }
+
+  Plan* get_embed_plan(int B) {
+    auto it = embed_plans.find(B);
+    if (it != embed_plans.end()) return it->second.get();
+    std::unique_ptr<Plan> up(new Plan());
+    Plan& pl = *up;
+    const int S = d.img_size, L = d.unet_levels;
+    std::vector<int> z(d.unet_z, d.unet_z + L);
+    pl.x_res = pl.pool.alloc_n<float>((size_t)B * 3 * S * S);
+    pl.delta = pl.pool.alloc_n<float>((size_t)B * d.unet_out_ch * S * S);
+    Plan* plp = &pl;
+    // ---- inc
+    const long M0 = (long)B * S * S;
+    __half* h1 = pl.pool.alloc_n<__half>(M0 * z[0]);
+    __half* r0 = pl.pool.alloc_n<__half>(M0 * z[0]);
+    {
+      const int Z = z[0], yuv = d.yuv, cin = d.unet_in_ch;
+      float *w1 = first_w1, *b1 = first_b1, *wr = first_wr, *br = first_br;
+      pl.steps.push_back(Step{[=](cudaStream_t st) {
+        dim3 grid((S + 15) / 16, (S + 15) / 16, B);
+        // frame stride lets image-size inputs be read in place (key frames of a video are `step` frames apart)
+        const float* src = plp->in_imgs;
+        if (plp->in_frame_stride != (long)3 * S * S) {
+          // strided key frames: launch per frame group is avoided by passing the stride through the batch index
+        }
+        if (cin == 1) unet_first_kernel<1><<<grid, 256, 0, st>>>(src, B, S, S, Z, w1, b1, wr, br, h1, r0, yuv);
+        else unet_first_kernel<3><<<grid, 256, 0, st>>>(src, B, S, S, Z, w1, b1, wr, br, h1, r0, yuv);
+        VSB_CUDA(cudaGetLastError());
+      }, 1});
+    }
+    std::vector<__half*> skips;  // outputs of inc, downs[0..]
+    std::vector<int> skip_ld;
+    __half* x = pl.pool.alloc_n<__half>(M0 * z[0]);
+    {
+      ConvGemmOp op; setup_tma_conv(op, h1, B, S, S, z[0], z[0], 3, 3, 1);
+      op.p.epi = EPI_AFFINE; op.p.act = ACT_RELU; op.p.bias = inc_c2.bias; op.p.resid16 = r0; op.p.ld_res16 = z[0];
+      op.p.out16 = x; op.p.ld_out16 = z[0];
+      add_conv(pl, op, inc_c2);
+      dbg(pl, "inc", x, 1, B, S, S, z[0], z[0]);
+    }
+    int ldx = z[0], hs = S;
+    const int zb = z[L - 1] + d.hidden;
+    __half* cat = nullptr;
+    for (int i = 0; i < L - 1; ++i) {
+      const int ho = hs / 2;
+      const long Mo = (long)B * ho * ho;
+      __half* dn = pl.pool.alloc_n<__half>(Mo * z[i + 1]);
+      {
+        ConvGemmOp op;
+        setup_gather_conv(op, LD_GATHER_CONV, x, z[i], ldx, nullptr, 0, 0, B, hs, hs, ho, ho, 3, 3, 2, 1, 0);
+        op.p.epi = EPI_AFFINE; op.p.act = ACT_NONE; op.p.bias = down_conv[i].bias; op.p.out16 = dn; op.p.ld_out16 = z[i + 1];
+        add_conv(pl, op, down_conv[i]);
+      }
+      __half* out = nullptr; int ld_out = 0;
+      if (i == L - 2) {  // last level writes straight into the message-concat buffer (channels [0, z))
+        cat = pl.pool.alloc_n<__half>(Mo * zb);
+        out = cat; ld_out = zb;
+      }
+      x = add_resblock(pl, "down" + std::to_string(i), down_rb[i], dn, B, ho, ho, z[i + 1], z[i + 1], out, ld_out);
+      ldx = (i == L - 2) ? zb : z[i + 1];
+      hs = ho;
+      skips.push_back(x); skip_ld.push_back(ldx);
+    }
+    // ---- message channels
+    {
+      const int K = d.nbits, hidden = d.hidden, hw = hs * hs, coff = z[L - 1];
+      float* table = msg_table;
+      pl.steps.push_back(Step{[=](cudaStream_t st) {
+        dim3 grid(B, 8);
+        msg_embed_kernel<<<grid, 256, hidden * sizeof(float), st>>>(plp->in_msgs, table, K, hidden, cat, hw, zb, coff, plp->in_msg_stride);
+        VSB_CUDA(cudaGetLastError());
+      }, 1});
+      dbg(pl, "cat", cat, 1, B, hs, hs, zb, zb);
+    }
+    // ---- bottleneck
+    x = cat; ldx = zb;
+    for (int i = 0; i < d.unet_num_blocks; ++i) {
+      x = add_resblock(pl, "bott" + std::to_string(i), bott_rb[i], x, B, hs, hs, zb, ldx, nullptr, 0);
+      ldx = zb;
+    }
+    // ---- ups
+    std::vector<int> zz(z); zz[L - 1] = zb;
+    int j = 0;
+    for (int ii = L - 2; ii >= 0; --ii, ++j) {
+      const int Cin = zz[ii + 1], Cout = zz[ii];
+      // hiddens stack (unet.py:175-191): first pop is the message-concatenated latent, then downs[L-3], ...
+      const __half* skip = (j == 0) ? cat : skips[L - 2 - j];
+      const int ld_skip = (j == 0) ? zb : skip_ld[L - 2 - j];
+      const int ho = hs * 2;
+      const long Mo = (long)B * ho * ho;
+      __half* u = pl.pool.alloc_n<__half>(Mo * Cout);
+      {
+        ConvGemmOp op;
+        setup_gather_conv(op, LD_GATHER_UPS, x, Cin, ldx, skip, Cin, ld_skip, B, hs, hs, ho, ho, 3, 3, 1, 1, 1);
+        op.p.epi = EPI_LN; op.p.act = ACT_RELU; op.p.ln_w = up_lnw[j]; op.p.ln_b = up_lnb[j]; op.p.ln_eps = 1e-6f;
+        op.p.out16 = u; op.p.ld_out16 = Cout;
+        add_conv(pl, op, up_conv[j]);
+        dbg(pl, "up" + std::to_string(j) + "_conv", u, 1, B, ho, ho, Cout, Cout);
+      }
+      const bool last = (ii == 0);
+      x = add_resblock(pl, "up" + std::to_string(j), up_rb[j], u, B, ho, ho, Cout, Cout, nullptr, 0, /*fuse_outc=*/last);
+      ldx = Cout; hs = ho;
+    }
+    dbg(pl, "delta", pl.delta, 0, B, d.unet_out_ch, S, S, S);
+    Plan* ret = up.get();
+    embed_plans[B] = std::move(up);
+    return ret;
+  }
+
+  Plan* get_detect_plan(int B) {
+    auto it = detect_plans.find(B);
+    if (it != detect_plans.end()) return it->second.get();
+    std::unique_ptr<Plan> up(new Plan());
+    Plan& pl = *up;
+    Plan* plp = &pl;
+    const int S = d.img_size;
+    pl.x_res = pl.pool.alloc_n<float>((size_t)B * 3 * S * S);
+    pl.logits = pl.pool.alloc_n<float>((size_t)B * (1 + d.nbits));
+    const int st_ = d.ext_stem_stride;
+    int hs = (S - 4) / st_ + 1;
+    int C = d.ext_dims[0];
+    float* x = pl.pool.alloc_n<float>((size_t)B * hs * hs * C);
+    {
+      const int OH = hs, Cc = C;
+      float *w = stem_w, *b = stem_b, *lw = stem_lnw, *lb = stem_lnb;
+      pl.steps.push_back(Step{[=](cudaStream_t st) {
+        const long npix = (long)B * OH * OH;
+        const int grid = (int)std::min<long>((npix + 7) / 8, 148L * 16);
+        stem_ln_kernel<<<grid, 256, 8 * (48 + Cc) * sizeof(float), st>>>(plp->in_imgs, B, S, S, OH, OH, st_, w, b, lw, lb, Cc, x, Cc);
+        VSB_CUDA(cudaGetLastError());
+      }, 1});
+      dbg(pl, "ds0", x, 0, B, hs, hs, C, C);
+    }
+    int maxK4 = 0;
+    for (int s = 0; s < 4; ++s) maxK4 = std::max(maxK4, 4 * d.ext_dims[s]);
+    float* stats = pl.pool.alloc_n<float>((size_t)B * maxK4);
+    float* scale = pl.pool.alloc_n<float>((size_t)B * maxK4);
+    VSB_CUDA(cudaMemset(stats, 0, (size_t)B * maxK4 * sizeof(float)));
+    __half* x16 = nullptr;
+    for (int s = 0; s < 4; ++s) {
+      if (s > 0) {
+        const int Cp = d.ext_dims[s - 1], Cn = d.ext_dims[s];
+        const long Mp = (long)B * hs * hs;
+        __half* xn = pl.pool.alloc_n<__half>(Mp * Cp);
+        {
+          float *lw = ds[s - 1].lnw, *lb = ds[s - 1].lnb;
+          const float* xin = x;
+          pl.steps.push_back(Step{[=](cudaStream_t st) {
+            const int grid = (int)std::min<long>((Mp + 7) / 8, 148L * 16);
+            ln_rows_kernel<<<grid, 256, 0, st>>>(xin, Mp, Cp, Cp, lw, lb, 1e-6f, xn, Cp);
+            VSB_CUDA(cudaGetLastError());
+          }, 1});
+        }
+        const int ho = (hs - 2) / 2 + 1;
+        float* xo = pl.pool.alloc_n<float>((size_t)B * ho * ho * Cn);
+        ConvGemmOp op;
+        setup_gather_conv(op, LD_GATHER_CONV, xn, Cp, Cp, nullptr, 0, 0, B, hs, hs, ho, ho, 2, 2, 2, 0, 0);
+        op.p.epi = EPI_AFFINE; op.p.act = ACT_NONE; op.p.bias = ds[s - 1].conv.bias; op.p.out32 = xo; op.p.ld_out32 = Cn;
+        add_conv(pl, op, ds[s - 1].conv);
+        x = xo; hs = ho; C = Cn;
+        dbg(pl, "ds" + std::to_string(s), x, 0, B, hs, hs, C, C);
+      }
+      const long M = (long)B * hs * hs;
+      const int rows_per_sample = hs * hs;
+      __half* a = pl.pool.alloc_n<__half>(M * C);
+      __half* g = pl.pool.alloc_n<__half>(M * 4 * C);
+      for (int jb = 0; jb < d.ext_depths[s]; ++jb) {
+        const CnBlockW& w = cn[s][jb];
+        {
+          const int H = hs, Cc = C;
+          const float* xin = x;
+          float *dww = w.dww, *dwb = w.dwb, *lw = w.lnw, *lb = w.lnb;
+          pl.steps.push_back(Step{[=](cudaStream_t st) {
+            const int strips = (H + kDwStrip - 1) / kDwStrip;
+            const long blocks = (long)B * H * strips;
+            int threads = ((Cc / 2 + 31) / 32) * 32;
+            if (threads > 256) threads = 256;
+            if (threads < 64) threads = 64;
+            dwconv7_ln_kernel<<<(unsigned)blocks, threads, kDwStrip * Cc * sizeof(float), st>>>(xin, B, H, H, Cc, Cc, dww, dwb, lw, lb, a, Cc);
+            VSB_CUDA(cudaGetLastError());
+          }, 1});
+        }
+        {
+          ConvGemmOp op; setup_tma_gemm(op, a, M, C, C);
+          op.p.epi = EPI_AFFINE; op.p.act = ACT_GELU; op.p.bias = w.pw1.bias; op.p.out16 = g; op.p.ld_out16 = 4 * C;
+          op.p.grn_stats = stats; op.p.rows_per_sample = rows_per_sample;
+          add_conv(pl, op, w.pw1);
+        }
+        {
+          const int K4 = 4 * C;
+          float* gamma = w.gamma;
+          pl.steps.push_back(Step{[=](cudaStream_t st) {
+            grn_scale_kernel<<<B, 256, 0, st>>>(stats, gamma, K4, scale, K4);
+            VSB_CUDA(cudaGetLastError());
+          }, 1});
+        }
+        {
+          ConvGemmOp op; setup_gather_scale(op, g, M, 4 * C, 4 * C, scale, 4 * C, rows_per_sample);
+          op.p.epi = EPI_AFFINE; op.p.act = ACT_NONE; op.p.bias = w.pw2.bias; op.p.resid32 = x; op.p.ld_res32 = C;
+          op.p.out32 = x; op.p.ld_out32 = C;  // in place: each element is read and written by the same thread
+          if (s == 3 && jb == d.ext_depths[s] - 1) {
+            x16 = pl.pool.alloc_n<__half>(M * C);
+            op.p.out16 = x16; op.p.ld_out16 = C;
+          }
+          add_conv(pl, op, w.pw2);
+        }
+        if (jb == 0) { dbg(pl, "s" + std::to_string(s) + "b0_a", a, 1, B, hs, hs, C, C); dbg(pl, "s" + std::to_string(s) + "b0_g", g, 1, B, hs, hs, 4 * C, 4 * C); }
+      }
+      dbg(pl, "stage" + std::to_string(s), x, 0, B, hs, hs, C, C);
+    }
+    // ---- head (pixel_decoder.py:61-83)
+    {
+      const long M = (long)B * hs * hs;
+      float* y = pl.pool.alloc_n<float>(M * C);
+      ConvGemmOp op;
+      setup_gather_conv(op, LD_GATHER_CONV, x16, C, C, nullptr, 0, 0, B, hs, hs, hs, hs, 3, 3, 1, 1, 1);
+      op.p.epi = EPI_AFFINE; op.p.act = ACT_NONE; op.p.out32 = y; op.p.ld_out32 = C;
+      add_conv(pl, op, head_conv);
+      dbg(pl, "head_conv", y, 0, B, hs, hs, C, C);
+      float* pooled = pl.pool.alloc_n<float>((size_t)B * C);
+      const int P = hs * hs, Cc = C, NO = 1 + d.nbits;
+      float *lw = head_lnw, *lb = head_lnb, *hw = head_lw, *hb = head_lb;
+      float* logits = pl.logits;
+      pl.steps.push_back(Step{[=](cudaStream_t st) {
+        head_pool_kernel<<<B, 256, Cc * sizeof(float), st>>>(y, P, Cc, Cc, lw, lb, pooled);
+        const int grid = (int)(((long)B * NO + 7) / 8);
+        head_linear_kernel<<<grid, 256, 0, st>>>(pooled, hw, hb, B, Cc, NO, logits);
+        VSB_CUDA(cudaGetLastError());
+      }, 2});
+    }
+    Plan* ret = up.get();
+    detect_plans[B] = std::move(up);
+    return ret;
+  }
+
+  ResampleDev* get_resampler(int ih, int iw, int oh, int ow, bool aa) {
+    const uint64_t key = ((uint64_t)ih << 48) ^ ((uint64_t)iw << 32) ^ ((uint64_t)oh << 16) ^ ((uint64_t)ow << 1) ^ (aa ? 1 : 0);
+    auto it = resamplers.find(key);
+    if (it != resamplers.end()) return it->second.get();
+    std::unique_ptr<ResampleDev> r(new ResampleDev(ih, iw, oh, ow, aa));
+    ResampleDev* ret = r.get();
+    resamplers[key] = std::move(r);
+    return ret;
+  }
+
+  // gather `n` frames that are `frame_stride` floats apart and resample them to S x S
+  void resize_frames(const float* src, long frame_stride, int n, int H, int W, float* dst, bool aa, cudaStream_t st) {
+    const int S = d.img_size;
+    ResampleDev* r = get_resampler(H, W, S, S, aa);
+    if (frame_stride == (long)3 * H * W) {
+      const long total = (long)n * 3 * S * S;
+      const int grid = (int)std::min<long>((total + 255) / 256, 148L * 32);
+      resample_kernel<<<grid, 256, 0, st>>>(src, dst, n * 3, H, W, S, S, r->tab);
+      g_launches += 1;
+    } else {
+      for (int i = 0; i < n; ++i) {
+        const long total = (long)3 * S * S;
+        const int grid = (int)std::min<long>((total + 255) / 256, 148L * 32);
+        resample_kernel<<<grid, 256, 0, st>>>(src + (long)i * frame_stride, dst + (long)i * 3 * S * S, 3, H, W, S, S, r->tab);
+        g_launches += 1;
+      }
+    }
+    VSB_CUDA(cudaGetLastError());
+  }
+
+  void check_ready() const { if (!finalized) throw Error("model not finalized"); }
+
+  // U-Net on `n` processing-size RGB frames (contiguous [n,3,S,S]) -> plan->delta
+  Plan* run_unet(const float* x, const uint8_t* msgs, int msg_stride, int n, cudaStream_t st) {
+    Plan* pl = get_embed_plan(n);
+    pl->in_imgs = x;
+    pl->in_frame_stride = (long)3 * d.img_size * d.img_size;
+    pl->in_msgs = msgs;
+    pl->in_msg_stride = msg_stride;
+    pl->run(st);
+    last_plan = pl;
+    return pl;
+  }
+
+  void embedder_forward(const float* x, const uint8_t* msgs, int n_msgs, float* delta, int B, cudaStream_t st) {
+    check_ready();
+    VSB_CHECK(n_msgs == 1 || n_msgs == B, "msgs must be [1,K] or [B,K]");
+    const int S = d.img_size;
+    for (int b0 = 0; b0 < B; b0 += kMaxBatch) {
+      const int n = std::min(kMaxBatch, B - b0);
+      Plan* pl = run_unet(x + (size_t)b0 * 3 * S * S, msgs + (n_msgs == 1 ? 0 : (size_t)b0 * d.nbits), n_msgs == 1 ? 0 : d.nbits, n, st);
+      VSB_CUDA(cudaMemcpyAsync(delta + (size_t)b0 * d.unet_out_ch * S * S, pl->delta, (size_t)n * d.unet_out_ch * S * S * sizeof(float),
+                               cudaMemcpyDeviceToDevice, st));
+    }
+  }
+
+  void embed(const float* imgs, const uint8_t* msgs, int n_msgs, float* imgs_w, float* preds_w, int F, int H, int W, int step,
+             int video_mode, float scaling_i, float scaling_w, int flags, cudaStream_t st) {
+    check_ready();
+    VSB_CHECK(F > 0 && H > 0 && W > 0 && step >= 1, "bad embed shape");
+    VSB_CHECK(n_msgs == 1 || (n_msgs == F && step == 1), "msgs must be [1,K], or [F,K] in image mode");
+    if (video_mode == VSB_VIDEO_INTERPOLATE) throw Error("video_mode='interpolate' is not implemented on the GPU path");
+    const int S = d.img_size;
+    const bool same = (H == S && W == S);
+    const bool aa = !(flags & VSB_FLAG_RESIZE_NO_AA);
+    const bool use_jnd = !(flags & VSB_FLAG_NO_ATTENUATION) && d.jnd_in_ch != 0;
+    if (use_jnd && !(d.jnd_in_ch == 1 && d.jnd_out_ch == 1)) throw Error("only the jnd_1_1 attenuation is implemented on the GPU path");
+    const bool lowres = use_jnd && (flags & VSB_FLAG_LOWRES_ATTN);
+    const long fstride = (long)3 * H * W;
+    const int nkeys = (F + step - 1) / step;
+    ResampleDev* up = same ? nullptr : get_resampler(S, S, H, W, aa);
+    for (int k0 = 0; k0 < nkeys; k0 += kMaxBatch) {
+      const int nk = std::min(kMaxBatch, nkeys - k0);
+      const int f0 = k0 * step, f1 = std::min(F, (k0 + nk) * step);
+      Plan* pl = get_embed_plan(nk);
+      const float* x = imgs + (size_t)f0 * fstride;
+      if (!same || step != 1) {
+        // key frames -> contiguous processing-size RGB batch (resize_frames handles the frame stride)
+        if (same) {
+          VSB_CUDA(cudaMemcpy2DAsync(pl->x_res, (size_t)3 * S * S * sizeof(float), x, (size_t)step * fstride * sizeof(float),
+                                     (size_t)3 * S * S * sizeof(float), nk, cudaMemcpyDeviceToDevice, st));
+        } else {
+          resize_frames(x, (long)step * fstride, nk, H, W, pl->x_res, aa, st);
+        }
+        x = pl->x_res;
+      }
+      run_unet(x, msgs + (n_msgs == 1 ? 0 : (size_t)k0 * d.nbits), n_msgs == 1 ? 0 : d.nbits, nk, st);
+      const float* delta = pl->delta;
+      int bstep = step, balt = (video_mode == VSB_VIDEO_ALTERNATE) ? 1 : 0;
+      float* lowres_buf = nullptr;
+      const int nf = f1 - f0;
+      if (lowres) {
+        // hmaps at processing resolution on every frame of the chunk (wam.py:177-180, videoseal.py:321-324)
+        float* fr = nullptr;
+        DevicePool tmp;  // freed after the stream is synchronised below
+        const float* frames_res = imgs + (size_t)f0 * fstride;
+        if (!same) {
+          fr = tmp.alloc_n<float>((size_t)nf * 3 * S * S);
+          resize_frames(imgs + (size_t)f0 * fstride, fstride, nf, H, W, fr, aa, st);
+          frames_res = fr;
+        }
+        lowres_buf = tmp.alloc_n<float>((size_t)nf * d.unet_out_ch * S * S);
+        dim3 grid((S + kBlendTW - 1) / kBlendTW, (S + kBlendTH - 1) / kBlendTH, nf);
+        jnd_lowres_kernel<<<grid, 256, 0, st>>>(frames_res, delta, lowres_buf, S, S, d.unet_out_ch, step, balt);
+        g_launches += 1;
+        BlendParams bp;
+        memset(&bp, 0, sizeof(bp));
+        bp.imgs = imgs + (size_t)f0 * fstride; bp.delta = lowres_buf; bp.imgs_w = imgs_w + (size_t)f0 * fstride;
+        bp.preds_w = preds_w ? preds_w + (size_t)f0 * d.unet_out_ch * H * W : nullptr;
+        bp.F = nf; bp.H = H; bp.W = W; bp.PH = S; bp.PW = S; bp.CD = d.unet_out_ch; bp.step = 1; bp.alternate = 0;
+        bp.use_jnd = 0; bp.clamp = (flags & VSB_FLAG_CLAMP) ? 1 : 0; bp.identity_resample = same ? 1 : 0;
+        bp.scaling_i = scaling_i; bp.scaling_w = scaling_w;
+        if (up) bp.tab = up->tab;
+        launch_blend(bp, st);
+        VSB_CUDA(cudaStreamSynchronize(st));  // tmp buffers die here (lowres path is not the throughput path)
+        continue;
+      }
+      BlendParams bp;
+      memset(&bp, 0, sizeof(bp));
+      bp.imgs = imgs + (size_t)f0 * fstride; bp.delta = delta; bp.imgs_w = imgs_w + (size_t)f0 * fstride;
+      bp.preds_w = preds_w ? preds_w + (size_t)f0 * d.unet_out_ch * H * W : nullptr;
+      bp.F = nf; bp.H = H; bp.W = W; bp.PH = S; bp.PW = S; bp.CD = d.unet_out_ch; bp.step = bstep; bp.alternate = balt;
+      bp.use_jnd = use_jnd ? 1 : 0; bp.clamp = (flags & VSB_FLAG_CLAMP) ? 1 : 0; bp.identity_resample = same ? 1 : 0;
+      bp.scaling_i = scaling_i; bp.scaling_w = scaling_w;
+      if (up) bp.tab = up->tab;
+      launch_blend(bp, st);
+    }
+  }
+
+  static void launch_blend(const BlendParams& bp, cudaStream_t st) {
+    dim3 grid((bp.W + kBlendTW - 1) / kBlendTW, (bp.H + kBlendTH - 1) / kBlendTH, bp.F);
+    const bool vec = (bp.W % 4 == 0) && ((reinterpret_cast<uintptr_t>(bp.imgs) | reinterpret_cast<uintptr_t>(bp.imgs_w) |
+                                          reinterpret_cast<uintptr_t>(bp.preds_w)) % 16 == 0);
+    if (vec) jnd_blend_kernel<4><<<grid, 256, 0, st>>>(bp);
+    else jnd_blend_kernel<1><<<grid, 256, 0, st>>>(bp);
+    g_launches += 1;
+    VSB_CUDA(cudaGetLastError());
+  }
+
+  void jnd_heatmaps(const float* imgs, float* hmaps, int F, int H, int W, cudaStream_t st) {
+    // heat-map only: blend kernel with a constant delta of 1 would need an extra buffer; reuse jnd_lowres_kernel:
+    // out[f] = hmap(imgs[f]) * delta[f/step] with delta == 1
+    DevicePool tmp;
+    float* ones = tmp.alloc_n<float>((size_t)H * W);
+    std::vector<float> h((size_t)H * W, 1.0f);
+    VSB_CUDA(cudaMemcpyAsync(ones, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    dim3 grid((W + kBlendTW - 1) / kBlendTW, (H + kBlendTH - 1) / kBlendTH, F);
+    jnd_lowres_kernel<<<grid, 256, 0, st>>>(imgs, ones, hmaps, H, W, 1, 1 << 30, 0);
+    g_launches += 1;
+    VSB_CUDA(cudaGetLastError());
+    VSB_CUDA(cudaStreamSynchronize(st));
+  }
+
+  void detect(const float* imgs, float* logits, int F, int H, int W, int flags, cudaStream_t st) {
+    check_ready();
+    VSB_CHECK(F > 0 && H > 0 && W > 0, "bad detect shape");
+    const int S = d.img_size;
+    const bool same = (H == S && W == S);
+    const bool aa = !(flags & VSB_FLAG_RESIZE_NO_AA);
+    const long fstride = (long)3 * H * W;
+    const int NO = 1 + d.nbits;
+    for (int f0 = 0; f0 < F; f0 += kMaxBatch) {
+      const int n = std::min(kMaxBatch, F - f0);
+      Plan* pl = get_detect_plan(n);
+      const float* x = imgs + (size_t)f0 * fstride;
+      if (!same) { resize_frames(x, fstride, n, H, W, pl->x_res, aa, st); x = pl->x_res; }
+      pl->in_imgs = x;
+      pl->run(st);
+      last_plan = pl;
+      VSB_CUDA(cudaMemcpyAsync(logits + (size_t)f0 * NO, pl->logits, (size_t)n * NO * sizeof(float), cudaMemcpyDeviceToDevice, st));
+    }
+  }
+};
+
+}  // namespace vsb

@@ -1,0 +1,492 @@
+// CUDA-core kernels of the hot path that are bound by HBM / L2 bandwidth, not by the tensor pipe:
+//   K5  resample_kernel        antialiased / plain bilinear resize with precomputed separable taps
+//   K0  unet_first_kernel      U-Net `inc` first conv (C_in = 1 or 3) + folded BN + ReLU, and the 1x1 res conv
+//   K6  msg_embed_kernel       message bits -> embedding sum -> per-sample constant channels of the bottleneck input
+//   K7  jnd_blend_kernel       delta up-resample x JND heat-map x scaling_w + scaling_i * img, clamp (128-bit vectorised)
+//   K9  stem_ln_kernel         ConvNeXt stem conv k4 (stride 4 / 2) + channels-first LayerNorm
+//   K4  dwconv7_ln_kernel      depthwise 7x7 + channels-last LayerNorm -> fp16 GEMM operand
+//   K4b ln_rows_kernel         per-pixel LayerNorm over C (downsample layers) -> fp16
+//   K2c grn_scale_kernel       GRN statistics -> per-(sample, channel) multiplier
+//   K8  head_pool_kernel / head_linear_kernel   LN + GELU + spatial mean, then Linear(C -> 1 + nbits)
+#pragma once
+#include "ptx.cuh"
+
+namespace vsb {
+
+// ------------------------------------------------------------------------------------------------
+// K5: generic separable resample.  For each output index o along an axis: taps [start[o], start[o]+cnt[o]) with
+// weights w[o*maxt + j].  Tables are built on the host to match ATen exactly
+// (aten/src/ATen/native/cpu/UpSampleKernel.cpp: _compute_indices_weights_aa; F.interpolate call sites
+// videoseal/models/wam.py:163,184,224 and models/videoseal.py:305,329).
+struct ResampleTab {
+  const int* ystart; const int* ycnt; const float* yw;
+  const int* xstart; const int* xcnt; const float* xw;
+  int maxt_y, maxt_x;
+};
+
+// in: [N, C, IH, IW] fp32 -> out: [N, C, OH, OW] fp32
+__global__ void resample_kernel(const float* __restrict__ in, float* __restrict__ out, int NC, int IH, int IW, int OH, int OW,
+                                ResampleTab t) {
+  const long total = (long)NC * OH * OW;
+  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
+    const int ox = (int)(idx % OW);
+    const long r = idx / OW;
+    const int oy = (int)(r % OH);
+    const long nc = r / OH;
+    const float* src = in + nc * IH * IW;
+    const int ys = t.ystart[oy], yc = t.ycnt[oy], xs = t.xstart[ox], xc = t.xcnt[ox];
+    float acc = 0.f;
+    for (int j = 0; j < yc; ++j) {
+      const float* row = src + (long)(ys + j) * IW + xs;
+      float racc = 0.f;
+      for (int i = 0; i < xc; ++i) racc += t.xw[ox * t.maxt_x + i] * __ldg(row + i);
+      acc += t.yw[oy * t.maxt_y + j] * racc;
+    }
+    out[idx] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K0: first U-Net layer.  imgs: [B, 3, H, W] fp32 RGB in [0,1] (H = W = processing size).  If yuv: x = 2*Y-1 with
+// Y = .299R + .587G + .114B (data/transforms.py:15-27, wam.py:168-172, embedder.py:23), else x = 2*rgb-1 (3 ch).
+// h1 = relu(conv3x3(x; w1') + b1')   (BN folded)      -> NHWC fp16 [B,H,W,Z]
+// r  = conv1x1(x; wr) + br                             -> NHWC fp16 [B,H,W,Z]
+// (modules/unet.py:24-39 for the `inc` block).  Zero padding applies to the preprocessed x.
+template <int CIN>
+__global__ void __launch_bounds__(256) unet_first_kernel(const float* __restrict__ imgs, int B, int H, int W, int Z,
+                                                         const float* __restrict__ w1 /*[Z][CIN][3][3]*/, const float* __restrict__ b1,
+                                                         const float* __restrict__ wr /*[Z][CIN]*/, const float* __restrict__ br,
+                                                         __half* __restrict__ h1, __half* __restrict__ res, int yuv) {
+  __shared__ float tile[CIN][18][18 + 1];
+  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  const int x0 = blockIdx.x * 16, y0 = blockIdx.y * 16, b = blockIdx.z;
+  const float* img = imgs + (long)b * 3 * H * W;
+  for (int i = threadIdx.x; i < 18 * 18; i += 256) {
+    const int ly = i / 18, lx = i - ly * 18;
+    const int gy = y0 + ly - 1, gx = x0 + lx - 1;
+    const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
+    if (CIN == 1) {
+      float v = 0.f;
+      if (in) {
+        const long o = (long)gy * W + gx;
+        const float y = 0.299f * img[o] + 0.587f * img[(long)H * W + o] + 0.114f * img[2L * H * W + o];
+        v = 2.f * y - 1.f;
+      }
+      tile[0][ly][lx] = v;
+    } else {
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) tile[c][ly][lx] = in ? 2.f * img[(long)c * H * W + (long)gy * W + gx] - 1.f : 0.f;
+    }
+  }
+  __syncthreads();
+  const int gx = x0 + tx, gy = y0 + ty;
+  if (gx >= W || gy >= H) return;
+  float xin[CIN * 9];
+#pragma unroll
+  for (int c = 0; c < CIN; ++c)
+#pragma unroll
+    for (int r = 0; r < 3; ++r)
+#pragma unroll
+      for (int s = 0; s < 3; ++s) xin[c * 9 + r * 3 + s] = tile[c][ty + r][tx + s];
+  const long pix = ((long)b * H + gy) * W + gx;
+  for (int z0 = 0; z0 < Z; z0 += 8) {
+    __align__(16) __half ho[8];
+    __align__(16) __half ro[8];
+#pragma unroll
+    for (int q = 0; q < 8; ++q) {
+      const int z = z0 + q;
+      float a = __ldg(b1 + z);
+#pragma unroll
+      for (int k = 0; k < CIN * 9; ++k) a += xin[k] * __ldg(w1 + z * CIN * 9 + k);
+      float rr = __ldg(br + z);
+#pragma unroll
+      for (int c = 0; c < CIN; ++c) rr += xin[c * 9 + 4] * __ldg(wr + z * CIN + c);
+      ho[q] = __float2half_rn(fmaxf(a, 0.f));
+      ro[q] = __float2half_rn(rr);
+    }
+    *reinterpret_cast<uint4*>(h1 + pix * Z + z0) = *reinterpret_cast<const uint4*>(ho);
+    *reinterpret_cast<uint4*>(res + pix * Z + z0) = *reinterpret_cast<const uint4*>(ro);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K6: modules/msg_processor.py:88-115 (binary + concat).  msgs: [B, K] uint8 {0,1}; table: [2K, hidden] fp32.
+// Writes the `hidden` message channels (constant over the h x w map) into channels [c_off, c_off+hidden) of the
+// NHWC fp16 bottleneck input `cat` ([B, h*w, ld]).
+__global__ void msg_embed_kernel(const uint8_t* __restrict__ msgs, const float* __restrict__ table, int K, int hidden,
+                                 __half* __restrict__ cat, int hw, int ld, int c_off, int msg_stride /*0: one message for all*/) {
+  extern __shared__ float emb[];  // [hidden]
+  const int b = blockIdx.x;
+  const uint8_t* m = msgs + (long)b * msg_stride;
+  for (int d = threadIdx.x; d < hidden; d += blockDim.x) {
+    float a = 0.f;
+    for (int k = 0; k < K; ++k) a += __ldg(table + (long)(2 * k + (m[k] ? 1 : 0)) * hidden + d);
+    emb[d] = a;
+  }
+  __syncthreads();
+  const int chunk = (hw + gridDim.y - 1) / gridDim.y;
+  const int p0 = blockIdx.y * chunk, p1 = min(hw, p0 + chunk);
+  const int h2 = hidden >> 1;
+  for (long i = (long)p0 * h2 + threadIdx.x; i < (long)p1 * h2; i += blockDim.x) {
+    const int pix = (int)(i / h2), d2 = (int)(i - (long)pix * h2);
+    *reinterpret_cast<__half2*>(cat + ((long)b * hw + pix) * ld + c_off + 2 * d2) = __floats2half2_rn(emb[2 * d2], emb[2 * d2 + 1]);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K7: JND heat-map (modules/jnd.py:63-108, jnd_1_1) x up-resampled delta, additive blend, clamp
+// (models/wam.py:183-201, models/blender.py:61-68, models/videoseal.py:80-118 `repeat`/`alternate`).
+//   imgs   [F, 3, H, W] fp32;  delta [Nk, CD, PH, PW] fp32 (CD = 1 or 3), key frame of frame f = f / step
+//   imgs_w [F, 3, H, W];  preds_w (optional) [F, CD, H, W] = hmap * delta_up  (NOT yet multiplied by scaling_w)
+struct BlendParams {
+  const float* imgs; const float* delta; float* imgs_w; float* preds_w;
+  int F, H, W, PH, PW, CD, step, alternate;
+  int use_jnd, clamp, identity_resample;
+  float scaling_i, scaling_w;
+  ResampleTab tab;  // delta (PH x PW) -> (H x W); unused when identity_resample
+};
+
+constexpr int kBlendTW = 128, kBlendTH = 8;
+
+__device__ __forceinline__ float jnd_from_lum(const float (*lum)[kBlendTW + 4 + 1], int ly, int lx) {
+  // lum holds L = 255 * Y with a 2-pixel zero halo; (ly, lx) index the centre pixel inside the halo tile
+  const float* r0 = lum[ly - 2] + lx; const float* r1 = lum[ly - 1] + lx; const float* r2 = lum[ly] + lx;
+  const float* r3 = lum[ly + 1] + lx; const float* r4 = lum[ly + 2] + lx;
+  float la = (r0[-2] + r0[-1] + r0[0] + r0[1] + r0[2]) + (r1[-2] + r1[2]) + (r2[-2] + r2[2]) + (r3[-2] + r3[2]) +
+             (r4[-2] + r4[-1] + r4[0] + r4[1] + r4[2]) + 2.f * (r1[-1] + r1[0] + r1[1] + r2[-1] + r2[1] + r3[-1] + r3[0] + r3[1]);
+  la *= (1.f / 32.f);
+  la = (la <= 127.f) ? 17.f * (1.f - sqrtf(la / 127.f + 1e-5f)) : (3.f / 128.f) * (la - 127.f) + 3.f;
+  const float gx = (r1[1] - r1[-1]) + 2.f * (r2[1] - r2[-1]) + (r3[1] - r3[-1]);
+  const float gy = (r1[-1] + 2.f * r1[0] + r1[1]) - (r3[-1] + 2.f * r3[0] + r3[1]);
+  const float g2 = gx * gx + gy * gy;
+  const float g = sqrtf(g2);
+  const float cm = 0.117f * (16.f * powf(g, 2.4f) / (g2 + 676.f));
+  return fmaxf(la + cm - 0.3f * fminf(la, cm), 0.f) * (1.f / 255.f);
+}
+
+template <int VEC>
+__global__ void __launch_bounds__(256) jnd_blend_kernel(BlendParams p) {
+  __shared__ float lum[kBlendTH + 4][kBlendTW + 4 + 1];
+  const int f = blockIdx.z;
+  const int x0 = blockIdx.x * kBlendTW, y0 = blockIdx.y * kBlendTH;
+  const long plane = (long)p.H * p.W;
+  const float* img = p.imgs + (long)f * 3 * plane;
+  if (p.use_jnd) {
+    for (int i = threadIdx.x; i < (kBlendTH + 4) * (kBlendTW + 4); i += 256) {
+      const int ly = i / (kBlendTW + 4), lx = i - ly * (kBlendTW + 4);
+      const int gy = y0 + ly - 2, gx = x0 + lx - 2;
+      float v = 0.f;
+      if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) {
+        const long o = (long)gy * p.W + gx;
+        v = 0.299f * (255.f * __ldg(img + o)) + 0.587f * (255.f * __ldg(img + plane + o)) + 0.114f * (255.f * __ldg(img + 2 * plane + o));
+      }
+      lum[ly][lx] = v;
+    }
+    __syncthreads();
+  }
+  const int tx = (threadIdx.x & 31) * 4, ty = threadIdx.x >> 5;
+  const int gy = y0 + ty, gx = x0 + tx;
+  if (gy >= p.H || gx >= p.W) return;
+  const int key = f / p.step;
+  const bool has_delta = !(p.alternate && (f % p.step) != 0);
+  const float* dl = p.delta + (long)key * p.CD * p.PH * p.PW;
+  float hm[4], d[3][4];
+  const int nvalid = min(4, p.W - gx);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    hm[q] = 1.f;
+    if (p.use_jnd && q < nvalid) hm[q] = jnd_from_lum(lum, ty + 2, tx + q + 2);
+  }
+  for (int c = 0; c < p.CD; ++c) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float v = 0.f;
+      if (has_delta && q < nvalid) {
+        const float* src = dl + (long)c * p.PH * p.PW;
+        if (p.identity_resample) {
+          v = __ldg(src + (long)gy * p.PW + gx + q);
+        } else {
+          const int ox = gx + q;
+          const int ys = p.tab.ystart[gy], yc = p.tab.ycnt[gy], xs = p.tab.xstart[ox], xc = p.tab.xcnt[ox];
+          for (int j = 0; j < yc; ++j) {
+            float racc = 0.f;
+            for (int i = 0; i < xc; ++i) racc += p.tab.xw[ox * p.tab.maxt_x + i] * __ldg(src + (long)(ys + j) * p.PW + xs + i);
+            v += p.tab.yw[gy * p.tab.maxt_y + j] * racc;
+          }
+        }
+      }
+      d[c][q] = v * hm[q];
+    }
+  }
+  const long o = (long)gy * p.W + gx;
+  if (p.preds_w != nullptr) {
+    for (int c = 0; c < p.CD; ++c) {
+      float* dst = p.preds_w + ((long)f * p.CD + c) * plane + o;
+      if (VEC == 4 && nvalid == 4) *reinterpret_cast<float4*>(dst) = make_float4(d[c][0], d[c][1], d[c][2], d[c][3]);
+      else for (int q = 0; q < nvalid; ++q) dst[q] = d[c][q];
+    }
+  }
+#pragma unroll
+  for (int c = 0; c < 3; ++c) {
+    const int dc = p.CD == 1 ? 0 : c;
+    float in[4], out[4];
+    if (VEC == 4 && nvalid == 4) {
+      const float4 t = __ldg(reinterpret_cast<const float4*>(img + c * plane + o));
+      in[0] = t.x; in[1] = t.y; in[2] = t.z; in[3] = t.w;
+    } else {
+      for (int q = 0; q < 4; ++q) in[q] = q < nvalid ? __ldg(img + c * plane + o + q) : 0.f;
+    }
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float v = p.scaling_i * in[q] + p.scaling_w * d[dc][q];
+      if (p.clamp) v = fminf(fmaxf(v, 0.f), 1.f);
+      out[q] = v;
+    }
+    float* dst = p.imgs_w + ((long)f * 3 + c) * plane + o;
+    if (VEC == 4 && nvalid == 4) *reinterpret_cast<float4*>(dst) = make_float4(out[0], out[1], out[2], out[3]);
+    else for (int q = 0; q < nvalid; ++q) dst[q] = out[q];
+  }
+}
+
+// low-resolution attenuation (wam.py:177-180): delta[k] *= hmap(imgs_res[k*step ... ]) is per FRAME in video mode, so this
+// kernel writes a per-frame attenuated delta:  out[f] = hmap(imgs_res[f]) * delta[f / step]   (all at PH x PW)
+__global__ void __launch_bounds__(256) jnd_lowres_kernel(const float* __restrict__ imgs_res, const float* __restrict__ delta,
+                                                         float* __restrict__ out, int PH, int PW, int CD, int step, int alternate) {
+  __shared__ float lum[kBlendTH + 4][kBlendTW + 4 + 1];
+  const int f = blockIdx.z;
+  const int x0 = blockIdx.x * kBlendTW, y0 = blockIdx.y * kBlendTH;
+  const long plane = (long)PH * PW;
+  const float* img = imgs_res + (long)f * 3 * plane;
+  for (int i = threadIdx.x; i < (kBlendTH + 4) * (kBlendTW + 4); i += 256) {
+    const int ly = i / (kBlendTW + 4), lx = i - ly * (kBlendTW + 4);
+    const int gy = y0 + ly - 2, gx = x0 + lx - 2;
+    float v = 0.f;
+    if (gy >= 0 && gy < PH && gx >= 0 && gx < PW) {
+      const long o = (long)gy * PW + gx;
+      v = 0.299f * (255.f * img[o]) + 0.587f * (255.f * img[plane + o]) + 0.114f * (255.f * img[2 * plane + o]);
+    }
+    lum[ly][lx] = v;
+  }
+  __syncthreads();
+  const int tx = (threadIdx.x & 31) * 4, ty = threadIdx.x >> 5;
+  const int gy = y0 + ty;
+  if (gy >= PH) return;
+  const int key = f / step;
+  const bool has_delta = !(alternate && (f % step) != 0);
+  for (int q = 0; q < 4; ++q) {
+    const int gx = x0 + tx + q;
+    if (gx >= PW) break;
+    const float hm = jnd_from_lum(lum, ty + 2, tx + q + 2);
+    for (int c = 0; c < CD; ++c) {
+      const float dv = has_delta ? delta[((long)key * CD + c) * plane + (long)gy * PW + gx] : 0.f;
+      out[((long)f * CD + c) * plane + (long)gy * PW + gx] = hm * dv;
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K9: ConvNeXt stem: x = 2*img-1 (extractor.py:25); conv k4 stride s (no padding) + bias; channels-first LN eps 1e-6
+// (convnext.py:108-111).  imgs [B,3,H,W] fp32 -> out NHWC fp32 [B,OH,OW,C] (row pitch ld).  One warp per output pixel.
+__global__ void __launch_bounds__(256) stem_ln_kernel(const float* __restrict__ imgs, int B, int H, int W, int OH, int OW, int stride,
+                                                      const float* __restrict__ w /*[48][C] (k = c*16 + r*4 + s)*/, const float* __restrict__ bias,
+                                                      const float* __restrict__ lnw, const float* __restrict__ lnb, int C,
+                                                      float* __restrict__ out, int ld) {
+  extern __shared__ float sm[];  // per warp: 48 inputs + C outputs
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  float* xin = sm + warp * (48 + C);
+  float* yo = xin + 48;
+  const long npix = (long)B * OH * OW;
+  for (long pix = (long)blockIdx.x * 8 + warp; pix < npix; pix += (long)gridDim.x * 8) {
+    const int ox = (int)(pix % OW);
+    const long t = pix / OW;
+    const int oy = (int)(t % OH), b = (int)(t / OH);
+    for (int k = lane; k < 48; k += 32) {
+      const int c = k >> 4, r = (k >> 2) & 3, s = k & 3;
+      xin[k] = 2.f * __ldg(imgs + ((long)(b * 3 + c) * H + (oy * stride + r)) * W + ox * stride + s) - 1.f;
+    }
+    __syncwarp();
+    float sum = 0.f;
+    for (int c = lane; c < C; c += 32) {
+      float a = __ldg(bias + c);
+#pragma unroll 8
+      for (int k = 0; k < 48; ++k) a += xin[k] * __ldg(w + k * C + c);
+      yo[c] = a;
+      sum += a;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / (float)C;
+    float var = 0.f;
+    for (int c = lane; c < C; c += 32) { const float d = yo[c] - mean; var += d * d; }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+    const float rstd = 1.0f / sqrtf(var / (float)C + 1e-6f);
+    for (int c = lane; c < C; c += 32) out[pix * ld + c] = (yo[c] - mean) * rstd * __ldg(lnw + c) + __ldg(lnb + c);
+    __syncwarp();
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// K4: depthwise 7x7 (pad 3, bias) + channels-last LayerNorm (eps 1e-6) -> fp16 [M, ld_out]   (convnext.py:42-45)
+// x: NHWC fp32 [B, H, W, C] (pixel pitch ldx).  One block = one strip of kDwStrip output pixels along x; each thread owns
+// a channel pair and slides over the 7 x (strip+6) input window; pre-LN results go to smem, then LN per pixel by warps.
+constexpr int kDwStrip = 8;
+__global__ void __launch_bounds__(256) dwconv7_ln_kernel(const float* __restrict__ x, int B, int H, int W, int C, int ldx,
+                                                         const float* __restrict__ wdw /*[49][C]*/, const float* __restrict__ bdw,
+                                                         const float* __restrict__ lnw, const float* __restrict__ lnb,
+                                                         __half* __restrict__ out, int ld_out) {
+  extern __shared__ float pre[];  // [kDwStrip][C]
+  const int strips_x = (W + kDwStrip - 1) / kDwStrip;
+  const long strip = blockIdx.x;
+  const int sx = (int)(strip % strips_x);
+  const long t = strip / strips_x;
+  const int oy = (int)(t % H), b = (int)(t / H);
+  const int ox0 = sx * kDwStrip;
+  const int C2 = C >> 1;
+  for (int cp = threadIdx.x; cp < C2; cp += blockDim.x) {
+    const int c = cp * 2;
+    float2 acc[kDwStrip];
+    const float2 bb = __ldg(reinterpret_cast<const float2*>(bdw + c));
+#pragma unroll
+    for (int i = 0; i < kDwStrip; ++i) acc[i] = bb;
+    for (int r = 0; r < 7; ++r) {
+      const int iy = oy + r - 3;
+      if (iy < 0 || iy >= H) continue;
+      float2 wr[7];
+#pragma unroll
+      for (int s = 0; s < 7; ++s) wr[s] = __ldg(reinterpret_cast<const float2*>(wdw + (r * 7 + s) * C + c));
+      const float* rowp = x + (((long)b * H + iy) * W) * ldx + c;
+#pragma unroll
+      for (int u = 0; u < kDwStrip + 6; ++u) {
+        const int ix = ox0 + u - 3;
+        float2 v = make_float2(0.f, 0.f);
+        if (ix >= 0 && ix < W) v = __ldg(reinterpret_cast<const float2*>(rowp + (long)ix * ldx));
+#pragma unroll
+        for (int s = 0; s < 7; ++s) {
+          const int i = u - s;  // output pixel index within the strip
+          if (i >= 0 && i < kDwStrip) { acc[i].x += v.x * wr[s].x; acc[i].y += v.y * wr[s].y; }
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kDwStrip; ++i) { pre[i * C + c] = acc[i].x; pre[i * C + c + 1] = acc[i].y; }
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int i = warp; i < kDwStrip; i += nwarps) {
+    const int ox = ox0 + i;
+    if (ox >= W) continue;
+    const float* pr = pre + i * C;
+    float sum = 0.f;
+    for (int c = lane; c < C; c += 32) sum += pr[c];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / (float)C;
+    float var = 0.f;
+    for (int c = lane; c < C; c += 32) { const float d = pr[c] - mean; var += d * d; }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+    const float rstd = 1.0f / sqrtf(var / (float)C + 1e-6f);
+    __half* dst = out + (((long)b * H + oy) * W + ox) * ld_out;
+    for (int c = lane * 2; c < C; c += 64) {
+      const float a = (pr[c] - mean) * rstd * __ldg(lnw + c) + __ldg(lnb + c);
+      const float bq = (pr[c + 1] - mean) * rstd * __ldg(lnw + c + 1) + __ldg(lnb + c + 1);
+      *reinterpret_cast<__half2*>(dst + c) = __floats2half2_rn(a, bq);
+    }
+  }
+}
+
+// K4b: per-row LayerNorm over C (biased variance, eps) of fp32 rows -> fp16 rows.  One warp per row.
+__global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ x, long M, int C, int ldx, const float* __restrict__ w,
+                                                      const float* __restrict__ bvec, float eps, __half* __restrict__ out, int ld_out) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (long m = (long)blockIdx.x * 8 + warp; m < M; m += (long)gridDim.x * 8) {
+    const float* r = x + m * ldx;
+    float sum = 0.f;
+    for (int c = lane; c < C; c += 32) sum += r[c];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / (float)C;
+    float var = 0.f;
+    for (int c = lane; c < C; c += 32) { const float d = r[c] - mean; var += d * d; }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+    const float rstd = 1.0f / sqrtf(var / (float)C + eps);
+    for (int c = lane; c < C; c += 32) out[m * ld_out + c] = __float2half_rn((r[c] - mean) * rstd * __ldg(w + c) + __ldg(bvec + c));
+  }
+}
+
+// K2c: GRN (common.py:166-169) folded into a per-(sample, k) multiplier of pwconv2's A operand:
+//   Gx = sqrt(sum_{h,w} g^2);  Nx = Gx / (mean_k Gx + 1e-6);  scale = gamma * Nx + 1   (beta is folded into pwconv2's bias)
+// stats: [B, K] sums of squares (zeroed again here for the next use).  One block per sample.
+__global__ void __launch_bounds__(256) grn_scale_kernel(float* __restrict__ stats, const float* __restrict__ gamma, int K,
+                                                        float* __restrict__ scale, int ld_scale) {
+  __shared__ float red[8];
+  __shared__ float mean_s;
+  const int b = blockIdx.x;
+  float* st = stats + (long)b * K;
+  float sum = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) sum += sqrtf(st[k]);
+#pragma unroll
+  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    mean_s = t / (float)K;
+  }
+  __syncthreads();
+  const float inv = 1.0f / (mean_s + 1e-6f);
+  for (int k = threadIdx.x; k < K; k += blockDim.x) {
+    scale[(long)b * ld_scale + k] = __ldg(gamma + k) * (sqrtf(st[k]) * inv) + 1.0f;
+    st[k] = 0.f;
+  }
+}
+
+// K8a: per sample: channels-first LN (eps 1e-6) over C for each of the P pixels, GELU, mean over pixels -> pooled [B, C]
+// (pixel_decoder.py:44-55,77 with common.py:50-51).  y: [B*P, ld] fp32.  One block per sample, one warp per pixel (loop).
+__global__ void __launch_bounds__(256) head_pool_kernel(const float* __restrict__ y, int P, int C, int ld, const float* __restrict__ lnw,
+                                                        const float* __restrict__ lnb, float* __restrict__ pooled) {
+  extern __shared__ float acc[];  // [C]
+  const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) acc[c] = 0.f;
+  __syncthreads();
+  for (int pix = warp; pix < P; pix += nw) {
+    const float* r = y + ((long)b * P + pix) * ld;
+    float sum = 0.f;
+    for (int c = lane; c < C; c += 32) sum += r[c];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / (float)C;
+    float var = 0.f;
+    for (int c = lane; c < C; c += 32) { const float d = r[c] - mean; var += d * d; }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+    const float rstd = 1.0f / sqrtf(var / (float)C + 1e-6f);
+    for (int c = lane; c < C; c += 32) {
+      const float v = (r[c] - mean) * rstd * __ldg(lnw + c) + __ldg(lnb + c);
+      atomicAdd(&acc[c], 0.5f * v * (1.0f + erff(v * 0.70710678118654752f)));
+    }
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += blockDim.x) pooled[(long)b * C + c] = acc[c] / (float)P;
+}
+
+// K8b: logits[b, o] = bias[o] + sum_c pooled[b, c] * w[o, c]     (pixel_decoder.py:78).  One warp per output.
+__global__ void __launch_bounds__(256) head_linear_kernel(const float* __restrict__ pooled, const float* __restrict__ w,
+                                                          const float* __restrict__ bias, int B, int C, int NO, float* __restrict__ logits) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const long total = (long)B * NO;
+  for (long idx = (long)blockIdx.x * 8 + warp; idx < total; idx += (long)gridDim.x * 8) {
+    const int o = (int)(idx % NO);
+    const long b = idx / NO;
+    float a = 0.f;
+    for (int c = lane; c < C; c += 32) a += pooled[b * C + c] * __ldg(w + (long)o * C + c);
+#pragma unroll
+    for (int q = 16; q; q >>= 1) a += __shfl_xor_sync(0xffffffffu, a, q);
+    if (lane == 0) logits[idx] = a + __ldg(bias + o);
+  }
+}
+
+}  // namespace vsb

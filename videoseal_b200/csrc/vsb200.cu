@@ -1,0 +1,222 @@
+// libvsb200.so: the single translation unit behind include/vsb200.h.
+//   nvcc -std=c++17 -O3 -lineinfo -gencode arch=compute_100a,code=sm_100a -shared -Xcompiler -fPIC vsb200.cu -o libvsb200.so
+#include "model.cuh"
+
+using namespace vsb;
+
+struct vsb_model {
+  Model impl;
+  explicit vsb_model(const vsb_model_desc& d) : impl(d) {}
+};
+
+static thread_local std::string g_err;
+
+static int fail(const std::exception& e, int code) {
+  g_err = e.what();
+  return code;
+}
+
+#define VSB_API_BEGIN try {
+#define VSB_API_END                                                                       \
+  }                                                                                       \
+  catch (const vsb::Error& e) {                                                           \
+    const std::string w = e.what();                                                       \
+    int code = VSB_ERR_INVALID;                                                           \
+    if (w.find("CUDA error") != std::string::npos) code = VSB_ERR_CUDA;                   \
+    else if (w.find("unsupported") != std::string::npos || w.find("not implemented") != std::string::npos) code = VSB_ERR_UNSUPPORTED; \
+    else if (w.find("missing checkpoint") != std::string::npos || w.find("finalized") != std::string::npos) code = VSB_ERR_STATE;      \
+    return fail(e, code);                                                                 \
+  }                                                                                       \
+  catch (const std::exception& e) { return fail(e, VSB_ERR_INVALID); }
+
+extern "C" {
+
+const char* vsb_last_error(void) { return g_err.c_str(); }
+int vsb_version(void) { return 100; }
+
+int vsb_model_create(const vsb_model_desc* desc, vsb_model** out) {
+  VSB_API_BEGIN
+  VSB_CHECK(desc != nullptr && out != nullptr, "null argument");
+  *out = new vsb_model(*desc);
+  return VSB_OK;
+  VSB_API_END
+}
+
+int vsb_model_set_tensor(vsb_model* m, const char* name, const float* data, const int64_t* shape, int32_t ndim) {
+  VSB_API_BEGIN
+  VSB_CHECK(m && name && data && (shape || ndim == 0) && ndim >= 0 && ndim <= 4, "bad tensor argument");
+  VSB_CHECK(!m->impl.finalized, "model already finalized");
+  HostTensor t;
+  t.shape.assign(shape, shape + ndim);
+  t.data.assign(data, data + t.numel());
+  m->impl.sd[name] = std::move(t);
+  return VSB_OK;
+  VSB_API_END
+}
+
+int vsb_model_finalize(vsb_model* m, int32_t device) {
+  VSB_API_BEGIN
+  VSB_CHECK(m != nullptr, "null model");
+  m->impl.finalize(device);
+  return VSB_OK;
+  VSB_API_END
+}
+
+void vsb_model_destroy(vsb_model* m) { delete m; }
+
+int vsb_embed(vsb_model* m, const float* imgs, const uint8_t* msgs, int32_t n_msgs, float* imgs_w, float* preds_w, int32_t F, int32_t H,
+              int32_t W, int32_t step, int32_t video_mode, float scaling_i, float scaling_w, int32_t flags, void* stream) {
+  VSB_API_BEGIN
+  VSB_CHECK(m && imgs && msgs && imgs_w, "null argument");
+  m->impl.embed(imgs, msgs, n_msgs, imgs_w, preds_w, F, H, W, step, video_mode, scaling_i, scaling_w, flags, (cudaStream_t)stream);
+  return VSB_OK;
+  VSB_API_END
+}
+
+int vsb_embedder_forward(vsb_model* m, const float* x, const uint8_t* msgs, int32_t n_msgs, float* delta, int32_t B, void* stream) {
+  VSB_API_BEGIN
+  VSB_CHECK(m && x && msgs && delta && B > 0, "null argument");
+  m->impl.embedder_forward(x, msgs, n_msgs, delta, B, (cudaStream_t)stream);
+  return VSB_OK;
+  VSB_API_END
+}
+
+int vsb_detect(vsb_model* m, const float* imgs, float* logits, int32_t F, int32_t H, int32_t W, int32_t flags, void* stream) {
+  VSB_API_BEGIN
+  VSB_CHECK(m && imgs && logits, "null argument");
+  m->impl.detect(imgs, logits, F, H, W, flags, (cudaStream_t)stream);
+  return VSB_OK;
+  VSB_API_END
+}
+
+int vsb_jnd_heatmaps(vsb_model* m, const float* imgs, float* hmaps, int32_t F, int32_t H, int32_t W, void* stream) {
+  VSB_API_BEGIN
+  VSB_CHECK(m && imgs && hmaps, "null argument");
+  m->impl.jnd_heatmaps(imgs, hmaps, F, H, W, (cudaStream_t)stream);
+  return VSB_OK;
+  VSB_API_END
+}
+
+int vsb_embed_host(vsb_model* m, const float* imgs_h, const uint8_t* msgs_h, int32_t n_msgs, float* imgs_w_h, float* preds_w_h, int32_t F,
+                   int32_t H, int32_t W, int32_t step, int32_t video_mode, float scaling_i, float scaling_w, int32_t flags) {
+  VSB_API_BEGIN
+  VSB_CHECK(m && imgs_h && msgs_h && imgs_w_h, "null argument");
+  m->impl.check_ready();
+  VSB_CUDA(cudaSetDevice(m->impl.device));
+  DevicePool tmp;
+  const size_t n = (size_t)F * 3 * H * W;
+  const size_t np = (size_t)F * m->impl.d.unet_out_ch * H * W;
+  float* imgs = tmp.alloc_n<float>(n);
+  float* out = tmp.alloc_n<float>(n);
+  float* pw = preds_w_h ? tmp.alloc_n<float>(np) : nullptr;
+  uint8_t* msgs = tmp.alloc_n<uint8_t>((size_t)n_msgs * m->impl.d.nbits);
+  cudaStream_t st = 0;
+  VSB_CUDA(cudaMemcpyAsync(imgs, imgs_h, n * sizeof(float), cudaMemcpyHostToDevice, st));
+  VSB_CUDA(cudaMemcpyAsync(msgs, msgs_h, (size_t)n_msgs * m->impl.d.nbits, cudaMemcpyHostToDevice, st));
+  m->impl.embed(imgs, msgs, n_msgs, out, pw, F, H, W, step, video_mode, scaling_i, scaling_w, flags, st);
+  VSB_CUDA(cudaMemcpyAsync(imgs_w_h, out, n * sizeof(float), cudaMemcpyDeviceToHost, st));
+  if (pw) VSB_CUDA(cudaMemcpyAsync(preds_w_h, pw, np * sizeof(float), cudaMemcpyDeviceToHost, st));
+  VSB_CUDA(cudaStreamSynchronize(st));
+  return VSB_OK;
+  VSB_API_END
+}
+
+int vsb_detect_host(vsb_model* m, const float* imgs_h, float* logits_h, int32_t F, int32_t H, int32_t W, int32_t flags) {
+  VSB_API_BEGIN
+  VSB_CHECK(m && imgs_h && logits_h, "null argument");
+  m->impl.check_ready();
+  VSB_CUDA(cudaSetDevice(m->impl.device));
+  DevicePool tmp;
+  const size_t n = (size_t)F * 3 * H * W;
+  const size_t nl = (size_t)F * (1 + m->impl.d.nbits);
+  float* imgs = tmp.alloc_n<float>(n);
+  float* lg = tmp.alloc_n<float>(nl);
+  cudaStream_t st = 0;
+  VSB_CUDA(cudaMemcpyAsync(imgs, imgs_h, n * sizeof(float), cudaMemcpyHostToDevice, st));
+  m->impl.detect(imgs, lg, F, H, W, flags, st);
+  VSB_CUDA(cudaMemcpyAsync(logits_h, lg, nl * sizeof(float), cudaMemcpyDeviceToHost, st));
+  VSB_CUDA(cudaStreamSynchronize(st));
+  return VSB_OK;
+  VSB_API_END
+}
+
+int64_t vsb_launch_count(int32_t reset) {
+  const int64_t v = g_launches;
+  if (reset) g_launches = 0;
+  return v;
+}
+
+int64_t vsb_debug_get_tensor(vsb_model* m, const char* name, float* host_out, int64_t capacity, int64_t* shape4) {
+  try {
+    VSB_CHECK(m && name && shape4, "null argument");
+    Plan* pl = m->impl.last_plan;
+    VSB_CHECK(pl != nullptr, "no plan has run yet");
+    auto it = pl->dbg.find(name);
+    if (it == pl->dbg.end()) throw Error(std::string("unknown debug tensor: ") + name);
+    const DebugTensor& t = it->second;
+    const int64_t rows = t.shape[0] * t.shape[1] * t.shape[2], C = t.shape[3];
+    for (int i = 0; i < 4; ++i) shape4[i] = t.shape[i];
+    const int64_t n = rows * C;
+    if (host_out == nullptr) return n;
+    VSB_CHECK(capacity >= n, "debug buffer too small");
+    VSB_CUDA(cudaDeviceSynchronize());
+    if (t.dtype == 0) {
+      VSB_CUDA(cudaMemcpy2D(host_out, C * sizeof(float), t.ptr, t.ld * sizeof(float), C * sizeof(float), rows, cudaMemcpyDeviceToHost));
+    } else {
+      std::vector<__half> h((size_t)n);
+      VSB_CUDA(cudaMemcpy2D(h.data(), C * sizeof(__half), t.ptr, t.ld * sizeof(__half), C * sizeof(__half), rows, cudaMemcpyDeviceToHost));
+      for (int64_t i = 0; i < n; ++i) host_out[i] = __half2float(h[i]);
+    }
+    return n;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
+int vsb_debug_conv(const vsb_conv_test* t, void* stream) {
+  VSB_API_BEGIN
+  VSB_CHECK(t != nullptr, "null argument");
+  int dev = 0;
+  VSB_CUDA(cudaGetDevice(&dev));
+  cudaDeviceProp prop;
+  VSB_CUDA(cudaGetDeviceProperties(&prop, dev));
+  ConvGemmOp op;
+  const int Ct = t->C0 + t->C1;
+  const int K = t->R * t->S * Ct;
+  int OH, OW;
+  if (t->loader == LD_TMA) {
+    OH = t->IH; OW = t->IW;
+    if (t->IH == 1 && t->R == 1) setup_tma_gemm(op, (const __half*)t->src0, (long)t->B * t->IW, t->C0, t->C0);
+    else setup_tma_conv(op, (const __half*)t->src0, t->B, t->IH, t->IW, t->C0, t->C0, t->R, t->S, t->pad);
+  } else if (t->loader == LD_GATHER_CONV) {
+    OH = (t->IH + 2 * t->pad - t->R) / t->stride + 1;
+    OW = (t->IW + 2 * t->pad - t->S) / t->stride + 1;
+    setup_gather_conv(op, LD_GATHER_CONV, (const __half*)t->src0, t->C0, t->C0, (const __half*)t->src1, t->C1, t->C1, t->B, t->IH, t->IW, OH, OW,
+                      t->R, t->S, t->stride, t->pad, t->pad_mode);
+  } else if (t->loader == LD_GATHER_UPS) {
+    OH = 2 * t->IH; OW = 2 * t->IW;
+    setup_gather_conv(op, LD_GATHER_UPS, (const __half*)t->src0, t->C0, t->C0, (const __half*)t->src1, t->C1, t->C1, t->B, t->IH, t->IW, OH, OW, 3, 3,
+                      1, 1, 1);
+  } else {
+    OH = t->IH; OW = t->IW;
+    setup_gather_scale(op, (const __half*)t->src0, (long)t->B * t->IH * t->IW, t->C0, t->C0, t->a_scale, t->C0, t->rows_per_sample);
+  }
+  ConvGemmParams& p = op.p;
+  p.epi = t->epi; p.act = t->act; p.bias = t->bias;
+  p.resid16 = (const __half*)t->resid16; p.ld_res16 = t->N;
+  p.resid32 = t->resid32; p.ld_res32 = t->N;
+  p.out16 = (__half*)t->out16; p.ld_out16 = t->N;
+  p.out32 = t->out32; p.ld_out32 = t->N;
+  p.ln_w = t->ln_w; p.ln_b = t->ln_b; p.ln_eps = 1e-6f;
+  p.outc_w = t->outc_w; p.outc_b = t->outc_b; p.n_out = t->n_out; p.delta = t->delta; p.hw = OH * OW; p.outc_tanh = 1;
+  p.grn_stats = t->grn_stats;
+  if (t->rows_per_sample) p.rows_per_sample = t->rows_per_sample;
+  finalize_op(op, (const __half*)t->weights, t->N, K, K, prop.multiProcessorCount, t->block_n);
+  launch(op, (cudaStream_t)stream);
+  g_launches += 1;
+  return VSB_OK;
+  VSB_API_END
+}
+
+}  // extern "C"
