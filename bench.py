@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""Benchmark of the embed+detect hot path (BASELINE.json metric: embed+detect frames/s).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference] [--card C] [--batch B] [--size S]
+
+One "step" = model.embed(batch, msgs, is_video=False) followed by model.detect(imgs_w, is_video=False) on one batch of
+synthetic frames (configs[1] of BASELINE.json by default: videoseal_1.0, 256-bit, 64 x 3x256x256 per GPU).  Under torchrun
+every rank processes its own batch (frames are independent units: weak scaling, no data-path collective except the
+all-gather of the [B, 1+K] logits that reassembles the detection output).  Prints ONE JSON line on rank 0.
+
+--impl reference times the CPU restatement of the reference path (oracle/restate.py, pinned bit-exact to the reference
+modules) on the host cores; the unmodified reference itself needs packages that are not installed here.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+FLOPS_PER_FRAME = {  # 2*MAC over every Conv2d/Linear at processing size 256 (embed, detect)
+    "videoseal_1.0": (56.55e9, 12.32e9), "pixelseal": (119.30e9, 12.32e9), "chunkyseal": (2248.96e9, 1227.24e9),
+}
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--card", default="videoseal_1.0")
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--profile-out", default="", help="write the per-kernel table (JSON) here")
+    return ap.parse_args()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
+    Q = "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, gpu_index: int):
+        self.idx, self.lines, self.proc = gpu_index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                                          "-i", str(self.idx)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        for l in self.lines:
+            f = [x.strip() for x in l.split(",")]
+            if len(f) < 8:
+                continue
+            try:
+                sm.append(float(f[1])); mx = float(f[2])
+            except ValueError:
+                continue
+            for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], f[4:8]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def conv_flops(name: str, B: int) -> float:
+    """algorithmic FLOPs (2*MAC) of one launch of a named plan step, from its shape tag (model.cuh step names)"""
+    try:
+        kind, rest = name.rsplit(".", 1)
+        dims, hs = rest.split("@")
+        h = int(hs)
+        M = B * h * h
+        if kind in ("unet.conv3x3", "unet.conv3x3+outc", "unet.down3x3s2", "unet.up3x3"):
+            cin, cout = (int(x) for x in dims.split("-"))
+            return 2.0 * M * cout * 9 * cin
+        if kind == "unet.conv1x1":
+            cin, cout = (int(x) for x in dims.split("-"))
+            return 2.0 * M * cout * cin
+        if kind == "cnx.down2x2s2":
+            cin, cout = (int(x) for x in dims.split("-"))
+            return 2.0 * M * cout * 4 * cin
+        if kind in ("cnx.pwconv1", "cnx.pwconv2"):
+            c = int(dims)
+            return 2.0 * M * c * 4 * c
+        if kind == "cnx.head3x3":
+            c = int(dims)
+            return 2.0 * M * c * 9 * c
+    except Exception:
+        pass
+    return 0.0
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return {"hbm_gbs": d["hbm_gbs"], "tf_burst": d["bf16_tflops"], "tf_sustained": d.get("bf16_tflops_sustained", d["bf16_tflops"]),
+                "src": "measured"}
+    return {"hbm_gbs": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "src": "fallback"}
+
+
+def build_card_on_disk(card_name: str, seed: int = 0):
+    """synthetic checkpoint (no network) + a card YAML pointing at it, under a temp dir"""
+    import tempfile
+    import yaml
+    from videoseal_b200 import synth
+    d = tempfile.mkdtemp(prefix="vsb200_bench_")
+    card = yaml.safe_load(open(os.path.join(ROOT, "videoseal_b200", "cards", card_name + ".yaml")))
+    ckpt = os.path.join(d, card_name + ".pth")
+    synth.write_synthetic_checkpoint(card, ckpt, seed)
+    card["checkpoint_path"] = ckpt
+    cpath = os.path.join(d, card_name + ".yaml")
+    yaml.safe_dump(card, open(cpath, "w"))
+    return cpath, card
+
+
+def cpu_oracle_fps(card_name: str, size: int, sample: int, runs: int, threads: int):
+    """embed+detect frames/s of the CPU restatement of the reference path (test infrastructure, timed as the baseline)"""
+    import torch
+    import yaml
+    from oracle import restate
+    torch.set_num_threads(threads)
+    card = yaml.safe_load(open(os.path.join(ROOT, "videoseal_b200", "cards", card_name + ".yaml")))
+    spec = restate.spec_from_card(card)
+    orc = restate.OracleModel(spec, restate.synth_state_dict(spec, 0))
+    g = torch.Generator().manual_seed(0)
+    imgs = torch.rand(sample, 3, size, size, generator=g)
+    msgs = torch.randint(0, 2, (sample, spec["nbits"]), generator=g)
+    times = []
+    with torch.no_grad():
+        for i in range(runs + 1):  # 1 warm-up, as evals/speed.py:51-52
+            t0 = time.perf_counter()
+            o = orc.embed(imgs, msgs, is_video=False)
+            orc.detect(o["imgs_w"], is_video=False)
+            if i > 0:
+                times.append(time.perf_counter() - t0)
+    return sample * len(times) / sum(times), times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    sample = 8
+    fps, times = cpu_oracle_fps(args.card, args.size, sample, args.steps + max(0, args.warmup - 1), threads)
+    line = {
+        "impl": "reference", "metric": "embed+detect frames/sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * sum(times) / len(times), "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{args.card} embed+detect, image mode, 3x{args.size}x{args.size}, CPU sample of {sample} frames/step",
+                   "card": args.card, "batch_per_step": sample, "size": args.size},
+        "cpu_baseline": {"value": fps, "unit": "frames/s", "cores": threads, "kind": "port",
+                         "sample": f"{sample} frames per step; oracle/restate.py (bit-exact restatement of the reference modules)"},
+        "e2e": {"value": fps, "unit": "frames/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    import ctypes as C
+    import videoseal_b200
+    from videoseal_b200 import _lib
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl=ours) needs a B200; there is no CPU fallback")
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L = _lib.lib()
+    cpath, card = build_card_on_disk(args.card, seed=0)
+    from pathlib import Path
+    import contextlib
+    import io
+    with contextlib.redirect_stdout(io.StringIO()):
+        model = videoseal_b200.load(Path(cpath)).eval().to(dev)
+    B, S, K = args.batch, args.size, model.spec["nbits"]
+    NB = 4  # rotating input batches: NB * B*3*S*S*4 bytes (201 MB at the default shape) > 126 MB L2
+    g = torch.Generator().manual_seed(1000 + rank)
+    imgs = [torch.rand(B, 3, S, S, generator=g).to(dev) for _ in range(NB)]
+    msgs = torch.randint(0, 2, (B, K), generator=g).to(dev)
+    gathered = [torch.empty(B, 1 + K, device=dev) for _ in range(world)] if world > 1 else None
+
+    def step(i):
+        out = model.embed(imgs[i % NB], msgs, is_video=False)
+        preds = model.detect(out["imgs_w"], is_video=False)["preds"]
+        if world > 1:
+            dist.all_gather(gathered, preds)   # reassemble the detection output on every rank ([B,1+K] per rank)
+        return preds
+
+    def sync_all():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    for i in range(max(3, args.warmup)):
+        step(i)
+    sync_all()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    L.vsb_launch_count(1)
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    sync_all()
+    ev0.record()
+    for i in range(args.steps):
+        step(i)
+    ev1.record()
+    sync_all()
+    ms = ev0.elapsed_time(ev1)
+    launches = int(L.vsb_launch_count(0))
+    clocks = sampler.stop() if rank == 0 else None
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    fps = world * B * args.steps / (ms / 1000.0)
+
+    # ---- end-to-end through the C ABI with HOST buffers (pinned): H2D + embed + D2H, H2D + detect + D2H, every step
+    e2e = None
+    if not args.no_e2e:
+        CD = model.spec["unet"]["out_channels"]
+        h_in = [torch.rand(B, 3, S, S, generator=g).pin_memory() for _ in range(2)]
+        h_msgs = torch.randint(0, 2, (B, K), generator=g).to(torch.uint8).pin_memory()
+        h_out = torch.empty(B, 3, S, S).pin_memory()
+        h_log = torch.empty(B, 1 + K).pin_memory()
+        flags = _lib.FLAG_CLAMP
+        h = model._handle()
+
+        def e2e_step(i):
+            _lib.check(L.vsb_embed_host(h, h_in[i % 2].data_ptr(), h_msgs.data_ptr(), B, h_out.data_ptr(), None, B, S, S, 1, 0,
+                                        float(model.blender.scaling_i), float(model.blender.scaling_w), flags))
+            _lib.check(L.vsb_detect_host(h, h_out.data_ptr(), h_log.data_ptr(), B, S, S, 0))
+
+        for i in range(3):
+            e2e_step(i)
+        sync_all()
+        t0 = time.perf_counter()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        n_e2e = max(5, args.steps // 2)
+        for i in range(n_e2e):
+            e2e_step(i)
+        e1.record()
+        sync_all()
+        e_ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1000.0 * 0.0)  # device clock; host calls are synchronous
+        if world > 1:
+            t = torch.tensor([e_ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            e_ms = t.item()
+        e2e = {"value": world * B * n_e2e / (e_ms / 1000.0), "unit": "frames/s",
+               "h2d_bytes_per_step": 2 * B * 3 * S * S * 4 + B * K, "d2h_bytes_per_step": B * 3 * S * S * 4 + B * (1 + K) * 4,
+               "path": "vsb_embed_host + vsb_detect_host (pinned host buffers, synchronous)"}
+
+    # ---- per-kernel profile (CUDA events around every plan step) -> roofline of the dominant kernel
+    roofline, table = None, []
+    if rank == 0:
+        L.vsb_profile_enable(1)
+        for i in range(3):
+            step(i)
+        torch.cuda.synchronize()
+        n = L.vsb_profile_read(None, 0)
+        buf = C.create_string_buffer(int(n) + 16)
+        L.vsb_profile_read(buf, len(buf))
+        L.vsb_profile_enable(0)
+        tot = 0.0
+        for line in buf.value.decode().splitlines():
+            name, tms, cnt = line.split("\t")
+            tms, cnt = float(tms), int(cnt)
+            fl = conv_flops(name, B)
+            table.append({"name": name, "ms_per_step": tms / 3, "launches_per_step": cnt // 3, "avg_us": 1000 * tms / cnt,
+                          "tflops": (fl / (tms / cnt * 1e-3) / 1e12) if fl else None})
+            tot += tms / 3
+        table.sort(key=lambda r: -r["ms_per_step"])
+        for r in table:
+            r["share"] = r["ms_per_step"] / tot if tot else 0
+        peaks = load_peaks()
+        dom = next((r for r in table if r["tflops"]), None)
+        if dom:
+            roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel<LD_TMA> " + dom["name"], "achieved": dom["tflops"],
+                        "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": dom["tflops"] / peaks["tf_sustained"],
+                        "peak_source": peaks["src"] + " bf16 cuBLAS, sustained (kernel timed inside a long step)",
+                        "share_of_step": dom["share"], "avg_launch_us": dom["avg_us"], "traffic": None,
+                        "step_ms_under_events": tot}
+        if args.profile_out:
+            json.dump({"batch": B, "card": args.card, "table": table}, open(args.profile_out, "w"), indent=1)
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        sample = 8
+        v, times = cpu_oracle_fps(args.card, S, sample, 3, threads)
+        cpu = {"value": v, "unit": "frames/s", "cores": threads, "kind": "port",
+               "sample": f"{sample} frames embed+detect, 1 warm-up + 3 runs ({sum(times):.1f} s), oracle/restate.py"}
+
+    if rank == 0:
+        fe, fd = FLOPS_PER_FRAME.get(args.card, (0, 0))
+        line = {
+            "metric": "embed+detect frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f16 operands, f32 accumulate (API tensors f32)", "data": "synthetic",
+            "config": {"workload": f"{args.card} {K}-bit embed+detect, image mode, batch {B} x 3x{S}x{S} per GPU (BASELINE configs[1])",
+                       "card": args.card, "batch_per_gpu": B, "size": S, "parallelism": f"dp{world} (frames sharded, weak scaling)",
+                       "l2": f"{NB} rotating input batches ({NB * B * 3 * S * S * 4 / 1e6:.0f} MB > 126 MB L2); activations per step >> L2"},
+            "step_tflops": (fe + fd) * world * B * args.steps / (ms / 1000.0) / 1e12,
+            "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
+            "top_kernels": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()} for r in table[:8]],
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -104,6 +104,10 @@ int vsb_detect_host(vsb_model* m, const float* imgs_host, float* logits_host, in
 /* number of kernels launched by this library since the last call with reset != 0 (bench.py's gpu_launches) */
 int64_t vsb_launch_count(int32_t reset);
 
+/* per-step CUDA-event profile used by bench.py's roofline leg: enable(1), run steps, read "name\ttotal_ms\tcount\n" lines */
+int vsb_profile_enable(int32_t on);
+int64_t vsb_profile_read(char* buf, int64_t capacity);
+
 /* ---- debug / test seams (used by tests/ only) ------------------------------------------------------------- */
 /* copy a named intermediate activation of the most recent embed/detect sub-batch to the host as fp32.
  * shape4 receives [B, H, W, C] (NHWC) or [M, C, 1, 1]-style dims; returns the element count or <0. */

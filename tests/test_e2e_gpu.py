@@ -1,0 +1,237 @@
+"""GPU parity of the whole embed/detect path, through the public API (-> C ABI), against the CPU oracle on the same
+seeded inputs and synthetic checkpoints, and against the golden fixtures generated from the unmodified reference.
+
+Tolerances (BASELINE.json north_star): watermarked pixels <= 1e-3 abs; bit logits <= 1e-2 relative to
+max(|ref|, 0.01*||ref||_inf) (element-wise relative error is meaningless for near-zero logits);
+recovered bits exact wherever |ref logit| > margin (margin = 1e-2*||ref||_inf; count of sub-margin logits reported)."""
+import os
+
+import pytest
+import torch
+
+from oracle import restate
+from tests.util import make_model_pair, SEED
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+PIX_TOL = 1e-3
+LOGIT_RTOL = 1e-2
+
+
+def logits_ok(got, ref):
+    scale = ref.abs().max()
+    denom = torch.maximum(ref.abs(), 0.01 * scale)
+    rel = ((got - ref).abs() / denom).max().item()
+    margin = 1e-2 * scale
+    sure = ref[:, 1:].abs() > margin
+    flips = int((((got[:, 1:] > 0) != (ref[:, 1:] > 0)) & sure).sum())
+    return rel, flips, int((~sure).sum())
+
+
+@pytest.fixture(scope="module")
+def v1():
+    return make_model_pair("videoseal_1.0")
+
+
+@pytest.fixture(scope="module")
+def px():
+    return make_model_pair("pixelseal")
+
+
+def _img_case(pair, B, H, W, seed):
+    model, orc, spec = pair
+    g = torch.Generator().manual_seed(seed)
+    imgs = torch.rand(B, 3, H, W, generator=g)
+    msgs = torch.randint(0, 2, (B, spec["nbits"]), generator=g)
+    with torch.no_grad():
+        ref = orc.embed(imgs, msgs, is_video=False)
+        ref_det = orc.detect(ref["imgs_w"], is_video=False)["preds"]
+    out = model.embed(imgs.cuda(), msgs, is_video=False)
+    assert out["imgs_w"].device.type == "cuda" and out["imgs_w"].shape == imgs.shape
+    e_img = (out["imgs_w"].cpu() - ref["imgs_w"]).abs().max().item()
+    e_pw = (out["preds_w"].cpu() - ref["preds_w"]).abs().max().item()
+    det = model.detect(out["imgs_w"], is_video=False)["preds"].cpu()
+    rel, flips, unsure = logits_ok(det, ref_det)
+    assert e_img <= PIX_TOL, e_img
+    assert e_pw <= 5 * PIX_TOL, e_pw          # preds_w is the unscaled delta (x scaling_w = 0.2 -> pixels)
+    assert rel <= LOGIT_RTOL, rel
+    assert flips == 0, (flips, unsure)
+    assert abs(restate.psnr(out["imgs_w"].cpu(), imgs).mean() - restate.psnr(ref["imgs_w"], imgs).mean()) < 0.01
+    acc_g = restate.bit_accuracy(det, msgs).mean().item()
+    acc_r = restate.bit_accuracy(ref_det, msgs).mean().item()
+    assert abs(acc_g - acc_r) <= (unsure + 0.5) / det[:, 1:].numel()
+    return out
+
+
+def test_v1_image_256(v1):
+    _img_case(v1, 3, 256, 256, 0)
+
+
+def test_v1_image_resized_non_square(v1):
+    _img_case(v1, 2, 384, 480, 1)
+
+
+def test_v1_image_768(v1):
+    _img_case(v1, 1, 768, 768, 2)
+
+
+def test_v1_image_small_upscaled_input_and_odd_width(v1):
+    _img_case(v1, 1, 200, 333, 3)      # smaller than the processing size in H, W % 4 != 0 (scalar blend path)
+
+
+def test_pixelseal_image_256_and_768(px):
+    _img_case(px, 2, 256, 256, 4)
+    _img_case(px, 1, 768, 768, 5)
+
+
+def test_v1_batch_larger_than_internal_subbatch(v1):
+    model, orc, spec = v1
+    g = torch.Generator().manual_seed(6)
+    imgs = torch.rand(70, 3, 256, 256, generator=g)     # > 64 -> two internal sub-batches (64 + 6)
+    msgs = torch.randint(0, 2, (70, spec["nbits"]), generator=g)
+    out = model.embed(imgs.cuda(), msgs, is_video=False)
+    sel = [0, 63, 64, 69]
+    with torch.no_grad():
+        ref = orc.embed(imgs[sel], msgs[sel], is_video=False)
+    assert (out["imgs_w"][sel].cpu() - ref["imgs_w"]).abs().max().item() <= PIX_TOL
+
+
+@pytest.mark.parametrize("F_,H,W,chunk,step,mode", [(10, 320, 288, 2, 4, "repeat"), (9, 256, 256, 32, 4, "repeat"),
+                                                     (7, 272, 304, 32, 3, "alternate")])
+def test_v1_video(v1, F_, H, W, chunk, step, mode):
+    model, orc, spec = v1
+    g = torch.Generator().manual_seed(7)
+    vid = torch.rand(F_, 3, H, W, generator=g)
+    msgs = torch.randint(0, 2, (1, spec["nbits"]), generator=g)
+    old = (model.chunk_size, model.step_size, model.video_mode)
+    try:
+        model.chunk_size = orc.chunk_size = chunk
+        model.step_size = orc.step_size = step
+        model.video_mode = orc.video_mode = mode
+        with torch.no_grad():
+            ref = orc.embed(vid, msgs, is_video=True)
+            ref_det = orc.detect(ref["imgs_w"], is_video=True)["preds"]
+            ref_msg = orc.extract_message(ref["imgs_w"])
+        out = model.embed(vid.cuda(), msgs, is_video=True)
+        assert set(out) == {"imgs_w", "msgs"} and out["msgs"].shape == (F_, spec["nbits"])
+        assert (out["imgs_w"].cpu() - ref["imgs_w"]).abs().max().item() <= PIX_TOL
+        det = model.detect(out["imgs_w"], is_video=True)["preds"].cpu()
+        rel, flips, unsure = logits_ok(det, ref_det)
+        assert rel <= LOGIT_RTOL and flips == 0, (rel, flips, unsure)
+        got_msg = model.extract_message(out["imgs_w"]).cpu()
+        agg = ref_det[:, 1:].mean(0)
+        sure = agg.abs() > 1e-2 * agg.abs().max()
+        assert (got_msg[0][sure] == ref_msg[0][sure]).all()
+    finally:
+        model.chunk_size, model.step_size, model.video_mode = old
+        orc.chunk_size, orc.step_size, orc.video_mode = old
+
+
+def test_v1_cpu_resident_input_returns_cpu(v1):
+    model, orc, spec = v1
+    g = torch.Generator().manual_seed(8)
+    imgs = torch.rand(2, 3, 300, 260, generator=g)
+    msgs = torch.randint(0, 2, (2, spec["nbits"]), generator=g)
+    out = model.embed(imgs, msgs, is_video=False)          # reference keeps full-res frames on the CPU (evals/full.py:117-120)
+    assert out["imgs_w"].device.type == "cpu"
+    with torch.no_grad():
+        ref = orc.embed(imgs, msgs, is_video=False)
+    assert (out["imgs_w"] - ref["imgs_w"]).abs().max().item() <= PIX_TOL
+    assert model.detect(out["imgs_w"], is_video=False)["preds"].device.type == "cpu"
+
+
+def test_v1_attribute_overrides_lowres_and_no_attenuation(v1):
+    model, orc, spec = v1
+    g = torch.Generator().manual_seed(9)
+    imgs = torch.rand(2, 3, 320, 400, generator=g)
+    msgs = torch.randint(0, 2, (2, spec["nbits"]), generator=g)
+    # lowres attenuation (recommended setting in the reference's CLIs, wam.py:177-180)
+    with torch.no_grad():
+        ref = orc.embed(imgs, msgs, is_video=False, lowres_attenuation=True)
+    out = model.embed(imgs.cuda(), msgs, is_video=False, lowres_attenuation=True)
+    assert (out["imgs_w"].cpu() - ref["imgs_w"]).abs().max().item() <= PIX_TOL
+    # scaling_w override + attenuation=None + clamp=False  (post-load attribute writes, evals/full.py:317-336)
+    att_m, att_o = model.attenuation, orc.attenuation
+    try:
+        model.attenuation = None; orc.attenuation = None
+        model.blender.scaling_w = orc.scaling_w = 0.05
+        model.clamp = orc.clamp = False
+        with torch.no_grad():
+            ref = orc.embed(imgs, msgs, is_video=False)
+        out = model.embed(imgs.cuda(), msgs, is_video=False)
+        assert (out["imgs_w"].cpu() - ref["imgs_w"]).abs().max().item() <= PIX_TOL
+    finally:
+        model.attenuation, orc.attenuation = att_m, att_o
+        model.blender.scaling_w = orc.scaling_w = spec["scaling_w"]
+        model.clamp = orc.clamp = True
+
+
+def test_operator_seams(v1):
+    model, orc, spec = v1
+    g = torch.Generator().manual_seed(10)
+    imgs = torch.rand(2, 3, 256, 256, generator=g)
+    msgs = torch.randint(0, 2, (2, spec["nbits"]), generator=g)
+    with torch.no_grad():
+        d_ref = orc.embedder(imgs, msgs)
+        h_ref = orc.heatmaps(imgs)
+        l_ref = orc.detector(imgs)
+    d = model.embedder(imgs.cuda(), msgs).cpu()
+    assert (d - d_ref).abs().max().item() <= 5e-3          # delta in (-1,1); x 0.2*hmap(<=0.12) -> <= 1.2e-4 in pixels
+    h = model.attenuation.heatmaps(imgs.cuda()).cpu()
+    assert (h - h_ref).abs().max().item() <= 1e-5
+    l = model.detector(imgs.cuda()).cpu()
+    rel, flips, _ = logits_ok(l, l_ref)
+    assert rel <= LOGIT_RTOL and flips == 0
+
+
+@pytest.mark.parametrize("card", ["videoseal_1.0", "pixelseal"])
+def test_against_reference_golden(card, v1, px):
+    """fixtures written by oracle/make_golden.py from the UNMODIFIED reference modules"""
+    model, orc, spec = v1 if card == "videoseal_1.0" else px
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", f"{card}.pt"))
+    assert gold["seed"] == SEED
+    c = gold["cases"]["img256"]
+    g = torch.Generator().manual_seed(c["gen_seed"])
+    imgs = torch.rand(c["B"], 3, c["H"], c["W"], generator=g)
+    msgs = torch.randint(0, 2, (c["B"], spec["nbits"]), generator=g)
+    out = model.embed(imgs.cuda(), msgs, is_video=False)
+    assert (out["imgs_w"].cpu()[..., ::8, ::8] - c["imgs_w_s"]).abs().max().item() <= PIX_TOL
+    det = model.detect(out["imgs_w"], is_video=False)["preds"].cpu()
+    rel, flips, _ = logits_ok(det, c["preds"])
+    assert rel <= LOGIT_RTOL and flips == 0, (rel, flips)
+    assert (restate.psnr(out["imgs_w"].cpu(), imgs) - c["psnr"]).abs().max().item() < 0.01
+    c = gold["cases"]["vid10"]
+    g = torch.Generator().manual_seed(c["gen_seed"])
+    vid = torch.rand(c["F"], 3, c["H"], c["W"], generator=g)
+    msgs = torch.randint(0, 2, (1, spec["nbits"]), generator=g)
+    old = (model.chunk_size, model.step_size)
+    try:
+        model.chunk_size, model.step_size = c["chunk_size"], c["step_size"]
+        out = model.embed(vid.cuda(), msgs, is_video=True)
+        assert (out["imgs_w"].cpu()[..., ::8, ::8] - c["imgs_w_s"]).abs().max().item() <= PIX_TOL
+        det = model.detect(out["imgs_w"], is_video=True)["preds"].cpu()
+        rel, flips, _ = logits_ok(det, c["preds"])
+        assert rel <= LOGIT_RTOL and flips == 0
+    finally:
+        model.chunk_size, model.step_size = old
+
+
+def test_size_independent_properties_full_batch(v1):
+    """BASELINE configs[1] size (batch 64 @ 256^2), no oracle: embed->detect round trip is deterministic, the watermark
+    is bounded by scaling_w * max(hmap), frames are independent (batch of 64 == the same frames run as 2 x 32)."""
+    model, orc, spec = v1
+    g = torch.Generator().manual_seed(11)
+    imgs = torch.rand(64, 3, 256, 256, generator=g).cuda()
+    msgs = torch.randint(0, 2, (64, spec["nbits"]), generator=g)
+    a = model.embed(imgs, msgs, is_video=False)
+    b = model.embed(imgs, msgs, is_video=False)
+    assert torch.equal(a["imgs_w"], b["imgs_w"])                                  # idempotent / deterministic
+    assert (a["imgs_w"] - imgs).abs().max().item() <= model.blender.scaling_w * 0.13  # |delta|<1, hmap <= ~0.12
+    assert a["imgs_w"].min().item() >= 0 and a["imgs_w"].max().item() <= 1
+    h1 = model.embed(imgs[:32], msgs[:32], is_video=False)["imgs_w"]
+    h2 = model.embed(imgs[32:], msgs[32:], is_video=False)["imgs_w"]
+    assert torch.equal(torch.cat([h1, h2]), a["imgs_w"])                          # frames are independent units
+    d64 = model.detect(a["imgs_w"], is_video=False)["preds"]
+    d32 = torch.cat([model.detect(a["imgs_w"][:32], is_video=False)["preds"], model.detect(a["imgs_w"][32:], is_video=False)["preds"]])
+    assert (d64 - d32).abs().max().item() <= 1e-3 * d64.abs().max().item()        # GRN statistics use fp32 atomics

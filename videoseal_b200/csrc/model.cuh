@@ -55,7 +55,27 @@ struct DebugTensor { const void* ptr; int dtype; /*0 f32, 1 f16*/ int64_t shape[
 struct Step {
   std::function<void(cudaStream_t)> fn;
   int launches = 1;
+  std::string name = "";
 };
+
+// optional per-step CUDA-event profile (bench.py roofline leg): name -> (total ms, launches)
+struct Profile {
+  bool enabled = false;
+  std::map<std::string, std::pair<double, long>> acc;
+  std::vector<std::pair<std::string, std::pair<cudaEvent_t, cudaEvent_t>>> pending;
+  void flush() {
+    for (auto& e : pending) {
+      float ms = 0.f;
+      cudaEventSynchronize(e.second.second);
+      cudaEventElapsedTime(&ms, e.second.first, e.second.second);
+      auto& a = acc[e.first];
+      a.first += ms; a.second += 1;
+      cudaEventDestroy(e.second.first); cudaEventDestroy(e.second.second);
+    }
+    pending.clear();
+  }
+};
+static Profile g_profile;
 
 struct Plan {
   DevicePool pool;
@@ -70,7 +90,19 @@ struct Plan {
   float* delta = nullptr;   // [B,CD,S,S]
   float* logits = nullptr;  // [B,1+K]
   void run(cudaStream_t st) {
-    for (auto& s : steps) { s.fn(st); g_launches += s.launches; }
+    if (!g_profile.enabled) {
+      for (auto& s : steps) { s.fn(st); g_launches += s.launches; }
+      return;
+    }
+    for (auto& s : steps) {
+      cudaEvent_t a, b;
+      cudaEventCreate(&a); cudaEventCreate(&b);
+      cudaEventRecord(a, st);
+      s.fn(st);
+      cudaEventRecord(b, st);
+      g_launches += s.launches;
+      g_profile.pending.push_back({s.name, {a, b}});
+    }
   }
 };
 
@@ -162,6 +194,21 @@ class Model {
   std::vector<std::vector<CnBlockW>> cn;
   ConvW head_conv;
   float *head_lnw = nullptr, *head_lnb = nullptr, *head_lw = nullptr, *head_lb = nullptr;
+
+  // grow-only device staging for the host-buffer entry points (no cudaMalloc on the steady-state path)
+  struct Staging { void* p = nullptr; size_t cap = 0; };
+  Staging staging[4];
+  void* stage(int slot, size_t bytes) {
+    Staging& s = staging[slot];
+    if (bytes > s.cap) {
+      if (s.p) cudaFree(s.p);
+      s.p = nullptr; s.cap = 0;
+      VSB_CUDA(cudaMalloc(&s.p, bytes));
+      s.cap = bytes;
+    }
+    return s.p;
+  }
+  ~Model() { for (auto& s : staging) if (s.p) cudaFree(s.p); }
 
   std::map<int, std::unique_ptr<Plan>> embed_plans, detect_plans;
   std::map<uint64_t, std::unique_ptr<ResampleDev>> resamplers;
@@ -356,9 +403,9 @@ class Model {
   static void dbg(Plan& pl, const std::string& name, const void* p, int dtype, int64_t B, int64_t H, int64_t W, int64_t C, int64_t ld) {
     pl.dbg[name] = DebugTensor{p, dtype, {B, H, W, C}, ld};
   }
-  void add_conv(Plan& pl, ConvGemmOp op, const ConvW& w, int block_n = 0) {
+  void add_conv(Plan& pl, ConvGemmOp op, const ConvW& w, const std::string& name, int block_n = 0) {
     finalize_op(op, w.w, w.N, w.K, w.K, num_sms, block_n);
-    pl.steps.push_back(Step{[op](cudaStream_t st) { launch(op, st); }, 1});
+    pl.steps.push_back(Step{[op](cudaStream_t st) { launch(op, st); }, 1, name});
   }
   // ResnetBlock on NHWC fp16 (modules/unet.py:17-39):  out = relu(conv3'(relu(conv3'(x)))) + (conv1(x) + b)
   // `x` has pixel pitch ldx; output written with pitch ld_out.  If fuse_outc: the 1x1 outc + tanh is fused and the
@@ -373,12 +420,12 @@ class Model {
     {  // res 1x1
       ConvGemmOp op; setup_tma_conv(op, x, B, H, W, Cin, ldx, 1, 1, 0);
       op.p.epi = EPI_AFFINE; op.p.act = ACT_NONE; op.p.bias = w.res.bias; op.p.out16 = r; op.p.ld_out16 = Cout;
-      add_conv(pl, op, w.res);
+      add_conv(pl, op, w.res, "unet.conv1x1." + std::to_string(Cin) + "-" + std::to_string(Cout) + "@" + std::to_string(H));
     }
     {  // conv3 + BN + ReLU
       ConvGemmOp op; setup_tma_conv(op, x, B, H, W, Cin, ldx, 3, 3, 1);
       op.p.epi = EPI_AFFINE; op.p.act = ACT_RELU; op.p.bias = w.c1.bias; op.p.out16 = h; op.p.ld_out16 = Cout;
-      add_conv(pl, op, w.c1);
+      add_conv(pl, op, w.c1, "unet.conv3x3." + std::to_string(Cin) + "-" + std::to_string(Cout) + "@" + std::to_string(H));
     }
     {  // conv3 + BN + ReLU, + res
       ConvGemmOp op; setup_tma_conv(op, h, B, H, W, Cout, Cout, 3, 3, 1);
@@ -390,7 +437,7 @@ class Model {
       } else {
         op.p.out16 = out; op.p.ld_out16 = ld_out;
       }
-      add_conv(pl, op, w.c2);
+      add_conv(pl, op, w.c2, std::string(fuse_outc ? "unet.conv3x3+outc." : "unet.conv3x3.") + std::to_string(Cout) + "-" + std::to_string(Cout) + "@" + std::to_string(H));
     }
     if (out) dbg(pl, name, out, 1, B, H, W, Cout, ld_out);
     return out;
@@ -423,7 +470,7 @@ class Model {
         if (cin == 1) unet_first_kernel<1><<<grid, 256, 0, st>>>(src, B, S, S, Z, w1, b1, wr, br, h1, r0, yuv);
         else unet_first_kernel<3><<<grid, 256, 0, st>>>(src, B, S, S, Z, w1, b1, wr, br, h1, r0, yuv);
         VSB_CUDA(cudaGetLastError());
-      }, 1});
+      }, 1, "unet.first"});
     }
     std::vector<__half*> skips;  // outputs of inc, downs[0..]
     std::vector<int> skip_ld;
@@ -432,7 +479,7 @@ class Model {
       ConvGemmOp op; setup_tma_conv(op, h1, B, S, S, z[0], z[0], 3, 3, 1);
       op.p.epi = EPI_AFFINE; op.p.act = ACT_RELU; op.p.bias = inc_c2.bias; op.p.resid16 = r0; op.p.ld_res16 = z[0];
       op.p.out16 = x; op.p.ld_out16 = z[0];
-      add_conv(pl, op, inc_c2);
+      add_conv(pl, op, inc_c2, "unet.conv3x3." + std::to_string(z[0]) + "-" + std::to_string(z[0]) + "@" + std::to_string(S));
       dbg(pl, "inc", x, 1, B, S, S, z[0], z[0]);
     }
     int ldx = z[0], hs = S;
@@ -446,7 +493,7 @@ class Model {
         ConvGemmOp op;
         setup_gather_conv(op, LD_GATHER_CONV, x, z[i], ldx, nullptr, 0, 0, B, hs, hs, ho, ho, 3, 3, 2, 1, 0);
         op.p.epi = EPI_AFFINE; op.p.act = ACT_NONE; op.p.bias = down_conv[i].bias; op.p.out16 = dn; op.p.ld_out16 = z[i + 1];
-        add_conv(pl, op, down_conv[i]);
+        add_conv(pl, op, down_conv[i], "unet.down3x3s2." + std::to_string(z[i]) + "-" + std::to_string(z[i + 1]) + "@" + std::to_string(ho));
       }
       __half* out = nullptr; int ld_out = 0;
       if (i == L - 2) {  // last level writes straight into the message-concat buffer (channels [0, z))
@@ -466,7 +513,7 @@ class Model {
         dim3 grid(B, 8);
         msg_embed_kernel<<<grid, 256, hidden * sizeof(float), st>>>(plp->in_msgs, table, K, hidden, cat, hw, zb, coff, plp->in_msg_stride);
         VSB_CUDA(cudaGetLastError());
-      }, 1});
+      }, 1, "unet.msg"});
       dbg(pl, "cat", cat, 1, B, hs, hs, zb, zb);
     }
     // ---- bottleneck
@@ -491,7 +538,7 @@ class Model {
         setup_gather_conv(op, LD_GATHER_UPS, x, Cin, ldx, skip, Cin, ld_skip, B, hs, hs, ho, ho, 3, 3, 1, 1, 1);
         op.p.epi = EPI_LN; op.p.act = ACT_RELU; op.p.ln_w = up_lnw[j]; op.p.ln_b = up_lnb[j]; op.p.ln_eps = 1e-6f;
         op.p.out16 = u; op.p.ld_out16 = Cout;
-        add_conv(pl, op, up_conv[j]);
+        add_conv(pl, op, up_conv[j], "unet.up3x3." + std::to_string(2 * Cin) + "-" + std::to_string(Cout) + "@" + std::to_string(ho));
         dbg(pl, "up" + std::to_string(j) + "_conv", u, 1, B, ho, ho, Cout, Cout);
       }
       const bool last = (ii == 0);
@@ -525,7 +572,7 @@ class Model {
         const int grid = (int)std::min<long>((npix + 7) / 8, 148L * 16);
         stem_ln_kernel<<<grid, 256, 8 * (48 + Cc) * sizeof(float), st>>>(plp->in_imgs, B, S, S, OH, OH, st_, w, b, lw, lb, Cc, x, Cc);
         VSB_CUDA(cudaGetLastError());
-      }, 1});
+      }, 1, "cnx.stem"});
       dbg(pl, "ds0", x, 0, B, hs, hs, C, C);
     }
     int maxK4 = 0;
@@ -546,14 +593,14 @@ class Model {
             const int grid = (int)std::min<long>((Mp + 7) / 8, 148L * 16);
             ln_rows_kernel<<<grid, 256, 0, st>>>(xin, Mp, Cp, Cp, lw, lb, 1e-6f, xn, Cp);
             VSB_CUDA(cudaGetLastError());
-          }, 1});
+          }, 1, "cnx.ln_rows"});
         }
         const int ho = (hs - 2) / 2 + 1;
         float* xo = pl.pool.alloc_n<float>((size_t)B * ho * ho * Cn);
         ConvGemmOp op;
         setup_gather_conv(op, LD_GATHER_CONV, xn, Cp, Cp, nullptr, 0, 0, B, hs, hs, ho, ho, 2, 2, 2, 0, 0);
         op.p.epi = EPI_AFFINE; op.p.act = ACT_NONE; op.p.bias = ds[s - 1].conv.bias; op.p.out32 = xo; op.p.ld_out32 = Cn;
-        add_conv(pl, op, ds[s - 1].conv);
+        add_conv(pl, op, ds[s - 1].conv, "cnx.down2x2s2." + std::to_string(Cp) + "-" + std::to_string(Cn) + "@" + std::to_string(ho));
         x = xo; hs = ho; C = Cn;
         dbg(pl, "ds" + std::to_string(s), x, 0, B, hs, hs, C, C);
       }
@@ -575,13 +622,13 @@ class Model {
             if (threads < 64) threads = 64;
             dwconv7_ln_kernel<<<(unsigned)blocks, threads, kDwStrip * Cc * sizeof(float), st>>>(xin, B, H, H, Cc, Cc, dww, dwb, lw, lb, a, Cc);
             VSB_CUDA(cudaGetLastError());
-          }, 1});
+          }, 1, "cnx.dwconv7_ln"});
         }
         {
           ConvGemmOp op; setup_tma_gemm(op, a, M, C, C);
           op.p.epi = EPI_AFFINE; op.p.act = ACT_GELU; op.p.bias = w.pw1.bias; op.p.out16 = g; op.p.ld_out16 = 4 * C;
           op.p.grn_stats = stats; op.p.rows_per_sample = rows_per_sample;
-          add_conv(pl, op, w.pw1);
+          add_conv(pl, op, w.pw1, "cnx.pwconv1." + std::to_string(C) + "@" + std::to_string(hs));
         }
         {
           const int K4 = 4 * C;
@@ -589,7 +636,7 @@ class Model {
           pl.steps.push_back(Step{[=](cudaStream_t st) {
             grn_scale_kernel<<<B, 256, 0, st>>>(stats, gamma, K4, scale, K4);
             VSB_CUDA(cudaGetLastError());
-          }, 1});
+          }, 1, "cnx.grn_scale"});
         }
         {
           ConvGemmOp op; setup_gather_scale(op, g, M, 4 * C, 4 * C, scale, 4 * C, rows_per_sample);
@@ -599,7 +646,7 @@ class Model {
             x16 = pl.pool.alloc_n<__half>(M * C);
             op.p.out16 = x16; op.p.ld_out16 = C;
           }
-          add_conv(pl, op, w.pw2);
+          add_conv(pl, op, w.pw2, "cnx.pwconv2." + std::to_string(C) + "@" + std::to_string(hs));
         }
         if (jb == 0) { dbg(pl, "s" + std::to_string(s) + "b0_a", a, 1, B, hs, hs, C, C); dbg(pl, "s" + std::to_string(s) + "b0_g", g, 1, B, hs, hs, 4 * C, 4 * C); }
       }
@@ -612,7 +659,7 @@ class Model {
       ConvGemmOp op;
       setup_gather_conv(op, LD_GATHER_CONV, x16, C, C, nullptr, 0, 0, B, hs, hs, hs, hs, 3, 3, 1, 1, 1);
       op.p.epi = EPI_AFFINE; op.p.act = ACT_NONE; op.p.out32 = y; op.p.ld_out32 = C;
-      add_conv(pl, op, head_conv);
+      add_conv(pl, op, head_conv, "cnx.head3x3." + std::to_string(C) + "@" + std::to_string(hs));
       dbg(pl, "head_conv", y, 0, B, hs, hs, C, C);
       float* pooled = pl.pool.alloc_n<float>((size_t)B * C);
       const int P = hs * hs, Cc = C, NO = 1 + d.nbits;
@@ -623,7 +670,7 @@ class Model {
         const int grid = (int)(((long)B * NO + 7) / 8);
         head_linear_kernel<<<grid, 256, 0, st>>>(pooled, hw, hb, B, Cc, NO, logits);
         VSB_CUDA(cudaGetLastError());
-      }, 2});
+      }, 2, "cnx.head_tail"});
     }
     Plan* ret = up.get();
     detect_plans[B] = std::move(up);

@@ -103,13 +103,12 @@ int vsb_embed_host(vsb_model* m, const float* imgs_h, const uint8_t* msgs_h, int
   VSB_CHECK(m && imgs_h && msgs_h && imgs_w_h, "null argument");
   m->impl.check_ready();
   VSB_CUDA(cudaSetDevice(m->impl.device));
-  DevicePool tmp;
   const size_t n = (size_t)F * 3 * H * W;
   const size_t np = (size_t)F * m->impl.d.unet_out_ch * H * W;
-  float* imgs = tmp.alloc_n<float>(n);
-  float* out = tmp.alloc_n<float>(n);
-  float* pw = preds_w_h ? tmp.alloc_n<float>(np) : nullptr;
-  uint8_t* msgs = tmp.alloc_n<uint8_t>((size_t)n_msgs * m->impl.d.nbits);
+  float* imgs = (float*)m->impl.stage(0, n * sizeof(float));
+  float* out = (float*)m->impl.stage(1, n * sizeof(float));
+  float* pw = preds_w_h ? (float*)m->impl.stage(2, np * sizeof(float)) : nullptr;
+  uint8_t* msgs = (uint8_t*)m->impl.stage(3, (size_t)n_msgs * m->impl.d.nbits + 256);
   cudaStream_t st = 0;
   VSB_CUDA(cudaMemcpyAsync(imgs, imgs_h, n * sizeof(float), cudaMemcpyHostToDevice, st));
   VSB_CUDA(cudaMemcpyAsync(msgs, msgs_h, (size_t)n_msgs * m->impl.d.nbits, cudaMemcpyHostToDevice, st));
@@ -126,11 +125,10 @@ int vsb_detect_host(vsb_model* m, const float* imgs_h, float* logits_h, int32_t 
   VSB_CHECK(m && imgs_h && logits_h, "null argument");
   m->impl.check_ready();
   VSB_CUDA(cudaSetDevice(m->impl.device));
-  DevicePool tmp;
   const size_t n = (size_t)F * 3 * H * W;
   const size_t nl = (size_t)F * (1 + m->impl.d.nbits);
-  float* imgs = tmp.alloc_n<float>(n);
-  float* lg = tmp.alloc_n<float>(nl);
+  float* imgs = (float*)m->impl.stage(0, n * sizeof(float));
+  float* lg = (float*)m->impl.stage(2, nl * sizeof(float));
   cudaStream_t st = 0;
   VSB_CUDA(cudaMemcpyAsync(imgs, imgs_h, n * sizeof(float), cudaMemcpyHostToDevice, st));
   m->impl.detect(imgs, lg, F, H, W, flags, st);
@@ -220,3 +218,18 @@ int vsb_debug_conv(const vsb_conv_test* t, void* stream) {
 }
 
 }  // extern "C"
+
+// ---- per-step profile (bench.py roofline leg): enable, run some steps, then read "name\ttotal_ms\tcount\n" lines
+extern "C" int vsb_profile_enable(int32_t on) {
+  g_profile.flush();
+  if (on) g_profile.acc.clear();
+  g_profile.enabled = on != 0;
+  return VSB_OK;
+}
+extern "C" int64_t vsb_profile_read(char* buf, int64_t capacity) {
+  g_profile.flush();
+  std::string out;
+  for (auto& kv : g_profile.acc) out += kv.first + "\t" + std::to_string(kv.second.first) + "\t" + std::to_string(kv.second.second) + "\n";
+  if (buf && capacity > (int64_t)out.size()) memcpy(buf, out.c_str(), out.size() + 1);
+  return (int64_t)out.size() + 1;
+}
