@@ -114,7 +114,7 @@ int64_t vsb_profile_read(char* buf, int64_t capacity);
 int64_t vsb_debug_get_tensor(vsb_model* m, const char* name, float* host_out, int64_t capacity, int64_t* shape4);
 /* standalone conv/GEMM on the tcgen05 kernel for unit tests: see tests/test_conv_gemm_gpu.py */
 typedef struct vsb_conv_test {
-  int32_t loader;            /* 0 TMA, 1 gather conv, 2 gather bilinear-x2+reflect (UBlock), 3 gather GRN-scale */
+  int32_t loader;            /* 0 TMA per tap, 1 gather conv, 2 halo bilinear-x2+reflect (UBlock), 3 gather GRN-scale, 4 halo conv3x3 */
   int32_t B, IH, IW, C0, C1; /* input NHWC fp16 [B,IH,IW,C0] (+ optional second source [.., C1]) */
   int32_t R, S, stride, pad, pad_mode;
   int32_t N;                 /* C_out; weights fp16 [N][R*S*(C0+C1)] */

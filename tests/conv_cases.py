@@ -8,7 +8,7 @@ import torch.nn.functional as F
 
 from videoseal_b200 import _lib
 
-LD_TMA, LD_GCONV, LD_GUPS, LD_GSCALE = 0, 1, 2, 3
+LD_TMA, LD_GCONV, LD_GUPS, LD_GSCALE, LD_HALO = 0, 1, 2, 3, 4
 
 CASES = {
     # name: dict(loader, B, IH, IW, C0, C1, R, S, stride, pad, pad_mode, N, extras...)
@@ -23,6 +23,13 @@ CASES = {
     "conv3_bott":      dict(loader=LD_TMA, B=24, IH=32, IW=32, C0=384, N=384, R=3, S=3, pad=1, bias=True, act=1, resid16=True, out="f16"),
     "outc":            dict(loader=LD_TMA, B=1, IH=128, IW=128, C0=16, N=16, R=3, S=3, pad=1, bias=True, act=1, resid16=True, n_out=1, out="none"),
     "outc3":           dict(loader=LD_TMA, B=1, IH=128, IW=128, C0=64, N=64, R=3, S=3, pad=1, bias=True, act=1, resid16=True, n_out=3, out="none"),
+    "halo_c64":        dict(loader=LD_HALO, B=2, IH=32, IW=32, C0=64, N=64, R=3, S=3, pad=1, bias=True, act=1, out="f16"),
+    "halo_c16":        dict(loader=LD_HALO, B=1, IH=128, IW=128, C0=16, N=16, R=3, S=3, pad=1, bias=True, act=1, resid16=True, out="f16"),
+    "halo_c32":        dict(loader=LD_HALO, B=3, IH=64, IW=64, C0=32, N=32, R=3, S=3, pad=1, bias=True, act=1, resid16=True, out="f16"),
+    "halo_bott":       dict(loader=LD_HALO, B=24, IH=32, IW=32, C0=384, N=384, R=3, S=3, pad=1, bias=True, act=1, resid16=True, out="f16"),
+    "halo_outc":       dict(loader=LD_HALO, B=2, IH=128, IW=128, C0=16, N=16, R=3, S=3, pad=1, bias=True, act=1, resid16=True, n_out=1, out="none"),
+    "halo_outc3":      dict(loader=LD_HALO, B=1, IH=64, IW=64, C0=64, N=64, R=3, S=3, pad=1, bias=True, act=1, resid16=True, n_out=3, out="none"),
+    "gups_c16":        dict(loader=LD_GUPS, B=1, IH=64, IW=64, C0=16, C1=16, N=16, R=3, S=3, epi=1, act=1, out="f16"),
     "gconv_s2":        dict(loader=LD_GCONV, B=2, IH=64, IW=64, C0=16, N=32, R=3, S=3, stride=2, pad=1, bias=True, out="f16"),
     "gconv_patch":     dict(loader=LD_GCONV, B=2, IH=16, IW=16, C0=96, N=192, R=2, S=2, stride=2, pad=0, bias=True, out="f32"),
     "gconv_reflect":   dict(loader=LD_GCONV, B=3, IH=8, IW=8, C0=64, N=64, R=3, S=3, stride=1, pad=1, pad_mode=1, out="f32"),

@@ -1,17 +1,24 @@
 // K1/K2: implicit-GEMM convolution / linear layer on the 5th-gen tensor cores (tcgen05.mma,
 // accumulators in TMEM), persistent and warp-specialised:
 //
-//   warp 0      : TMA producer (weights always; activations too when LOADER == LD_TMA)
-//   warp 1      : single-thread tcgen05.mma issuer
-//   warp 2      : TMEM allocator
-//   warps 4..7  : epilogue (TMEM -> registers -> fused bias/BN-fold/act/residual/LN/tanh/GRN-stats -> HBM)
-//   warps 8..11 : (gather loaders only) build the im2col-free A tile in swizzled shared memory from
-//                 NHWC activations: strided / reflect-padded convs, fused bilinear x2 + reflect-pad +
-//                 virtual skip-concat (UBlock), GRN per-(sample,k) scaling (ConvNeXt pwconv2).
+//   warp 0        : TMA producer (weights always; activations for LD_TMA; input halo tiles for LD_HALO_*)
+//   warp 1        : single-thread tcgen05.mma issuer
+//   warp 2        : TMEM allocator
+//   warps 4..11   : epilogue (TMEM -> registers -> fused bias/BN-fold/act/residual/LN/tanh/GRN-stats -> HBM);
+//                   warp w owns TMEM lane quadrant w%4 and every second 16-column chunk ((w-4)/4)
+//   warps 12..15  : A-tile builders (all loaders except LD_TMA):
+//       LD_HALO_CONV3 : on-chip im2col - the (8+2)x(16+2) input halo of an 8x16 output tile is TMA-loaded ONCE per channel
+//                       chunk (zero fill = conv padding) and the 9 tap tiles are copied smem->smem into the swizzled
+//                       UMMA layout (input pixels cross L2->SM once instead of nine times)
+//       LD_HALO_UPS   : same, with the UBlock's bilinear x2 (align_corners=False) + ReflectionPad2d(1) + virtual
+//                       skip-concat evaluated from a 6x10 low-resolution halo tile in shared memory
+//       LD_GATHER_CONV: generic strided / reflect-padded conv gathered from global memory (stride-2 3x3, k2s2 patchify,
+//                       reflect-padded head conv)
+//       LD_GATHER_SCALE: A[m,k] = G[m,k] * scale[sample(m), k]  (ConvNeXt pwconv2 with the GRN factor folded in)
 //
-// GEMM view: D[M = output pixels, N = C_out] = A[M, K = taps*C_in] * W[N, K]^T, fp16 operands,
-// fp32 accumulation.  BLOCK_M = 128 (one UMMA M=128 atom, cta_group::1), BLOCK_N <= 256, two TMEM
-// accumulator stages so the epilogue of tile i overlaps the main loop of tile i+1.
+// GEMM view: D[M = output pixels, N = C_out] = A[M, K = taps*C_in] * W[N, K]^T, fp16 operands, fp32 accumulation.
+// BLOCK_M = 128 (one UMMA M=128 atom, cta_group::1), BLOCK_N <= 256, two TMEM accumulator stages so the epilogue of
+// tile i overlaps the main loop of tile i+1.
 //
 // Replaces: nn.Conv2d / nn.Linear + BatchNorm2d(eval) + ReLU / LayerNorm / GELU / GRN / tanh call sites of
 // videoseal/modules/unet.py:17-197, modules/common.py:45-52,150-169, modules/convnext.py:41-57,
@@ -21,23 +28,29 @@
 
 namespace vsb {
 
-enum : int { LD_TMA = 0, LD_GATHER_CONV = 1, LD_GATHER_UPS = 2, LD_GATHER_SCALE = 3 };
+enum : int { LD_TMA = 0, LD_GATHER_CONV = 1, LD_HALO_UPS = 2, LD_GATHER_SCALE = 3, LD_HALO_CONV3 = 4 };
 enum : int { EPI_AFFINE = 0, EPI_LN = 1 };
 enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
 
 constexpr int kBlockM = 128;
-constexpr int kMaxStages = 8;
+constexpr int kMaxStages = 24;
 constexpr int kTmemCols = 512;
-constexpr int kAccStride = 256;  // TMEM columns between the two accumulator stages
+constexpr int kAccStride = 256;   // TMEM columns between the two accumulator stages
+constexpr int kHeaderBytes = 8192;  // barriers | bias x2 | LN w,b | outc partials
+constexpr int kHaloTW = 16, kHaloTH = 8;
 
 struct ConvGemmParams {
   // ---- GEMM view
   int M, N, num_kb, kblk, block_n, n_tiles, m_tiles, num_tiles, stages;
   uint32_t a_stage_bytes, b_stage_bytes, stage_bytes, idesc;
-  // ---- A via TMA
-  int a_is_conv;  // 0: 2D map (K, M)   1: 4D map (C, W, H, B) with zero-fill halo
-  int H, W, tile_w, tile_h, tiles_x, tiles_per_img, R, S, pad, c_blocks;
-  // ---- A via gather (NHWC fp16 sources; K order = (r, s, c) with c over the virtual concat [src0 | src1])
+  // ---- output-tile geometry: tile_mode 0: rows are consecutive GEMM rows; 1: tile_h x tile_w pixel patch of an H x W map
+  int tile_mode, H, W, tile_w, tile_h, tiles_x, tiles_per_img;
+  // ---- A via TMA (LD_TMA): a_is_conv 0: 2D map (K, M); 1: 4D map (C, W, H, B) with zero-fill halo, one load per tap
+  int a_is_conv, R, S, pad, c_blocks;
+  // ---- halo loaders: c_blocks = channel chunks of the (virtual-concat) input; c0_blocks of them come from source 0
+  int c0_blocks;
+  uint32_t halo_bytes /*TMA box bytes*/, halo_stride /*buffer pitch*/, halo_off, resid_off;
+  // ---- gather loaders (NHWC fp16 sources; K order = (r, s, c) with c over the virtual concat [src0 | src1])
   const __half* src0;
   const __half* src1;
   int C0, C1, ld0, ld1, IH, IW, OH, OW, stride, pad_mode /*0 zero, 1 reflect*/, Ktot;
@@ -81,40 +94,77 @@ __device__ __forceinline__ uint4 lerp4_h8(uint4 a, uint4 b, uint4 c, uint4 d, fl
   return o;
 }
 
+// byte offset of 16-byte chunk j of row r inside a K-major operand tile with `kblk` fp16 per row and the matching
+// 32/64/128-byte swizzle (Swizzle<1|2|3,4,3>: address bits [4,4+b) ^= bits [7,7+b))
+__device__ __forceinline__ uint32_t swz_off(int r, int j, int kblk) {
+  if (kblk == 64) return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4));
+  if (kblk == 32) return (uint32_t)(r * 64 + ((j ^ ((r >> 1) & 3)) << 4));
+  return (uint32_t)(r * 32 + ((j ^ ((r >> 2) & 1)) << 4));
+}
+
+__device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+
 template <int LOADER>
-__global__ void __launch_bounds__(LOADER == LD_TMA ? 256 : 384, 1)
-conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
-                 const __grid_constant__ ConvGemmParams p) {
+__global__ void __launch_bounds__(LOADER == LD_TMA ? 384 : 512, 1)
+conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
+                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvGemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  // carve-up: [0,1024) barriers + tmem pointer; then `stages` x (A tile | B tile), 1024-aligned
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // header (kHeaderBytes): barriers | tmem ptr | s_bias[2][256] | s_lnw[256] s_lnb[256] | s_dot[128][3]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tfull_bar = empty_bar + kMaxStages;
   uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-  uint8_t* tiles = smem + 1024;
+  uint64_t* hfull_bar = tempty_bar + 2;
+  uint64_t* hempty_bar = hfull_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(hempty_bar + 2);
+  float* s_bias = reinterpret_cast<float*>(smem + 1024);        // [2][256]
+  float* s_lnw = reinterpret_cast<float*>(smem + 3072);         // [256]  (LN weight | outc row 0)
+  float* s_lnb = reinterpret_cast<float*>(smem + 4096);         // [256]  (LN bias   | outc row 1)
+  float* s_oc2 = reinterpret_cast<float*>(smem + 5120);         // [256]  (            outc row 2)
+  float* s_dot = reinterpret_cast<float*>(smem + 6144);         // [128][3]
+  uint8_t* tiles = smem + kHeaderBytes;
+  uint8_t* halo = smem + p.halo_off;
+  uint8_t* rbuf = smem + p.resid_off;
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  constexpr uint32_t kNumGather = 128;
+  constexpr uint32_t kNumBuilders = 128;
+  constexpr bool kHalo = (LOADER == LD_HALO_CONV3 || LOADER == LD_HALO_UPS);
 
   if (threadIdx.x == 0) {
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&full_bar[s], LOADER == LD_TMA ? 1u : 1u + kNumGather);
+      mbar_init(&full_bar[s], LOADER == LD_TMA ? 1u : 1u + kNumBuilders);
       mbar_init(&empty_bar[s], 1u);
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1u);
-      mbar_init(&tempty_bar[s], 128u);
+      mbar_init(&tempty_bar[s], 256u);
+      mbar_init(&hfull_bar[s], 1u);
+      mbar_init(&hempty_bar[s], kNumBuilders);
     }
     fence_barrier_init();
-    if (LOADER == LD_TMA) tma_prefetch_desc(&tmA);
+    if (LOADER == LD_TMA || kHalo) tma_prefetch_desc(&tmA);
+    if (LOADER == LD_HALO_UPS) tma_prefetch_desc(&tmA2);
     tma_prefetch_desc(&tmB);
   }
   if (warp == 2) {
     tmem_alloc(tmem_ptr_smem, kTmemCols);
     tmem_relinquish();
+  }
+  if (p.epi == EPI_LN) {
+    for (int i = threadIdx.x; i < p.N; i += blockDim.x) { s_lnw[i] = p.ln_w[i]; s_lnb[i] = p.ln_b[i]; }
+  } else if (p.outc_w != nullptr) {  // fused 1x1 outc: N <= 256 (n_tiles == 1), up to 3 output channels
+    for (int i = threadIdx.x; i < p.N; i += blockDim.x) {
+      s_lnw[i] = p.outc_w[i];
+      s_lnb[i] = p.n_out > 1 ? p.outc_w[p.N + i] : 0.f;
+      s_oc2[i] = p.n_out > 2 ? p.outc_w[2 * p.N + i] : 0.f;
+    }
   }
   tc_fence_before();
   __syncthreads();
@@ -127,34 +177,59 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (elect_one()) {
       int stage = 0;
       uint32_t phase = 0;
+      int hb = 0;
+      uint32_t hphase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
         int cb = 0, cx = 0, cy = 0;
-        if (LOADER == LD_TMA && p.a_is_conv) {
+        if (p.tile_mode == 1) {
           cb = m_tile / p.tiles_per_img;
           const int rem = m_tile - cb * p.tiles_per_img;
           const int ty = rem / p.tiles_x;
           cy = ty * p.tile_h;
           cx = (rem - ty * p.tiles_x) * p.tile_w;
         }
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          mbar_wait(&empty_bar[stage], phase ^ 1u);
-          uint8_t* sa = tiles + (size_t)stage * p.stage_bytes;
-          uint8_t* sb = sa + p.a_stage_bytes;
-          if (LOADER == LD_TMA) {
-            mbar_arrive_expect_tx(&full_bar[stage], p.a_stage_bytes + p.b_stage_bytes);
-            if (p.a_is_conv) {
-              const int tap = kb / p.c_blocks, cblk = kb - tap * p.c_blocks;
-              const int r = tap / p.S, s = tap - r * p.S;
-              tma_load_4d(&tmA, &full_bar[stage], sa, cblk * p.kblk, cx + s - p.pad, cy + r - p.pad, cb);
+        if (kHalo) {
+          for (int c = 0; c < p.c_blocks; ++c) {
+            mbar_wait(&hempty_bar[hb], hphase ^ 1u);
+            mbar_arrive_expect_tx(&hfull_bar[hb], p.halo_bytes);
+            if (LOADER == LD_HALO_CONV3) {
+              tma_load_4d(&tmA, &hfull_bar[hb], halo + (size_t)hb * p.halo_stride, c * p.kblk, cx - 1, cy - 1, cb);
             } else {
-              tma_load_2d(&tmA, &full_bar[stage], sa, kb * p.kblk, m_tile * kBlockM);
+              const bool s0 = c < p.c0_blocks;
+              tma_load_4d(s0 ? &tmA : &tmA2, &hfull_bar[hb], halo + (size_t)hb * p.halo_stride,
+                          (s0 ? c : c - p.c0_blocks) * p.kblk, (cx >> 1) - 1, (cy >> 1) - 1, cb);
             }
-          } else {
-            mbar_arrive_expect_tx(&full_bar[stage], p.b_stage_bytes);
+            hb ^= 1;
+            if (hb == 0) hphase ^= 1u;
+            for (int tap = 0; tap < 9; ++tap) {
+              mbar_wait(&empty_bar[stage], phase ^ 1u);
+              mbar_arrive_expect_tx(&full_bar[stage], p.b_stage_bytes);
+              tma_load_2d(&tmB, &full_bar[stage], tiles + (size_t)stage * p.stage_bytes + p.a_stage_bytes,
+                          (tap * p.c_blocks + c) * p.kblk, n_tile * p.block_n);
+              if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            }
           }
-          tma_load_2d(&tmB, &full_bar[stage], sb, kb * p.kblk, n_tile * p.block_n);
-          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        } else {
+          for (int kb = 0; kb < p.num_kb; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            uint8_t* sa = tiles + (size_t)stage * p.stage_bytes;
+            uint8_t* sb = sa + p.a_stage_bytes;
+            if (LOADER == LD_TMA) {
+              mbar_arrive_expect_tx(&full_bar[stage], p.a_stage_bytes + p.b_stage_bytes);
+              if (p.a_is_conv) {
+                const int tap = kb / p.c_blocks, cblk = kb - tap * p.c_blocks;
+                const int r = tap / p.S, s = tap - r * p.S;
+                tma_load_4d(&tmA, &full_bar[stage], sa, cblk * p.kblk, cx + s - p.pad, cy + r - p.pad, cb);
+              } else {
+                tma_load_2d(&tmA, &full_bar[stage], sa, kb * p.kblk, m_tile * kBlockM);
+              }
+            } else {
+              mbar_arrive_expect_tx(&full_bar[stage], p.b_stage_bytes);
+            }
+            tma_load_2d(&tmB, &full_bar[stage], sb, kb * p.kblk, n_tile * p.block_n);
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          }
         }
       }
     }
@@ -188,18 +263,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (as == 0) aphase ^= 1u;
       }
     }
-  } else if (warp >= 4 && warp < 8) {
-    // ===================================================================== epilogue
-    const int ew = warp - 4;  // == warp % 4 -> TMEM lane quadrant this warp may access
-    const int row = ew * 32 + lane;
+  } else if (warp >= 4 && warp < 12) {
+    // ===================================================================== epilogue (8 warps)
+    const int q = warp & 3;            // TMEM lane quadrant this warp may access
+    const int half = (warp - 4) >> 2;  // which 16-column chunks: chunk index parity
+    const int row = q * 32 + lane;
+    const int et = threadIdx.x - 128;  // 0..255
+    const int nchunks = p.block_n >> 4;
     int as = 0;
     uint32_t aphase = 0;
+    int bsel = 0;
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
       const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
       const int n0 = n_tile * p.block_n;
       long m;
       bool mvalid;
-      if (LOADER == LD_TMA && p.a_is_conv) {
+      if (p.tile_mode == 1) {
         const int b = m_tile / p.tiles_per_img;
         const int rem = m_tile - b * p.tiles_per_img;
         const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
@@ -210,65 +289,88 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         m = (long)m_tile * kBlockM + row;
         mvalid = m < p.M;
       }
+      // ---- prologue, overlapped with the main loop of this tile: bias -> smem, residual row -> smem (cp.async)
+      float* sb = s_bias + bsel * 256;
+      if (et < p.block_n) sb[et] = (p.bias != nullptr && n0 + et < p.N) ? __ldg(p.bias + n0 + et) : 0.f;
+      const bool res_fast = mvalid && (n0 + p.block_n <= p.N);
+      if (res_fast && p.resid16 != nullptr) {
+        const __half* r = p.resid16 + m * p.ld_res16 + n0;
+        for (int ch = half; ch < nchunks; ch += 2) {
+          cp_async16(rbuf + ((size_t)(2 * ch) * 128 + row) * 16, r + ch * 16);
+          cp_async16(rbuf + ((size_t)(2 * ch + 1) * 128 + row) * 16, r + ch * 16 + 8);
+        }
+      } else if (res_fast && p.resid32 != nullptr) {
+        const float* r = p.resid32 + m * p.ld_res32 + n0;
+        for (int ch = half; ch < nchunks; ch += 2) {
+#pragma unroll
+          for (int u = 0; u < 4; ++u) cp_async16(rbuf + ((size_t)(4 * ch + u) * 128 + row) * 16, r + ch * 16 + 4 * u);
+        }
+      }
+      cp_async_commit();
+      epi_bar_sync();  // bias visible to all epilogue warps (double-buffered across tiles)
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-      const uint32_t trow = tmem_base + ((uint32_t)(ew * 32) << 16) + (uint32_t)(as * kAccStride);
+      cp_async_wait_all();
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kAccStride);
 
       if (p.epi == EPI_LN) {
-        // channels-first LayerNorm over the full C_out row (biased variance), then activation
-        const int N = p.N;
-        float sum = 0.f;
-        for (int c = 0; c < p.block_n; c += 16) {
-          float v[16];
-          tmem_ld16(trow + c, v);
+        // channels-first LayerNorm over the full C_out row (biased variance), then activation; half-0 warps only
+        if (half == 0) {
+          const int N = p.N;
+          float sum = 0.f;
+          for (int c = 0; c < p.block_n; c += 16) {
+            float v[16];
+            tmem_ld16(trow + c, v);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) sum += (c + j < N) ? v[j] : 0.f;
-        }
-        const float mean = sum / (float)N;
-        float var = 0.f;
-        for (int c = 0; c < p.block_n; c += 16) {
-          float v[16];
-          tmem_ld16(trow + c, v);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const float d = v[j] - mean;
-            var += (c + j < N) ? d * d : 0.f;
+            for (int j = 0; j < 16; ++j) sum += (c + j < N) ? v[j] : 0.f;
           }
-        }
-        const float rstd = 1.0f / sqrtf(var / (float)N + p.ln_eps);
-        for (int c = 0; c < p.block_n; c += 16) {
-          float v[16];
-          tmem_ld16(trow + c, v);
-          if (c >= N) continue;
-          __align__(16) __half h[16];
+          const float mean = sum / (float)N;
+          float var = 0.f;
+          for (int c = 0; c < p.block_n; c += 16) {
+            float v[16];
+            tmem_ld16(trow + c, v);
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            const int n = c + j;
-            float y = 0.f;
-            if (n < N) {
-              y = (v[j] - mean) * rstd * p.ln_w[n] + p.ln_b[n];
-              if (p.act == ACT_RELU) y = fmaxf(y, 0.f);
-              else if (p.act == ACT_GELU) y = gelu_erf(y);
+            for (int j = 0; j < 16; ++j) {
+              const float d = v[j] - mean;
+              var += (c + j < N) ? d * d : 0.f;
             }
-            h[j] = __float2half_rn(y);
           }
-          if (mvalid) {
-            __half* o = p.out16 + m * p.ld_out16 + c;
-            if (c + 16 <= N) {
-              reinterpret_cast<uint4*>(o)[0] = reinterpret_cast<const uint4*>(h)[0];
-              reinterpret_cast<uint4*>(o)[1] = reinterpret_cast<const uint4*>(h)[1];
-            } else {
-              for (int j = 0; j < 16 && c + j < N; ++j) o[j] = h[j];
+          const float rstd = 1.0f / sqrtf(var / (float)N + p.ln_eps);
+          for (int c = 0; c < p.block_n; c += 16) {
+            float v[16];
+            tmem_ld16(trow + c, v);
+            if (c >= N) continue;
+            __align__(16) __half h[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const int n = c + j;
+              float y = 0.f;
+              if (n < N) {
+                y = (v[j] - mean) * rstd * s_lnw[n] + s_lnb[n];
+                if (p.act == ACT_RELU) y = fmaxf(y, 0.f);
+                else if (p.act == ACT_GELU) y = gelu_erf(y);
+              }
+              h[j] = __float2half_rn(y);
+            }
+            if (mvalid) {
+              __half* o = p.out16 + m * p.ld_out16 + c;
+              if (c + 16 <= N) {
+                reinterpret_cast<uint4*>(o)[0] = reinterpret_cast<const uint4*>(h)[0];
+                reinterpret_cast<uint4*>(o)[1] = reinterpret_cast<const uint4*>(h)[1];
+              } else {
+                for (int j = 0; j < 16 && c + j < N; ++j) o[j] = h[j];
+              }
             }
           }
         }
       } else {
-        float dot[3] = {0.f, 0.f, 0.f};
+        float dot0 = 0.f, dot1 = 0.f, dot2 = 0.f;
         const bool grn_uniform =
             p.grn_stats != nullptr &&
-            ((long)m_tile * kBlockM + ew * 32) / p.rows_per_sample == ((long)m_tile * kBlockM + ew * 32 + 31) / p.rows_per_sample &&
-            ((long)m_tile * kBlockM + ew * 32 + 31) < p.M;
-        for (int c = 0; c < p.block_n; c += 16) {
+            ((long)m_tile * kBlockM + q * 32) / p.rows_per_sample == ((long)m_tile * kBlockM + q * 32 + 31) / p.rows_per_sample &&
+            ((long)m_tile * kBlockM + q * 32 + 31) < p.M;
+        for (int ch = half; ch < nchunks; ch += 2) {
+          const int c = ch * 16;
           float v[16];
           tmem_ld16(trow + c, v);
           const int n = n0 + c;
@@ -276,43 +378,45 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const bool full = (n + 16 <= p.N);
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            float x = v[j];
-            if (p.bias != nullptr && (full || n + j < p.N)) x += __ldg(p.bias + n + j);
+            float x = v[j] + sb[c + j];
             if (p.act == ACT_RELU) x = fmaxf(x, 0.f);
             else if (p.act == ACT_GELU) x = gelu_erf(x);
             v[j] = x;
           }
           if (mvalid) {
             if (p.resid16 != nullptr) {
-              const __half* r = p.resid16 + m * p.ld_res16 + n;
-              if (full) {
+              if (res_fast) {
                 __align__(16) __half h[16];
-                reinterpret_cast<uint4*>(h)[0] = __ldg(reinterpret_cast<const uint4*>(r));
-                reinterpret_cast<uint4*>(h)[1] = __ldg(reinterpret_cast<const uint4*>(r) + 1);
+                reinterpret_cast<uint4*>(h)[0] = *reinterpret_cast<const uint4*>(rbuf + ((size_t)(2 * ch) * 128 + row) * 16);
+                reinterpret_cast<uint4*>(h)[1] = *reinterpret_cast<const uint4*>(rbuf + ((size_t)(2 * ch + 1) * 128 + row) * 16);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] += __half2float(h[j]);
               } else {
+                const __half* r = p.resid16 + m * p.ld_res16 + n;
                 for (int j = 0; j < 16; ++j) if (n + j < p.N) v[j] += __half2float(r[j]);
               }
             }
             if (p.resid32 != nullptr) {
-              const float* r = p.resid32 + m * p.ld_res32 + n;
-              if (full) {
+              if (res_fast) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q) {
-                  const float4 t = __ldg(reinterpret_cast<const float4*>(r) + q);
-                  v[4 * q + 0] += t.x; v[4 * q + 1] += t.y; v[4 * q + 2] += t.z; v[4 * q + 3] += t.w;
+                for (int u = 0; u < 4; ++u) {
+                  const float4 t = *reinterpret_cast<const float4*>(rbuf + ((size_t)(4 * ch + u) * 128 + row) * 16);
+                  v[4 * u + 0] += t.x; v[4 * u + 1] += t.y; v[4 * u + 2] += t.z; v[4 * u + 3] += t.w;
                 }
               } else {
+                const float* r = p.resid32 + m * p.ld_res32 + n;
                 for (int j = 0; j < 16; ++j) if (n + j < p.N) v[j] += r[j];
               }
             }
           }
           if (p.outc_w != nullptr) {
-            for (int o = 0; o < p.n_out; ++o) {
 #pragma unroll
-              for (int j = 0; j < 16; ++j)
-                if (full || n + j < p.N) dot[o] += v[j] * __ldg(p.outc_w + o * p.N + n + j);
+            for (int j = 0; j < 16; ++j) {
+              if (full || n + j < p.N) {
+                dot0 += v[j] * s_lnw[n + j];
+                dot1 += v[j] * s_lnb[n + j];
+                dot2 += v[j] * s_oc2[n + j];
+              }
             }
           }
           if (mvalid) {
@@ -333,8 +437,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               float* o = p.out32 + m * p.ld_out32 + n;
               if (full) {
 #pragma unroll
-                for (int q = 0; q < 4; ++q)
-                  reinterpret_cast<float4*>(o)[q] = make_float4(v[4 * q], v[4 * q + 1], v[4 * q + 2], v[4 * q + 3]);
+                for (int u = 0; u < 4; ++u)
+                  reinterpret_cast<float4*>(o)[u] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
               } else {
                 for (int j = 0; j < 16; ++j) if (n + j < p.N) o[j] = v[j];
               }
@@ -342,53 +446,62 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           if (p.grn_stats != nullptr) {
             // column sums of squares over this warp's 32 rows (GRN: ||x||_2 over H,W per (sample, channel))
-            float q[16];
+            float sq[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) q[j] = (mvalid && (full || n + j < p.N)) ? v[j] * v[j] : 0.f;
+            for (int j = 0; j < 16; ++j) sq[j] = (mvalid && (full || n + j < p.N)) ? v[j] * v[j] : 0.f;
             if (grn_uniform) {
               // halving butterfly: after xor 16,8,4,2 each lane holds one column summed over 16 rows
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
-                const float send = (lane & 16) ? q[i] : q[i + 8];
-                const float keep = (lane & 16) ? q[i + 8] : q[i];
-                q[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+                const float send = (lane & 16) ? sq[i] : sq[i + 8];
+                const float keep = (lane & 16) ? sq[i + 8] : sq[i];
+                sq[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
               }
 #pragma unroll
               for (int i = 0; i < 4; ++i) {
-                const float send = (lane & 8) ? q[i] : q[i + 4];
-                const float keep = (lane & 8) ? q[i + 4] : q[i];
-                q[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+                const float send = (lane & 8) ? sq[i] : sq[i + 4];
+                const float keep = (lane & 8) ? sq[i + 4] : sq[i];
+                sq[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
               }
 #pragma unroll
               for (int i = 0; i < 2; ++i) {
-                const float send = (lane & 4) ? q[i] : q[i + 2];
-                const float keep = (lane & 4) ? q[i + 2] : q[i];
-                q[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+                const float send = (lane & 4) ? sq[i] : sq[i + 2];
+                const float keep = (lane & 4) ? sq[i + 2] : sq[i];
+                sq[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
               }
               {
-                const float send = (lane & 2) ? q[0] : q[1];
-                const float keep = (lane & 2) ? q[1] : q[0];
-                q[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+                const float send = (lane & 2) ? sq[0] : sq[1];
+                const float keep = (lane & 2) ? sq[1] : sq[0];
+                sq[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
               }
-              q[0] += __shfl_xor_sync(0xffffffffu, q[0], 1);
+              sq[0] += __shfl_xor_sync(0xffffffffu, sq[0], 1);
               const int col = (lane >> 1) & 15;
               if ((lane & 1) == 0 && n + col < p.N) {
-                const long sample = ((long)m_tile * kBlockM + ew * 32) / p.rows_per_sample;
-                atomicAdd(p.grn_stats + sample * p.N + n + col, q[0]);
+                const long sample = ((long)m_tile * kBlockM + q * 32) / p.rows_per_sample;
+                atomicAdd(p.grn_stats + sample * p.N + n + col, sq[0]);
               }
             } else if (mvalid) {
               const long sample = m / p.rows_per_sample;
               for (int j = 0; j < 16; ++j)
-                if (n + j < p.N) atomicAdd(p.grn_stats + sample * p.N + n + j, q[j]);
+                if (n + j < p.N) atomicAdd(p.grn_stats + sample * p.N + n + j, sq[j]);
             }
           }
         }
-        if (p.outc_w != nullptr && mvalid) {
-          const long b = m / p.hw, pix = m - b * p.hw;
-          for (int o = 0; o < p.n_out; ++o) {
-            float d = dot[o] + p.outc_b[o];
-            if (p.outc_tanh) d = tanhf(d);
-            p.delta[(b * p.n_out + o) * p.hw + pix] = d;
+        if (p.outc_w != nullptr) {
+          // the two warps sharing a row each hold a partial dot product: combine through shared memory
+          if (half == 1) { s_dot[row * 3 + 0] = dot0; s_dot[row * 3 + 1] = dot1; s_dot[row * 3 + 2] = dot2; }
+          epi_bar_sync();
+          if (half == 0 && mvalid) {
+            const long b = m / p.hw, pix = m - b * p.hw;
+            float dd[3] = {dot0 + s_dot[row * 3 + 0], dot1 + s_dot[row * 3 + 1], dot2 + s_dot[row * 3 + 2]};
+#pragma unroll
+            for (int o = 0; o < 3; ++o) {
+              if (o < p.n_out) {
+                float d = dd[o] + __ldg(p.outc_b + o);
+                if (p.outc_tanh) d = tanhf(d);
+                p.delta[(b * p.n_out + o) * p.hw + pix] = d;
+              }
+            }
           }
         }
       }
@@ -396,69 +509,142 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_arrive(&tempty_bar[as]);
       as ^= 1;
       if (as == 0) aphase ^= 1u;
+      bsel ^= 1;
     }
-  } else if (LOADER != LD_TMA && warp >= 8) {
-    // ===================================================================== gather producers (A tile)
-    const int gt = threadIdx.x - 256;  // 0..127
-    const int j = gt & 7;              // 16-byte chunk (8 fp16 K-elements) within the 128-byte swizzled row
-    const int rg = gt >> 3;            // rows rg + 16*i
+  } else if (LOADER != LD_TMA && warp >= 12) {
+    // ===================================================================== A-tile builders (4 warps)
+    const int gt = threadIdx.x - 384;  // 0..127
     int stage = 0;
     uint32_t phase = 0;
-    const int Ct = p.C0 + p.C1;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int m_tile = tile / p.n_tiles;
-      int pb[8], py[8], px[8];
-#pragma unroll
-      for (int i = 0; i < 8; ++i) {
-        const long m = (long)m_tile * kBlockM + rg + 16 * i;
-        if (m < p.M) {
-          if (LOADER == LD_GATHER_SCALE) {
-            pb[i] = (int)(m / p.rows_per_sample);
-            py[i] = 0;
-            px[i] = (int)m;
-          } else {
-            const int ox = (int)(m % p.OW);
-            const long t = m / p.OW;
-            px[i] = ox;
-            py[i] = (int)(t % p.OH);
-            pb[i] = (int)(t / p.OH);
+    if (kHalo) {
+      const int cpr = p.kblk >> 3;          // 16-byte chunks per row: 2, 4, 8
+      const int j = gt % cpr;
+      const int rg = gt / cpr;
+      const int rpp = 128 / cpr;            // rows per pass
+      const uint32_t rb = (uint32_t)p.kblk * 2u;
+      int hb = 0;
+      uint32_t hphase = 0;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.n_tiles;
+        int cy = 0, cx = 0;
+        {
+          const int b = m_tile / p.tiles_per_img;
+          const int rem = m_tile - b * p.tiles_per_img;
+          const int ty = rem / p.tiles_x;
+          cy = ty * p.tile_h;
+          cx = (rem - ty * p.tiles_x) * p.tile_w;
+        }
+        for (int c = 0; c < p.c_blocks; ++c) {
+          mbar_wait(&hfull_bar[hb], hphase);
+          const uint8_t* hsrc = halo + (size_t)hb * p.halo_stride;
+          for (int tap = 0; tap < 9; ++tap) {
+            const int tr = tap / 3, ts = tap - tr * 3;
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            uint8_t* sa = tiles + (size_t)stage * p.stage_bytes;
+            if (LOADER == LD_HALO_CONV3) {
+              // halo tile: (8+2) x (16+2) pixels, row-major, `rb` bytes per pixel; zero outside the image (TMA fill)
+              for (int i = 0; i < cpr; ++i) {
+                const int r = rg + rpp * i;
+                const int ry = r >> 4, rx = r & 15;
+                const uint4 val = *reinterpret_cast<const uint4*>(hsrc + (size_t)((ry + tr) * (kHaloTW + 2) + rx + ts) * rb + j * 16);
+                *reinterpret_cast<uint4*>(sa + swz_off(r, j, p.kblk)) = val;
+              }
+            } else {
+              // low-res halo tile: 6 x 10 source pixels starting at (cy/2 - 1, cx/2 - 1); output = conv3x3(valid) o
+              // reflect-pad(1) o bilinear-x2(align_corners=False)
+              const int sy0 = (cy >> 1) - 1, sx0 = (cx >> 1) - 1;
+              for (int i = 0; i < cpr; ++i) {
+                const int r = rg + rpp * i;
+                const int ry = r >> 4, rx = r & 15;
+                const int uy = reflect_idx(cy + ry + tr - 1, 2 * p.IH);
+                const int ux = reflect_idx(cx + rx + ts - 1, 2 * p.IW);
+                const int iy = uy >> 1, ix = ux >> 1;
+                int ya, yb, xa, xb;
+                float wya, wxa;
+                if (uy & 1) { ya = iy; yb = min(iy + 1, p.IH - 1); wya = 0.75f; }
+                else        { ya = max(iy - 1, 0); yb = iy; wya = 0.25f; }
+                if (ux & 1) { xa = ix; xb = min(ix + 1, p.IW - 1); wxa = 0.75f; }
+                else        { xa = max(ix - 1, 0); xb = ix; wxa = 0.25f; }
+                const uint8_t* base = hsrc + j * 16;
+                const uint4 v00 = *reinterpret_cast<const uint4*>(base + (size_t)((ya - sy0) * 10 + (xa - sx0)) * rb);
+                const uint4 v01 = *reinterpret_cast<const uint4*>(base + (size_t)((ya - sy0) * 10 + (xb - sx0)) * rb);
+                const uint4 v10 = *reinterpret_cast<const uint4*>(base + (size_t)((yb - sy0) * 10 + (xa - sx0)) * rb);
+                const uint4 v11 = *reinterpret_cast<const uint4*>(base + (size_t)((yb - sy0) * 10 + (xb - sx0)) * rb);
+                *reinterpret_cast<uint4*>(sa + swz_off(r, j, p.kblk)) =
+                    lerp4_h8(v00, v01, v10, v11, wya * wxa, wya * (1.f - wxa), (1.f - wya) * wxa, (1.f - wya) * (1.f - wxa));
+              }
+            }
+            fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
+            mbar_arrive(&full_bar[stage]);
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
-        } else {
-          pb[i] = -1; py[i] = 0; px[i] = 0;
+          mbar_arrive(&hempty_bar[hb]);
+          hb ^= 1;
+          if (hb == 0) hphase ^= 1u;
         }
       }
-      for (int kb = 0; kb < p.num_kb; ++kb) {
-        mbar_wait(&empty_bar[stage], phase ^ 1u);
-        uint8_t* sa = tiles + (size_t)stage * p.stage_bytes;
-        const int k = kb * 64 + j * 8;
-        const bool kvalid = k < p.Ktot;
-        if (LOADER == LD_GATHER_SCALE) {
+    } else {
+      const int j = gt & 7;              // 16-byte chunk (8 fp16 K-elements) within the 128-byte swizzled row
+      const int rg = gt >> 3;            // rows rg + 16*i
+      const int Ct = p.C0 + p.C1;
+      for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+        const int m_tile = tile / p.n_tiles;
+        int pb[8], py[8], px[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i) {
-            uint4 val = make_uint4(0, 0, 0, 0);
-            if (kvalid && pb[i] >= 0) {
-              const uint4 g = __ldg(reinterpret_cast<const uint4*>(p.src0 + (long)px[i] * p.ld0 + k));
-              const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.a_scale + (long)pb[i] * p.ld_scale + k));
-              const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.a_scale + (long)pb[i] * p.ld_scale + k) + 1);
-              const __half2* ph = reinterpret_cast<const __half2*>(&g);
-              __half2* po = reinterpret_cast<__half2*>(&val);
-              float2 f;
-              f = __half22float2(ph[0]); f.x *= s0.x; f.y *= s0.y; po[0] = __float22half2_rn(f);
-              f = __half22float2(ph[1]); f.x *= s0.z; f.y *= s0.w; po[1] = __float22half2_rn(f);
-              f = __half22float2(ph[2]); f.x *= s1.x; f.y *= s1.y; po[2] = __float22half2_rn(f);
-              f = __half22float2(ph[3]); f.x *= s1.z; f.y *= s1.w; po[3] = __float22half2_rn(f);
+        for (int i = 0; i < 8; ++i) {
+          const long m = (long)m_tile * kBlockM + rg + 16 * i;
+          if (m < p.M) {
+            if (LOADER == LD_GATHER_SCALE) {
+              pb[i] = (int)(m / p.rows_per_sample);
+              py[i] = 0;
+              px[i] = (int)m;
+            } else {
+              const int ox = (int)(m % p.OW);
+              const long t = m / p.OW;
+              px[i] = ox;
+              py[i] = (int)(t % p.OH);
+              pb[i] = (int)(t / p.OH);
             }
-            const int r = rg + 16 * i;
-            *reinterpret_cast<uint4*>(sa + r * 128 + ((j ^ (r & 7)) << 4)) = val;
+          } else {
+            pb[i] = -1; py[i] = 0; px[i] = 0;
           }
-        } else {
-          const int tap = kvalid ? k / Ct : 0;
-          const int c = k - tap * Ct;
-          const int tr = tap / p.S, ts = tap - tr * p.S;
-          const __half* src = (c < p.C0) ? p.src0 : p.src1;
-          const int ld = (c < p.C0) ? p.ld0 : p.ld1;
-          const int cc = (c < p.C0) ? c : c - p.C0;
-          if (LOADER == LD_GATHER_CONV) {
+        }
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sa = tiles + (size_t)stage * p.stage_bytes;
+          const int k = kb * 64 + j * 8;
+          const bool kvalid = k < p.Ktot;
+          if (LOADER == LD_GATHER_SCALE) {
+            uint4 g[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              g[i] = make_uint4(0, 0, 0, 0);
+              if (kvalid && pb[i] >= 0) g[i] = __ldg(reinterpret_cast<const uint4*>(p.src0 + (long)px[i] * p.ld0 + k));
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+              uint4 val = make_uint4(0, 0, 0, 0);
+              if (kvalid && pb[i] >= 0) {
+                const float4 s0 = __ldg(reinterpret_cast<const float4*>(p.a_scale + (long)pb[i] * p.ld_scale + k));
+                const float4 s1 = __ldg(reinterpret_cast<const float4*>(p.a_scale + (long)pb[i] * p.ld_scale + k) + 1);
+                const __half2* ph = reinterpret_cast<const __half2*>(&g[i]);
+                __half2* po = reinterpret_cast<__half2*>(&val);
+                float2 f;
+                f = __half22float2(ph[0]); f.x *= s0.x; f.y *= s0.y; po[0] = __float22half2_rn(f);
+                f = __half22float2(ph[1]); f.x *= s0.z; f.y *= s0.w; po[1] = __float22half2_rn(f);
+                f = __half22float2(ph[2]); f.x *= s1.x; f.y *= s1.y; po[2] = __float22half2_rn(f);
+                f = __half22float2(ph[3]); f.x *= s1.z; f.y *= s1.w; po[3] = __float22half2_rn(f);
+              }
+              const int r = rg + 16 * i;
+              *reinterpret_cast<uint4*>(sa + r * 128 + ((j ^ (r & 7)) << 4)) = val;
+            }
+          } else {
+            const int tap = kvalid ? k / Ct : 0;
+            const int c = k - tap * Ct;
+            const int tr = tap / p.S, ts = tap - tr * p.S;
+            const __half* src = (c < p.C0) ? p.src0 : p.src1;
+            const int ld = (c < p.C0) ? p.ld0 : p.ld1;
+            const int cc = (c < p.C0) ? c : c - p.C0;
             uint4 val[8];
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
@@ -481,43 +667,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const int r = rg + 16 * i;
               *reinterpret_cast<uint4*>(sa + r * 128 + ((j ^ (r & 7)) << 4)) = val[i];
             }
-          } else {  // LD_GATHER_UPS: conv3x3(valid) o reflect-pad(1) o bilinear-x2(align_corners=False) of the IHxIW source
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-              uint4 val[4];
-#pragma unroll
-              for (int ii = 0; ii < 4; ++ii) {
-                const int i = half * 4 + ii;
-                val[ii] = make_uint4(0, 0, 0, 0);
-                if (kvalid && pb[i] >= 0) {
-                  const int uy = reflect_idx(py[i] + tr - 1, 2 * p.IH);
-                  const int ux = reflect_idx(px[i] + ts - 1, 2 * p.IW);
-                  const int iy = uy >> 1, ix = ux >> 1;
-                  int ya, yb, xa, xb;
-                  float wya, wxa;
-                  if (uy & 1) { ya = iy; yb = min(iy + 1, p.IH - 1); wya = 0.75f; }
-                  else        { ya = max(iy - 1, 0); yb = iy; wya = 0.25f; }
-                  if (ux & 1) { xa = ix; xb = min(ix + 1, p.IW - 1); wxa = 0.75f; }
-                  else        { xa = max(ix - 1, 0); xb = ix; wxa = 0.25f; }
-                  const __half* base = src + (long)pb[i] * p.IH * p.IW * ld + cc;
-                  const uint4 v00 = __ldg(reinterpret_cast<const uint4*>(base + ((long)ya * p.IW + xa) * ld));
-                  const uint4 v01 = __ldg(reinterpret_cast<const uint4*>(base + ((long)ya * p.IW + xb) * ld));
-                  const uint4 v10 = __ldg(reinterpret_cast<const uint4*>(base + ((long)yb * p.IW + xa) * ld));
-                  const uint4 v11 = __ldg(reinterpret_cast<const uint4*>(base + ((long)yb * p.IW + xb) * ld));
-                  val[ii] = lerp4_h8(v00, v01, v10, v11, wya * wxa, wya * (1.f - wxa), (1.f - wya) * wxa, (1.f - wya) * (1.f - wxa));
-                }
-              }
-#pragma unroll
-              for (int ii = 0; ii < 4; ++ii) {
-                const int r = rg + 16 * (half * 4 + ii);
-                *reinterpret_cast<uint4*>(sa + r * 128 + ((j ^ (r & 7)) << 4)) = val[ii];
-              }
-            }
           }
+          fence_proxy_async_smem();
+          mbar_arrive(&full_bar[stage]);
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
-        fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-        mbar_arrive(&full_bar[stage]);
-        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
     }
   }

@@ -47,7 +47,7 @@ inline CUtensorMapSwizzle swizzle_for(int kblk) {
 
 // fp16 tensor map, dims innermost-first; strides (bytes) for dims 1..rank-1
 inline void encode_map(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                       const uint32_t* box, int kblk) {
+                       const uint32_t* box, int kblk, bool no_swizzle = false) {
   cuuint64_t gd[5], gs[4];
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
@@ -55,7 +55,8 @@ inline void encode_map(CUtensorMap* tm, const void* base, int rank, const uint64
   VSB_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base must be 16B aligned");
   for (int i = 0; i + 1 < rank; ++i) VSB_CHECK(gs[i] % 16 == 0, "TMA strides must be multiples of 16B");
   CUresult r = get_encode_fn()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(kblk), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, no_swizzle ? CU_TENSOR_MAP_SWIZZLE_NONE : swizzle_for(kblk),
+                               CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   VSB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
 }
@@ -63,11 +64,11 @@ inline void encode_map(CUtensorMap* tm, const void* base, int rank, const uint64
 struct ConvGemmOp {
   int loader = LD_TMA;
   ConvGemmParams p;
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmA2, tmB;
   int grid = 0, threads = 0;
   size_t smem = 0;
   const char* name = "";
-  ConvGemmOp() { memset(&p, 0, sizeof(p)); memset(&tmA, 0, sizeof(tmA)); memset(&tmB, 0, sizeof(tmB)); }
+  ConvGemmOp() { memset(&p, 0, sizeof(p)); memset(&tmA, 0, sizeof(tmA)); memset(&tmA2, 0, sizeof(tmA2)); memset(&tmB, 0, sizeof(tmB)); }
 };
 
 inline int pick_block_n(int N) {
@@ -92,22 +93,31 @@ inline void finalize_op(ConvGemmOp& op, const __half* W, int N, int Kw, int ldw,
   p.b_stage_bytes = (uint32_t)(p.block_n * p.kblk * 2);
   p.stage_bytes = p.a_stage_bytes + ((p.b_stage_bytes + 1023u) & ~1023u);
   VSB_CHECK(p.a_stage_bytes % 1024 == 0, "A stage must be 1024B aligned");
-  const size_t budget = 220 * 1024;
+  // shared memory: [header | stages x (A|B) | 2 halo tiles | residual prefetch buffer]
+  size_t resid_bytes = 0;
+  if (p.resid16) resid_bytes = (size_t)kBlockM * p.block_n * 2;
+  if (p.resid32) resid_bytes = (size_t)kBlockM * p.block_n * 4;
+  const size_t halo_total = 2 * (((size_t)p.halo_bytes + 1023) & ~size_t(1023));
+  const size_t budget = 225 * 1024 - kHeaderBytes - resid_bytes - halo_total;
+  VSB_CHECK(resid_bytes + halo_total + kHeaderBytes + 2 * (size_t)p.stage_bytes <= 225 * 1024, "tile does not fit in shared memory");
   int stages = (int)(budget / p.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
   VSB_CHECK(stages >= 2, "not enough shared memory for 2 stages");
   p.stages = stages;
-  op.smem = 1024 /*align slack*/ + 1024 /*barriers*/ + (size_t)stages * p.stage_bytes;
+  p.halo_stride = (uint32_t)(((size_t)p.halo_bytes + 1023) & ~size_t(1023));
+  p.halo_off = (uint32_t)(kHeaderBytes + (size_t)stages * p.stage_bytes);
+  p.resid_off = (uint32_t)(p.halo_off + halo_total);
+  op.smem = 1024 /*align slack*/ + p.resid_off + resid_bytes;
   // instruction descriptor (kind::f16): D=f32 (bit 4), A=B=f16 (0), K-major both, N>>3 at bit 17, M>>4 at bit 24
   p.idesc = (1u << 4) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
-  if (p.epi == EPI_LN) VSB_CHECK(p.n_tiles == 1, "LN epilogue needs the full row in one tile");
+  if (p.epi == EPI_LN || p.outc_w) VSB_CHECK(p.n_tiles == 1 && N <= 256, "LN / fused-outc epilogues need the full row in one tile");
   // weights: dims (K, N)
   uint64_t dims[2] = {(uint64_t)Kw, (uint64_t)N};
   uint64_t strides[1] = {(uint64_t)ldw * 2};
   uint32_t box[2] = {(uint32_t)p.kblk, (uint32_t)p.block_n};
   encode_map(&op.tmB, W, 2, dims, strides, box, p.kblk);
   op.grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-  op.threads = op.loader == LD_TMA ? 256 : 384;
+  op.threads = op.loader == LD_TMA ? 384 : 512;
 }
 
 // A = NHWC fp16 activation [B, H, W, C] (pixel pitch ld elements); conv RxS stride 1, zero padding `pad`
@@ -116,6 +126,7 @@ inline void setup_tma_conv(ConvGemmOp& op, const __half* src, int B, int H, int 
   ConvGemmParams& p = op.p;
   op.loader = LD_TMA;
   p.a_is_conv = 1;
+  p.tile_mode = 1;
   p.kblk = C >= 64 ? 64 : C;
   VSB_CHECK(p.kblk == 64 || p.kblk == 32 || p.kblk == 16, "TMA conv: C must be 16, 32 or a multiple of 64");
   VSB_CHECK(C % p.kblk == 0, "TMA conv: C must be a multiple of the K block");
@@ -134,6 +145,67 @@ inline void setup_tma_conv(ConvGemmOp& op, const __half* src, int B, int H, int 
   uint64_t strides[3] = {(uint64_t)ld * 2, (uint64_t)W * ld * 2, (uint64_t)H * W * ld * 2};
   uint32_t box[4] = {(uint32_t)p.kblk, (uint32_t)p.tile_w, (uint32_t)p.tile_h, 1u};
   encode_map(&op.tmA, src, 4, dims, strides, box, p.kblk);
+}
+
+
+// 3x3 stride-1 zero-padded conv with on-chip im2col: the (8+2)x(16+2) input halo of each 8x16 output tile is loaded once
+// per channel chunk.  Weights [N][9*C] with K order (r, s, c).
+inline void setup_halo_conv3(ConvGemmOp& op, const __half* src, int B, int H, int W, int C, int ld) {
+  ConvGemmParams& p = op.p;
+  op.loader = LD_HALO_CONV3;
+  p.tile_mode = 1;
+  p.kblk = C >= 64 ? 64 : C;
+  VSB_CHECK(p.kblk == 64 || p.kblk == 32 || p.kblk == 16, "halo conv: C must be 16, 32 or a multiple of 64");
+  VSB_CHECK(C % p.kblk == 0, "halo conv: C must be a multiple of the K block");
+  VSB_CHECK(W % kHaloTW == 0 && H % kHaloTH == 0, "halo conv: map must tile by 8x16");
+  p.c_blocks = C / p.kblk; p.c0_blocks = p.c_blocks;
+  p.R = 3; p.S = 3; p.pad = 1;
+  p.H = H; p.W = W; p.tile_w = kHaloTW; p.tile_h = kHaloTH;
+  p.tiles_x = W / kHaloTW;
+  p.tiles_per_img = p.tiles_x * (H / kHaloTH);
+  p.m_tiles = B * p.tiles_per_img;
+  p.M = B * H * W;
+  p.num_kb = 9 * p.c_blocks;
+  p.halo_bytes = (uint32_t)((kHaloTH + 2) * (kHaloTW + 2) * p.kblk * 2);
+  uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
+  uint64_t strides[3] = {(uint64_t)ld * 2, (uint64_t)W * ld * 2, (uint64_t)H * W * ld * 2};
+  uint32_t box[4] = {(uint32_t)p.kblk, (uint32_t)(kHaloTW + 2), (uint32_t)(kHaloTH + 2), 1u};
+  encode_map(&op.tmA, src, 4, dims, strides, box, p.kblk, /*no_swizzle=*/true);
+}
+
+// UBlock up-conv (modules/common.py:45-52 after the skip concat of unet.py:187-190): conv3x3(valid) o ReflectionPad2d(1) o
+// bilinear x2 of the virtual concat [src0 (C0) | src1 (C1)], both NHWC fp16 at IH x IW; output at 2IH x 2IW.
+inline void setup_halo_ups(ConvGemmOp& op, const __half* src0, int C0, int ld0, const __half* src1, int C1, int ld1, int B, int IH, int IW) {
+  ConvGemmParams& p = op.p;
+  op.loader = LD_HALO_UPS;
+  p.tile_mode = 1;
+  const int Cm = C0 < C1 || C1 == 0 ? C0 : C1;
+  p.kblk = Cm >= 64 ? 64 : Cm;
+  VSB_CHECK(p.kblk == 64 || p.kblk == 32 || p.kblk == 16, "halo ups: C must be 16, 32 or a multiple of 64");
+  VSB_CHECK(C0 % p.kblk == 0 && C1 % p.kblk == 0, "halo ups: channels must be multiples of the K block");
+  const int OH = 2 * IH, OW = 2 * IW;
+  VSB_CHECK(OW % kHaloTW == 0 && OH % kHaloTH == 0, "halo ups: output map must tile by 8x16");
+  p.c0_blocks = C0 / p.kblk; p.c_blocks = (C0 + C1) / p.kblk;
+  p.R = 3; p.S = 3; p.pad = 1;
+  p.IH = IH; p.IW = IW; p.OH = OH; p.OW = OW;
+  p.H = OH; p.W = OW; p.tile_w = kHaloTW; p.tile_h = kHaloTH;
+  p.tiles_x = OW / kHaloTW;
+  p.tiles_per_img = p.tiles_x * (OH / kHaloTH);
+  p.m_tiles = B * p.tiles_per_img;
+  p.M = B * OH * OW;
+  p.num_kb = 9 * p.c_blocks;
+  p.halo_bytes = (uint32_t)(6 * 10 * p.kblk * 2);
+  uint32_t box[4] = {(uint32_t)p.kblk, 10u, 6u, 1u};
+  {
+    uint64_t dims[4] = {(uint64_t)C0, (uint64_t)IW, (uint64_t)IH, (uint64_t)B};
+    uint64_t strides[3] = {(uint64_t)ld0 * 2, (uint64_t)IW * ld0 * 2, (uint64_t)IH * IW * ld0 * 2};
+    encode_map(&op.tmA, src0, 4, dims, strides, box, p.kblk, true);
+  }
+  if (C1 > 0) {
+    uint64_t dims[4] = {(uint64_t)C1, (uint64_t)IW, (uint64_t)IH, (uint64_t)B};
+    uint64_t strides[3] = {(uint64_t)ld1 * 2, (uint64_t)IW * ld1 * 2, (uint64_t)IH * IW * ld1 * 2};
+    encode_map(&op.tmA2, src1, 4, dims, strides, box, p.kblk, true);
+  }
 }
 
 // A = [M, K] fp16 row-major (row pitch ld elements)
@@ -188,14 +260,15 @@ inline void launch_one(const ConvGemmOp& op, cudaStream_t st) {
     VSB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<LOADER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  conv_gemm_kernel<LOADER><<<op.grid, op.threads, op.smem, st>>>(op.tmA, op.tmB, op.p);
+  conv_gemm_kernel<LOADER><<<op.grid, op.threads, op.smem, st>>>(op.tmA, op.tmA2, op.tmB, op.p);
 }
 
 inline void launch(const ConvGemmOp& op, cudaStream_t st) {
   switch (op.loader) {
     case LD_TMA: launch_one<LD_TMA>(op, st); break;
     case LD_GATHER_CONV: launch_one<LD_GATHER_CONV>(op, st); break;
-    case LD_GATHER_UPS: launch_one<LD_GATHER_UPS>(op, st); break;
+    case LD_HALO_UPS: launch_one<LD_HALO_UPS>(op, st); break;
+    case LD_HALO_CONV3: launch_one<LD_HALO_CONV3>(op, st); break;
     case LD_GATHER_SCALE: launch_one<LD_GATHER_SCALE>(op, st); break;
     default: throw Error("bad loader");
   }

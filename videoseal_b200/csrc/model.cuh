@@ -407,6 +407,18 @@ class Model {
     finalize_op(op, w.w, w.N, w.K, w.K, num_sms, block_n);
     pl.steps.push_back(Step{[op](cudaStream_t st) { launch(op, st); }, 1, name});
   }
+  // 3x3 stride-1 zero-padded conv: on-chip im2col from a shared-memory halo tile (input crosses L2->SM once) up to
+  // `halo_max_c` input channels, one TMA load per tap above (VSB_HALO_MAXC overrides, for experiments)
+  int halo_max_c = -1;
+  void setup_conv3(ConvGemmOp& op, const __half* x, int B, int H, int W, int C, int ld) {
+    if (halo_max_c < 0) {
+      const char* e = getenv("VSB_HALO_MAXC");
+      halo_max_c = e ? atoi(e) : (1 << 30);
+    }
+    if (C <= halo_max_c && W % kHaloTW == 0 && H % kHaloTH == 0) setup_halo_conv3(op, x, B, H, W, C, ld);
+    else setup_tma_conv(op, x, B, H, W, C, ld, 3, 3, 1);
+  }
+
   // ResnetBlock on NHWC fp16 (modules/unet.py:17-39):  out = relu(conv3'(relu(conv3'(x)))) + (conv1(x) + b)
   // `x` has pixel pitch ldx; output written with pitch ld_out.  If fuse_outc: the 1x1 outc + tanh is fused and the
   // block output itself is not written.
@@ -423,12 +435,12 @@ class Model {
       add_conv(pl, op, w.res, "unet.conv1x1." + std::to_string(Cin) + "-" + std::to_string(Cout) + "@" + std::to_string(H));
     }
     {  // conv3 + BN + ReLU
-      ConvGemmOp op; setup_tma_conv(op, x, B, H, W, Cin, ldx, 3, 3, 1);
+      ConvGemmOp op; setup_conv3(op, x, B, H, W, Cin, ldx);
       op.p.epi = EPI_AFFINE; op.p.act = ACT_RELU; op.p.bias = w.c1.bias; op.p.out16 = h; op.p.ld_out16 = Cout;
       add_conv(pl, op, w.c1, "unet.conv3x3." + std::to_string(Cin) + "-" + std::to_string(Cout) + "@" + std::to_string(H));
     }
     {  // conv3 + BN + ReLU, + res
-      ConvGemmOp op; setup_tma_conv(op, h, B, H, W, Cout, Cout, 3, 3, 1);
+      ConvGemmOp op; setup_conv3(op, h, B, H, W, Cout, Cout);
       op.p.epi = EPI_AFFINE; op.p.act = ACT_RELU; op.p.bias = w.c2.bias; op.p.resid16 = r; op.p.ld_res16 = Cout;
       if (fuse_outc) {
         op.p.outc_w = outc_w; op.p.outc_b = outc_b; op.p.n_out = d.unet_out_ch; op.p.delta = pl.delta; op.p.hw = H * W;
@@ -476,7 +488,7 @@ class Model {
     std::vector<int> skip_ld;
     __half* x = pl.pool.alloc_n<__half>(M0 * z[0]);
     {
-      ConvGemmOp op; setup_tma_conv(op, h1, B, S, S, z[0], z[0], 3, 3, 1);
+      ConvGemmOp op; setup_conv3(op, h1, B, S, S, z[0], z[0]);
       op.p.epi = EPI_AFFINE; op.p.act = ACT_RELU; op.p.bias = inc_c2.bias; op.p.resid16 = r0; op.p.ld_res16 = z[0];
       op.p.out16 = x; op.p.ld_out16 = z[0];
       add_conv(pl, op, inc_c2, "unet.conv3x3." + std::to_string(z[0]) + "-" + std::to_string(z[0]) + "@" + std::to_string(S));
@@ -535,7 +547,7 @@ class Model {
       __half* u = pl.pool.alloc_n<__half>(Mo * Cout);
       {
         ConvGemmOp op;
-        setup_gather_conv(op, LD_GATHER_UPS, x, Cin, ldx, skip, Cin, ld_skip, B, hs, hs, ho, ho, 3, 3, 1, 1, 1);
+        setup_halo_ups(op, x, Cin, ldx, skip, Cin, ld_skip, B, hs, hs);
         op.p.epi = EPI_LN; op.p.act = ACT_RELU; op.p.ln_w = up_lnw[j]; op.p.ln_b = up_lnb[j]; op.p.ln_eps = 1e-6f;
         op.p.out16 = u; op.p.ld_out16 = Cout;
         add_conv(pl, op, up_conv[j], "unet.up3x3." + std::to_string(2 * Cin) + "-" + std::to_string(Cout) + "@" + std::to_string(ho));

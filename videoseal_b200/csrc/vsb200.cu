@@ -192,10 +192,12 @@ int vsb_debug_conv(const vsb_conv_test* t, void* stream) {
     OW = (t->IW + 2 * t->pad - t->S) / t->stride + 1;
     setup_gather_conv(op, LD_GATHER_CONV, (const __half*)t->src0, t->C0, t->C0, (const __half*)t->src1, t->C1, t->C1, t->B, t->IH, t->IW, OH, OW,
                       t->R, t->S, t->stride, t->pad, t->pad_mode);
-  } else if (t->loader == LD_GATHER_UPS) {
+  } else if (t->loader == LD_HALO_UPS) {
     OH = 2 * t->IH; OW = 2 * t->IW;
-    setup_gather_conv(op, LD_GATHER_UPS, (const __half*)t->src0, t->C0, t->C0, (const __half*)t->src1, t->C1, t->C1, t->B, t->IH, t->IW, OH, OW, 3, 3,
-                      1, 1, 1);
+    setup_halo_ups(op, (const __half*)t->src0, t->C0, t->C0, (const __half*)t->src1, t->C1, t->C1, t->B, t->IH, t->IW);
+  } else if (t->loader == LD_HALO_CONV3) {
+    OH = t->IH; OW = t->IW;
+    setup_halo_conv3(op, (const __half*)t->src0, t->B, t->IH, t->IW, t->C0, t->C0);
   } else {
     OH = t->IH; OW = t->IW;
     setup_gather_scale(op, (const __half*)t->src0, (long)t->B * t->IH * t->IW, t->C0, t->C0, t->a_scale, t->C0, t->rows_per_sample);
