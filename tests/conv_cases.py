@@ -89,7 +89,7 @@ def reference(cfg, x0, x1, w, bias, resid, scale, lnw, lnb):
     return y, pre_resid
 
 
-def run_case(name, seed=0, verbose=False):
+def run_case(name, seed=0, verbose=False, time_iters=0):
     cfg = dict(CASES[name])
     dev = "cuda"
     g = torch.Generator(device="cpu").manual_seed(seed)
@@ -138,10 +138,30 @@ def run_case(name, seed=0, verbose=False):
     t.out16, t.out32, t.delta, t.grn_stats = _ptr(out16), _ptr(out32), _ptr(delta), _ptr(stats)
     _lib.check(_lib.lib().vsb_debug_conv(C.byref(t), None))
     torch.cuda.synchronize()
+    timing = None
+    if time_iters:
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        keep = out32 is not None and resid32 is not None
+        e0.record()
+        for _ in range(time_iters):
+            _lib.lib().vsb_debug_conv(C.byref(t), None)
+        e1.record()
+        torch.cuda.synchronize()
+        timing = 1000.0 * e0.elapsed_time(e1) / time_iters
+        if keep:                  # in-place residual accumulates across launches: redo one clean launch
+            out32.copy_(resid32)
+        if stats is not None:
+            stats.zero_()
+        if keep or stats is not None:
+            _lib.check(_lib.lib().vsb_debug_conv(C.byref(t), None))
+            torch.cuda.synchronize()
 
     resid = resid16 if resid16 is not None else resid32
     ref, pre = reference(cfg, x0, x1, w, bias, resid, scale, lnw, lnb)
     res = {}
+    if timing is not None:
+        res["us"] = timing
+        res["tflops"] = 2.0 * M * N * K / (timing * 1e-6) / 1e12
     scale_ref = ref.abs().max().item()
     if out16 is not None or out32 is not None:
         got = (out16 if out16 is not None else out32).float().permute(0, 3, 1, 2)

@@ -26,10 +26,15 @@ BIG = {
 cc.CASES.update(BIG)
 
 if __name__ == "__main__":
-    names = sys.argv[1:] or list(BIG)
+    iters = 0
+    args = sys.argv[1:]
+    if args and args[0] == "--time":
+        iters = 10
+        args = args[1:]
+    names = args or list(BIG)
     for n in names:
         torch.cuda.synchronize()
         t0 = time.time()
-        r = cc.run_case(n)
+        r = cc.run_case(n, time_iters=iters)
         # re-launch for timing: run_case again under CUDA events (includes input generation only outside events? no -> use ncu/bench for exact)
-        print(n, {k: (round(v, 5) if isinstance(v, float) else v) for k, v in r.items() if k in ("ok", "out_maxerr", "delta_maxerr", "stats_relerr")}, f"{time.time()-t0:.2f}s", flush=True)
+        print(n, {k: (round(v, 5) if isinstance(v, float) else v) for k, v in r.items() if k in ("ok", "out_maxerr", "delta_maxerr", "stats_relerr", "us", "tflops")}, f"{time.time()-t0:.2f}s", flush=True)

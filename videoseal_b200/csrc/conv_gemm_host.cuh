@@ -71,9 +71,14 @@ struct ConvGemmOp {
   ConvGemmOp() { memset(&p, 0, sizeof(p)); memset(&tmA, 0, sizeof(tmA)); memset(&tmA2, 0, sizeof(tmA2)); memset(&tmB, 0, sizeof(tmB)); }
 };
 
-inline int pick_block_n(int N) {
+inline int pick_block_n(int N, int max_bn = 256) {
   const int n16 = (N + 15) / 16 * 16;
-  if (n16 <= 256) return n16;
+  if (n16 <= max_bn) return n16;
+  if (max_bn < 256) {
+    for (int bn = max_bn / 16 * 16; bn >= 64; bn -= 16)
+      if (n16 % bn == 0) return bn;
+    return max_bn / 16 * 16;
+  }
   // prefer the largest tile in {256,...,128} (multiples of 16) that divides n16; else 256 with a ragged last tile
   for (int bn = 256; bn >= 128; bn -= 16)
     if (n16 % bn == 0) return bn;
@@ -85,7 +90,8 @@ inline int pick_block_n(int N) {
 inline void finalize_op(ConvGemmOp& op, const __half* W, int N, int Kw, int ldw, int num_sms, int block_n_override = 0) {
   ConvGemmParams& p = op.p;
   p.N = N;
-  p.block_n = block_n_override ? block_n_override : pick_block_n(N);
+  // an fp32 residual tile is prefetched into shared memory: keep it <= 64 KB
+  p.block_n = block_n_override ? block_n_override : pick_block_n(N, p.resid32 ? 128 : 256);
   VSB_CHECK(p.block_n % 16 == 0 && p.block_n >= 16 && p.block_n <= 256, "bad block_n");
   p.n_tiles = (N + p.block_n - 1) / p.block_n;
   p.num_tiles = p.m_tiles * p.n_tiles;
