@@ -42,6 +42,18 @@ CASES = {
 }
 
 
+def halo_layout(w, C0, C1):
+    """[N, 3, 3, C0+C1] (tap-major) -> the halo loaders' [N][chunk][tap][cc] layout, chunks zero-padded to kb_per_c*64"""
+    N, Ct = w.shape[0], C0 + C1
+    cc = min(C0, 64)
+    kbc = (9 * cc + 63) // 64
+    nchunks = Ct // cc
+    out = torch.zeros(N, nchunks, kbc * 64, dtype=w.dtype, device=w.device)
+    wc = w.reshape(N, 9, nchunks, cc).permute(0, 2, 1, 3).reshape(N, nchunks, 9 * cc)
+    out[:, :, :9 * cc] = wc
+    return out.reshape(N, nchunks * kbc * 64).contiguous()
+
+
 def _ptr(t):
     return C.c_void_p(t.data_ptr()) if t is not None else None
 
@@ -130,7 +142,8 @@ def run_case(name, seed=0, verbose=False, time_iters=0):
     t.loader, t.B, t.IH, t.IW, t.C0, t.C1 = ld, B, IH, IW, C0, C1
     t.R, t.S, t.stride, t.pad, t.pad_mode = R, S, cfg.get("stride", 1), cfg.get("pad", 0), cfg.get("pad_mode", 0)
     t.N, t.epi, t.act, t.rows_per_sample, t.block_n = N, cfg.get("epi", 0), cfg.get("act", 0), cfg.get("rps", 0), cfg.get("block_n", 0)
-    t.src0, t.src1, t.weights = _ptr(x0), _ptr(x1), _ptr(w)
+    w_dev = halo_layout(w, C0, C1) if ld in (LD_GUPS, LD_HALO) else w
+    t.src0, t.src1, t.weights = _ptr(x0), _ptr(x1), _ptr(w_dev)
     t.bias, t.resid16 = _ptr(bias), _ptr(resid16)
     t.resid32 = _ptr(out32) if resid32 is not None else None     # in place, like the ConvNeXt residual stream
     t.a_scale, t.ln_w, t.ln_b = _ptr(scale), _ptr(lnw), _ptr(lnb)

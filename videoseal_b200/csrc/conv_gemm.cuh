@@ -1,24 +1,25 @@
 // K1/K2: implicit-GEMM convolution / linear layer on the 5th-gen tensor cores (tcgen05.mma,
 // accumulators in TMEM), persistent and warp-specialised:
 //
-//   warp 0        : TMA producer (weights always; activations for LD_TMA; input halo tiles for LD_HALO_*)
+//   warp 0        : TMA producer (weights unless resident; activations for LD_TMA; input halo tiles for LD_HALO_*)
 //   warp 1        : single-thread tcgen05.mma issuer
 //   warp 2        : TMEM allocator
 //   warps 4..11   : epilogue (TMEM -> registers -> fused bias/BN-fold/act/residual/LN/tanh/GRN-stats -> HBM);
 //                   warp w owns TMEM lane quadrant w%4 and every second 16-column chunk ((w-4)/4)
 //   warps 12..15  : A-tile builders (all loaders except LD_TMA):
 //       LD_HALO_CONV3 : on-chip im2col - the (8+2)x(16+2) input halo of an 8x16 output tile is TMA-loaded ONCE per channel
-//                       chunk (zero fill = conv padding) and the 9 tap tiles are copied smem->smem into the swizzled
+//                       chunk (zero fill = conv padding) and the tap tiles are copied smem->smem into the swizzled
 //                       UMMA layout (input pixels cross L2->SM once instead of nine times)
-//       LD_HALO_UPS   : same, with the UBlock's bilinear x2 (align_corners=False) + ReflectionPad2d(1) + virtual
-//                       skip-concat evaluated from a 6x10 low-resolution halo tile in shared memory
+//       LD_HALO_UPS   : the UBlock's bilinear x2 (align_corners=False) + ReflectionPad2d(1) + virtual skip-concat: a 6x10
+//                       low-resolution halo is TMA-loaded, the 10x18 upsampled+padded halo is built from it in shared
+//                       memory once, then tap tiles are copied as in LD_HALO_CONV3
 //       LD_GATHER_CONV: generic strided / reflect-padded conv gathered from global memory (stride-2 3x3, k2s2 patchify,
 //                       reflect-padded head conv)
 //       LD_GATHER_SCALE: A[m,k] = G[m,k] * scale[sample(m), k]  (ConvNeXt pwconv2 with the GRN factor folded in)
 //
 // GEMM view: D[M = output pixels, N = C_out] = A[M, K = taps*C_in] * W[N, K]^T, fp16 operands, fp32 accumulation.
 // BLOCK_M = 128 (one UMMA M=128 atom, cta_group::1), BLOCK_N <= 256, two TMEM accumulator stages so the epilogue of
-// tile i overlaps the main loop of tile i+1.
+// tile i overlaps the main loop of tile i+1.  Small weight matrices stay resident in shared memory.
 //
 // Replaces: nn.Conv2d / nn.Linear + BatchNorm2d(eval) + ReLU / LayerNorm / GELU / GRN / tanh call sites of
 // videoseal/modules/unet.py:17-197, modules/common.py:45-52,150-169, modules/convnext.py:41-57,
@@ -35,21 +36,28 @@ enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
 constexpr int kBlockM = 128;
 constexpr int kMaxStages = 24;
 constexpr int kTmemCols = 512;
-constexpr int kAccStride = 256;   // TMEM columns between the two accumulator stages
-constexpr int kHeaderBytes = 8192;  // barriers | bias x2 | LN w,b | outc partials
+constexpr int kAccStride = 256;     // TMEM columns between the two accumulator stages
+constexpr int kHeaderBytes = 8192;  // barriers | bias x2 | LN w,b / outc rows | outc partials
 constexpr int kHaloTW = 16, kHaloTH = 8;
+constexpr int kHaloW = kHaloTW + 2, kHaloH = kHaloTH + 2;   // 18 x 10 input (or upsampled) halo of an 8x16 output tile
 
 struct ConvGemmParams {
   // ---- GEMM view
   int M, N, num_kb, kblk, block_n, n_tiles, m_tiles, num_tiles, stages;
   uint32_t a_stage_bytes, b_stage_bytes, stage_bytes, idesc;
+  int b_resident;                 // whole [block_n x K] weight slab lives in shared memory for the kernel's lifetime
+  uint32_t bres_off;
   // ---- output-tile geometry: tile_mode 0: rows are consecutive GEMM rows; 1: tile_h x tile_w pixel patch of an H x W map
   int tile_mode, H, W, tile_w, tile_h, tiles_x, tiles_per_img;
   // ---- A via TMA (LD_TMA): a_is_conv 0: 2D map (K, M); 1: 4D map (C, W, H, B) with zero-fill halo, one load per tap
   int a_is_conv, R, S, pad, c_blocks;
-  // ---- halo loaders: c_blocks = channel chunks of the (virtual-concat) input; c0_blocks of them come from source 0
-  int c0_blocks;
-  uint32_t halo_bytes /*TMA box bytes*/, halo_stride /*buffer pitch*/, halo_off, resid_off;
+  // ---- halo loaders: the input is cut into `c_blocks` channel chunks of `cc` (= min(C, 64)) channels, the first c0_blocks
+  //      from source 0; each chunk contributes kb_per_c K-blocks of 64 (K order inside a chunk: (tap, channel), zero padded)
+  int c0_blocks, cc, kb_per_c;
+  uint32_t halo_bytes /*TMA box bytes*/, halo_stride /*buffer pitch*/, halo_off, u_off;
+  // ---- residual prefetch ring (thread-private slots)
+  uint32_t resid_off, resid_stride;
+  int resid_depth;
   // ---- gather loaders (NHWC fp16 sources; K order = (r, s, c) with c over the virtual concat [src0 | src1])
   const __half* src0;
   const __half* src1;
@@ -68,7 +76,17 @@ struct ConvGemmParams {
   float* grn_stats;      // [num_samples, N] sum of squares of the epilogue output (GRN), or null
 };
 
-__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+// exact-erf GELU (nn.GELU default).  erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7), branch-free.
+__device__ __forceinline__ float gelu_erf(float x) {
+  const float z = fabsf(x) * 0.70710678118654752f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float poly = fmaf(1.061405429f, t, -1.453152027f);
+  poly = fmaf(poly, t, 1.421413741f);
+  poly = fmaf(poly, t, -0.284496736f);
+  poly = fmaf(poly, t, 0.254829592f);
+  const float e = 1.0f - poly * t * __expf(-z * z);
+  return 0.5f * x * (1.0f + copysignf(e, x));
+}
 
 __device__ __forceinline__ int reflect_idx(int i, int n) {
   if (i < 0) i = -i;
@@ -76,7 +94,10 @@ __device__ __forceinline__ int reflect_idx(int i, int n) {
   return i;
 }
 
-__device__ __forceinline__ uint4 lerp4_h8(uint4 a, uint4 b, uint4 c, uint4 d, float wa, float wb, float wc, float wd) {
+// separable bilinear tap: (wy*(wx*a + (1-wx)*b) + (1-wy)*(wx*c + (1-wx)*d)) on 8 packed halves
+__device__ __forceinline__ uint4 lerp2x2_h8(uint4 a, uint4 b, uint4 c, uint4 d, float wx, float wy) {
+  const __half2 hx = __float2half2_rn(wx), hx1 = __float2half2_rn(1.f - wx);
+  const __half2 hy = __float2half2_rn(wy), hy1 = __float2half2_rn(1.f - wy);
   const __half2* pa = reinterpret_cast<const __half2*>(&a);
   const __half2* pb = reinterpret_cast<const __half2*>(&b);
   const __half2* pc = reinterpret_cast<const __half2*>(&c);
@@ -85,29 +106,27 @@ __device__ __forceinline__ uint4 lerp4_h8(uint4 a, uint4 b, uint4 c, uint4 d, fl
   __half2* po = reinterpret_cast<__half2*>(&o);
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
-    float2 fa = __half22float2(pa[i]), fb = __half22float2(pb[i]), fc = __half22float2(pc[i]), fd = __half22float2(pd[i]);
-    float2 r;
-    r.x = wa * fa.x + wb * fb.x + wc * fc.x + wd * fd.x;
-    r.y = wa * fa.y + wb * fb.y + wc * fc.y + wd * fd.y;
-    po[i] = __float22half2_rn(r);
+    const __half2 t0 = __hfma2(hx, pa[i], __hmul2(hx1, pb[i]));
+    const __half2 t1 = __hfma2(hx, pc[i], __hmul2(hx1, pd[i]));
+    po[i] = __hfma2(hy, t0, __hmul2(hy1, t1));
   }
   return o;
-}
-
-// byte offset of 16-byte chunk j of row r inside a K-major operand tile with `kblk` fp16 per row and the matching
-// 32/64/128-byte swizzle (Swizzle<1|2|3,4,3>: address bits [4,4+b) ^= bits [7,7+b))
-__device__ __forceinline__ uint32_t swz_off(int r, int j, int kblk) {
-  if (kblk == 64) return (uint32_t)(r * 128 + ((j ^ (r & 7)) << 4));
-  if (kblk == 32) return (uint32_t)(r * 64 + ((j ^ ((r >> 1) & 3)) << 4));
-  return (uint32_t)(r * 32 + ((j ^ ((r >> 2) & 1)) << 4));
 }
 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void cp_async_wait_pending(int n) {   // wait until at most n groups are pending
+  switch (n) {
+    case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+    case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+    case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+    default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+  }
+}
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+__device__ __forceinline__ void bld_bar_sync() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
 
 template <int LOADER>
 __global__ void __launch_bounds__(LOADER == LD_TMA ? 384 : 512, 1)
@@ -115,14 +134,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvGemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  // header (kHeaderBytes): barriers | tmem ptr | s_bias[2][256] | s_lnw[256] s_lnb[256] | s_dot[128][3]
+  // header (kHeaderBytes): barriers | tmem ptr | s_bias[2][256] | s_lnw[256] s_lnb[256] s_oc2[256] | s_dot[128][3]
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem);
   uint64_t* empty_bar = full_bar + kMaxStages;
   uint64_t* tfull_bar = empty_bar + kMaxStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* hfull_bar = tempty_bar + 2;
   uint64_t* hempty_bar = hfull_bar + 2;
-  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(hempty_bar + 2);
+  uint64_t* bres_bar = hempty_bar + 2;
+  uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bres_bar + 1);
   float* s_bias = reinterpret_cast<float*>(smem + 1024);        // [2][256]
   float* s_lnw = reinterpret_cast<float*>(smem + 3072);         // [256]  (LN weight | outc row 0)
   float* s_lnb = reinterpret_cast<float*>(smem + 4096);         // [256]  (LN bias   | outc row 1)
@@ -130,6 +150,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   float* s_dot = reinterpret_cast<float*>(smem + 6144);         // [128][3]
   uint8_t* tiles = smem + kHeaderBytes;
   uint8_t* halo = smem + p.halo_off;
+  uint8_t* ubuf = smem + p.u_off;
+  uint8_t* bres = smem + p.bres_off;
   uint8_t* rbuf = smem + p.resid_off;
 
   const int warp = threadIdx.x >> 5;
@@ -138,8 +160,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   constexpr bool kHalo = (LOADER == LD_HALO_CONV3 || LOADER == LD_HALO_UPS);
 
   if (threadIdx.x == 0) {
+    const uint32_t full_count = LOADER == LD_TMA ? 1u : kNumBuilders + (p.b_resident ? 0u : 1u);
     for (int s = 0; s < p.stages; ++s) {
-      mbar_init(&full_bar[s], LOADER == LD_TMA ? 1u : 1u + kNumBuilders);
+      mbar_init(&full_bar[s], full_count);
       mbar_init(&empty_bar[s], 1u);
     }
     for (int s = 0; s < 2; ++s) {
@@ -148,6 +171,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       mbar_init(&hfull_bar[s], 1u);
       mbar_init(&hempty_bar[s], kNumBuilders);
     }
+    mbar_init(bres_bar, 1u);
     fence_barrier_init();
     if (LOADER == LD_TMA || kHalo) tma_prefetch_desc(&tmA);
     if (LOADER == LD_HALO_UPS) tma_prefetch_desc(&tmA2);
@@ -179,6 +203,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t phase = 0;
       int hb = 0;
       uint32_t hphase = 0;
+      if (p.b_resident) {  // n_tiles == 1: the whole weight slab once
+        mbar_arrive_expect_tx(bres_bar, (uint32_t)p.num_kb * p.b_stage_bytes);
+        for (int kb = 0; kb < p.num_kb; ++kb) tma_load_2d(&tmB, bres_bar, bres + (size_t)kb * p.b_stage_bytes, kb * p.kblk, 0);
+      }
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
         int cb = 0, cx = 0, cy = 0;
@@ -194,40 +222,44 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             mbar_wait(&hempty_bar[hb], hphase ^ 1u);
             mbar_arrive_expect_tx(&hfull_bar[hb], p.halo_bytes);
             if (LOADER == LD_HALO_CONV3) {
-              tma_load_4d(&tmA, &hfull_bar[hb], halo + (size_t)hb * p.halo_stride, c * p.kblk, cx - 1, cy - 1, cb);
+              tma_load_4d(&tmA, &hfull_bar[hb], halo + (size_t)hb * p.halo_stride, c * p.cc, cx - 1, cy - 1, cb);
             } else {
               const bool s0 = c < p.c0_blocks;
               tma_load_4d(s0 ? &tmA : &tmA2, &hfull_bar[hb], halo + (size_t)hb * p.halo_stride,
-                          (s0 ? c : c - p.c0_blocks) * p.kblk, (cx >> 1) - 1, (cy >> 1) - 1, cb);
+                          (s0 ? c : c - p.c0_blocks) * p.cc, (cx >> 1) - 1, (cy >> 1) - 1, cb);
             }
             hb ^= 1;
             if (hb == 0) hphase ^= 1u;
-            for (int tap = 0; tap < 9; ++tap) {
-              mbar_wait(&empty_bar[stage], phase ^ 1u);
-              mbar_arrive_expect_tx(&full_bar[stage], p.b_stage_bytes);
-              tma_load_2d(&tmB, &full_bar[stage], tiles + (size_t)stage * p.stage_bytes + p.a_stage_bytes,
-                          (tap * p.c_blocks + c) * p.kblk, n_tile * p.block_n);
-              if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            if (!p.b_resident) {
+              int kcoord = c * p.kb_per_c * 64;
+              for (int kbi = 0; kbi < p.kb_per_c; ++kbi, kcoord += 64) {
+                mbar_wait(&empty_bar[stage], phase ^ 1u);
+                mbar_arrive_expect_tx(&full_bar[stage], p.b_stage_bytes);
+                tma_load_2d(&tmB, &full_bar[stage], tiles + (size_t)stage * p.stage_bytes + p.a_stage_bytes, kcoord, n_tile * p.block_n);
+                if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+              }
             }
           }
-        } else {
+        } else if (LOADER == LD_TMA) {
+          int tap_r = 0, tap_s = 0, cblk = 0;
           for (int kb = 0; kb < p.num_kb; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1u);
             uint8_t* sa = tiles + (size_t)stage * p.stage_bytes;
-            uint8_t* sb = sa + p.a_stage_bytes;
-            if (LOADER == LD_TMA) {
-              mbar_arrive_expect_tx(&full_bar[stage], p.a_stage_bytes + p.b_stage_bytes);
-              if (p.a_is_conv) {
-                const int tap = kb / p.c_blocks, cblk = kb - tap * p.c_blocks;
-                const int r = tap / p.S, s = tap - r * p.S;
-                tma_load_4d(&tmA, &full_bar[stage], sa, cblk * p.kblk, cx + s - p.pad, cy + r - p.pad, cb);
-              } else {
-                tma_load_2d(&tmA, &full_bar[stage], sa, kb * p.kblk, m_tile * kBlockM);
-              }
+            mbar_arrive_expect_tx(&full_bar[stage], p.a_stage_bytes + (p.b_resident ? 0u : p.b_stage_bytes));
+            if (p.a_is_conv) {
+              tma_load_4d(&tmA, &full_bar[stage], sa, cblk * p.kblk, cx + tap_s - p.pad, cy + tap_r - p.pad, cb);
+              if (++cblk == p.c_blocks) { cblk = 0; if (++tap_s == p.S) { tap_s = 0; ++tap_r; } }
             } else {
-              mbar_arrive_expect_tx(&full_bar[stage], p.b_stage_bytes);
+              tma_load_2d(&tmA, &full_bar[stage], sa, kb * p.kblk, m_tile * kBlockM);
             }
-            tma_load_2d(&tmB, &full_bar[stage], sb, kb * p.kblk, n_tile * p.block_n);
+            if (!p.b_resident) tma_load_2d(&tmB, &full_bar[stage], sa + p.a_stage_bytes, kb * p.kblk, n_tile * p.block_n);
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+          }
+        } else if (!p.b_resident) {  // gather loaders: weights only
+          for (int kb = 0; kb < p.num_kb; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1u);
+            mbar_arrive_expect_tx(&full_bar[stage], p.b_stage_bytes);
+            tma_load_2d(&tmB, &full_bar[stage], tiles + (size_t)stage * p.stage_bytes + p.a_stage_bytes, kb * p.kblk, n_tile * p.block_n);
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
         }
@@ -241,6 +273,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int as = 0;
       uint32_t aphase = 0;
       const int nmma = p.kblk >> 4;
+      if (p.b_resident) { mbar_wait(bres_bar, 0u); tc_fence_after(); }
+      const uint32_t bres_addr = smem_u32(bres);
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         mbar_wait(&tempty_bar[as], aphase ^ 1u);
         tc_fence_after();
@@ -250,7 +284,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           tc_fence_after();
           const uint32_t sa = smem_u32(tiles + (size_t)stage * p.stage_bytes);
           const uint64_t adesc = make_smem_desc(sa, row_bytes);
-          const uint64_t bdesc = make_smem_desc(sa + p.a_stage_bytes, row_bytes);
+          const uint64_t bdesc = make_smem_desc(p.b_resident ? bres_addr + (uint32_t)kb * p.b_stage_bytes : sa + p.a_stage_bytes, row_bytes);
           for (int j = 0; j < nmma; ++j) {
             // advance 16 K-elements = 32 bytes inside the swizzled row: +2 in the (addr >> 4) field
             umma_f16_ss(d_tmem, adesc + (uint64_t)(2 * j), bdesc + (uint64_t)(2 * j), p.idesc, (uint32_t)((kb | j) != 0));
@@ -270,14 +304,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int row = q * 32 + lane;
     const int et = threadIdx.x - 128;  // 0..255
     const int nchunks = p.block_n >> 4;
-    int as = 0;
-    uint32_t aphase = 0;
-    int bsel = 0;
-    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
-      const int n0 = n_tile * p.block_n;
-      long m;
-      bool mvalid;
+    const int D = p.resid_depth;
+    const bool has_res = (p.resid16 != nullptr) || (p.resid32 != nullptr);
+
+    // geometry of this thread's row in a given tile
+    auto tile_row = [&](int tile, long& m, bool& mvalid, int& n0, int& m_tile) {
+      m_tile = tile / p.n_tiles;
+      n0 = (tile - m_tile * p.n_tiles) * p.block_n;
       if (p.tile_mode == 1) {
         const int b = m_tile / p.tiles_per_img;
         const int rem = m_tile - b * p.tiles_per_img;
@@ -289,28 +322,57 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         m = (long)m_tile * kBlockM + row;
         mvalid = m < p.M;
       }
-      // ---- prologue, overlapped with the main loop of this tile: bias -> smem, residual row -> smem (cp.async)
-      float* sb = s_bias + bsel * 256;
-      if (et < p.block_n) sb[et] = (p.bias != nullptr && n0 + et < p.N) ? __ldg(p.bias + n0 + et) : 0.f;
-      const bool res_fast = mvalid && (n0 + p.block_n <= p.N);
-      if (res_fast && p.resid16 != nullptr) {
-        const __half* r = p.resid16 + m * p.ld_res16 + n0;
-        for (int ch = half; ch < nchunks; ch += 2) {
-          cp_async16(rbuf + ((size_t)(2 * ch) * 128 + row) * 16, r + ch * 16);
-          cp_async16(rbuf + ((size_t)(2 * ch + 1) * 128 + row) * 16, r + ch * 16 + 8);
-        }
-      } else if (res_fast && p.resid32 != nullptr) {
-        const float* r = p.resid32 + m * p.ld_res32 + n0;
-        for (int ch = half; ch < nchunks; ch += 2) {
+    };
+    // residual row of `tile` -> ring slot (thread-private region, layout [16-byte chunk][row] = conflict-free)
+    auto prefetch_resid = [&](int tile, int slot) {
+      if (has_res && tile < p.num_tiles) {
+        long m; bool mvalid; int n0, m_tile;
+        tile_row(tile, m, mvalid, n0, m_tile);
+        if (mvalid && n0 + p.block_n <= p.N) {
+          uint8_t* dst = rbuf + (size_t)slot * p.resid_stride;
+          if (p.resid16 != nullptr) {
+            const __half* r = p.resid16 + m * p.ld_res16 + n0;
+            for (int ch = half; ch < nchunks; ch += 2) {
+              cp_async16(dst + ((size_t)(2 * ch) * 128 + row) * 16, r + ch * 16);
+              cp_async16(dst + ((size_t)(2 * ch + 1) * 128 + row) * 16, r + ch * 16 + 8);
+            }
+          } else {
+            const float* r = p.resid32 + m * p.ld_res32 + n0;
+            for (int ch = half; ch < nchunks; ch += 2) {
 #pragma unroll
-          for (int u = 0; u < 4; ++u) cp_async16(rbuf + ((size_t)(4 * ch + u) * 128 + row) * 16, r + ch * 16 + 4 * u);
+              for (int u = 0; u < 4; ++u) cp_async16(dst + ((size_t)(4 * ch + u) * 128 + row) * 16, r + ch * 16 + 4 * u);
+            }
+          }
         }
       }
       cp_async_commit();
+    };
+
+    int as = 0;
+    uint32_t aphase = 0;
+    int bsel = 0;
+    int slot = 0;
+    {
+      int t = blockIdx.x;
+      for (int i = 0; i < D - 1; ++i, t += gridDim.x) prefetch_resid(t, i);
+    }
+    for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
+      long m; bool mvalid; int n0, m_tile;
+      tile_row(tile, m, mvalid, n0, m_tile);
+      // ---- prologue, overlapped with the main loop: bias -> smem; residual of tile (+D-1) -> ring
+      float* sb = s_bias + bsel * 256;
+      if (et < p.block_n) sb[et] = (p.bias != nullptr && n0 + et < p.N) ? __ldg(p.bias + n0 + et) : 0.f;
+      {
+        int pslot = slot + D - 1;
+        if (pslot >= D) pslot -= D;
+        prefetch_resid(tile + (D - 1) * (int)gridDim.x, pslot);
+      }
+      const bool res_fast = mvalid && (n0 + p.block_n <= p.N);
+      const uint8_t* rb_ = rbuf + (size_t)slot * p.resid_stride;
       epi_bar_sync();  // bias visible to all epilogue warps (double-buffered across tiles)
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
-      cp_async_wait_all();
+      cp_async_wait_pending(D - 1);
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kAccStride);
 
       if (p.epi == EPI_LN) {
@@ -387,8 +449,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (p.resid16 != nullptr) {
               if (res_fast) {
                 __align__(16) __half h[16];
-                reinterpret_cast<uint4*>(h)[0] = *reinterpret_cast<const uint4*>(rbuf + ((size_t)(2 * ch) * 128 + row) * 16);
-                reinterpret_cast<uint4*>(h)[1] = *reinterpret_cast<const uint4*>(rbuf + ((size_t)(2 * ch + 1) * 128 + row) * 16);
+                reinterpret_cast<uint4*>(h)[0] = *reinterpret_cast<const uint4*>(rb_ + ((size_t)(2 * ch) * 128 + row) * 16);
+                reinterpret_cast<uint4*>(h)[1] = *reinterpret_cast<const uint4*>(rb_ + ((size_t)(2 * ch + 1) * 128 + row) * 16);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] += __half2float(h[j]);
               } else {
@@ -400,7 +462,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               if (res_fast) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
-                  const float4 t = *reinterpret_cast<const float4*>(rbuf + ((size_t)(4 * ch + u) * 128 + row) * 16);
+                  const float4 t = *reinterpret_cast<const float4*>(rb_ + ((size_t)(4 * ch + u) * 128 + row) * 16);
                   v[4 * u + 0] += t.x; v[4 * u + 1] += t.y; v[4 * u + 2] += t.z; v[4 * u + 3] += t.w;
                 }
               } else {
@@ -510,23 +572,23 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       as ^= 1;
       if (as == 0) aphase ^= 1u;
       bsel ^= 1;
+      if (++slot == D) slot = 0;
     }
   } else if (LOADER != LD_TMA && warp >= 12) {
     // ===================================================================== A-tile builders (4 warps)
     const int gt = threadIdx.x - 384;  // 0..127
+    const int j = gt & 7;              // 16-byte chunk (8 fp16 K-elements) within the 128-byte swizzled row
+    const int rg = gt >> 3;            // rows rg + 16*i
     int stage = 0;
     uint32_t phase = 0;
     if (kHalo) {
-      const int cpr = p.kblk >> 3;          // 16-byte chunks per row: 2, 4, 8
-      const int j = gt % cpr;
-      const int rg = gt / cpr;
-      const int rpp = 128 / cpr;            // rows per pass
-      const uint32_t rb = (uint32_t)p.kblk * 2u;
+      const uint32_t pb = (uint32_t)p.cc * 2u;   // bytes per halo pixel
+      const int cpp = p.cc >> 3;                 // 16-byte chunks per halo pixel
       int hb = 0;
       uint32_t hphase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int m_tile = tile / p.n_tiles;
-        int cy = 0, cx = 0;
+        int cy, cx;
         {
           const int b = m_tile / p.tiles_per_img;
           const int rem = m_tile - b * p.tiles_per_img;
@@ -537,55 +599,69 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int c = 0; c < p.c_blocks; ++c) {
           mbar_wait(&hfull_bar[hb], hphase);
           const uint8_t* hsrc = halo + (size_t)hb * p.halo_stride;
-          for (int tap = 0; tap < 9; ++tap) {
+          if (LOADER == LD_HALO_UPS) {
+            // phase 1: build the 10 x 18 upsampled + reflect-padded halo (once per channel chunk) from the 6 x 10
+            // low-resolution tile that starts at source pixel (cy/2 - 1, cx/2 - 1)
+            bld_bar_sync();  // everyone is done reading the previous U
+            const int sy0 = (cy >> 1) - 1, sx0 = (cx >> 1) - 1;
+            for (int e = gt; e < kHaloH * kHaloW * cpp; e += 128) {
+              const int ch = e % cpp;
+              const int px = e / cpp;
+              const int hy = px / kHaloW, hx = px - hy * kHaloW;
+              const int uy = reflect_idx(cy + hy - 1, 2 * p.IH);
+              const int ux = reflect_idx(cx + hx - 1, 2 * p.IW);
+              const int iy = uy >> 1, ix = ux >> 1;
+              int ya, yb, xa, xb;
+              float wya, wxa;
+              if (uy & 1) { ya = iy; yb = min(iy + 1, p.IH - 1); wya = 0.75f; }
+              else        { ya = max(iy - 1, 0); yb = iy; wya = 0.25f; }
+              if (ux & 1) { xa = ix; xb = min(ix + 1, p.IW - 1); wxa = 0.75f; }
+              else        { xa = max(ix - 1, 0); xb = ix; wxa = 0.25f; }
+              const uint8_t* base = hsrc + ch * 16;
+              const uint4 v00 = *reinterpret_cast<const uint4*>(base + (size_t)((ya - sy0) * 10 + (xa - sx0)) * pb);
+              const uint4 v01 = *reinterpret_cast<const uint4*>(base + (size_t)((ya - sy0) * 10 + (xb - sx0)) * pb);
+              const uint4 v10 = *reinterpret_cast<const uint4*>(base + (size_t)((yb - sy0) * 10 + (xa - sx0)) * pb);
+              const uint4 v11 = *reinterpret_cast<const uint4*>(base + (size_t)((yb - sy0) * 10 + (xb - sx0)) * pb);
+              *reinterpret_cast<uint4*>(ubuf + (size_t)px * pb + ch * 16) = lerp2x2_h8(v00, v01, v10, v11, wxa, wya);
+            }
+            mbar_arrive(&hempty_bar[hb]);  // low-res tile consumed
+            bld_bar_sync();                // U complete
+            hsrc = ubuf;
+          }
+          // phase 2: tap tiles.  K-block kbi of this chunk holds K indices [64*kbi, 64*kbi+64) of the (tap, channel)
+          // order; 16-byte chunk j covers k = 64*kbi + 8*j -> tap = k / cc, channel offset = k % cc
+          for (int kbi = 0; kbi < p.kb_per_c; ++kbi) {
+            const int k = kbi * 64 + j * 8;
+            const int tap = k / p.cc;
+            const int coff = (k - tap * p.cc) * 2;
             const int tr = tap / 3, ts = tap - tr * 3;
             mbar_wait(&empty_bar[stage], phase ^ 1u);
             uint8_t* sa = tiles + (size_t)stage * p.stage_bytes;
-            if (LOADER == LD_HALO_CONV3) {
-              // halo tile: (8+2) x (16+2) pixels, row-major, `rb` bytes per pixel; zero outside the image (TMA fill)
-              for (int i = 0; i < cpr; ++i) {
-                const int r = rg + rpp * i;
+            if (tap < 9) {
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int r = rg + 16 * i;
                 const int ry = r >> 4, rx = r & 15;
-                const uint4 val = *reinterpret_cast<const uint4*>(hsrc + (size_t)((ry + tr) * (kHaloTW + 2) + rx + ts) * rb + j * 16);
-                *reinterpret_cast<uint4*>(sa + swz_off(r, j, p.kblk)) = val;
+                const uint4 val = *reinterpret_cast<const uint4*>(hsrc + (size_t)((ry + tr) * kHaloW + rx + ts) * pb + coff);
+                *reinterpret_cast<uint4*>(sa + r * 128 + ((j ^ (r & 7)) << 4)) = val;
               }
             } else {
-              // low-res halo tile: 6 x 10 source pixels starting at (cy/2 - 1, cx/2 - 1); output = conv3x3(valid) o
-              // reflect-pad(1) o bilinear-x2(align_corners=False)
-              const int sy0 = (cy >> 1) - 1, sx0 = (cx >> 1) - 1;
-              for (int i = 0; i < cpr; ++i) {
-                const int r = rg + rpp * i;
-                const int ry = r >> 4, rx = r & 15;
-                const int uy = reflect_idx(cy + ry + tr - 1, 2 * p.IH);
-                const int ux = reflect_idx(cx + rx + ts - 1, 2 * p.IW);
-                const int iy = uy >> 1, ix = ux >> 1;
-                int ya, yb, xa, xb;
-                float wya, wxa;
-                if (uy & 1) { ya = iy; yb = min(iy + 1, p.IH - 1); wya = 0.75f; }
-                else        { ya = max(iy - 1, 0); yb = iy; wya = 0.25f; }
-                if (ux & 1) { xa = ix; xb = min(ix + 1, p.IW - 1); wxa = 0.75f; }
-                else        { xa = max(ix - 1, 0); xb = ix; wxa = 0.25f; }
-                const uint8_t* base = hsrc + j * 16;
-                const uint4 v00 = *reinterpret_cast<const uint4*>(base + (size_t)((ya - sy0) * 10 + (xa - sx0)) * rb);
-                const uint4 v01 = *reinterpret_cast<const uint4*>(base + (size_t)((ya - sy0) * 10 + (xb - sx0)) * rb);
-                const uint4 v10 = *reinterpret_cast<const uint4*>(base + (size_t)((yb - sy0) * 10 + (xa - sx0)) * rb);
-                const uint4 v11 = *reinterpret_cast<const uint4*>(base + (size_t)((yb - sy0) * 10 + (xb - sx0)) * rb);
-                *reinterpret_cast<uint4*>(sa + swz_off(r, j, p.kblk)) =
-                    lerp4_h8(v00, v01, v10, v11, wya * wxa, wya * (1.f - wxa), (1.f - wya) * wxa, (1.f - wya) * (1.f - wxa));
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const int r = rg + 16 * i;
+                *reinterpret_cast<uint4*>(sa + r * 128 + ((j ^ (r & 7)) << 4)) = make_uint4(0, 0, 0, 0);
               }
             }
             fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
             mbar_arrive(&full_bar[stage]);
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
-          mbar_arrive(&hempty_bar[hb]);
+          if (LOADER == LD_HALO_CONV3) mbar_arrive(&hempty_bar[hb]);
           hb ^= 1;
           if (hb == 0) hphase ^= 1u;
         }
       }
     } else {
-      const int j = gt & 7;              // 16-byte chunk (8 fp16 K-elements) within the 128-byte swizzled row
-      const int rg = gt >> 3;            // rows rg + 16*i
       const int Ct = p.C0 + p.C1;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         const int m_tile = tile / p.n_tiles;

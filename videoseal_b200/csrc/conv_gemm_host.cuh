@@ -99,20 +99,33 @@ inline void finalize_op(ConvGemmOp& op, const __half* W, int N, int Kw, int ldw,
   p.b_stage_bytes = (uint32_t)(p.block_n * p.kblk * 2);
   p.stage_bytes = p.a_stage_bytes + ((p.b_stage_bytes + 1023u) & ~1023u);
   VSB_CHECK(p.a_stage_bytes % 1024 == 0, "A stage must be 1024B aligned");
-  // shared memory: [header | stages x (A|B) | 2 halo tiles | residual prefetch buffer]
-  size_t resid_bytes = 0;
-  if (p.resid16) resid_bytes = (size_t)kBlockM * p.block_n * 2;
-  if (p.resid32) resid_bytes = (size_t)kBlockM * p.block_n * 4;
-  const size_t halo_total = 2 * (((size_t)p.halo_bytes + 1023) & ~size_t(1023));
-  const size_t budget = 225 * 1024 - kHeaderBytes - resid_bytes - halo_total;
-  VSB_CHECK(resid_bytes + halo_total + kHeaderBytes + 2 * (size_t)p.stage_bytes <= 225 * 1024, "tile does not fit in shared memory");
-  int stages = (int)(budget / p.stage_bytes);
-  if (stages > kMaxStages) stages = kMaxStages;
-  VSB_CHECK(stages >= 2, "not enough shared memory for 2 stages");
-  p.stages = stages;
+  // shared memory: [header | stages x (A|B) | 2 halo tiles | upsampled halo | resident weights | residual ring]
+  size_t resid_one = 0;
+  if (p.resid16) resid_one = (size_t)kBlockM * p.block_n * 2;
+  if (p.resid32) resid_one = (size_t)kBlockM * p.block_n * 4;
+  int depth = 1;
+  if (resid_one) { depth = (int)(32768 / resid_one); if (depth > 4) depth = 4; if (depth < 1) depth = 1; }
+  p.resid_depth = depth;
+  p.resid_stride = (uint32_t)resid_one;
+  const size_t resid_bytes = resid_one * depth;
   p.halo_stride = (uint32_t)(((size_t)p.halo_bytes + 1023) & ~size_t(1023));
+  const size_t halo_total = 2 * (size_t)p.halo_stride;
+  const size_t u_bytes = op.loader == LD_HALO_UPS ? (((size_t)kHaloH * kHaloW * p.cc * 2 + 1023) & ~size_t(1023)) : 0;
+  // resident weights: one N tile, whole K slab <= 48 KB -> loaded once per CTA instead of once per tile
+  const size_t bslab = (size_t)p.num_kb * p.b_stage_bytes;
+  p.b_resident = (p.n_tiles == 1 && bslab <= 48 * 1024) ? 1 : 0;
+  if (getenv("VSB_NO_BRES")) p.b_resident = 0;
+  const size_t bres_bytes = p.b_resident ? bslab : 0;
+  if (p.b_resident) p.stage_bytes = p.a_stage_bytes;
+  const size_t fixed = kHeaderBytes + resid_bytes + halo_total + u_bytes + bres_bytes;
+  VSB_CHECK(fixed + 2 * (size_t)p.stage_bytes <= 225 * 1024, "tile does not fit in shared memory");
+  int stages = (int)((225 * 1024 - fixed) / p.stage_bytes);
+  if (stages > kMaxStages) stages = kMaxStages;
+  p.stages = stages;
   p.halo_off = (uint32_t)(kHeaderBytes + (size_t)stages * p.stage_bytes);
-  p.resid_off = (uint32_t)(p.halo_off + halo_total);
+  p.u_off = (uint32_t)(p.halo_off + halo_total);
+  p.bres_off = (uint32_t)(p.u_off + u_bytes);
+  p.resid_off = (uint32_t)(p.bres_off + bres_bytes);
   op.smem = 1024 /*align slack*/ + p.resid_off + resid_bytes;
   // instruction descriptor (kind::f16): D=f32 (bit 4), A=B=f16 (0), K-major both, N>>3 at bit 17, M>>4 at bit 24
   p.idesc = (1u << 4) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
@@ -156,27 +169,43 @@ inline void setup_tma_conv(ConvGemmOp& op, const __half* src, int B, int H, int 
 
 // 3x3 stride-1 zero-padded conv with on-chip im2col: the (8+2)x(16+2) input halo of each 8x16 output tile is loaded once
 // per channel chunk.  Weights [N][9*C] with K order (r, s, c).
+inline int halo_kpad(int C0, int C1) {   // padded K of the chunk-major halo weight layout
+  const int cc = C0 < 64 ? C0 : 64;
+  const int kb_per_c = (9 * cc + 63) / 64;
+  return ((C0 + C1) / cc) * kb_per_c * 64;
+}
+
+// Halo-loader weight layout: [N][chunk][tap][cc] with each chunk zero-padded to kb_per_c*64 (see ConvGemmParams).
+inline void setup_halo_common(ConvGemmParams& p, int C0, int C1, int B, int OH, int OW) {
+  p.tile_mode = 1;
+  p.kblk = 64;
+  p.cc = C0 < 64 ? C0 : 64;
+  VSB_CHECK(p.cc == 64 || p.cc == 32 || p.cc == 16, "halo loader: C must be 16, 32 or a multiple of 64");
+  VSB_CHECK(C0 % p.cc == 0 && C1 % p.cc == 0, "halo loader: channels must be multiples of the chunk size");
+  VSB_CHECK(OW % kHaloTW == 0 && OH % kHaloTH == 0, "halo loader: output map must tile by 8x16");
+  p.c0_blocks = C0 / p.cc;
+  p.c_blocks = (C0 + C1) / p.cc;
+  p.kb_per_c = (9 * p.cc + 63) / 64;
+  p.R = 3; p.S = 3; p.pad = 1;
+  p.H = OH; p.W = OW; p.tile_w = kHaloTW; p.tile_h = kHaloTH;
+  p.tiles_x = OW / kHaloTW;
+  p.tiles_per_img = p.tiles_x * (OH / kHaloTH);
+  p.m_tiles = B * p.tiles_per_img;
+  p.M = B * OH * OW;
+  p.num_kb = p.c_blocks * p.kb_per_c;
+}
+
+// 3x3 stride-1 zero-padded conv with on-chip im2col: the (8+2)x(16+2) input halo of each 8x16 output tile is loaded once
+// per channel chunk.
 inline void setup_halo_conv3(ConvGemmOp& op, const __half* src, int B, int H, int W, int C, int ld) {
   ConvGemmParams& p = op.p;
   op.loader = LD_HALO_CONV3;
-  p.tile_mode = 1;
-  p.kblk = C >= 64 ? 64 : C;
-  VSB_CHECK(p.kblk == 64 || p.kblk == 32 || p.kblk == 16, "halo conv: C must be 16, 32 or a multiple of 64");
-  VSB_CHECK(C % p.kblk == 0, "halo conv: C must be a multiple of the K block");
-  VSB_CHECK(W % kHaloTW == 0 && H % kHaloTH == 0, "halo conv: map must tile by 8x16");
-  p.c_blocks = C / p.kblk; p.c0_blocks = p.c_blocks;
-  p.R = 3; p.S = 3; p.pad = 1;
-  p.H = H; p.W = W; p.tile_w = kHaloTW; p.tile_h = kHaloTH;
-  p.tiles_x = W / kHaloTW;
-  p.tiles_per_img = p.tiles_x * (H / kHaloTH);
-  p.m_tiles = B * p.tiles_per_img;
-  p.M = B * H * W;
-  p.num_kb = 9 * p.c_blocks;
-  p.halo_bytes = (uint32_t)((kHaloTH + 2) * (kHaloTW + 2) * p.kblk * 2);
+  setup_halo_common(p, C, 0, B, H, W);
+  p.halo_bytes = (uint32_t)(kHaloH * kHaloW * p.cc * 2);
   uint64_t dims[4] = {(uint64_t)C, (uint64_t)W, (uint64_t)H, (uint64_t)B};
   uint64_t strides[3] = {(uint64_t)ld * 2, (uint64_t)W * ld * 2, (uint64_t)H * W * ld * 2};
-  uint32_t box[4] = {(uint32_t)p.kblk, (uint32_t)(kHaloTW + 2), (uint32_t)(kHaloTH + 2), 1u};
-  encode_map(&op.tmA, src, 4, dims, strides, box, p.kblk, /*no_swizzle=*/true);
+  uint32_t box[4] = {(uint32_t)p.cc, (uint32_t)kHaloW, (uint32_t)kHaloH, 1u};
+  encode_map(&op.tmA, src, 4, dims, strides, box, 64, /*no_swizzle=*/true);
 }
 
 // UBlock up-conv (modules/common.py:45-52 after the skip concat of unet.py:187-190): conv3x3(valid) o ReflectionPad2d(1) o
@@ -184,33 +213,20 @@ inline void setup_halo_conv3(ConvGemmOp& op, const __half* src, int B, int H, in
 inline void setup_halo_ups(ConvGemmOp& op, const __half* src0, int C0, int ld0, const __half* src1, int C1, int ld1, int B, int IH, int IW) {
   ConvGemmParams& p = op.p;
   op.loader = LD_HALO_UPS;
-  p.tile_mode = 1;
-  const int Cm = C0 < C1 || C1 == 0 ? C0 : C1;
-  p.kblk = Cm >= 64 ? 64 : Cm;
-  VSB_CHECK(p.kblk == 64 || p.kblk == 32 || p.kblk == 16, "halo ups: C must be 16, 32 or a multiple of 64");
-  VSB_CHECK(C0 % p.kblk == 0 && C1 % p.kblk == 0, "halo ups: channels must be multiples of the K block");
-  const int OH = 2 * IH, OW = 2 * IW;
-  VSB_CHECK(OW % kHaloTW == 0 && OH % kHaloTH == 0, "halo ups: output map must tile by 8x16");
-  p.c0_blocks = C0 / p.kblk; p.c_blocks = (C0 + C1) / p.kblk;
-  p.R = 3; p.S = 3; p.pad = 1;
-  p.IH = IH; p.IW = IW; p.OH = OH; p.OW = OW;
-  p.H = OH; p.W = OW; p.tile_w = kHaloTW; p.tile_h = kHaloTH;
-  p.tiles_x = OW / kHaloTW;
-  p.tiles_per_img = p.tiles_x * (OH / kHaloTH);
-  p.m_tiles = B * p.tiles_per_img;
-  p.M = B * OH * OW;
-  p.num_kb = 9 * p.c_blocks;
-  p.halo_bytes = (uint32_t)(6 * 10 * p.kblk * 2);
-  uint32_t box[4] = {(uint32_t)p.kblk, 10u, 6u, 1u};
+  VSB_CHECK(C1 == 0 || C1 == C0, "halo ups: both sources must have the same channel count");
+  setup_halo_common(p, C0, C1, B, 2 * IH, 2 * IW);
+  p.IH = IH; p.IW = IW; p.OH = 2 * IH; p.OW = 2 * IW;
+  p.halo_bytes = (uint32_t)(6 * 10 * p.cc * 2);
+  uint32_t box[4] = {(uint32_t)p.cc, 10u, 6u, 1u};
   {
     uint64_t dims[4] = {(uint64_t)C0, (uint64_t)IW, (uint64_t)IH, (uint64_t)B};
     uint64_t strides[3] = {(uint64_t)ld0 * 2, (uint64_t)IW * ld0 * 2, (uint64_t)IH * IW * ld0 * 2};
-    encode_map(&op.tmA, src0, 4, dims, strides, box, p.kblk, true);
+    encode_map(&op.tmA, src0, 4, dims, strides, box, 64, true);
   }
   if (C1 > 0) {
     uint64_t dims[4] = {(uint64_t)C1, (uint64_t)IW, (uint64_t)IH, (uint64_t)B};
     uint64_t strides[3] = {(uint64_t)ld1 * 2, (uint64_t)IW * ld1 * 2, (uint64_t)IH * IW * ld1 * 2};
-    encode_map(&op.tmA2, src1, 4, dims, strides, box, p.kblk, true);
+    encode_map(&op.tmA2, src1, 4, dims, strides, box, 64, true);
   }
 }
 

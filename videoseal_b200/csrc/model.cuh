@@ -251,6 +251,40 @@ class Model {
     cw.bias = bias.empty() ? nullptr : wpool.upload(bias);
     return cw;
   }
+  // 3x3 conv weight [N][C0+C1][3][3] -> halo-loader layout [N][chunk][tap][cc], chunks zero-padded to kb_per_c*64
+  ConvW pack_conv_halo(const std::string& wkey, const std::vector<float>* out_scale, const std::vector<float>& bias, int C0, int C1,
+                       const std::vector<float>* in_scale = nullptr) {
+    const HostTensor& w = get(wkey);
+    VSB_CHECK(w.shape.size() == 4 && w.shape[2] == 3 && w.shape[3] == 3 && (int)w.shape[1] == C0 + C1, "halo conv weight shape");
+    const int N = (int)w.shape[0], Ct = C0 + C1;
+    const int cc = C0 < 64 ? C0 : 64, kbc = (9 * cc + 63) / 64, Kpad = halo_kpad(C0, C1);
+    std::vector<float> p((size_t)N * Kpad, 0.f);
+    for (int n = 0; n < N; ++n)
+      for (int c = 0; c < Ct; ++c)
+        for (int t = 0; t < 9; ++t) {
+          float v = w.data[((size_t)n * Ct + c) * 9 + t];
+          if (out_scale) v *= (*out_scale)[n];
+          if (in_scale) v *= (*in_scale)[c];
+          p[(size_t)n * Kpad + (size_t)(c / cc) * kbc * 64 + t * cc + (c % cc)] = v;
+        }
+    ConvW cw;
+    cw.N = N; cw.K = Kpad;
+    cw.w = wpool.upload(to_half(p));
+    cw.bias = bias.empty() ? nullptr : wpool.upload(bias);
+    return cw;
+  }
+  int halo_max_c = -1;
+  bool use_halo(int C) {
+    if (halo_max_c < 0) {
+      const char* e = getenv("VSB_HALO_MAXC");
+      halo_max_c = e ? atoi(e) : (1 << 30);
+    }
+    return C <= halo_max_c;
+  }
+  ConvW pack_conv3(const std::string& wkey, const std::vector<float>* out_scale, const std::vector<float>& bias) {
+    const int C = (int)get(wkey).shape[1];
+    return use_halo(C) ? pack_conv_halo(wkey, out_scale, bias, C, 0) : pack_conv(wkey, out_scale, bias);
+  }
   // eval-mode BatchNorm2d folded into the preceding bias-free conv: w' = w*g/sqrt(var+eps), b' = beta - mean*g/sqrt(var+eps)
   void bn_fold(const std::string& bn, std::vector<float>& scale, std::vector<float>& bias) const {
     const HostTensor &g = get(bn + ".weight"), &b = get(bn + ".bias"), &mu = get(bn + ".running_mean"), &var = get(bn + ".running_var");
@@ -266,9 +300,9 @@ class Model {
     ResBlockW rb;
     std::vector<float> s, b;
     bn_fold(key + ".double_conv.1", s, b);
-    rb.c1 = pack_conv(key + ".double_conv.0.weight", &s, b);
+    rb.c1 = pack_conv3(key + ".double_conv.0.weight", &s, b);
     bn_fold(key + ".double_conv.4", s, b);
-    rb.c2 = pack_conv(key + ".double_conv.3.weight", &s, b);
+    rb.c2 = pack_conv3(key + ".double_conv.3.weight", &s, b);
     rb.res = pack_conv(key + ".res_conv.weight", nullptr, get(key + ".res_conv.bias").data);
     return rb;
   }
@@ -306,7 +340,7 @@ class Model {
       first_wr = wpool.upload(get(P + "inc.res_conv.weight").data);
       first_br = wpool.upload(get(P + "inc.res_conv.bias").data);
       bn_fold(P + "inc.double_conv.4", s, b);
-      inc_c2 = pack_conv(P + "inc.double_conv.3.weight", &s, b);
+      inc_c2 = pack_conv3(P + "inc.double_conv.3.weight", &s, b);
     }
     for (int i = 0; i < L - 1; ++i) {
       down_conv.push_back(pack_conv(P + "downs." + std::to_string(i) + ".down.weight", nullptr, get(P + "downs." + std::to_string(i) + ".down.bias").data));
@@ -322,7 +356,7 @@ class Model {
         // virtual concat (x | skip * 2^-1/2): fold the skip scale into the second half of the input channels
         std::vector<float> in_scale(2 * zz[ii + 1], 1.0f);
         for (int c = zz[ii + 1]; c < 2 * zz[ii + 1]; ++c) in_scale[c] = 0.70710678118654752440f;
-        up_conv.push_back(pack_conv(U + ".up.upsample_block.2.weight", nullptr, {}, &in_scale));
+        up_conv.push_back(pack_conv_halo(U + ".up.upsample_block.2.weight", nullptr, {}, zz[ii + 1], zz[ii + 1], &in_scale));
         up_lnw.push_back(wpool.upload(get(U + ".up.upsample_block.3.weight").data));
         up_lnb.push_back(wpool.upload(get(U + ".up.upsample_block.3.bias").data));
         up_rb.push_back(pack_resblock(U + ".conv"));
@@ -408,14 +442,10 @@ class Model {
     pl.steps.push_back(Step{[op](cudaStream_t st) { launch(op, st); }, 1, name});
   }
   // 3x3 stride-1 zero-padded conv: on-chip im2col from a shared-memory halo tile (input crosses L2->SM once) up to
-  // `halo_max_c` input channels, one TMA load per tap above (VSB_HALO_MAXC overrides, for experiments)
-  int halo_max_c = -1;
+  // `halo_max_c` input channels, one TMA load per tap above (VSB_HALO_MAXC overrides, for experiments); the weight layout
+  // was chosen by the same rule at pack time (pack_conv3)
   void setup_conv3(ConvGemmOp& op, const __half* x, int B, int H, int W, int C, int ld) {
-    if (halo_max_c < 0) {
-      const char* e = getenv("VSB_HALO_MAXC");
-      halo_max_c = e ? atoi(e) : (1 << 30);
-    }
-    if (C <= halo_max_c && W % kHaloTW == 0 && H % kHaloTH == 0) setup_halo_conv3(op, x, B, H, W, C, ld);
+    if (use_halo(C)) setup_halo_conv3(op, x, B, H, W, C, ld);
     else setup_tma_conv(op, x, B, H, W, C, ld, 3, 3, 1);
   }
 

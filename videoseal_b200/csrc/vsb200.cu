@@ -175,13 +175,16 @@ int64_t vsb_debug_get_tensor(vsb_model* m, const char* name, float* host_out, in
 int vsb_debug_conv(const vsb_conv_test* t, void* stream) {
   VSB_API_BEGIN
   VSB_CHECK(t != nullptr, "null argument");
-  int dev = 0;
-  VSB_CUDA(cudaGetDevice(&dev));
-  cudaDeviceProp prop;
-  VSB_CUDA(cudaGetDeviceProperties(&prop, dev));
+  static int num_sms = 0;
+  if (num_sms == 0) {
+    int dev = 0;
+    VSB_CUDA(cudaGetDevice(&dev));
+    VSB_CUDA(cudaDeviceGetAttribute(&num_sms, cudaDevAttrMultiProcessorCount, dev));
+  }
   ConvGemmOp op;
   const int Ct = t->C0 + t->C1;
-  const int K = t->R * t->S * Ct;
+  int K = t->R * t->S * Ct;
+  if (t->loader == LD_HALO_UPS || t->loader == LD_HALO_CONV3) K = halo_kpad(t->C0, t->C1);  // weights in halo layout
   int OH, OW;
   if (t->loader == LD_TMA) {
     OH = t->IH; OW = t->IW;
@@ -212,7 +215,7 @@ int vsb_debug_conv(const vsb_conv_test* t, void* stream) {
   p.outc_w = t->outc_w; p.outc_b = t->outc_b; p.n_out = t->n_out; p.delta = t->delta; p.hw = OH * OW; p.outc_tanh = 1;
   p.grn_stats = t->grn_stats;
   if (t->rows_per_sample) p.rows_per_sample = t->rows_per_sample;
-  finalize_op(op, (const __half*)t->weights, t->N, K, K, prop.multiProcessorCount, t->block_n);
+  finalize_op(op, (const __half*)t->weights, t->N, K, K, num_sms, t->block_n);
   launch(op, (cudaStream_t)stream);
   g_launches += 1;
   return VSB_OK;
