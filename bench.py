@@ -93,6 +93,9 @@ def conv_flops(name: str, B: int) -> float:
         if kind in ("unet.conv3x3", "unet.conv3x3+outc", "unet.down3x3s2", "unet.up3x3"):
             cin, cout = (int(x) for x in dims.split("-"))
             return 2.0 * M * cout * 9 * cin
+        if kind == "unet.uptap1x1":
+            cin, cout = (int(x) for x in dims.split("-"))
+            return 2.0 * M * cout * cin
         if kind == "unet.conv1x1":
             cin, cout = (int(x) for x in dims.split("-"))
             return 2.0 * M * cout * cin
@@ -134,36 +137,60 @@ def build_card_on_disk(card_name: str, seed: int = 0):
     return cpath, card
 
 
-def cpu_oracle_fps(card_name: str, size: int, sample: int, runs: int, threads: int):
-    """embed+detect frames/s of the CPU restatement of the reference path (test infrastructure, timed as the baseline)"""
+def cpu_oracle_setup(card_name: str, size: int):
     import torch
     import yaml
     from oracle import restate
-    torch.set_num_threads(threads)
     card = yaml.safe_load(open(os.path.join(ROOT, "videoseal_b200", "cards", card_name + ".yaml")))
     spec = restate.spec_from_card(card)
     orc = restate.OracleModel(spec, restate.synth_state_dict(spec, 0))
     g = torch.Generator().manual_seed(0)
-    imgs = torch.rand(sample, 3, size, size, generator=g)
-    msgs = torch.randint(0, 2, (sample, spec["nbits"]), generator=g)
-    times = []
-    with torch.no_grad():
-        for i in range(runs + 1):  # 1 warm-up, as evals/speed.py:51-52
+    imgs = torch.rand(8, 3, size, size, generator=g)
+    msgs = torch.randint(0, 2, (8, spec["nbits"]), generator=g)
+
+    def run(n):
+        with torch.no_grad():
             t0 = time.perf_counter()
-            o = orc.embed(imgs, msgs, is_video=False)
+            o = orc.embed(imgs[:n], msgs[:n], is_video=False)
             orc.detect(o["imgs_w"], is_video=False)
-            if i > 0:
-                times.append(time.perf_counter() - t0)
-    return sample * len(times) / sum(times), times
+            return time.perf_counter() - t0
+    return run
+
+
+def cpu_pick_threads(run):
+    """the host may expose more logical CPUs than this process can use: calibrate the torch thread count on one frame"""
+    import torch
+    try:
+        avail = len(os.sched_getaffinity(0))
+    except AttributeError:
+        avail = os.cpu_count() or 1
+    best, best_t = 1, float("inf")
+    for th in sorted({avail, min(avail, 64), min(avail, 32), min(avail, 16), min(avail, 8)}):
+        torch.set_num_threads(th)
+        run(1)
+        t = run(1)
+        if t < best_t:
+            best, best_t = th, t
+    torch.set_num_threads(best)
+    return best, best_t
+
+
+def cpu_oracle_fps(card_name: str, size: int, runs: int, budget_s: float):
+    """embed+detect frames/s of the CPU restatement of the reference path (test infrastructure, timed as the baseline).
+    1 warm-up + `runs` timed runs (evals/speed.py:51-52) on a sample sized to fit `budget_s` seconds."""
+    run = cpu_oracle_setup(card_name, size)
+    threads, t1 = cpu_pick_threads(run)
+    sample = int(max(1, min(8, budget_s / max(1e-3, t1 * (runs + 1)))))
+    run(sample)
+    times = [run(sample) for _ in range(runs)]
+    return sample * len(times) / sum(times), times, threads, sample
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    threads = os.cpu_count() or 1
-    sample = 8
-    fps, times = cpu_oracle_fps(args.card, args.size, sample, args.steps + max(0, args.warmup - 1), threads)
+    fps, times, threads, sample = cpu_oracle_fps(args.card, args.size, args.steps, budget_s=150.0)
     line = {
         "impl": "reference", "metric": "embed+detect frames/sec", "value": fps, "unit": "frames/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1000.0 * sum(times) / len(times), "higher_is_better": True,
@@ -315,11 +342,9 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and not args.no_cpu_baseline:
-        threads = os.cpu_count() or 1
-        sample = 8
-        v, times = cpu_oracle_fps(args.card, S, sample, 3, threads)
+        v, times, threads, sample = cpu_oracle_fps(args.card, S, 3, budget_s=25.0)
         cpu = {"value": v, "unit": "frames/s", "cores": threads, "kind": "port",
-               "sample": f"{sample} frames embed+detect, 1 warm-up + 3 runs ({sum(times):.1f} s), oracle/restate.py"}
+               "sample": f"{sample} frames embed+detect per run, 1 warm-up + 3 runs ({sum(times):.1f} s), oracle/restate.py"}
 
     if rank == 0:
         fe, fd = FLOPS_PER_FRAME.get(args.card, (0, 0))

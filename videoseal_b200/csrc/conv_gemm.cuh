@@ -84,8 +84,9 @@ __device__ __forceinline__ float gelu_erf(float x) {
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
-  const float e = 1.0f - poly * t * __expf(-z * z);
-  return 0.5f * x * (1.0f + copysignf(e, x));
+  const float e = fmaf(-poly * t, __expf(-z * z), 1.0f);   // erf(|x|/sqrt2) >= 0
+  const float h = 0.5f * x;
+  return fmaf(fabsf(h), e, h);                              // 0.5*x*(1 + sign(x)*e)
 }
 
 __device__ __forceinline__ int reflect_idx(int i, int n) {
@@ -128,7 +129,7 @@ __device__ __forceinline__ void cp_async_wait_pending(int n) {   // wait until a
 __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 __device__ __forceinline__ void bld_bar_sync() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
 
-template <int LOADER>
+template <int LOADER, int ACT>
 __global__ void __launch_bounds__(LOADER == LD_TMA ? 384 : 512, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvGemmParams p) {
@@ -174,7 +175,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     mbar_init(bres_bar, 1u);
     fence_barrier_init();
     if (LOADER == LD_TMA || kHalo) tma_prefetch_desc(&tmA);
-    if (LOADER == LD_HALO_UPS) tma_prefetch_desc(&tmA2);
+    if (LOADER == LD_HALO_UPS || (LOADER == LD_TMA && p.c0_blocks != 0)) tma_prefetch_desc(&tmA2);
     tma_prefetch_desc(&tmB);
   }
   if (warp == 2) {
@@ -250,7 +251,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               tma_load_4d(&tmA, &full_bar[stage], sa, cblk * p.kblk, cx + tap_s - p.pad, cy + tap_r - p.pad, cb);
               if (++cblk == p.c_blocks) { cblk = 0; if (++tap_s == p.S) { tap_s = 0; ++tap_r; } }
             } else {
-              tma_load_2d(&tmA, &full_bar[stage], sa, kb * p.kblk, m_tile * kBlockM);
+              // 2D GEMM operand, optionally the virtual concat [A0 | A1] along K (c0_blocks K-blocks come from A0)
+              if (p.c0_blocks == 0 || kb < p.c0_blocks) tma_load_2d(&tmA, &full_bar[stage], sa, kb * p.kblk, m_tile * kBlockM);
+              else tma_load_2d(&tmA2, &full_bar[stage], sa, (kb - p.c0_blocks) * p.kblk, m_tile * kBlockM);
             }
             if (!p.b_resident) tma_load_2d(&tmB, &full_bar[stage], sa + p.a_stage_bytes, kb * p.kblk, n_tile * p.block_n);
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -409,8 +412,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               float y = 0.f;
               if (n < N) {
                 y = (v[j] - mean) * rstd * s_lnw[n] + s_lnb[n];
-                if (p.act == ACT_RELU) y = fmaxf(y, 0.f);
-                else if (p.act == ACT_GELU) y = gelu_erf(y);
+                if (ACT == ACT_RELU) y = fmaxf(y, 0.f);
+                else if (ACT == ACT_GELU) y = gelu_erf(y);
               }
               h[j] = __float2half_rn(y);
             }
@@ -431,19 +434,30 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             p.grn_stats != nullptr &&
             ((long)m_tile * kBlockM + q * 32) / p.rows_per_sample == ((long)m_tile * kBlockM + q * 32 + 31) / p.rows_per_sample &&
             ((long)m_tile * kBlockM + q * 32 + 31) < p.M;
+        uint32_t vnext[16];
+        if (half < nchunks) tmem_ld16_issue(trow + half * 16, vnext);
         for (int ch = half; ch < nchunks; ch += 2) {
           const int c = ch * 16;
           float v[16];
-          tmem_ld16(trow + c, v);
+          tmem_ld_wait(vnext);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(vnext[j]);
+          if (ch + 2 < nchunks) tmem_ld16_issue(trow + c + 32, vnext);   // overlaps the math below
           const int n = n0 + c;
           if (n >= p.N) continue;  // uniform across the warp
           const bool full = (n + 16 <= p.N);
+          {
+            const float4* sb4 = reinterpret_cast<const float4*>(sb + c);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float4 bq = sb4[u];
+              v[4 * u + 0] += bq.x; v[4 * u + 1] += bq.y; v[4 * u + 2] += bq.z; v[4 * u + 3] += bq.w;
+            }
+          }
 #pragma unroll
           for (int j = 0; j < 16; ++j) {
-            float x = v[j] + sb[c + j];
-            if (p.act == ACT_RELU) x = fmaxf(x, 0.f);
-            else if (p.act == ACT_GELU) x = gelu_erf(x);
-            v[j] = x;
+            if (ACT == ACT_RELU) v[j] = fmaxf(v[j], 0.f);
+            else if (ACT == ACT_GELU) v[j] = gelu_erf(v[j]);
           }
           if (mvalid) {
             if (p.resid16 != nullptr) {
@@ -485,9 +499,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (p.out16 != nullptr) {
               __half* o = p.out16 + m * p.ld_out16 + n;
               if (full) {
-                __align__(16) __half h[16];
+                __align__(16) __half2 h[8];
 #pragma unroll
-                for (int j = 0; j < 16; ++j) h[j] = __float2half_rn(fminf(fmaxf(v[j], -65504.f), 65504.f));
+                for (int j = 0; j < 8; ++j) {
+                  float a = fminf(v[2 * j], 65504.f), b2 = fminf(v[2 * j + 1], 65504.f);
+                  if (ACT != ACT_RELU || p.resid16 != nullptr || p.resid32 != nullptr) { a = fmaxf(a, -65504.f); b2 = fmaxf(b2, -65504.f); }
+                  h[j] = __floats2half2_rn(a, b2);
+                }
                 reinterpret_cast<uint4*>(o)[0] = reinterpret_cast<const uint4*>(h)[0];
                 reinterpret_cast<uint4*>(o)[1] = reinterpret_cast<const uint4*>(h)[1];
               } else {

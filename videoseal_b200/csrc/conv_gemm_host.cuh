@@ -246,6 +246,31 @@ inline void setup_tma_gemm(ConvGemmOp& op, const __half* A, long M, int K, int l
   encode_map(&op.tmA, A, 2, dims, strides, box, p.kblk);
 }
 
+// A = [A0 | A1] virtual concat along K of two [M, K0] / [M, K1] fp16 matrices (row pitches ld0 / ld1)
+inline void setup_tma_gemm2(ConvGemmOp& op, const __half* A0, int K0, int ld0, const __half* A1, int K1, int ld1, long M) {
+  ConvGemmParams& p = op.p;
+  op.loader = LD_TMA;
+  p.a_is_conv = 0;
+  p.kblk = K0 >= 64 ? 64 : K0;
+  VSB_CHECK(p.kblk == 64 || p.kblk == 32 || p.kblk == 16, "TMA gemm2: K0 must be 16, 32 or a multiple of 64");
+  VSB_CHECK(K0 % p.kblk == 0 && K1 % p.kblk == 0, "TMA gemm2: K0, K1 must be multiples of the K block");
+  p.M = (int)M;
+  p.m_tiles = (int)((M + kBlockM - 1) / kBlockM);
+  p.c0_blocks = K0 / p.kblk;
+  p.num_kb = (K0 + K1) / p.kblk;
+  uint32_t box[2] = {(uint32_t)p.kblk, (uint32_t)kBlockM};
+  {
+    uint64_t dims[2] = {(uint64_t)K0, (uint64_t)M};
+    uint64_t strides[1] = {(uint64_t)ld0 * 2};
+    encode_map(&op.tmA, A0, 2, dims, strides, box, p.kblk);
+  }
+  {
+    uint64_t dims[2] = {(uint64_t)K1, (uint64_t)M};
+    uint64_t strides[1] = {(uint64_t)ld1 * 2};
+    encode_map(&op.tmA2, A1, 2, dims, strides, box, p.kblk);
+  }
+}
+
 // generic gathered conv: out[b,oy,ox,:] over taps (r,s) of the virtual concat [src0 (C0 ch) | src1 (C1 ch)]
 inline void setup_gather_conv(ConvGemmOp& op, int loader, const __half* src0, int C0, int ld0, const __half* src1, int C1, int ld1,
                               int B, int IH, int IW, int OH, int OW, int R, int S, int stride, int pad, int pad_mode) {
@@ -275,23 +300,42 @@ inline void setup_gather_scale(ConvGemmOp& op, const __half* G, long M, int K, i
   p.num_kb = (K + 63) / 64;
 }
 
-template <int LOADER>
+template <int LOADER, int ACT>
 inline void launch_one(const ConvGemmOp& op, cudaStream_t st) {
   static bool attr_set = false;
   if (!attr_set) {
-    VSB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<LOADER>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VSB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<LOADER, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
-  conv_gemm_kernel<LOADER><<<op.grid, op.threads, op.smem, st>>>(op.tmA, op.tmA2, op.tmB, op.p);
+  conv_gemm_kernel<LOADER, ACT><<<op.grid, op.threads, op.smem, st>>>(op.tmA, op.tmA2, op.tmB, op.p);
 }
 
+// instantiated (loader, activation) pairs: only what the networks need, to bound compile time
 inline void launch(const ConvGemmOp& op, cudaStream_t st) {
+  const int a = op.p.act;
   switch (op.loader) {
-    case LD_TMA: launch_one<LD_TMA>(op, st); break;
-    case LD_GATHER_CONV: launch_one<LD_GATHER_CONV>(op, st); break;
-    case LD_HALO_UPS: launch_one<LD_HALO_UPS>(op, st); break;
-    case LD_HALO_CONV3: launch_one<LD_HALO_CONV3>(op, st); break;
-    case LD_GATHER_SCALE: launch_one<LD_GATHER_SCALE>(op, st); break;
+    case LD_TMA:
+      if (a == ACT_NONE) launch_one<LD_TMA, ACT_NONE>(op, st);
+      else if (a == ACT_RELU) launch_one<LD_TMA, ACT_RELU>(op, st);
+      else launch_one<LD_TMA, ACT_GELU>(op, st);
+      break;
+    case LD_GATHER_CONV:
+      if (a == ACT_NONE) launch_one<LD_GATHER_CONV, ACT_NONE>(op, st);
+      else if (a == ACT_RELU) launch_one<LD_GATHER_CONV, ACT_RELU>(op, st);
+      else throw Error("gather conv: unsupported activation");
+      break;
+    case LD_HALO_UPS:
+      if (a == ACT_RELU) launch_one<LD_HALO_UPS, ACT_RELU>(op, st);
+      else throw Error("halo ups: unsupported activation");
+      break;
+    case LD_HALO_CONV3:
+      if (a == ACT_RELU) launch_one<LD_HALO_CONV3, ACT_RELU>(op, st);
+      else throw Error("halo conv3: unsupported activation");
+      break;
+    case LD_GATHER_SCALE:
+      if (a == ACT_NONE) launch_one<LD_GATHER_SCALE, ACT_NONE>(op, st);
+      else throw Error("gather scale: unsupported activation");
+      break;
     default: throw Error("bad loader");
   }
   VSB_CUDA(cudaGetLastError());

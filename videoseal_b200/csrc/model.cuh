@@ -273,11 +273,25 @@ class Model {
     cw.bias = bias.empty() ? nullptr : wpool.upload(bias);
     return cw;
   }
+  // UBlock up-conv as a low-resolution tap GEMM (see ups_gather_ln_kernel): rows n' = tap*Cout + co, K = concat channels
+  ConvW pack_upconv_taps(const std::string& wkey, const std::vector<float>& in_scale) {
+    const HostTensor& w = get(wkey);
+    VSB_CHECK(w.shape.size() == 4 && w.shape[2] == 3 && w.shape[3] == 3, "up conv weight shape");
+    const int Co = (int)w.shape[0], Ct = (int)w.shape[1];
+    std::vector<float> p((size_t)9 * Co * Ct);
+    for (int co = 0; co < Co; ++co)
+      for (int c = 0; c < Ct; ++c)
+        for (int t = 0; t < 9; ++t) p[((size_t)t * Co + co) * Ct + c] = w.data[((size_t)co * Ct + c) * 9 + t] * in_scale[c];
+    ConvW cw;
+    cw.N = 9 * Co; cw.K = Ct;
+    cw.w = wpool.upload(to_half(p));
+    return cw;
+  }
   int halo_max_c = -1;
   bool use_halo(int C) {
     if (halo_max_c < 0) {
       const char* e = getenv("VSB_HALO_MAXC");
-      halo_max_c = e ? atoi(e) : (1 << 30);
+      halo_max_c = e ? atoi(e) : 16;
     }
     return C <= halo_max_c;
   }
@@ -356,7 +370,7 @@ class Model {
         // virtual concat (x | skip * 2^-1/2): fold the skip scale into the second half of the input channels
         std::vector<float> in_scale(2 * zz[ii + 1], 1.0f);
         for (int c = zz[ii + 1]; c < 2 * zz[ii + 1]; ++c) in_scale[c] = 0.70710678118654752440f;
-        up_conv.push_back(pack_conv_halo(U + ".up.upsample_block.2.weight", nullptr, {}, zz[ii + 1], zz[ii + 1], &in_scale));
+        up_conv.push_back(pack_upconv_taps(U + ".up.upsample_block.2.weight", in_scale));
         up_lnw.push_back(wpool.upload(get(U + ".up.upsample_block.3.weight").data));
         up_lnb.push_back(wpool.upload(get(U + ".up.upsample_block.3.bias").data));
         up_rb.push_back(pack_resblock(U + ".conv"));
@@ -576,11 +590,23 @@ class Model {
       const long Mo = (long)B * ho * ho;
       __half* u = pl.pool.alloc_n<__half>(Mo * Cout);
       {
+        // channel mixing first, at low resolution: y[b,i,j, tap*Cout + co] = sum_c W[co,c,tap] * [x | skip/sqrt2][b,i,j,c]
+        const long Mi = (long)B * hs * hs;
+        __half* ytap = pl.pool.alloc_n<__half>(Mi * 9 * Cout);
         ConvGemmOp op;
-        setup_halo_ups(op, x, Cin, ldx, skip, Cin, ld_skip, B, hs, hs);
-        op.p.epi = EPI_LN; op.p.act = ACT_RELU; op.p.ln_w = up_lnw[j]; op.p.ln_b = up_lnb[j]; op.p.ln_eps = 1e-6f;
-        op.p.out16 = u; op.p.ld_out16 = Cout;
-        add_conv(pl, op, up_conv[j], "unet.up3x3." + std::to_string(2 * Cin) + "-" + std::to_string(Cout) + "@" + std::to_string(ho));
+        setup_tma_gemm2(op, x, Cin, ldx, skip, Cin, ld_skip, Mi);
+        op.p.epi = EPI_AFFINE; op.p.act = ACT_NONE; op.p.out16 = ytap; op.p.ld_out16 = 9 * Cout;
+        add_conv(pl, op, up_conv[j], "unet.uptap1x1." + std::to_string(2 * Cin) + "-" + std::to_string(9 * Cout) + "@" + std::to_string(hs));
+        // then bilinear x2 + reflect pad + 3x3 tap sum + LayerNorm + ReLU (CUDA cores, memory-bound)
+        const int IH = hs, Cc = Cout;
+        float *lw = up_lnw[j], *lb = up_lnb[j];
+        VSB_CHECK(Cc % 8 == 0 && Cc / 8 <= 32 && ((Cc / 8) & (Cc / 8 - 1)) == 0, "up conv: C_out must be 8 * 2^k <= 256");
+        pl.steps.push_back(Step{[=](cudaStream_t st) {
+          const int ppb = 256 / (Cc / 8);
+          const long blocks = (Mo + ppb - 1) / ppb;
+          ups_gather_ln_kernel<<<(unsigned)std::min<long>(blocks, 148L * 32), 256, 0, st>>>(ytap, B, IH, IH, Cc, lw, lb, 1e-6f, u, Cc);
+          VSB_CUDA(cudaGetLastError());
+        }, 1, "unet.upgather." + std::to_string(Cout) + "@" + std::to_string(ho)});
         dbg(pl, "up" + std::to_string(j) + "_conv", u, 1, B, ho, ho, Cout, Cout);
       }
       const bool last = (ii == 0);

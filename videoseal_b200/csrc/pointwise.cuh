@@ -285,6 +285,90 @@ __global__ void __launch_bounds__(256) jnd_lowres_kernel(const float* __restrict
 }
 
 // ------------------------------------------------------------------------------------------------
+// K3: second half of the UBlock up-conv (modules/common.py:45-52 after unet.py:187-190).  Because bilinear up-sampling,
+// reflection padding and the 3x3 taps are all linear, conv3x3(pad(up(x))) == sum_taps shift_tap(pad(up(W_tap x))): the channel
+// mixing is done FIRST at low resolution by one tensor-core GEMM  y[b,i,j, tap*C + co] = sum_c W[co,c,tap] x[b,i,j,c]
+// (4x fewer MACs than convolving the up-sampled map, no im2col), and this kernel does the cheap spatial part
+//   out[b,oy,ox,co] = act(LN_c( sum_{r,s} bilinear_x2( y[.., (3r+s)*C + co] )(reflect(oy+r-1), reflect(ox+s-1)) ))
+// One group of C/8 threads per output pixel (8 channels = one 16-byte load per thread and tap corner).
+__global__ void __launch_bounds__(256) ups_gather_ln_kernel(const __half* __restrict__ y, int B, int IH, int IW, int C,
+                                                            const float* __restrict__ lnw, const float* __restrict__ lnb, float eps,
+                                                            __half* __restrict__ out, int ld_out) {
+  const int G = C >> 3;                       // threads per pixel (power of two, <= 32)
+  const int OH = 2 * IH, OW = 2 * IW;
+  const long npix = (long)B * OH * OW;
+  const int ppb = 256 / G;                    // pixels per block
+  const int lane_g = threadIdx.x % G;
+  const long ldy = 9L * C;
+  for (long pix = (long)blockIdx.x * ppb + threadIdx.x / G; pix < npix; pix += (long)gridDim.x * ppb) {
+    const int ox = (int)(pix % OW);
+    const long t = pix / OW;
+    const int oy = (int)(t % OH), b = (int)(t / OH);
+    int ya[3], yb[3], xa[3], xb[3];
+    float wy[3], wx[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      int u = oy + r - 1;
+      if (u < 0) u = -u;
+      if (u >= OH) u = 2 * OH - 2 - u;
+      const int i = u >> 1;
+      if (u & 1) { ya[r] = i; yb[r] = min(i + 1, IH - 1); wy[r] = 0.75f; }
+      else       { ya[r] = max(i - 1, 0); yb[r] = i; wy[r] = 0.25f; }
+      int v = ox + r - 1;
+      if (v < 0) v = -v;
+      if (v >= OW) v = 2 * OW - 2 - v;
+      const int jx = v >> 1;
+      if (v & 1) { xa[r] = jx; xb[r] = min(jx + 1, IW - 1); wx[r] = 0.75f; }
+      else       { xa[r] = max(jx - 1, 0); xb[r] = jx; wx[r] = 0.25f; }
+    }
+    float acc[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    const __half* yb_ = y + (long)b * IH * IW * ldy + lane_g * 8;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+      for (int s = 0; s < 3; ++s) {
+        const __half* base = yb_ + (r * 3 + s) * C;
+        const uint4 v00 = __ldg(reinterpret_cast<const uint4*>(base + ((long)ya[r] * IW + xa[s]) * ldy));
+        const uint4 v01 = __ldg(reinterpret_cast<const uint4*>(base + ((long)ya[r] * IW + xb[s]) * ldy));
+        const uint4 v10 = __ldg(reinterpret_cast<const uint4*>(base + ((long)yb[r] * IW + xa[s]) * ldy));
+        const uint4 v11 = __ldg(reinterpret_cast<const uint4*>(base + ((long)yb[r] * IW + xb[s]) * ldy));
+        const float w00 = wy[r] * wx[s], w01 = wy[r] * (1.f - wx[s]), w10 = (1.f - wy[r]) * wx[s], w11 = (1.f - wy[r]) * (1.f - wx[s]);
+        const __half2* p00 = reinterpret_cast<const __half2*>(&v00);
+        const __half2* p01 = reinterpret_cast<const __half2*>(&v01);
+        const __half2* p10 = reinterpret_cast<const __half2*>(&v10);
+        const __half2* p11 = reinterpret_cast<const __half2*>(&v11);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const float2 a = __half22float2(p00[k]), bq = __half22float2(p01[k]), cq = __half22float2(p10[k]), d = __half22float2(p11[k]);
+          acc[2 * k] += w00 * a.x + w01 * bq.x + w10 * cq.x + w11 * d.x;
+          acc[2 * k + 1] += w00 * a.y + w01 * bq.y + w10 * cq.y + w11 * d.y;
+        }
+      }
+    }
+    // channels-first LayerNorm over the C channels of this pixel (biased variance) + ReLU
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) sum += acc[k];
+    for (int o = G >> 1; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / (float)C;
+    float var = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8; ++k) { const float d = acc[k] - mean; var += d * d; }
+    for (int o = G >> 1; o; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+    const float rstd = 1.0f / sqrtf(var / (float)C + eps);
+    __align__(16) __half h[8];
+#pragma unroll
+    for (int k = 0; k < 8; ++k) {
+      const int c = lane_g * 8 + k;
+      h[k] = __float2half_rn(fmaxf((acc[k] - mean) * rstd * __ldg(lnw + c) + __ldg(lnb + c), 0.f));
+    }
+    *reinterpret_cast<uint4*>(out + pix * ld_out + lane_g * 8) = *reinterpret_cast<const uint4*>(h);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // K9: ConvNeXt stem: x = 2*img-1 (extractor.py:25); conv k4 stride s (no padding) + bias; channels-first LN eps 1e-6
 // (convnext.py:108-111).  imgs [B,3,H,W] fp32 -> out NHWC fp32 [B,OH,OW,C] (row pitch ld).  One warp per output pixel.
 __global__ void __launch_bounds__(256) stem_ln_kernel(const float* __restrict__ imgs, int B, int H, int W, int OH, int OW, int stride,
