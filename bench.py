@@ -105,6 +105,8 @@ def conv_flops(name: str, B: int) -> float:
         if kind in ("cnx.pwconv1", "cnx.pwconv2"):
             c = int(dims)
             return 2.0 * M * c * 4 * c
+        if kind == "cnx.stem_gemm":
+            return 2.0 * M * int(dims) * 48
         if kind == "cnx.head3x3":
             c = int(dims)
             return 2.0 * M * c * 9 * c

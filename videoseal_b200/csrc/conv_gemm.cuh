@@ -387,7 +387,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             float v[16];
             tmem_ld16(trow + c, v);
 #pragma unroll
-            for (int j = 0; j < 16; ++j) sum += (c + j < N) ? v[j] : 0.f;
+            for (int j = 0; j < 16; ++j) sum += (c + j < N) ? v[j] + sb[c + j] : 0.f;
           }
           const float mean = sum / (float)N;
           float var = 0.f;
@@ -396,7 +396,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             tmem_ld16(trow + c, v);
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              const float d = v[j] - mean;
+              const float d = v[j] + sb[c + j] - mean;
               var += (c + j < N) ? d * d : 0.f;
             }
           }
@@ -405,25 +405,39 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             float v[16];
             tmem_ld16(trow + c, v);
             if (c >= N) continue;
-            __align__(16) __half h[16];
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
               const int n = c + j;
               float y = 0.f;
               if (n < N) {
-                y = (v[j] - mean) * rstd * s_lnw[n] + s_lnb[n];
+                y = (v[j] + sb[c + j] - mean) * rstd * s_lnw[n] + s_lnb[n];
                 if (ACT == ACT_RELU) y = fmaxf(y, 0.f);
                 else if (ACT == ACT_GELU) y = gelu_erf(y);
               }
-              h[j] = __float2half_rn(y);
+              v[j] = y;
             }
             if (mvalid) {
-              __half* o = p.out16 + m * p.ld_out16 + c;
-              if (c + 16 <= N) {
-                reinterpret_cast<uint4*>(o)[0] = reinterpret_cast<const uint4*>(h)[0];
-                reinterpret_cast<uint4*>(o)[1] = reinterpret_cast<const uint4*>(h)[1];
-              } else {
-                for (int j = 0; j < 16 && c + j < N; ++j) o[j] = h[j];
+              if (p.out32 != nullptr) {
+                float* o = p.out32 + m * p.ld_out32 + c;
+                if (c + 16 <= N) {
+#pragma unroll
+                  for (int u = 0; u < 4; ++u)
+                    reinterpret_cast<float4*>(o)[u] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+                } else {
+                  for (int j = 0; j < 16 && c + j < N; ++j) o[j] = v[j];
+                }
+              }
+              if (p.out16 != nullptr) {
+                __align__(16) __half h[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) h[j] = __float2half_rn(v[j]);
+                __half* o = p.out16 + m * p.ld_out16 + c;
+                if (c + 16 <= N) {
+                  reinterpret_cast<uint4*>(o)[0] = reinterpret_cast<const uint4*>(h)[0];
+                  reinterpret_cast<uint4*>(o)[1] = reinterpret_cast<const uint4*>(h)[1];
+                } else {
+                  for (int j = 0; j < 16 && c + j < N; ++j) o[j] = h[j];
+                }
               }
             }
           }

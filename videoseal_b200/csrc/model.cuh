@@ -187,7 +187,8 @@ class Model {
   float *outc_w = nullptr, *outc_b = nullptr;
   float* msg_table = nullptr;
   // extractor
-  float *stem_w = nullptr, *stem_b = nullptr, *stem_lnw = nullptr, *stem_lnb = nullptr;
+  __half* stem_w16 = nullptr;
+  float *stem_b = nullptr, *stem_lnw = nullptr, *stem_lnb = nullptr;
   struct DsW { float* lnw; float* lnb; ConvW conv; };
   std::vector<DsW> ds;
   struct CnBlockW { float* dww; float* dwb; float* lnw; float* lnb; ConvW pw1; float* gamma; ConvW pw2; };
@@ -390,9 +391,9 @@ class Model {
       const HostTensor& w = get(Q + "downsample_layers.0.0.weight");  // [C0][3][4][4]
       const int C0 = d.ext_dims[0];
       VSB_CHECK((int)w.shape[0] == C0 && w.shape[1] == 3 && w.shape[2] == 4, "stem shape");
-      std::vector<float> t((size_t)48 * C0);
-      for (int c = 0; c < C0; ++c) for (int k = 0; k < 48; ++k) t[(size_t)k * C0 + c] = w.data[(size_t)c * 48 + k];
-      stem_w = wpool.upload(t);
+      std::vector<float> t((size_t)C0 * 64, 0.f);   // GEMM operand [C0][64], K = (c, r, t) zero-padded 48 -> 64
+      for (int c = 0; c < C0; ++c) for (int k = 0; k < 48; ++k) t[(size_t)c * 64 + k] = w.data[(size_t)c * 48 + k];
+      stem_w16 = wpool.upload(to_half(t));
       stem_b = wpool.upload(get(Q + "downsample_layers.0.0.bias").data);
       stem_lnw = wpool.upload(get(Q + "downsample_layers.0.1.weight").data);
       stem_lnb = wpool.upload(get(Q + "downsample_layers.0.1.bias").data);
@@ -633,14 +634,22 @@ class Model {
     int C = d.ext_dims[0];
     float* x = pl.pool.alloc_n<float>((size_t)B * hs * hs * C);
     {
-      const int OH = hs, Cc = C;
-      float *w = stem_w, *b = stem_b, *lw = stem_lnw, *lb = stem_lnb;
+      // stem (convnext.py:108-111): im2col of the k4 patches (x = 2*img-1 folded) -> tensor-core GEMM [M,64]x[64,C0] with the
+      // conv bias and the channels-first LayerNorm fused into the epilogue, fp32 NHWC output (the residual stream)
+      const int OH = hs;
+      const long M = (long)B * OH * OH;
+      __half* patches = pl.pool.alloc_n<__half>(M * 64);
       pl.steps.push_back(Step{[=](cudaStream_t st) {
-        const long npix = (long)B * OH * OH;
-        const int grid = (int)std::min<long>((npix + 7) / 8, 148L * 16);
-        stem_ln_kernel<<<grid, 256, 8 * (48 + Cc) * sizeof(float), st>>>(plp->in_imgs, B, S, S, OH, OH, st_, w, b, lw, lb, Cc, x, Cc);
+        const long total = M * 4;
+        const int grid = (int)std::min<long>((total + 255) / 256, 148L * 32);
+        stem_im2col_kernel<<<grid, 256, 0, st>>>(plp->in_imgs, B, S, S, OH, OH, st_, patches);
         VSB_CUDA(cudaGetLastError());
-      }, 1, "cnx.stem"});
+      }, 1, "cnx.stem_im2col"});
+      ConvGemmOp op; setup_tma_gemm(op, patches, M, 64, 64);
+      op.p.epi = EPI_LN; op.p.act = ACT_NONE; op.p.bias = stem_b; op.p.ln_w = stem_lnw; op.p.ln_b = stem_lnb; op.p.ln_eps = 1e-6f;
+      op.p.out32 = x; op.p.ld_out32 = C;
+      ConvW sw; sw.w = stem_w16; sw.N = C; sw.K = 64; sw.bias = stem_b;
+      add_conv(pl, op, sw, "cnx.stem_gemm." + std::to_string(C) + "@" + std::to_string(hs));
       dbg(pl, "ds0", x, 0, B, hs, hs, C, C);
     }
     int maxK4 = 0;
@@ -684,11 +693,14 @@ class Model {
           float *dww = w.dww, *dwb = w.dwb, *lw = w.lnw, *lb = w.lnb;
           pl.steps.push_back(Step{[=](cudaStream_t st) {
             const int strips = (H + kDwStrip - 1) / kDwStrip;
-            const long blocks = (long)B * H * strips;
-            int threads = ((Cc / 2 + 31) / 32) * 32;
-            if (threads > 256) threads = 256;
-            if (threads < 64) threads = 64;
-            dwconv7_ln_kernel<<<(unsigned)blocks, threads, kDwStrip * Cc * sizeof(float), st>>>(xin, B, H, H, Cc, Cc, dww, dwb, lw, lb, a, Cc);
+            const long nstrips = (long)B * H * strips;
+            const int C2 = Cc / 2;
+            int spb = 1;
+            for (int s2 = 1; s2 <= 4; s2 *= 2) if ((s2 * C2) % 32 == 0 && s2 * C2 <= 512) { spb = s2; break; }
+            if (spb * C2 > 768) throw Error("dwconv7: C/2 > 768 threads is not implemented (unsupported chunky extractor width)");
+            const long blocks = (nstrips + spb - 1) / spb;
+            dwconv7_ln_kernel<<<(unsigned)blocks, spb * C2, (size_t)spb * kDwStrip * Cc * sizeof(float), st>>>(
+                xin, B, H, H, Cc, Cc, dww, dwb, lw, lb, a, Cc, spb, nstrips);
             VSB_CUDA(cudaGetLastError());
           }, 1, "cnx.dwconv7_ln"});
         }
@@ -707,7 +719,16 @@ class Model {
           }, 1, "cnx.grn_scale"});
         }
         {
-          ConvGemmOp op; setup_gather_scale(op, g, M, 4 * C, 4 * C, scale, 4 * C, rows_per_sample);
+          const int K4 = 4 * C;
+          pl.steps.push_back(Step{[=](cudaStream_t st) {
+            const long total = M * (K4 / 8);
+            const int grid = (int)std::min<long>((total + 255) / 256, 148L * 32);
+            grn_apply_kernel<<<grid, 256, 0, st>>>(g, M, K4, K4, scale, K4, rows_per_sample);
+            VSB_CUDA(cudaGetLastError());
+          }, 1, "cnx.grn_apply"});
+        }
+        {
+          ConvGemmOp op; setup_tma_gemm(op, g, M, 4 * C, 4 * C);
           op.p.epi = EPI_AFFINE; op.p.act = ACT_NONE; op.p.bias = w.pw2.bias; op.p.resid32 = x; op.p.ld_res32 = C;
           op.p.out32 = x; op.p.ld_out32 = C;  // in place: each element is read and written by the same thread
           if (s == 3 && jb == d.ext_depths[s] - 1) {

@@ -415,19 +415,32 @@ __global__ void __launch_bounds__(256) stem_ln_kernel(const float* __restrict__ 
 // x: NHWC fp32 [B, H, W, C] (pixel pitch ldx).  One block = one strip of kDwStrip output pixels along x; each thread owns
 // a channel pair and slides over the 7 x (strip+6) input window; pre-LN results go to smem, then LN per pixel by warps.
 constexpr int kDwStrip = 8;
-__global__ void __launch_bounds__(256) dwconv7_ln_kernel(const float* __restrict__ x, int B, int H, int W, int C, int ldx,
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {   // Blackwell packed fp32 FMA (2 MACs / instruction)
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<const unsigned long long&>(a)), "l"(reinterpret_cast<const unsigned long long&>(b)),
+        "l"(reinterpret_cast<const unsigned long long&>(c)));
+  return d;
+}
+// blockDim.x = spb * C/2 threads: `spb` strips per block so that every warp is full
+__global__ void __launch_bounds__(768) dwconv7_ln_kernel(const float* __restrict__ x, int B, int H, int W, int C, int ldx,
                                                          const float* __restrict__ wdw /*[49][C]*/, const float* __restrict__ bdw,
                                                          const float* __restrict__ lnw, const float* __restrict__ lnb,
-                                                         __half* __restrict__ out, int ld_out) {
-  extern __shared__ float pre[];  // [kDwStrip][C]
+                                                         __half* __restrict__ out, int ld_out, int spb, long nstrips) {
+  extern __shared__ float pre[];  // [spb][kDwStrip][C]
   const int strips_x = (W + kDwStrip - 1) / kDwStrip;
-  const long strip = blockIdx.x;
-  const int sx = (int)(strip % strips_x);
-  const long t = strip / strips_x;
-  const int oy = (int)(t % H), b = (int)(t / H);
-  const int ox0 = sx * kDwStrip;
   const int C2 = C >> 1;
-  for (int cp = threadIdx.x; cp < C2; cp += blockDim.x) {
+  const int ls = threadIdx.x / C2;                 // local strip
+  const int cp = threadIdx.x - ls * C2;            // channel pair
+  const long strip = (long)blockIdx.x * spb + ls;
+  const bool active = (ls < spb) && (strip < nstrips);
+  int sx = 0, oy = 0, b = 0, ox0 = 0;
+  if (active) {
+    sx = (int)(strip % strips_x);
+    const long t = strip / strips_x;
+    oy = (int)(t % H); b = (int)(t / H);
+    ox0 = sx * kDwStrip;
     const int c = cp * 2;
     float2 acc[kDwStrip];
     const float2 bb = __ldg(reinterpret_cast<const float2*>(bdw + c));
@@ -438,7 +451,7 @@ __global__ void __launch_bounds__(256) dwconv7_ln_kernel(const float* __restrict
       if (iy < 0 || iy >= H) continue;
       float2 wr[7];
 #pragma unroll
-      for (int s = 0; s < 7; ++s) wr[s] = __ldg(reinterpret_cast<const float2*>(wdw + (r * 7 + s) * C + c));
+      for (int s2 = 0; s2 < 7; ++s2) wr[s2] = __ldg(reinterpret_cast<const float2*>(wdw + (r * 7 + s2) * C + c));
       const float* rowp = x + (((long)b * H + iy) * W) * ldx + c;
 #pragma unroll
       for (int u = 0; u < kDwStrip + 6; ++u) {
@@ -446,21 +459,28 @@ __global__ void __launch_bounds__(256) dwconv7_ln_kernel(const float* __restrict
         float2 v = make_float2(0.f, 0.f);
         if (ix >= 0 && ix < W) v = __ldg(reinterpret_cast<const float2*>(rowp + (long)ix * ldx));
 #pragma unroll
-        for (int s = 0; s < 7; ++s) {
-          const int i = u - s;  // output pixel index within the strip
-          if (i >= 0 && i < kDwStrip) { acc[i].x += v.x * wr[s].x; acc[i].y += v.y * wr[s].y; }
+        for (int s2 = 0; s2 < 7; ++s2) {
+          const int i = u - s2;  // output pixel index within the strip
+          if (i >= 0 && i < kDwStrip) acc[i] = ffma2(v, wr[s2], acc[i]);
         }
       }
     }
+    float* pr = pre + (size_t)ls * kDwStrip * C;
 #pragma unroll
-    for (int i = 0; i < kDwStrip; ++i) { pre[i * C + c] = acc[i].x; pre[i * C + c + 1] = acc[i].y; }
+    for (int i = 0; i < kDwStrip; ++i) { pr[i * C + c] = acc[i].x; pr[i * C + c + 1] = acc[i].y; }
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int i = warp; i < kDwStrip; i += nwarps) {
-    const int ox = ox0 + i;
+  for (int item = warp; item < spb * kDwStrip; item += nwarps) {
+    const int l2 = item / kDwStrip, i = item - l2 * kDwStrip;
+    const long st2 = (long)blockIdx.x * spb + l2;
+    if (st2 >= nstrips) continue;
+    const int sx2 = (int)(st2 % strips_x);
+    const long t2 = st2 / strips_x;
+    const int oy2 = (int)(t2 % H), b2 = (int)(t2 / H);
+    const int ox = sx2 * kDwStrip + i;
     if (ox >= W) continue;
-    const float* pr = pre + i * C;
+    const float* pr = pre + ((size_t)l2 * kDwStrip + i) * C;
     float sum = 0.f;
     for (int c = lane; c < C; c += 32) sum += pr[c];
 #pragma unroll
@@ -471,7 +491,7 @@ __global__ void __launch_bounds__(256) dwconv7_ln_kernel(const float* __restrict
 #pragma unroll
     for (int o = 16; o; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
     const float rstd = 1.0f / sqrtf(var / (float)C + 1e-6f);
-    __half* dst = out + (((long)b * H + oy) * W + ox) * ld_out;
+    __half* dst = out + (((long)b2 * H + oy2) * W + ox) * ld_out;
     for (int c = lane * 2; c < C; c += 64) {
       const float a = (pr[c] - mean) * rstd * __ldg(lnw + c) + __ldg(lnb + c);
       const float bq = (pr[c + 1] - mean) * rstd * __ldg(lnw + c + 1) + __ldg(lnb + c + 1);
@@ -525,6 +545,57 @@ __global__ void __launch_bounds__(256) grn_scale_kernel(float* __restrict__ stat
   for (int k = threadIdx.x; k < K; k += blockDim.x) {
     scale[(long)b * ld_scale + k] = __ldg(gamma + k) * (sqrtf(st[k]) * inv) + 1.0f;
     st[k] = 0.f;
+  }
+}
+
+// K2d: apply the GRN multiplier in place: g[m, k] *= scale[m / rows_per_sample, k]  (fp16, 128-bit vectorised).  For all but
+// the first stage g fits in the 126 MB L2, so this pass mostly runs out of L2; pwconv2 is then a plain TMA-fed GEMM.
+__global__ void __launch_bounds__(256) grn_apply_kernel(__half* __restrict__ g, long M, int K, int ld, const float* __restrict__ scale,
+                                                        int ld_scale, int rows_per_sample) {
+  const int k8 = K >> 3;
+  const long total = M * k8;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const long m = i / k8;
+    const int k = (int)(i - m * k8) * 8;
+    const float* sc = scale + (m / rows_per_sample) * ld_scale + k;
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(sc)), s1 = __ldg(reinterpret_cast<const float4*>(sc) + 1);
+    uint4* ptr = reinterpret_cast<uint4*>(g + m * ld + k);
+    uint4 v = *ptr;
+    __half2* h = reinterpret_cast<__half2*>(&v);
+    float2 f;
+    f = __half22float2(h[0]); f.x *= s0.x; f.y *= s0.y; h[0] = __float22half2_rn(f);
+    f = __half22float2(h[1]); f.x *= s0.z; f.y *= s0.w; h[1] = __float22half2_rn(f);
+    f = __half22float2(h[2]); f.x *= s1.x; f.y *= s1.y; h[2] = __float22half2_rn(f);
+    f = __half22float2(h[3]); f.x *= s1.z; f.y *= s1.w; h[3] = __float22half2_rn(f);
+    *ptr = v;
+  }
+}
+
+// K9a: stem im2col: x = 2*img-1 (extractor.py:25) patches of the k4 conv (stride s, no padding) -> fp16 [M, 64] rows
+// (k = c*16 + r*4 + t for k < 48, zero for 48..63) for the tensor-core stem GEMM.  One thread per (pixel, channel c).
+__global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ imgs, int B, int H, int W, int OH, int OW, int stride,
+                                                          __half* __restrict__ out) {
+  const long total = (long)B * OH * OW * 4;
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+    const int c = (int)(i & 3);
+    const long pix = i >> 2;
+    __align__(16) __half h[16];
+    if (c < 3) {
+      const int ox = (int)(pix % OW);
+      const long t = pix / OW;
+      const int oy = (int)(t % OH), b = (int)(t / OH);
+      const float* src = imgs + ((long)(b * 3 + c) * H + oy * stride) * W + ox * stride;
+#pragma unroll
+      for (int r = 0; r < 4; ++r)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) h[r * 4 + q] = __float2half_rn(2.f * __ldg(src + (long)r * W + q) - 1.f);
+    } else {
+#pragma unroll
+      for (int q = 0; q < 16; ++q) h[q] = __float2half_rn(0.f);
+    }
+    uint4* dst = reinterpret_cast<uint4*>(out + pix * 64 + c * 16);
+    dst[0] = reinterpret_cast<const uint4*>(h)[0];
+    dst[1] = reinterpret_cast<const uint4*>(h)[1];
   }
 }
 
