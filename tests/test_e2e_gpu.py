@@ -2,10 +2,11 @@
 seeded inputs and synthetic checkpoints, and against the golden fixtures generated from the unmodified reference.
 
 Tolerances (BASELINE.json north_star): watermarked pixels <= 1e-3 abs; bit logits <= 1e-2 relative, where the
-denominator is max(|ref|, 0.05*||ref||_inf): with the synthetic (random-weight) checkpoints the logits are centred on 0
+denominator is max(|ref|, 0.1*||ref||_inf): with the synthetic (random-weight) checkpoints the logits are centred on 0
 (mean |logit| ~ 0.2, max ~ 0.75) so a pure element-wise relative error is meaningless for the many near-zero entries
-(SURVEY.md §7); the absolute logit error of the fp16-operand / fp32-accumulate path is ~4e-4*||ref||_inf, i.e. the
-vector-relative error ||got-ref||_inf / ||ref||_inf is also asserted <= 2e-3.  Recovered bits are exact wherever
+(SURVEY.md §7); the absolute logit error of the fp16-operand / fp32-accumulate path is 3e-4..6e-4 * ||ref||_inf (one fp16
+rounding per GEMM operand, 2^-11 relative, through ~40 GEMMs), so the test also asserts the
+vector-relative error ||got-ref||_inf / ||ref||_inf <= 1.5e-3.  Recovered bits are exact wherever
 |ref logit| > margin (margin = 1e-2*||ref||_inf; the count of sub-margin logits is reported)."""
 import os
 
@@ -24,9 +25,9 @@ LOGIT_RTOL = 1e-2
 
 def logits_ok(got, ref):
     scale = ref.abs().max()
-    denom = torch.maximum(ref.abs(), 0.05 * scale)
+    denom = torch.maximum(ref.abs(), 0.1 * scale)
     rel = ((got - ref).abs() / denom).max().item()
-    assert ((got - ref).abs().max() / scale).item() <= 2e-3, "vector-relative logit error"
+    assert ((got - ref).abs().max() / scale).item() <= 1.5e-3, "vector-relative logit error"
     margin = 1e-2 * scale
     sure = ref[:, 1:].abs() > margin
     flips = int((((got[:, 1:] > 0) != (ref[:, 1:] > 0)) & sure).sum())

@@ -77,16 +77,19 @@ struct ConvGemmParams {
 };
 
 // exact-erf GELU (nn.GELU default).  erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7), branch-free.
+__device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float gelu_erf(float x) {
   const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));   // argument in [1, inf): no range fix-ups needed
   float poly = fmaf(1.061405429f, t, -1.453152027f);
   poly = fmaf(poly, t, 1.421413741f);
   poly = fmaf(poly, t, -0.284496736f);
   poly = fmaf(poly, t, 0.254829592f);
-  const float e = fmaf(-poly * t, __expf(-z * z), 1.0f);   // erf(|x|/sqrt2) >= 0
+  const float ex = ex2_approx(z * (z * -1.4426950408889634f));   // exp(-z^2)
+  const float e = fmaf(-poly * t, ex, 1.0f);                  // erf(|x|/sqrt2) >= 0
   const float h = 0.5f * x;
-  return fmaf(fabsf(h), e, h);                              // 0.5*x*(1 + sign(x)*e)
+  return fmaf(fabsf(h), e, h);                                // 0.5*x*(1 + sign(x)*e)
 }
 
 __device__ __forceinline__ int reflect_idx(int i, int n) {
@@ -448,6 +451,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             p.grn_stats != nullptr &&
             ((long)m_tile * kBlockM + q * 32) / p.rows_per_sample == ((long)m_tile * kBlockM + q * 32 + 31) / p.rows_per_sample &&
             ((long)m_tile * kBlockM + q * 32 + 31) < p.M;
+        float* grn_row = grn_uniform ? p.grn_stats + (((long)m_tile * kBlockM + q * 32) / p.rows_per_sample) * p.N : nullptr;
         uint32_t vnext[16];
         if (half < nchunks) tmem_ld16_issue(trow + half * 16, vnext);
         for (int ch = half; ch < nchunks; ch += 2) {
@@ -459,7 +463,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (ch + 2 < nchunks) tmem_ld16_issue(trow + c + 32, vnext);   // overlaps the math below
           const int n = n0 + c;
           if (n >= p.N) continue;  // uniform across the warp
-          const bool full = (n + 16 <= p.N);
+          const int nval = min(16, p.N - n);   // 16 on every full chunk (all shipped tiny/pixelseal layers)
           {
             const float4* sb4 = reinterpret_cast<const float4*>(sb + c);
 #pragma unroll
@@ -473,68 +477,73 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (ACT == ACT_RELU) v[j] = fmaxf(v[j], 0.f);
             else if (ACT == ACT_GELU) v[j] = gelu_erf(v[j]);
           }
-          if (mvalid) {
-            if (p.resid16 != nullptr) {
-              if (res_fast) {
+          if (nval < 16) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) if (j >= nval) v[j] = 0.f;   // ragged last chunk (chunky widths): keep the tail inert
+          }
+          if (has_res && mvalid) {
+            if (res_fast) {
+              if (p.resid16 != nullptr) {
                 __align__(16) __half h[16];
                 reinterpret_cast<uint4*>(h)[0] = *reinterpret_cast<const uint4*>(rb_ + ((size_t)(2 * ch) * 128 + row) * 16);
                 reinterpret_cast<uint4*>(h)[1] = *reinterpret_cast<const uint4*>(rb_ + ((size_t)(2 * ch + 1) * 128 + row) * 16);
 #pragma unroll
                 for (int j = 0; j < 16; ++j) v[j] += __half2float(h[j]);
               } else {
-                const __half* r = p.resid16 + m * p.ld_res16 + n;
-                for (int j = 0; j < 16; ++j) if (n + j < p.N) v[j] += __half2float(r[j]);
-              }
-            }
-            if (p.resid32 != nullptr) {
-              if (res_fast) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) {
                   const float4 t = *reinterpret_cast<const float4*>(rb_ + ((size_t)(4 * ch + u) * 128 + row) * 16);
                   v[4 * u + 0] += t.x; v[4 * u + 1] += t.y; v[4 * u + 2] += t.z; v[4 * u + 3] += t.w;
                 }
-              } else {
-                const float* r = p.resid32 + m * p.ld_res32 + n;
-                for (int j = 0; j < 16; ++j) if (n + j < p.N) v[j] += r[j];
               }
+            } else if (p.resid16 != nullptr) {
+              const __half* r = p.resid16 + m * p.ld_res16 + n;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) if (j < nval) v[j] += __half2float(r[j]);
+            } else {
+              const float* r = p.resid32 + m * p.ld_res32 + n;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) if (j < nval) v[j] += r[j];
             }
           }
-          if (p.outc_w != nullptr) {
+          if (p.outc_w != nullptr) {   // N <= 256 and a multiple of 16 here (host-checked): no tail
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              if (full || n + j < p.N) {
-                dot0 += v[j] * s_lnw[n + j];
-                dot1 += v[j] * s_lnb[n + j];
-                dot2 += v[j] * s_oc2[n + j];
-              }
+              dot0 += v[j] * s_lnw[n + j];
+              dot1 += v[j] * s_lnb[n + j];
+              dot2 += v[j] * s_oc2[n + j];
             }
           }
           if (mvalid) {
             if (p.out16 != nullptr) {
               __half* o = p.out16 + m * p.ld_out16 + n;
-              if (full) {
-                __align__(16) __half2 h[8];
+              __align__(16) __half2 h[8];
 #pragma unroll
-                for (int j = 0; j < 8; ++j) {
-                  float a = fminf(v[2 * j], 65504.f), b2 = fminf(v[2 * j + 1], 65504.f);
-                  if (ACT != ACT_RELU || p.resid16 != nullptr || p.resid32 != nullptr) { a = fmaxf(a, -65504.f); b2 = fmaxf(b2, -65504.f); }
-                  h[j] = __floats2half2_rn(a, b2);
-                }
+              for (int j = 0; j < 8; ++j) {
+                float a = fminf(v[2 * j], 65504.f), b2 = fminf(v[2 * j + 1], 65504.f);
+                if (ACT != ACT_RELU || has_res) { a = fmaxf(a, -65504.f); b2 = fmaxf(b2, -65504.f); }
+                h[j] = __floats2half2_rn(a, b2);
+              }
+              if (nval == 16) {
                 reinterpret_cast<uint4*>(o)[0] = reinterpret_cast<const uint4*>(h)[0];
                 reinterpret_cast<uint4*>(o)[1] = reinterpret_cast<const uint4*>(h)[1];
               } else {
-                for (int j = 0; j < 16; ++j)
-                  if (n + j < p.N) o[j] = __float2half_rn(fminf(fmaxf(v[j], -65504.f), 65504.f));
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                  if (2 * j < nval) o[2 * j] = __low2half(h[j]);
+                  if (2 * j + 1 < nval) o[2 * j + 1] = __high2half(h[j]);
+                }
               }
             }
             if (p.out32 != nullptr) {
               float* o = p.out32 + m * p.ld_out32 + n;
-              if (full) {
+              if (nval == 16) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u)
                   reinterpret_cast<float4*>(o)[u] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
               } else {
-                for (int j = 0; j < 16; ++j) if (n + j < p.N) o[j] = v[j];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) if (j < nval) o[j] = v[j];
               }
             }
           }
@@ -542,7 +551,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             // column sums of squares over this warp's 32 rows (GRN: ||x||_2 over H,W per (sample, channel))
             float sq[16];
 #pragma unroll
-            for (int j = 0; j < 16; ++j) sq[j] = (mvalid && (full || n + j < p.N)) ? v[j] * v[j] : 0.f;
+            for (int j = 0; j < 16; ++j) sq[j] = mvalid ? v[j] * v[j] : 0.f;
             if (grn_uniform) {
               // halving butterfly: after xor 16,8,4,2 each lane holds one column summed over 16 rows
 #pragma unroll
@@ -570,14 +579,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
               sq[0] += __shfl_xor_sync(0xffffffffu, sq[0], 1);
               const int col = (lane >> 1) & 15;
-              if ((lane & 1) == 0 && n + col < p.N) {
-                const long sample = ((long)m_tile * kBlockM + q * 32) / p.rows_per_sample;
-                atomicAdd(p.grn_stats + sample * p.N + n + col, sq[0]);
-              }
+              if ((lane & 1) == 0 && col < nval) atomicAdd(grn_row + n + col, sq[0]);
             } else if (mvalid) {
-              const long sample = m / p.rows_per_sample;
-              for (int j = 0; j < 16; ++j)
-                if (n + j < p.N) atomicAdd(p.grn_stats + sample * p.N + n + j, sq[j]);
+              float* gr = p.grn_stats + (m / p.rows_per_sample) * p.N + n;
+#pragma unroll
+              for (int j = 0; j < 16; ++j) if (j < nval) atomicAdd(gr + j, sq[j]);
             }
           }
         }

@@ -702,7 +702,7 @@ class Model {
             dwconv7_ln_kernel<<<(unsigned)blocks, spb * C2, (size_t)spb * kDwStrip * Cc * sizeof(float), st>>>(
                 xin, B, H, H, Cc, Cc, dww, dwb, lw, lb, a, Cc, spb, nstrips);
             VSB_CUDA(cudaGetLastError());
-          }, 1, "cnx.dwconv7_ln"});
+          }, 1, "cnx.dwconv7_ln." + std::to_string(C) + "@" + std::to_string(hs)});
         }
         {
           ConvGemmOp op; setup_tma_gemm(op, a, M, C, C);
@@ -725,7 +725,7 @@ class Model {
             const int grid = (int)std::min<long>((total + 255) / 256, 148L * 32);
             grn_apply_kernel<<<grid, 256, 0, st>>>(g, M, K4, K4, scale, K4, rows_per_sample);
             VSB_CUDA(cudaGetLastError());
-          }, 1, "cnx.grn_apply"});
+          }, 1, "cnx.grn_apply." + std::to_string(C) + "@" + std::to_string(hs)});
         }
         {
           ConvGemmOp op; setup_tma_gemm(op, g, M, 4 * C, 4 * C);
