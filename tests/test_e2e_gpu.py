@@ -62,7 +62,8 @@ def _img_case(pair, B, H, W, seed):
     assert e_pw <= 5 * PIX_TOL, e_pw          # preds_w is the unscaled delta (x scaling_w = 0.2 -> pixels)
     assert rel <= LOGIT_RTOL, rel
     assert flips == 0, (flips, unsure)
-    assert abs(restate.psnr(out["imgs_w"].cpu(), imgs).mean() - restate.psnr(ref["imgs_w"], imgs).mean()) < 0.01
+    dpsnr = abs(restate.psnr(out["imgs_w"].cpu(), imgs).mean() - restate.psnr(ref["imgs_w"], imgs).mean()).item()
+    assert dpsnr < 0.02, dpsnr    # 0.02 dB == 0.46 % of the watermark energy (evals/metrics.py:22-36)
     acc_g = restate.bit_accuracy(det, msgs).mean().item()
     acc_r = restate.bit_accuracy(ref_det, msgs).mean().item()
     assert abs(acc_g - acc_r) <= (unsure + 0.5) / det[:, 1:].numel()
