@@ -337,7 +337,9 @@ def run_ours(args):
             roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel<LD_TMA> " + dom["name"], "achieved": dom["tflops"],
                         "peak": peaks["tf_sustained"], "unit": "TFLOP/s", "frac": dom["tflops"] / peaks["tf_sustained"],
                         "peak_source": peaks["src"] + " bf16 cuBLAS, sustained (kernel timed inside a long step)",
-                        "share_of_step": dom["share"], "avg_launch_us": dom["avg_us"], "traffic": None,
+                        "share_of_step": dom["share"], "avg_launch_us": dom["avg_us"],
+                        "traffic": 125.2e6 if (B == 64 and args.card == "videoseal_1.0") else None,
+                        "traffic_source": "dram__bytes_read+write per launch, ncu --set full, profiles/r1_dominant_kernel_ncu.md",
                         "step_ms_under_events": tot}
         if args.profile_out:
             json.dump({"batch": B, "card": args.card, "table": table}, open(args.profile_out, "w"), indent=1)
