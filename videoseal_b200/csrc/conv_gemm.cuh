@@ -37,7 +37,7 @@ constexpr int kBlockM = 128;
 constexpr int kMaxStages = 24;
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;     // TMEM columns between the two accumulator stages
-constexpr int kHeaderBytes = 8192;  // barriers | bias x2 | LN w,b / outc rows | outc partials
+constexpr int kHeaderBytes = 11264;  // barriers | bias x2 | LN w,b / outc rows | outc partials (3 x [128][3])
 constexpr int kHaloTW = 16, kHaloTH = 8;
 constexpr int kHaloW = kHaloTW + 2, kHaloH = kHaloTH + 2;   // 18 x 10 input (or upsampled) halo of an 8x16 output tile
 
@@ -120,6 +120,13 @@ __device__ __forceinline__ uint4 lerp2x2_h8(uint4 a, uint4 b, uint4 c, uint4 d, 
 __device__ __forceinline__ void cp_async16(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
+__device__ __forceinline__ void cp_async16_zfill(void* smem_dst, const void* gsrc, uint32_t src_bytes) {   // src_bytes 16 or 0
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_u32(smem_dst)), "l"(gsrc), "r"(src_bytes) : "memory");
+}
+// the mbarrier receives one (counted) arrival once all prior cp.async of this thread have completed
+__device__ __forceinline__ void cp_async_mbar_arrive_noinc(uint64_t* bar) {
+  asm volatile("cp.async.mbarrier.arrive.noinc.shared::cta.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void cp_async_wait_pending(int n) {   // wait until at most n groups are pending
   switch (n) {
@@ -129,11 +136,15 @@ __device__ __forceinline__ void cp_async_wait_pending(int n) {   // wait until a
     default: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
   }
 }
-__device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
+template <int NT> __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
 __device__ __forceinline__ void bld_bar_sync() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
 
+// epilogue warps: 16 for the pure-TMA kernel (its epilogues - GELU, GRN statistics - are issue-bound), 8 when 4 builder
+// warps also need registers
+template <int LOADER> struct EpiCfg { static constexpr int kWarps = (LOADER == LD_TMA) ? 16 : 8; };
+
 template <int LOADER, int ACT>
-__global__ void __launch_bounds__(LOADER == LD_TMA ? 384 : 512, 1)
+__global__ void __launch_bounds__(LOADER == LD_TMA ? 640 : 512, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvGemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -162,6 +173,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int lane = threadIdx.x & 31;
   constexpr uint32_t kNumBuilders = 128;
   constexpr bool kHalo = (LOADER == LD_HALO_CONV3 || LOADER == LD_HALO_UPS);
+  constexpr int kEpiWarps = EpiCfg<LOADER>::kWarps;
+  constexpr int kEpiThreads = kEpiWarps * 32;
+  constexpr int kEpiSplit = kEpiWarps / 4;          // warps sharing one TMEM lane quadrant (interleaved 16-column chunks)
+  constexpr int kBuilderWarp0 = 4 + kEpiWarps;
 
   if (threadIdx.x == 0) {
     const uint32_t full_count = LOADER == LD_TMA ? 1u : kNumBuilders + (p.b_resident ? 0u : 1u);
@@ -171,7 +186,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     }
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1u);
-      mbar_init(&tempty_bar[s], 256u);
+      mbar_init(&tempty_bar[s], (uint32_t)kEpiThreads);
       mbar_init(&hfull_bar[s], 1u);
       mbar_init(&hempty_bar[s], kNumBuilders);
     }
@@ -287,6 +302,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * kAccStride);
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
+          if (LOADER == LD_GATHER_CONV) fence_proxy_async_smem();   // cp.async-written A tile -> async proxy
           tc_fence_after();
           const uint32_t sa = smem_u32(tiles + (size_t)stage * p.stage_bytes);
           const uint64_t adesc = make_smem_desc(sa, row_bytes);
@@ -303,12 +319,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         if (as == 0) aphase ^= 1u;
       }
     }
-  } else if (warp >= 4 && warp < 12) {
-    // ===================================================================== epilogue (8 warps)
+  } else if (warp >= 4 && warp < 4 + kEpiWarps) {
+    // ===================================================================== epilogue (8 or 16 warps)
     const int q = warp & 3;            // TMEM lane quadrant this warp may access
-    const int half = (warp - 4) >> 2;  // which 16-column chunks: chunk index parity
+    const int half = (warp - 4) >> 2;  // which 16-column chunks: chunk index modulo kEpiSplit
     const int row = q * 32 + lane;
-    const int et = threadIdx.x - 128;  // 0..255
+    const int et = threadIdx.x - 128;  // 0..kEpiThreads-1
     const int nchunks = p.block_n >> 4;
     const int D = p.resid_depth;
     const bool has_res = (p.resid16 != nullptr) || (p.resid32 != nullptr);
@@ -338,13 +354,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           uint8_t* dst = rbuf + (size_t)slot * p.resid_stride;
           if (p.resid16 != nullptr) {
             const __half* r = p.resid16 + m * p.ld_res16 + n0;
-            for (int ch = half; ch < nchunks; ch += 2) {
+            for (int ch = half; ch < nchunks; ch += kEpiSplit) {
               cp_async16(dst + ((size_t)(2 * ch) * 128 + row) * 16, r + ch * 16);
               cp_async16(dst + ((size_t)(2 * ch + 1) * 128 + row) * 16, r + ch * 16 + 8);
             }
           } else {
             const float* r = p.resid32 + m * p.ld_res32 + n0;
-            for (int ch = half; ch < nchunks; ch += 2) {
+            for (int ch = half; ch < nchunks; ch += kEpiSplit) {
 #pragma unroll
               for (int u = 0; u < 4; ++u) cp_async16(dst + ((size_t)(4 * ch + u) * 128 + row) * 16, r + ch * 16 + 4 * u);
             }
@@ -375,7 +391,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       }
       const bool res_fast = mvalid && (n0 + p.block_n <= p.N);
       const uint8_t* rb_ = rbuf + (size_t)slot * p.resid_stride;
-      epi_bar_sync();  // bias visible to all epilogue warps (double-buffered across tiles)
+      epi_bar_sync<kEpiThreads>();  // bias visible to all epilogue warps (double-buffered across tiles)
       mbar_wait(&tfull_bar[as], aphase);
       tc_fence_after();
       cp_async_wait_pending(D - 1);
@@ -454,13 +470,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         float* grn_row = grn_uniform ? p.grn_stats + (((long)m_tile * kBlockM + q * 32) / p.rows_per_sample) * p.N : nullptr;
         uint32_t vnext[16];
         if (half < nchunks) tmem_ld16_issue(trow + half * 16, vnext);
-        for (int ch = half; ch < nchunks; ch += 2) {
+        for (int ch = half; ch < nchunks; ch += kEpiSplit) {
           const int c = ch * 16;
           float v[16];
           tmem_ld_wait(vnext);
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(vnext[j]);
-          if (ch + 2 < nchunks) tmem_ld16_issue(trow + c + 32, vnext);   // overlaps the math below
+          if (ch + kEpiSplit < nchunks) tmem_ld16_issue(trow + c + 16 * kEpiSplit, vnext);   // overlaps the math below
           const int n = n0 + c;
           if (n >= p.N) continue;  // uniform across the warp
           const int nval = min(16, p.N - n);   // 16 on every full chunk (all shipped tiny/pixelseal layers)
@@ -588,12 +604,20 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
         if (p.outc_w != nullptr) {
-          // the two warps sharing a row each hold a partial dot product: combine through shared memory
-          if (half == 1) { s_dot[row * 3 + 0] = dot0; s_dot[row * 3 + 1] = dot1; s_dot[row * 3 + 2] = dot2; }
-          epi_bar_sync();
+          // the warps sharing a row each hold a partial dot product: combine through shared memory
+          if (half != 0) {
+            float* d = s_dot + ((half - 1) * 128 + row) * 3;
+            d[0] = dot0; d[1] = dot1; d[2] = dot2;
+          }
+          epi_bar_sync<kEpiThreads>();
           if (half == 0 && mvalid) {
+#pragma unroll
+            for (int h2 = 1; h2 < kEpiSplit; ++h2) {
+              const float* d = s_dot + ((h2 - 1) * 128 + row) * 3;
+              dot0 += d[0]; dot1 += d[1]; dot2 += d[2];
+            }
             const long b = m / p.hw, pix = m - b * p.hw;
-            float dd[3] = {dot0 + s_dot[row * 3 + 0], dot1 + s_dot[row * 3 + 1], dot2 + s_dot[row * 3 + 2]};
+            const float dd[3] = {dot0, dot1, dot2};
 #pragma unroll
             for (int o = 0; o < 3; ++o) {
               if (o < p.n_out) {
@@ -612,9 +636,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       bsel ^= 1;
       if (++slot == D) slot = 0;
     }
-  } else if (LOADER != LD_TMA && warp >= 12) {
+  } else if (LOADER != LD_TMA && warp >= kBuilderWarp0) {
     // ===================================================================== A-tile builders (4 warps)
-    const int gt = threadIdx.x - 384;  // 0..127
+    const int gt = threadIdx.x - kBuilderWarp0 * 32;  // 0..127
     const int j = gt & 7;              // 16-byte chunk (8 fp16 K-elements) within the 128-byte swizzled row
     const int rg = gt >> 3;            // rows rg + 16*i
     int stage = 0;
@@ -759,10 +783,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             const __half* src = (c < p.C0) ? p.src0 : p.src1;
             const int ld = (c < p.C0) ? p.ld0 : p.ld1;
             const int cc = (c < p.C0) ? c : c - p.C0;
-            uint4 val[8];
+            // asynchronous gather: 16-byte cp.async per (row, chunk) with zero fill for padding / tails; the mbarrier
+            // arrival fires when this thread's copies have landed, so the builder runs ahead by the ring depth
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-              val[i] = make_uint4(0, 0, 0, 0);
+              const __half* gsrc = p.src0;   // always a valid address (no bytes are read when nbytes == 0)
+              uint32_t nbytes = 0;
               if (kvalid && pb[i] >= 0) {
                 int iy = py[i] * p.stride + tr - p.pad;
                 int ix = px[i] * p.stride + ts - p.pad;
@@ -773,14 +799,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 } else {
                   ok = (iy >= 0) && (iy < p.IH) && (ix >= 0) && (ix < p.IW);
                 }
-                if (ok) val[i] = __ldg(reinterpret_cast<const uint4*>(src + (((long)pb[i] * p.IH + iy) * p.IW + ix) * ld + cc));
+                if (ok) { gsrc = src + (((long)pb[i] * p.IH + iy) * p.IW + ix) * ld + cc; nbytes = 16; }
               }
-            }
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
               const int r = rg + 16 * i;
-              *reinterpret_cast<uint4*>(sa + r * 128 + ((j ^ (r & 7)) << 4)) = val[i];
+              cp_async16_zfill(sa + r * 128 + ((j ^ (r & 7)) << 4), gsrc, nbytes);
             }
+            cp_async_mbar_arrive_noinc(&full_bar[stage]);
+            if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+            continue;
           }
           fence_proxy_async_smem();
           mbar_arrive(&full_bar[stage]);

@@ -136,7 +136,7 @@ inline void finalize_op(ConvGemmOp& op, const __half* W, int N, int Kw, int ldw,
   uint32_t box[2] = {(uint32_t)p.kblk, (uint32_t)p.block_n};
   encode_map(&op.tmB, W, 2, dims, strides, box, p.kblk);
   op.grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-  op.threads = op.loader == LD_TMA ? 384 : 512;
+  op.threads = op.loader == LD_TMA ? 640 : 512;
 }
 
 // A = NHWC fp16 activation [B, H, W, C] (pixel pitch ld elements); conv RxS stride 1, zero padding `pad`
