@@ -35,6 +35,7 @@ enum : int { ACT_NONE = 0, ACT_RELU = 1, ACT_GELU = 2 };
 
 constexpr int kBlockM = 128;
 constexpr int kMaxStages = 24;
+constexpr int kMaxHalo = 8;
 constexpr int kTmemCols = 512;
 constexpr int kAccStride = 256;     // TMEM columns between the two accumulator stages
 constexpr int kHeaderBytes = 11264;  // barriers | bias x2 | LN w,b / outc rows | outc partials (3 x [128][3])
@@ -55,6 +56,7 @@ struct ConvGemmParams {
   //      from source 0; each chunk contributes kb_per_c K-blocks of 64 (K order inside a chunk: (tap, channel), zero padded)
   int c0_blocks, cc, kb_per_c;
   uint32_t halo_bytes /*TMA box bytes*/, halo_stride /*buffer pitch*/, halo_off, u_off;
+  int halo_bufs;                  // ring depth of the halo tiles (prefetch distance of the producer)
   // ---- residual prefetch ring (thread-private slots)
   uint32_t resid_off, resid_stride;
   int resid_depth;
@@ -141,10 +143,10 @@ __device__ __forceinline__ void bld_bar_sync() { asm volatile("bar.sync 2, 128;"
 
 // epilogue warps: 16 for the pure-TMA kernel (its epilogues - GELU, GRN statistics - are issue-bound), 8 when 4 builder
 // warps also need registers
-template <int LOADER> struct EpiCfg { static constexpr int kWarps = (LOADER == LD_TMA) ? 16 : 8; };
+template <int LOADER, int ACT> struct EpiCfg { static constexpr int kWarps = (LOADER == LD_TMA && ACT == ACT_GELU) ? 16 : 8; };
 
 template <int LOADER, int ACT>
-__global__ void __launch_bounds__(LOADER == LD_TMA ? 640 : 512, 1)
+__global__ void __launch_bounds__(LOADER == LD_TMA ? (ACT == ACT_GELU ? 640 : 384) : 512, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvGemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -155,8 +157,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   uint64_t* tfull_bar = empty_bar + kMaxStages;
   uint64_t* tempty_bar = tfull_bar + 2;
   uint64_t* hfull_bar = tempty_bar + 2;
-  uint64_t* hempty_bar = hfull_bar + 2;
-  uint64_t* bres_bar = hempty_bar + 2;
+  uint64_t* hempty_bar = hfull_bar + kMaxHalo;
+  uint64_t* bres_bar = hempty_bar + kMaxHalo;
   uint32_t* tmem_ptr_smem = reinterpret_cast<uint32_t*>(bres_bar + 1);
   float* s_bias = reinterpret_cast<float*>(smem + 1024);        // [2][256]
   float* s_lnw = reinterpret_cast<float*>(smem + 3072);         // [256]  (LN weight | outc row 0)
@@ -173,7 +175,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   const int lane = threadIdx.x & 31;
   constexpr uint32_t kNumBuilders = 128;
   constexpr bool kHalo = (LOADER == LD_HALO_CONV3 || LOADER == LD_HALO_UPS);
-  constexpr int kEpiWarps = EpiCfg<LOADER>::kWarps;
+  constexpr int kEpiWarps = EpiCfg<LOADER, ACT>::kWarps;
   constexpr int kEpiThreads = kEpiWarps * 32;
   constexpr int kEpiSplit = kEpiWarps / 4;          // warps sharing one TMEM lane quadrant (interleaved 16-column chunks)
   constexpr int kBuilderWarp0 = 4 + kEpiWarps;
@@ -187,6 +189,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     for (int s = 0; s < 2; ++s) {
       mbar_init(&tfull_bar[s], 1u);
       mbar_init(&tempty_bar[s], (uint32_t)kEpiThreads);
+    }
+    for (int s = 0; s < kMaxHalo; ++s) {
       mbar_init(&hfull_bar[s], 1u);
       mbar_init(&hempty_bar[s], kNumBuilders);
     }
@@ -247,8 +251,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               tma_load_4d(s0 ? &tmA : &tmA2, &hfull_bar[hb], halo + (size_t)hb * p.halo_stride,
                           (s0 ? c : c - p.c0_blocks) * p.cc, (cx >> 1) - 1, (cy >> 1) - 1, cb);
             }
-            hb ^= 1;
-            if (hb == 0) hphase ^= 1u;
+            if (++hb == p.halo_bufs) { hb = 0; hphase ^= 1u; }
             if (!p.b_resident) {
               int kcoord = c * p.kb_per_c * 64;
               for (int kbi = 0; kbi < p.kb_per_c; ++kbi, kcoord += 64) {
@@ -465,9 +468,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         float dot0 = 0.f, dot1 = 0.f, dot2 = 0.f;
         const bool grn_uniform =
             p.grn_stats != nullptr &&
-            ((long)m_tile * kBlockM + q * 32) / p.rows_per_sample == ((long)m_tile * kBlockM + q * 32 + 31) / p.rows_per_sample &&
-            ((long)m_tile * kBlockM + q * 32 + 31) < p.M;
-        float* grn_row = grn_uniform ? p.grn_stats + (((long)m_tile * kBlockM + q * 32) / p.rows_per_sample) * p.N : nullptr;
+            (m_tile * kBlockM + q * 32) / p.rows_per_sample == (m_tile * kBlockM + q * 32 + 31) / p.rows_per_sample &&
+            (m_tile * kBlockM + q * 32 + 31) < p.M;
+        float* grn_row = grn_uniform ? p.grn_stats + (long)((m_tile * kBlockM + q * 32) / p.rows_per_sample) * p.N : nullptr;
         uint32_t vnext[16];
         if (half < nchunks) tmem_ld16_issue(trow + half * 16, vnext);
         for (int ch = half; ch < nchunks; ch += kEpiSplit) {
@@ -597,7 +600,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const int col = (lane >> 1) & 15;
               if ((lane & 1) == 0 && col < nval) atomicAdd(grn_row + n + col, sq[0]);
             } else if (mvalid) {
-              float* gr = p.grn_stats + (m / p.rows_per_sample) * p.N + n;
+              float* gr = p.grn_stats + (long)((int)m / p.rows_per_sample) * p.N + n;
 #pragma unroll
               for (int j = 0; j < 16; ++j) if (j < nval) atomicAdd(gr + j, sq[j]);
             }
@@ -616,14 +619,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const float* d = s_dot + ((h2 - 1) * 128 + row) * 3;
               dot0 += d[0]; dot1 += d[1]; dot2 += d[2];
             }
-            const long b = m / p.hw, pix = m - b * p.hw;
+            const int b = (int)m / p.hw, pix = (int)m - b * p.hw;
             const float dd[3] = {dot0, dot1, dot2};
 #pragma unroll
             for (int o = 0; o < 3; ++o) {
               if (o < p.n_out) {
                 float d = dd[o] + __ldg(p.outc_b + o);
                 if (p.outc_tanh) d = tanhf(d);
-                p.delta[(b * p.n_out + o) * p.hw + pix] = d;
+                p.delta[((long)b * p.n_out + o) * p.hw + pix] = d;
               }
             }
           }
@@ -719,8 +722,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
           if (LOADER == LD_HALO_CONV3) mbar_arrive(&hempty_bar[hb]);
-          hb ^= 1;
-          if (hb == 0) hphase ^= 1u;
+          if (++hb == p.halo_bufs) { hb = 0; hphase ^= 1u; }
         }
       }
     } else {
@@ -730,18 +732,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         int pb[8], py[8], px[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
-          const long m = (long)m_tile * kBlockM + rg + 16 * i;
+          const int m = m_tile * kBlockM + rg + 16 * i;      // M < 2^31 (host-checked)
           if (m < p.M) {
             if (LOADER == LD_GATHER_SCALE) {
-              pb[i] = (int)(m / p.rows_per_sample);
+              pb[i] = m / p.rows_per_sample;
               py[i] = 0;
-              px[i] = (int)m;
+              px[i] = m;
             } else {
-              const int ox = (int)(m % p.OW);
-              const long t = m / p.OW;
-              px[i] = ox;
-              py[i] = (int)(t % p.OH);
-              pb[i] = (int)(t / p.OH);
+              const int t = m / p.OW;
+              px[i] = m - t * p.OW;
+              pb[i] = t / p.OH;
+              py[i] = t - pb[i] * p.OH;
             }
           } else {
             pb[i] = -1; py[i] = 0; px[i] = 0;

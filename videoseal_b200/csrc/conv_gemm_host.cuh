@@ -109,7 +109,10 @@ inline void finalize_op(ConvGemmOp& op, const __half* W, int N, int Kw, int ldw,
   p.resid_stride = (uint32_t)resid_one;
   const size_t resid_bytes = resid_one * depth;
   p.halo_stride = (uint32_t)(((size_t)p.halo_bytes + 1023) & ~size_t(1023));
-  const size_t halo_total = 2 * (size_t)p.halo_stride;
+  // halo ring: as deep as ~48 KB allows (2..8): the producer prefetches that many tiles ahead of the builders
+  p.halo_bufs = 2;
+  if (p.halo_stride) { p.halo_bufs = (int)(49152 / p.halo_stride); if (p.halo_bufs > kMaxHalo) p.halo_bufs = kMaxHalo; if (p.halo_bufs < 2) p.halo_bufs = 2; }
+  const size_t halo_total = (size_t)p.halo_bufs * p.halo_stride;
   const size_t u_bytes = op.loader == LD_HALO_UPS ? (((size_t)kHaloH * kHaloW * p.cc * 2 + 1023) & ~size_t(1023)) : 0;
   // resident weights: one N tile, whole K slab <= 48 KB -> loaded once per CTA instead of once per tile
   const size_t bslab = (size_t)p.num_kb * p.b_stage_bytes;
@@ -136,7 +139,8 @@ inline void finalize_op(ConvGemmOp& op, const __half* W, int N, int Kw, int ldw,
   uint32_t box[2] = {(uint32_t)p.kblk, (uint32_t)p.block_n};
   encode_map(&op.tmB, W, 2, dims, strides, box, p.kblk);
   op.grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-  op.threads = op.loader == LD_TMA ? 640 : 512;
+  op.threads = op.loader == LD_TMA ? (p.act == ACT_GELU ? 640 : 384) : 512;
+  VSB_CHECK((long)p.m_tiles * kBlockM < (1L << 31), "M too large for 32-bit row indices");
 }
 
 // A = NHWC fp16 activation [B, H, W, C] (pixel pitch ld elements); conv RxS stride 1, zero padding `pad`

@@ -692,16 +692,15 @@ class Model {
           const float* xin = x;
           float *dww = w.dww, *dwb = w.dwb, *lw = w.lnw, *lb = w.lnb;
           pl.steps.push_back(Step{[=](cudaStream_t st) {
-            const long npatches = (long)B * ((H + kDwRows - 1) / kDwRows) * ((H + kDwStrip - 1) / kDwStrip);
+            const int strips = (H + kDwStrip - 1) / kDwStrip;
+            const long nstrips = (long)B * H * strips;
             const int C2 = Cc / 2;
             int spb = 1;
-            for (int s2 = 1; s2 <= 4; s2 *= 2) if ((s2 * C2) % 32 == 0 && s2 * C2 <= 384) { spb = s2; break; }
-            if (spb * C2 > 384) throw Error("dwconv7: C/2 > 384 threads is not implemented (unsupported chunky extractor width)");
-            const long blocks = (npatches + spb - 1) / spb;
-            const size_t smem = (size_t)spb * kDwRows * kDwStrip * Cc * sizeof(float);
-            static bool attr = false;
-            if (!attr) { VSB_CUDA(cudaFuncSetAttribute(dwconv7_ln_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
-            dwconv7_ln_kernel<<<(unsigned)blocks, spb * C2, smem, st>>>(xin, B, H, H, Cc, Cc, dww, dwb, lw, lb, a, Cc, spb, npatches);
+            for (int s2 = 1; s2 <= 4; s2 *= 2) if ((s2 * C2) % 32 == 0 && s2 * C2 <= 512) { spb = s2; break; }
+            if (spb * C2 > 512) throw Error("dwconv7: C/2 > 512 threads is not implemented (unsupported chunky extractor width)");
+            const long blocks = (nstrips + spb - 1) / spb;
+            dwconv7_ln_kernel<<<(unsigned)blocks, spb * C2, (size_t)spb * kDwStrip * Cc * sizeof(float), st>>>(
+                xin, B, H, H, Cc, Cc, dww, dwb, lw, lb, a, Cc, spb, nstrips);
             VSB_CUDA(cudaGetLastError());
           }, 1, "cnx.dwconv7_ln." + std::to_string(C) + "@" + std::to_string(hs)});
         }

@@ -301,9 +301,10 @@ __global__ void __launch_bounds__(256) ups_gather_ln_kernel(const __half* __rest
   const int lane_g = threadIdx.x % G;
   const long ldy = 9L * C;
   for (long pix = (long)blockIdx.x * ppb + threadIdx.x / G; pix < npix; pix += (long)gridDim.x * ppb) {
-    const int ox = (int)(pix % OW);
-    const long t = pix / OW;
-    const int oy = (int)(t % OH), b = (int)(t / OH);
+    const int pix32 = (int)pix;                 // B*OH*OW < 2^31
+    const int t = pix32 / OW;
+    const int ox = pix32 - t * OW;
+    const int b = t / OH, oy = t - b * OH;
     int ya[3], yb[3], xa[3], xb[3];
     float wy[3], wx[3];
 #pragma unroll
@@ -423,79 +424,64 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {   // Bla
         "l"(reinterpret_cast<const unsigned long long&>(c)));
   return d;
 }
-// Each thread owns one channel pair and a kDwRows x kDwStrip (4 x 8) patch of output pixels: every input row it loads
-// (14 float2) feeds up to 4 output rows, which cuts the L2 read amplification of the 7x7 window from 12x to 4.4x.
-// blockDim.x = spb * C/2 threads: `spb` patches per block so that every warp is full.  Pre-LN results go to shared memory,
-// then one warp per pixel does the channels-last LayerNorm and writes fp16.
-constexpr int kDwRows = 4;
-__global__ void __launch_bounds__(384) dwconv7_ln_kernel(const float* __restrict__ x, int B, int H, int W, int C, int ldx,
+// blockDim.x = spb * C/2 threads: `spb` strips per block so that every warp is full
+__global__ void __launch_bounds__(512) dwconv7_ln_kernel(const float* __restrict__ x, int B, int H, int W, int C, int ldx,
                                                          const float* __restrict__ wdw /*[49][C]*/, const float* __restrict__ bdw,
                                                          const float* __restrict__ lnw, const float* __restrict__ lnb,
-                                                         __half* __restrict__ out, int ld_out, int spb, long npatches) {
-  extern __shared__ float pre[];  // [spb][kDwRows*kDwStrip][C]
-  const int px_ = (W + kDwStrip - 1) / kDwStrip, py_ = (H + kDwRows - 1) / kDwRows;
+                                                         __half* __restrict__ out, int ld_out, int spb, long nstrips) {
+  extern __shared__ float pre[];  // [spb][kDwStrip][C]
+  const int strips_x = (W + kDwStrip - 1) / kDwStrip;
   const int C2 = C >> 1;
-  const int ls = threadIdx.x / C2;                 // local patch
+  const int ls = threadIdx.x / C2;                 // local strip
   const int cp = threadIdx.x - ls * C2;            // channel pair
-  const long patch = (long)blockIdx.x * spb + ls;
-  if (ls < spb && patch < npatches) {
-    const int sx = (int)(patch % px_);
-    const long t = patch / px_;
-    const int sy = (int)(t % py_), b = (int)(t / py_);
-    const int ox0 = sx * kDwStrip, oy0 = sy * kDwRows;
+  const long strip = (long)blockIdx.x * spb + ls;
+  const bool active = (ls < spb) && (strip < nstrips);
+  int sx = 0, oy = 0, b = 0, ox0 = 0;
+  if (active) {
+    sx = (int)(strip % strips_x);
+    const long t = strip / strips_x;
+    oy = (int)(t % H); b = (int)(t / H);
+    ox0 = sx * kDwStrip;
     const int c = cp * 2;
-    float2 acc[kDwRows][kDwStrip];
+    float2 acc[kDwStrip];
     const float2 bb = __ldg(reinterpret_cast<const float2*>(bdw + c));
 #pragma unroll
-    for (int r = 0; r < kDwRows; ++r)
-#pragma unroll
-      for (int i = 0; i < kDwStrip; ++i) acc[r][i] = bb;
-#pragma unroll 1
-    for (int iyr = 0; iyr < kDwRows + 6; ++iyr) {
-      const int iy = oy0 + iyr - 3;
+    for (int i = 0; i < kDwStrip; ++i) acc[i] = bb;
+    for (int r = 0; r < 7; ++r) {
+      const int iy = oy + r - 3;
       if (iy < 0 || iy >= H) continue;
-      float2 v[kDwStrip + 6];
+      float2 wr[7];
+#pragma unroll
+      for (int s2 = 0; s2 < 7; ++s2) wr[s2] = __ldg(reinterpret_cast<const float2*>(wdw + (r * 7 + s2) * C + c));
       const float* rowp = x + (((long)b * H + iy) * W) * ldx + c;
 #pragma unroll
       for (int u = 0; u < kDwStrip + 6; ++u) {
         const int ix = ox0 + u - 3;
-        v[u] = (ix >= 0 && ix < W) ? __ldg(reinterpret_cast<const float2*>(rowp + (long)ix * ldx)) : make_float2(0.f, 0.f);
-      }
+        float2 v = make_float2(0.f, 0.f);
+        if (ix >= 0 && ix < W) v = __ldg(reinterpret_cast<const float2*>(rowp + (long)ix * ldx));
 #pragma unroll
-      for (int r = 0; r < kDwRows; ++r) {
-        const int dy = iyr - r;                    // kernel row used by output row r for this input row
-        if (dy < 0 || dy > 6) continue;
-        float2 wr[7];
-#pragma unroll
-        for (int s2 = 0; s2 < 7; ++s2) wr[s2] = __ldg(reinterpret_cast<const float2*>(wdw + (dy * 7 + s2) * C + c));
-#pragma unroll
-        for (int i = 0; i < kDwStrip; ++i)
-#pragma unroll
-          for (int s2 = 0; s2 < 7; ++s2) acc[r][i] = ffma2(v[i + s2], wr[s2], acc[r][i]);
+        for (int s2 = 0; s2 < 7; ++s2) {
+          const int i = u - s2;  // output pixel index within the strip
+          if (i >= 0 && i < kDwStrip) acc[i] = ffma2(v, wr[s2], acc[i]);
+        }
       }
     }
-    float* pr = pre + (size_t)ls * kDwRows * kDwStrip * C;
+    float* pr = pre + (size_t)ls * kDwStrip * C;
 #pragma unroll
-    for (int r = 0; r < kDwRows; ++r)
-#pragma unroll
-      for (int i = 0; i < kDwStrip; ++i) {
-        pr[(r * kDwStrip + i) * C + c] = acc[r][i].x;
-        pr[(r * kDwStrip + i) * C + c + 1] = acc[r][i].y;
-      }
+    for (int i = 0; i < kDwStrip; ++i) { pr[i * C + c] = acc[i].x; pr[i * C + c + 1] = acc[i].y; }
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  constexpr int kPP = kDwRows * kDwStrip;
-  for (int item = warp; item < spb * kPP; item += nwarps) {
-    const int l2 = item / kPP, pi = item - l2 * kPP;
-    const long p2 = (long)blockIdx.x * spb + l2;
-    if (p2 >= npatches) continue;
-    const int sx2 = (int)(p2 % px_);
-    const long t2 = p2 / px_;
-    const int sy2 = (int)(t2 % py_), b2 = (int)(t2 / py_);
-    const int oy = sy2 * kDwRows + pi / kDwStrip, ox = sx2 * kDwStrip + pi % kDwStrip;
-    if (ox >= W || oy >= H) continue;
-    const float* pr = pre + ((size_t)l2 * kPP + pi) * C;
+  for (int item = warp; item < spb * kDwStrip; item += nwarps) {
+    const int l2 = item / kDwStrip, i = item - l2 * kDwStrip;
+    const long st2 = (long)blockIdx.x * spb + l2;
+    if (st2 >= nstrips) continue;
+    const int sx2 = (int)(st2 % strips_x);
+    const long t2 = st2 / strips_x;
+    const int oy2 = (int)(t2 % H), b2 = (int)(t2 / H);
+    const int ox = sx2 * kDwStrip + i;
+    if (ox >= W) continue;
+    const float* pr = pre + ((size_t)l2 * kDwStrip + i) * C;
     float sum = 0.f;
     for (int c = lane; c < C; c += 32) sum += pr[c];
 #pragma unroll
@@ -506,7 +492,7 @@ __global__ void __launch_bounds__(384) dwconv7_ln_kernel(const float* __restrict
 #pragma unroll
     for (int o = 16; o; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
     const float rstd = 1.0f / sqrtf(var / (float)C + 1e-6f);
-    __half* dst = out + (((long)b2 * H + oy) * W + ox) * ld_out;
+    __half* dst = out + (((long)b2 * H + oy2) * W + ox) * ld_out;
     for (int c = lane * 2; c < C; c += 64) {
       const float a = (pr[c] - mean) * rstd * __ldg(lnw + c) + __ldg(lnb + c);
       const float bq = (pr[c + 1] - mean) * rstd * __ldg(lnw + c + 1) + __ldg(lnb + c + 1);
