@@ -46,6 +46,7 @@ struct ConvGemmParams {
   // ---- GEMM view
   int M, N, num_kb, kblk, block_n, n_tiles, m_tiles, num_tiles, stages;
   uint32_t a_stage_bytes, b_stage_bytes, stage_bytes, idesc;
+  int group;                      // consecutive M tiles that share one accumulator round (amortises per-tile handshakes for small N)
   int b_resident;                 // whole [block_n x K] weight slab lives in shared memory for the kernel's lifetime
   uint32_t bres_off;
   // ---- output-tile geometry: tile_mode 0: rows are consecutive GEMM rows; 1: tile_h x tile_w pixel patch of an H x W map
@@ -231,7 +232,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = 0; kb < p.num_kb; ++kb) tma_load_2d(&tmB, bres_bar, bres + (size_t)kb * p.b_stage_bytes, kb * p.kblk, 0);
       }
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.n_tiles, n_tile = tile - m_tile * p.n_tiles;
+       const int st = tile / p.n_tiles, n_tile = tile - st * p.n_tiles;
+       for (int g = 0; g < p.group; ++g) {
+        const int m_tile = st * p.group + g;
+        if (m_tile >= p.m_tiles) break;
         int cb = 0, cx = 0, cy = 0;
         if (p.tile_mode == 1) {
           cb = m_tile / p.tiles_per_img;
@@ -287,6 +291,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
         }
+       }
       }
     }
   } else if (warp == 1) {
@@ -302,7 +307,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         mbar_wait(&tempty_bar[as], aphase ^ 1u);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(as * kAccStride);
+        const int st = tile / p.n_tiles;
+       for (int g = 0; g < p.group; ++g) {
+        if (st * p.group + g >= p.m_tiles) break;
+        const uint32_t d_tmem = tmem_base + (uint32_t)(as * kAccStride + g * p.block_n);
         for (int kb = 0; kb < p.num_kb; ++kb) {
           mbar_wait(&full_bar[stage], phase);
           if (LOADER == LD_GATHER_CONV) fence_proxy_async_smem();   // cp.async-written A tile -> async proxy
@@ -317,7 +325,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           umma_commit(&empty_bar[stage]);  // frees the smem slot once these MMAs have read it
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
-        umma_commit(&tfull_bar[as]);  // accumulator complete -> epilogue
+       }
+        umma_commit(&tfull_bar[as]);  // accumulators of the whole group complete -> epilogue
         as ^= 1;
         if (as == 0) aphase ^= 1u;
       }
@@ -332,10 +341,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int D = p.resid_depth;
     const bool has_res = (p.resid16 != nullptr) || (p.resid32 != nullptr);
 
-    // geometry of this thread's row in a given tile
-    auto tile_row = [&](int tile, long& m, bool& mvalid, int& n0, int& m_tile) {
-      m_tile = tile / p.n_tiles;
-      n0 = (tile - m_tile * p.n_tiles) * p.block_n;
+    // geometry of this thread's row in M tile `m_tile`
+    auto tile_row = [&](int m_tile, long& m, bool& mvalid) {
       if (p.tile_mode == 1) {
         const int b = m_tile / p.tiles_per_img;
         const int rem = m_tile - b * p.tiles_per_img;
@@ -348,24 +355,33 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         mvalid = m < p.M;
       }
     };
-    // residual row of `tile` -> ring slot (thread-private region, layout [16-byte chunk][row] = conflict-free)
-    auto prefetch_resid = [&](int tile, int slot) {
-      if (has_res && tile < p.num_tiles) {
-        long m; bool mvalid; int n0, m_tile;
-        tile_row(tile, m, mvalid, n0, m_tile);
-        if (mvalid && n0 + p.block_n <= p.N) {
-          uint8_t* dst = rbuf + (size_t)slot * p.resid_stride;
-          if (p.resid16 != nullptr) {
-            const __half* r = p.resid16 + m * p.ld_res16 + n0;
-            for (int ch = half; ch < nchunks; ch += kEpiSplit) {
-              cp_async16(dst + ((size_t)(2 * ch) * 128 + row) * 16, r + ch * 16);
-              cp_async16(dst + ((size_t)(2 * ch + 1) * 128 + row) * 16, r + ch * 16 + 8);
-            }
-          } else {
-            const float* r = p.resid32 + m * p.ld_res32 + n0;
-            for (int ch = half; ch < nchunks; ch += kEpiSplit) {
+    // residual row of sub-tile number `sq` (= iteration * group + g of this CTA) -> ring slot (thread-private region,
+    // layout [16-byte chunk][row] = conflict-free)
+    const int G = p.group;
+    auto prefetch_resid = [&](int sq, int slot) {
+      if (has_res) {
+        const int it = sq / G, g = sq - it * G;
+        const int tile = (int)blockIdx.x + it * (int)gridDim.x;
+        const int st = tile / p.n_tiles;
+        const int m_tile = st * G + g;
+        if (tile < p.num_tiles && m_tile < p.m_tiles) {
+          const int n0 = (tile - st * p.n_tiles) * p.block_n;
+          long m; bool mvalid;
+          tile_row(m_tile, m, mvalid);
+          if (mvalid && n0 + p.block_n <= p.N) {
+            uint8_t* dst = rbuf + (size_t)slot * p.resid_stride;
+            if (p.resid16 != nullptr) {
+              const __half* r = p.resid16 + m * p.ld_res16 + n0;
+              for (int ch = half; ch < nchunks; ch += kEpiSplit) {
+                cp_async16(dst + ((size_t)(2 * ch) * 128 + row) * 16, r + ch * 16);
+                cp_async16(dst + ((size_t)(2 * ch + 1) * 128 + row) * 16, r + ch * 16 + 8);
+              }
+            } else {
+              const float* r = p.resid32 + m * p.ld_res32 + n0;
+              for (int ch = half; ch < nchunks; ch += kEpiSplit) {
 #pragma unroll
-              for (int u = 0; u < 4; ++u) cp_async16(dst + ((size_t)(4 * ch + u) * 128 + row) * 16, r + ch * 16 + 4 * u);
+                for (int u = 0; u < 4; ++u) cp_async16(dst + ((size_t)(4 * ch + u) * 128 + row) * 16, r + ch * 16 + 4 * u);
+              }
             }
           }
         }
@@ -377,28 +393,35 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     uint32_t aphase = 0;
     int bsel = 0;
     int slot = 0;
-    {
-      int t = blockIdx.x;
-      for (int i = 0; i < D - 1; ++i, t += gridDim.x) prefetch_resid(t, i);
-    }
+    int sq = 0;
+    for (int i = 0; i < D - 1; ++i) prefetch_resid(i, i);
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      long m; bool mvalid; int n0, m_tile;
-      tile_row(tile, m, mvalid, n0, m_tile);
-      // ---- prologue, overlapped with the main loop: bias -> smem; residual of tile (+D-1) -> ring
+      const int st = tile / p.n_tiles;
+      const int n0 = (tile - st * p.n_tiles) * p.block_n;
+      // ---- prologue, overlapped with the main loop: bias -> smem
       float* sb = s_bias + bsel * 256;
       if (et < p.block_n) sb[et] = (p.bias != nullptr && n0 + et < p.N) ? __ldg(p.bias + n0 + et) : 0.f;
+      epi_bar_sync<kEpiThreads>();  // bias visible to all epilogue warps (double-buffered across tiles)
+     for (int g = 0; g < G; ++g, ++sq) {
+      // residual of the sub-tile D-1 ahead -> ring (issued before waiting for this group's accumulators)
       {
         int pslot = slot + D - 1;
         if (pslot >= D) pslot -= D;
-        prefetch_resid(tile + (D - 1) * (int)gridDim.x, pslot);
+        prefetch_resid(sq + D - 1, pslot);
       }
-      const bool res_fast = mvalid && (n0 + p.block_n <= p.N);
-      const uint8_t* rb_ = rbuf + (size_t)slot * p.resid_stride;
-      epi_bar_sync<kEpiThreads>();  // bias visible to all epilogue warps (double-buffered across tiles)
-      mbar_wait(&tfull_bar[as], aphase);
-      tc_fence_after();
+      if (g == 0) {
+        mbar_wait(&tfull_bar[as], aphase);
+        tc_fence_after();
+      }
       cp_async_wait_pending(D - 1);
-      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kAccStride);
+      const int m_tile = st * G + g;
+      const uint8_t* rb_ = rbuf + (size_t)slot * p.resid_stride;
+      if (++slot == D) slot = 0;
+      if (m_tile >= p.m_tiles) continue;     // ragged last group (uniform across the CTA)
+      long m; bool mvalid;
+      tile_row(m_tile, m, mvalid);
+      const bool res_fast = mvalid && (n0 + p.block_n <= p.N);
+      const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kAccStride + g * p.block_n);
 
       if (p.epi == EPI_LN) {
         // channels-first LayerNorm over the full C_out row (biased variance), then activation; half-0 warps only
@@ -632,12 +655,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         }
       }
+     }  // g
       tc_fence_before();
       mbar_arrive(&tempty_bar[as]);
       as ^= 1;
       if (as == 0) aphase ^= 1u;
       bsel ^= 1;
-      if (++slot == D) slot = 0;
     }
   } else if (LOADER != LD_TMA && warp >= kBuilderWarp0) {
     // ===================================================================== A-tile builders (4 warps)
@@ -652,7 +675,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       int hb = 0;
       uint32_t hphase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.n_tiles;
+       for (int g = 0; g < p.group; ++g) {
+        const int m_tile = (tile / p.n_tiles) * p.group + g;
+        if (m_tile >= p.m_tiles) break;
         int cy, cx;
         {
           const int b = m_tile / p.tiles_per_img;
@@ -724,11 +749,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (LOADER == LD_HALO_CONV3) mbar_arrive(&hempty_bar[hb]);
           if (++hb == p.halo_bufs) { hb = 0; hphase ^= 1u; }
         }
+       }
       }
     } else {
       const int Ct = p.C0 + p.C1;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-        const int m_tile = tile / p.n_tiles;
+       for (int g = 0; g < p.group; ++g) {
+        const int m_tile = (tile / p.n_tiles) * p.group + g;
+        if (m_tile >= p.m_tiles) break;
         int pb[8], py[8], px[8];
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -813,6 +841,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           mbar_arrive(&full_bar[stage]);
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
+       }
       }
     }
   }

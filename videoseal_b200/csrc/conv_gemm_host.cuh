@@ -94,7 +94,16 @@ inline void finalize_op(ConvGemmOp& op, const __half* W, int N, int Kw, int ldw,
   p.block_n = block_n_override ? block_n_override : pick_block_n(N, p.resid32 ? 128 : 256);
   VSB_CHECK(p.block_n % 16 == 0 && p.block_n >= 16 && p.block_n <= 256, "bad block_n");
   p.n_tiles = (N + p.block_n - 1) / p.block_n;
-  p.num_tiles = p.m_tiles * p.n_tiles;
+  // small-N layers: several consecutive M tiles share one accumulator round (TMEM columns g*block_n) so that the per-tile
+  // barrier handshakes / index math are amortised
+  p.group = 1;
+  if (!getenv("VSB_NO_GROUP")) {
+    p.group = kAccStride / p.block_n;
+    if (p.group > 4) p.group = 4;
+    if (p.group < 1) p.group = 1;
+    if (p.m_tiles < 4 * num_sms) p.group = 1;   // keep enough tiles for load balance
+  }
+  p.num_tiles = ((p.m_tiles + p.group - 1) / p.group) * p.n_tiles;
   p.a_stage_bytes = (uint32_t)(kBlockM * p.kblk * 2);
   p.b_stage_bytes = (uint32_t)(p.block_n * p.kblk * 2);
   p.stage_bytes = p.a_stage_bytes + ((p.b_stage_bytes + 1023u) & ~1023u);

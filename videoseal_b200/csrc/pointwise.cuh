@@ -425,7 +425,7 @@ __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {   // Bla
   return d;
 }
 // blockDim.x = spb * C/2 threads: `spb` strips per block so that every warp is full
-__global__ void __launch_bounds__(512) dwconv7_ln_kernel(const float* __restrict__ x, int B, int H, int W, int C, int ldx,
+__global__ void __launch_bounds__(768) dwconv7_ln_kernel(const float* __restrict__ x, int B, int H, int W, int C, int ldx,
                                                          const float* __restrict__ wdw /*[49][C]*/, const float* __restrict__ bdw,
                                                          const float* __restrict__ lnw, const float* __restrict__ lnb,
                                                          __half* __restrict__ out, int ld_out, int spb, long nstrips) {
