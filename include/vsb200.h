@@ -101,6 +101,14 @@ int vsb_embed_host(vsb_model* m, const float* imgs_host, const uint8_t* msgs_hos
                    float scaling_i, float scaling_w, int32_t flags);
 int vsb_detect_host(vsb_model* m, const float* imgs_host, float* logits_host, int32_t F, int32_t H, int32_t W, int32_t flags);
 
+/* Streaming form of embed followed by detect of the watermarked frames, HOST (ideally pinned) buffers in and out: the frames are
+ * processed in chunks of ~32 with the H2D copy of chunk k+1 and the D2H copy of chunk k-1 overlapped with the compute of chunk k
+ * (three internal streams).  This is how the reference's callers use the path on full-resolution video kept on the CPU
+ * (evals/full.py:117-120, inference_streaming.py:83-107).  imgs_w_host [F,3,H,W], logits_host [F,1+nbits]. */
+int vsb_embed_detect_host(vsb_model* m, const float* imgs_host, const uint8_t* msgs_host, int32_t n_msgs, float* imgs_w_host,
+                          float* logits_host, int32_t F, int32_t H, int32_t W, int32_t step, int32_t video_mode, float scaling_i,
+                          float scaling_w, int32_t flags);
+
 /* number of kernels launched by this library since the last call with reset != 0 (bench.py's gpu_launches) */
 int64_t vsb_launch_count(int32_t reset);
 

@@ -241,3 +241,24 @@ def test_size_independent_properties_full_batch(v1):
     d64 = model.detect(a["imgs_w"], is_video=False)["preds"]
     d32 = torch.cat([model.detect(a["imgs_w"][:32], is_video=False)["preds"], model.detect(a["imgs_w"][32:], is_video=False)["preds"]])
     assert (d64 - d32).abs().max().item() <= 1e-3 * d64.abs().max().item()        # GRN statistics use fp32 atomics
+
+
+def test_streaming_host_entry_matches_device_path(v1):
+    """vsb_embed_detect_host (pinned host frames, chunked, copies overlapped with compute) == embed() + detect() on device"""
+    import ctypes as C
+    from videoseal_b200 import _lib
+    model, orc, spec = v1
+    g = torch.Generator().manual_seed(12)
+    B, H, W = 70, 256, 256          # 3 chunks (32 + 32 + 6)
+    imgs = torch.rand(B, 3, H, W, generator=g).pin_memory()
+    msgs = torch.randint(0, 2, (B, spec["nbits"]), generator=g)
+    ref = model.embed(imgs.cuda(), msgs, is_video=False)
+    ref_log = model.detect(ref["imgs_w"], is_video=False)["preds"].cpu()
+    out = torch.empty(B, 3, H, W).pin_memory()
+    logits = torch.empty(B, 1 + spec["nbits"]).pin_memory()
+    m8 = msgs.to(torch.uint8).contiguous()
+    _lib.check(_lib.lib().vsb_embed_detect_host(model._handle(), imgs.data_ptr(), m8.data_ptr(), B, out.data_ptr(), logits.data_ptr(),
+                                                B, H, W, 1, 0, float(model.blender.scaling_i), float(model.blender.scaling_w),
+                                                _lib.FLAG_CLAMP))
+    assert torch.equal(out, ref["imgs_w"].cpu())
+    assert (logits - ref_log).abs().max().item() <= 1e-3 * ref_log.abs().max().item()

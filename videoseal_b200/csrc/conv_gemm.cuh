@@ -42,7 +42,15 @@ constexpr int kHeaderBytes = 11264;  // barriers | bias x2 | LN w,b / outc rows 
 constexpr int kHaloTW = 16, kHaloTH = 8;
 constexpr int kHaloW = kHaloTW + 2, kHaloH = kHaloTH + 2;   // 18 x 10 input (or upsampled) halo of an 8x16 output tile
 
+// division by a runtime constant as multiply-high + shift (valid for 0 <= n < 2^31); the host precomputes (mul, shr)
+struct FastDiv {
+  uint32_t mul, shr;
+  int d;
+  __device__ __forceinline__ int div(int n) const { return d == 1 ? n : (int)(__umulhi((uint32_t)n, mul) >> shr); }
+};
+
 struct ConvGemmParams {
+  FastDiv fd_ntiles, fd_tpi, fd_tx, fd_tw, fd_group, fd_rps, fd_hw, fd_cc, fd_ow, fd_oh, fd_ct, fd_s;
   // ---- GEMM view
   int M, N, num_kb, kblk, block_n, n_tiles, m_tiles, num_tiles, stages;
   uint32_t a_stage_bytes, b_stage_bytes, stage_bytes, idesc;
@@ -232,15 +240,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         for (int kb = 0; kb < p.num_kb; ++kb) tma_load_2d(&tmB, bres_bar, bres + (size_t)kb * p.b_stage_bytes, kb * p.kblk, 0);
       }
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-       const int st = tile / p.n_tiles, n_tile = tile - st * p.n_tiles;
+       const int st = p.fd_ntiles.div(tile), n_tile = tile - st * p.n_tiles;
        for (int g = 0; g < p.group; ++g) {
         const int m_tile = st * p.group + g;
         if (m_tile >= p.m_tiles) break;
         int cb = 0, cx = 0, cy = 0;
         if (p.tile_mode == 1) {
-          cb = m_tile / p.tiles_per_img;
+          cb = p.fd_tpi.div(m_tile);
           const int rem = m_tile - cb * p.tiles_per_img;
-          const int ty = rem / p.tiles_x;
+          const int ty = p.fd_tx.div(rem);
           cy = ty * p.tile_h;
           cx = (rem - ty * p.tiles_x) * p.tile_w;
         }
@@ -307,7 +315,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
         mbar_wait(&tempty_bar[as], aphase ^ 1u);
         tc_fence_after();
-        const int st = tile / p.n_tiles;
+        const int st = p.fd_ntiles.div(tile);
        for (int g = 0; g < p.group; ++g) {
         if (st * p.group + g >= p.m_tiles) break;
         const uint32_t d_tmem = tmem_base + (uint32_t)(as * kAccStride + g * p.block_n);
@@ -344,10 +352,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // geometry of this thread's row in M tile `m_tile`
     auto tile_row = [&](int m_tile, long& m, bool& mvalid) {
       if (p.tile_mode == 1) {
-        const int b = m_tile / p.tiles_per_img;
+        const int b = p.fd_tpi.div(m_tile);
         const int rem = m_tile - b * p.tiles_per_img;
-        const int ty = rem / p.tiles_x, tx = rem - ty * p.tiles_x;
-        const int ry = row / p.tile_w, rx = row - ry * p.tile_w;
+        const int ty = p.fd_tx.div(rem), tx = rem - ty * p.tiles_x;
+        const int ry = p.fd_tw.div(row), rx = row - ry * p.tile_w;
         m = ((long)b * p.H + (ty * p.tile_h + ry)) * p.W + (tx * p.tile_w + rx);
         mvalid = true;
       } else {
@@ -360,9 +368,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int G = p.group;
     auto prefetch_resid = [&](int sq, int slot) {
       if (has_res) {
-        const int it = sq / G, g = sq - it * G;
+        const int it = p.fd_group.div(sq), g = sq - it * G;
         const int tile = (int)blockIdx.x + it * (int)gridDim.x;
-        const int st = tile / p.n_tiles;
+        const int st = p.fd_ntiles.div(tile);
         const int m_tile = st * G + g;
         if (tile < p.num_tiles && m_tile < p.m_tiles) {
           const int n0 = (tile - st * p.n_tiles) * p.block_n;
@@ -396,7 +404,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     int sq = 0;
     for (int i = 0; i < D - 1; ++i) prefetch_resid(i, i);
     for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
-      const int st = tile / p.n_tiles;
+      const int st = p.fd_ntiles.div(tile);
       const int n0 = (tile - st * p.n_tiles) * p.block_n;
       // ---- prologue, overlapped with the main loop: bias -> smem
       float* sb = s_bias + bsel * 256;
@@ -491,9 +499,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         float dot0 = 0.f, dot1 = 0.f, dot2 = 0.f;
         const bool grn_uniform =
             p.grn_stats != nullptr &&
-            (m_tile * kBlockM + q * 32) / p.rows_per_sample == (m_tile * kBlockM + q * 32 + 31) / p.rows_per_sample &&
+            p.fd_rps.div(m_tile * kBlockM + q * 32) == p.fd_rps.div(m_tile * kBlockM + q * 32 + 31) &&
             (m_tile * kBlockM + q * 32 + 31) < p.M;
-        float* grn_row = grn_uniform ? p.grn_stats + (long)((m_tile * kBlockM + q * 32) / p.rows_per_sample) * p.N : nullptr;
+        float* grn_row = grn_uniform ? p.grn_stats + (long)p.fd_rps.div(m_tile * kBlockM + q * 32) * p.N : nullptr;
         uint32_t vnext[16];
         if (half < nchunks) tmem_ld16_issue(trow + half * 16, vnext);
         for (int ch = half; ch < nchunks; ch += kEpiSplit) {
@@ -623,7 +631,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const int col = (lane >> 1) & 15;
               if ((lane & 1) == 0 && col < nval) atomicAdd(grn_row + n + col, sq[0]);
             } else if (mvalid) {
-              float* gr = p.grn_stats + (long)((int)m / p.rows_per_sample) * p.N + n;
+              float* gr = p.grn_stats + (long)p.fd_rps.div((int)m) * p.N + n;
 #pragma unroll
               for (int j = 0; j < 16; ++j) if (j < nval) atomicAdd(gr + j, sq[j]);
             }
@@ -642,7 +650,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               const float* d = s_dot + ((h2 - 1) * 128 + row) * 3;
               dot0 += d[0]; dot1 += d[1]; dot2 += d[2];
             }
-            const int b = (int)m / p.hw, pix = (int)m - b * p.hw;
+            const int b = p.fd_hw.div((int)m), pix = (int)m - b * p.hw;
             const float dd[3] = {dot0, dot1, dot2};
 #pragma unroll
             for (int o = 0; o < 3; ++o) {
@@ -676,13 +684,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t hphase = 0;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
        for (int g = 0; g < p.group; ++g) {
-        const int m_tile = (tile / p.n_tiles) * p.group + g;
+        const int m_tile = p.fd_ntiles.div(tile) * p.group + g;
         if (m_tile >= p.m_tiles) break;
         int cy, cx;
         {
-          const int b = m_tile / p.tiles_per_img;
+          const int b = p.fd_tpi.div(m_tile);
           const int rem = m_tile - b * p.tiles_per_img;
-          const int ty = rem / p.tiles_x;
+          const int ty = p.fd_tx.div(rem);
           cy = ty * p.tile_h;
           cx = (rem - ty * p.tiles_x) * p.tile_w;
         }
@@ -722,7 +730,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           // order; 16-byte chunk j covers k = 64*kbi + 8*j -> tap = k / cc, channel offset = k % cc
           for (int kbi = 0; kbi < p.kb_per_c; ++kbi) {
             const int k = kbi * 64 + j * 8;
-            const int tap = k / p.cc;
+            const int tap = p.fd_cc.div(k);
             const int coff = (k - tap * p.cc) * 2;
             const int tr = tap / 3, ts = tap - tr * 3;
             mbar_wait(&empty_bar[stage], phase ^ 1u);
@@ -755,7 +763,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int Ct = p.C0 + p.C1;
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
        for (int g = 0; g < p.group; ++g) {
-        const int m_tile = (tile / p.n_tiles) * p.group + g;
+        const int m_tile = p.fd_ntiles.div(tile) * p.group + g;
         if (m_tile >= p.m_tiles) break;
         int pb[8], py[8], px[8];
 #pragma unroll
@@ -763,13 +771,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           const int m = m_tile * kBlockM + rg + 16 * i;      // M < 2^31 (host-checked)
           if (m < p.M) {
             if (LOADER == LD_GATHER_SCALE) {
-              pb[i] = m / p.rows_per_sample;
+              pb[i] = p.fd_rps.div(m);
               py[i] = 0;
               px[i] = m;
             } else {
-              const int t = m / p.OW;
+              const int t = p.fd_ow.div(m);
               px[i] = m - t * p.OW;
-              pb[i] = t / p.OH;
+              pb[i] = p.fd_oh.div(t);
               py[i] = t - pb[i] * p.OH;
             }
           } else {
@@ -806,9 +814,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               *reinterpret_cast<uint4*>(sa + r * 128 + ((j ^ (r & 7)) << 4)) = val;
             }
           } else {
-            const int tap = kvalid ? k / Ct : 0;
+            const int tap = kvalid ? p.fd_ct.div(k) : 0;
             const int c = k - tap * Ct;
-            const int tr = tap / p.S, ts = tap - tr * p.S;
+            const int tr = p.fd_s.div(tap), ts = tap - tr * p.S;
             const __half* src = (c < p.C0) ? p.src0 : p.src1;
             const int ld = (c < p.C0) ? p.ld0 : p.ld1;
             const int cc = (c < p.C0) ? c : c - p.C0;

@@ -61,6 +61,17 @@ inline void encode_map(CUtensorMap* tm, const void* base, int rank, const uint64
   VSB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
 }
 
+inline FastDiv make_fastdiv(int d) {
+  FastDiv f; f.d = d < 1 ? 1 : d; f.mul = 0; f.shr = 0;
+  if (f.d > 1) {
+    int l = 0; while ((1u << l) < (uint32_t)f.d) ++l;       // ceil(log2 d)
+    const int pp = 31 + l;
+    const unsigned long long m = ((1ull << pp) + (unsigned long long)f.d - 1) / (unsigned long long)f.d;
+    f.mul = (uint32_t)m; f.shr = (uint32_t)(pp - 32);
+  }
+  return f;
+}
+
 struct ConvGemmOp {
   int loader = LD_TMA;
   ConvGemmParams p;
@@ -98,12 +109,16 @@ inline void finalize_op(ConvGemmOp& op, const __half* W, int N, int Kw, int ldw,
   // barrier handshakes / index math are amortised
   p.group = 1;
   if (!getenv("VSB_NO_GROUP")) {
-    p.group = kAccStride / p.block_n;
+    p.group = p.block_n <= 32 ? kAccStride / p.block_n : 1;   // measured: only pays off for N <= 32
     if (p.group > 4) p.group = 4;
     if (p.group < 1) p.group = 1;
     if (p.m_tiles < 4 * num_sms) p.group = 1;   // keep enough tiles for load balance
   }
   p.num_tiles = ((p.m_tiles + p.group - 1) / p.group) * p.n_tiles;
+  p.fd_ntiles = make_fastdiv(p.n_tiles); p.fd_tpi = make_fastdiv(p.tiles_per_img); p.fd_tx = make_fastdiv(p.tiles_x);
+  p.fd_tw = make_fastdiv(p.tile_w); p.fd_group = make_fastdiv(p.group); p.fd_rps = make_fastdiv(p.rows_per_sample);
+  p.fd_hw = make_fastdiv(p.hw); p.fd_cc = make_fastdiv(p.cc); p.fd_ow = make_fastdiv(p.OW); p.fd_oh = make_fastdiv(p.OH);
+  p.fd_ct = make_fastdiv(p.C0 + p.C1); p.fd_s = make_fastdiv(p.S);
   p.a_stage_bytes = (uint32_t)(kBlockM * p.kblk * 2);
   p.b_stage_bytes = (uint32_t)(p.block_n * p.kblk * 2);
   p.stage_bytes = p.a_stage_bytes + ((p.b_stage_bytes + 1023u) & ~1023u);

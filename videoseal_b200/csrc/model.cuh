@@ -209,7 +209,12 @@ class Model {
     }
     return s.p;
   }
-  ~Model() { for (auto& s : staging) if (s.p) cudaFree(s.p); }
+  ~Model() {
+    for (auto& s : staging) if (s.p) cudaFree(s.p);
+    if (s_in) { cudaStreamDestroy(s_in); cudaStreamDestroy(s_cmp); cudaStreamDestroy(s_out); }
+    for (auto e : ev_in) cudaEventDestroy(e);
+    for (auto e : ev_cmp) cudaEventDestroy(e);
+  }
 
   std::map<int, std::unique_ptr<Plan>> embed_plans, detect_plans;
   std::map<uint64_t, std::unique_ptr<ResampleDev>> resamplers;
@@ -797,6 +802,52 @@ class Model {
   }
 
   void check_ready() const { if (!finalized) throw Error("model not finalized"); }
+
+  // ---- streaming host path: embed + detect of HOST frames with the PCIe copies overlapped with compute
+  cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
+  std::vector<cudaEvent_t> ev_in, ev_cmp;
+  void embed_detect_host(const float* imgs_h, const uint8_t* msgs_h, int n_msgs, float* imgs_w_h, float* logits_h, int F, int H, int W,
+                         int step, int video_mode, float scaling_i, float scaling_w, int flags) {
+    check_ready();
+    VSB_CUDA(cudaSetDevice(device));
+    if (!s_in) {
+      VSB_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+      VSB_CUDA(cudaStreamCreateWithFlags(&s_cmp, cudaStreamNonBlocking));
+      VSB_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+    }
+    const size_t fpx = (size_t)3 * H * W;
+    const int NO = 1 + d.nbits;
+    float* imgs = (float*)stage(0, (size_t)F * fpx * sizeof(float));
+    float* out = (float*)stage(1, (size_t)F * fpx * sizeof(float));
+    float* lg = (float*)stage(2, (size_t)F * NO * sizeof(float));
+    uint8_t* msgs = (uint8_t*)stage(3, (size_t)n_msgs * d.nbits + 256);
+    // chunks of ~32 frames (multiples of `step` so that key-frame groups stay whole)
+    int ch = 32;
+    if (ch % step) ch = ((ch + step - 1) / step) * step;
+    const int nch = (F + ch - 1) / ch;
+    while ((int)ev_in.size() < nch) {
+      cudaEvent_t a, b;
+      VSB_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+      VSB_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+      ev_in.push_back(a); ev_cmp.push_back(b);
+    }
+    VSB_CUDA(cudaMemcpyAsync(msgs, msgs_h, (size_t)n_msgs * d.nbits, cudaMemcpyHostToDevice, s_in));
+    for (int k = 0; k < nch; ++k) {
+      const int f0 = k * ch, n = std::min(ch, F - f0);
+      VSB_CUDA(cudaMemcpyAsync(imgs + (size_t)f0 * fpx, imgs_h + (size_t)f0 * fpx, (size_t)n * fpx * sizeof(float), cudaMemcpyHostToDevice, s_in));
+      VSB_CUDA(cudaEventRecord(ev_in[k], s_in));
+      VSB_CUDA(cudaStreamWaitEvent(s_cmp, ev_in[k], 0));
+      const uint8_t* mk = msgs + (n_msgs == 1 ? 0 : (size_t)f0 * d.nbits);
+      embed(imgs + (size_t)f0 * fpx, mk, n_msgs == 1 ? 1 : n, out + (size_t)f0 * fpx, nullptr, n, H, W, step, video_mode, scaling_i, scaling_w,
+            flags, s_cmp);
+      detect(out + (size_t)f0 * fpx, lg + (size_t)f0 * NO, n, H, W, flags & VSB_FLAG_RESIZE_NO_AA, s_cmp);
+      VSB_CUDA(cudaEventRecord(ev_cmp[k], s_cmp));
+      VSB_CUDA(cudaStreamWaitEvent(s_out, ev_cmp[k], 0));
+      VSB_CUDA(cudaMemcpyAsync(imgs_w_h + (size_t)f0 * fpx, out + (size_t)f0 * fpx, (size_t)n * fpx * sizeof(float), cudaMemcpyDeviceToHost, s_out));
+      VSB_CUDA(cudaMemcpyAsync(logits_h + (size_t)f0 * NO, lg + (size_t)f0 * NO, (size_t)n * NO * sizeof(float), cudaMemcpyDeviceToHost, s_out));
+    }
+    VSB_CUDA(cudaStreamSynchronize(s_out));
+  }
 
   // U-Net on `n` processing-size RGB frames (contiguous [n,3,S,S]) -> plan->delta
   Plan* run_unet(const float* x, const uint8_t* msgs, int msg_stride, int n, cudaStream_t st) {

@@ -138,6 +138,15 @@ int vsb_detect_host(vsb_model* m, const float* imgs_h, float* logits_h, int32_t 
   VSB_API_END
 }
 
+int vsb_embed_detect_host(vsb_model* m, const float* imgs_h, const uint8_t* msgs_h, int32_t n_msgs, float* imgs_w_h, float* logits_h,
+                          int32_t F, int32_t H, int32_t W, int32_t step, int32_t video_mode, float scaling_i, float scaling_w, int32_t flags) {
+  VSB_API_BEGIN
+  VSB_CHECK(m && imgs_h && msgs_h && imgs_w_h && logits_h, "null argument");
+  m->impl.embed_detect_host(imgs_h, msgs_h, n_msgs, imgs_w_h, logits_h, F, H, W, step, video_mode, scaling_i, scaling_w, flags);
+  return VSB_OK;
+  VSB_API_END
+}
+
 int64_t vsb_launch_count(int32_t reset) {
   const int64_t v = g_launches;
   if (reset) g_launches = 0;
