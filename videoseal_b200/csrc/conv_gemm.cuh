@@ -103,6 +103,40 @@ __device__ __forceinline__ float gelu_erf(float x) {
   return fmaf(fabsf(h), e, h);                                // 0.5*x*(1 + sign(x)*e)
 }
 
+// two GELUs at once with Blackwell's packed fp32 arithmetic (fma/mul .f32x2): the polynomial costs half the issue slots
+__device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<const unsigned long long&>(a)), "l"(reinterpret_cast<const unsigned long long&>(b)),
+        "l"(reinterpret_cast<const unsigned long long&>(c)));
+  return d;
+}
+__device__ __forceinline__ float2 f2mul(float2 a, float2 b) {
+  float2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<const unsigned long long&>(a)), "l"(reinterpret_cast<const unsigned long long&>(b)));
+  return d;
+}
+__device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
+  const float2 x = make_float2(x0, x1);
+  const float2 ax = make_float2(fabsf(x0), fabsf(x1));
+  const float2 z = f2mul(ax, make_float2(0.70710678118654752f, 0.70710678118654752f));
+  const float2 dn = f2fma(z, make_float2(0.3275911f, 0.3275911f), make_float2(1.f, 1.f));
+  const float2 t = make_float2(rcp_approx(dn.x), rcp_approx(dn.y));
+  float2 poly = f2fma(t, make_float2(1.061405429f, 1.061405429f), make_float2(-1.453152027f, -1.453152027f));
+  poly = f2fma(poly, t, make_float2(1.421413741f, 1.421413741f));
+  poly = f2fma(poly, t, make_float2(-0.284496736f, -0.284496736f));
+  poly = f2fma(poly, t, make_float2(0.254829592f, 0.254829592f));
+  const float2 ea = f2mul(z, f2mul(z, make_float2(-1.4426950408889634f, -1.4426950408889634f)));
+  const float2 ex = make_float2(ex2_approx(ea.x), ex2_approx(ea.y));
+  const float2 npt = f2mul(f2mul(poly, t), make_float2(-1.f, -1.f));
+  const float2 e = f2fma(npt, ex, make_float2(1.f, 1.f));            // erf(|x|/sqrt2)
+  const float2 h = f2mul(x, make_float2(0.5f, 0.5f));
+  const float2 ah = f2mul(ax, make_float2(0.5f, 0.5f));
+  const float2 r = f2fma(ah, e, h);                                   // 0.5*x*(1 + sign(x)*erf)
+  x0 = r.x; x1 = r.y;
+}
+
 __device__ __forceinline__ int reflect_idx(int i, int n) {
   if (i < 0) i = -i;
   if (i >= n) i = 2 * n - 2 - i;
@@ -522,10 +556,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               v[4 * u + 0] += bq.x; v[4 * u + 1] += bq.y; v[4 * u + 2] += bq.z; v[4 * u + 3] += bq.w;
             }
           }
+          if (ACT == ACT_GELU) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) {
-            if (ACT == ACT_RELU) v[j] = fmaxf(v[j], 0.f);
-            else if (ACT == ACT_GELU) v[j] = gelu_erf(v[j]);
+            for (int j = 0; j < 16; j += 2) gelu_erf2(v[j], v[j + 1]);
+          } else if (ACT == ACT_RELU) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
           }
           if (nval < 16) {
 #pragma unroll
@@ -728,6 +764,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
           // phase 2: tap tiles.  K-block kbi of this chunk holds K indices [64*kbi, 64*kbi+64) of the (tap, channel)
           // order; 16-byte chunk j covers k = 64*kbi + 8*j -> tap = k / cc, channel offset = k % cc
+          const int stage0 = stage;
+          const uint32_t phase0 = phase;
           for (int kbi = 0; kbi < p.kb_per_c; ++kbi) {
             const int k = kbi * 64 + j * 8;
             const int tap = p.fd_cc.div(k);
@@ -750,10 +788,22 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 *reinterpret_cast<uint4*>(sa + r * 128 + ((j ^ (r & 7)) << 4)) = make_uint4(0, 0, 0, 0);
               }
             }
-            fence_proxy_async_smem();  // generic-proxy smem writes -> visible to the tensor core (async proxy)
-            mbar_arrive(&full_bar[stage]);
+            if (p.kb_per_c > p.stages) {   // ring shorter than the chunk: publish each K-block immediately
+              fence_proxy_async_smem();
+              mbar_arrive(&full_bar[stage]);
+            }
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
+          if (p.kb_per_c <= p.stages) {
+            // one generic->async proxy fence for the whole chunk, then publish its K-blocks
+            fence_proxy_async_smem();
+            int sp = stage0;
+            for (int kbi = 0; kbi < p.kb_per_c; ++kbi) {
+              mbar_arrive(&full_bar[sp]);
+              if (++sp == p.stages) sp = 0;
+            }
+          }
+          (void)phase0;
           if (LOADER == LD_HALO_CONV3) mbar_arrive(&hempty_bar[hb]);
           if (++hb == p.halo_bufs) { hb = 0; hphase ^= 1u; }
         }
