@@ -104,19 +104,8 @@ __device__ __forceinline__ float gelu_erf(float x) {
 }
 
 // two GELUs at once with Blackwell's packed fp32 arithmetic (fma/mul .f32x2): the polynomial costs half the issue slots
-__device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) {
-  float2 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(reinterpret_cast<unsigned long long&>(d))
-      : "l"(reinterpret_cast<const unsigned long long&>(a)), "l"(reinterpret_cast<const unsigned long long&>(b)),
-        "l"(reinterpret_cast<const unsigned long long&>(c)));
-  return d;
-}
-__device__ __forceinline__ float2 f2mul(float2 a, float2 b) {
-  float2 d;
-  asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(reinterpret_cast<unsigned long long&>(d))
-      : "l"(reinterpret_cast<const unsigned long long&>(a)), "l"(reinterpret_cast<const unsigned long long&>(b)));
-  return d;
-}
+__device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
+__device__ __forceinline__ float2 f2mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
 __device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
   const float2 x = make_float2(x0, x1);
   const float2 ax = make_float2(fabsf(x0), fabsf(x1));

@@ -416,14 +416,7 @@ __global__ void __launch_bounds__(256) stem_ln_kernel(const float* __restrict__ 
 // x: NHWC fp32 [B, H, W, C] (pixel pitch ldx).  One block = one strip of kDwStrip output pixels along x; each thread owns
 // a channel pair and slides over the 7 x (strip+6) input window; pre-LN results go to smem, then LN per pixel by warps.
 constexpr int kDwStrip = 8;
-__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {   // Blackwell packed fp32 FMA (2 MACs / instruction)
-  float2 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;"
-      : "=l"(reinterpret_cast<unsigned long long&>(d))
-      : "l"(reinterpret_cast<const unsigned long long&>(a)), "l"(reinterpret_cast<const unsigned long long&>(b)),
-        "l"(reinterpret_cast<const unsigned long long&>(c)));
-  return d;
-}
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }   // Blackwell packed fp32 FMA
 // blockDim.x = spb * C/2 threads: `spb` strips per block so that every warp is full
 __global__ void __launch_bounds__(768) dwconv7_ln_kernel(const float* __restrict__ x, int B, int H, int W, int C, int ldx,
                                                          const float* __restrict__ wdw /*[49][C]*/, const float* __restrict__ bdw,
