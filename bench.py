@@ -36,6 +36,7 @@ def parse_args():
     ap.add_argument("--card", default="videoseal_1.0")
     ap.add_argument("--batch", type=int, default=64)
     ap.add_argument("--size", type=int, default=256)
+    ap.add_argument("--video", action="store_true", help="is_video=True: one message, key frames every step_size frames")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--profile-out", default="", help="write the per-kernel table (JSON) here")
@@ -243,9 +244,12 @@ def run_ours(args):
     msgs = torch.randint(0, 2, (B, K), generator=g).to(dev)
     gathered = [torch.empty(B, 1 + K, device=dev) for _ in range(world)] if world > 1 else None
 
+    vid = bool(args.video)
+    msgs_v = msgs[:1]
+
     def step_local(i):
-        out = model.embed(imgs[i % NB], msgs, is_video=False)
-        return model.detect(out["imgs_w"], is_video=False)["preds"]
+        out = model.embed(imgs[i % NB], msgs_v if vid else msgs, is_video=vid)
+        return model.detect(out["imgs_w"], is_video=vid)["preds"]
 
     def step(i):
         preds = step_local(i)
@@ -366,7 +370,8 @@ def run_ours(args):
             "metric": "embed+detect frames/sec", "value": fps, "unit": "frames/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f16 operands, f32 accumulate (API tensors f32)", "data": "synthetic",
-            "config": {"workload": f"{args.card} {K}-bit embed+detect, image mode, batch {B} x 3x{S}x{S} per GPU (BASELINE configs[1])",
+            "config": {"workload": f"{args.card} {K}-bit embed+detect, {'video (step ' + str(model.step_size) + ')' if vid else 'image'} mode, "
+                                   f"batch {B} x 3x{S}x{S} per GPU" + (" (BASELINE configs[1])" if (B, S, vid, args.card) == (64, 256, False, "videoseal_1.0") else ""),
                        "card": args.card, "batch_per_gpu": B, "size": S, "parallelism": f"dp{world} (frames sharded, weak scaling)",
                        "l2": f"{NB} rotating input batches ({NB * B * 3 * S * S * 4 / 1e6:.0f} MB > 126 MB L2); activations per step >> L2"},
             "step_tflops": (fe + fd) * world * B * args.steps / (ms / 1000.0) / 1e12,

@@ -697,10 +697,11 @@ class Model {
           const float* xin = x;
           float *dww = w.dww, *dwb = w.dwb, *lw = w.lnw, *lb = w.lnb;
           pl.steps.push_back(Step{[=](cudaStream_t st) {
-            // tiled kernel (input window staged in smem) when the map tiles by 4 x {16, 8} and C is a multiple of 96
+            // experimental tiled kernel (input window staged in smem), VSB_DW_TILED=1: measured no faster than the strip kernel
+            // (both are latency-bound per block, profiles/r1_history.md), kept for round-2 work
             const int TW = (H % 16 == 0) ? 16 : ((H % 8 == 0) ? 8 : 0);
             const size_t smem_t = TW ? ((size_t)(kDwTH + 6) * (TW + 6) * kDwCC + (size_t)kDwTH * TW * Cc) * sizeof(float) : 0;
-            if (TW && H % kDwTH == 0 && Cc % kDwCC == 0 && smem_t <= 200 * 1024 && !getenv("VSB_DW_STRIPS")) {
+            if (TW && H % kDwTH == 0 && Cc % kDwCC == 0 && smem_t <= 200 * 1024 && getenv("VSB_DW_TILED")) {
               static bool attr = false;
               if (!attr) { VSB_CUDA(cudaFuncSetAttribute(dwconv7_ln_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
               const int threads = (kDwCC / 2) * kDwTH * (TW / kDwStrip);
