@@ -300,7 +300,7 @@ def run_ours(args):
 
         def e2e_step(i):
             _lib.check(L.vsb_embed_detect_host(h, h_in[i % 2].data_ptr(), h_msgs.data_ptr(), B, h_out.data_ptr(), h_log.data_ptr(), B, S, S,
-                                               1, 0, float(model.blender.scaling_i), float(model.blender.scaling_w), flags))
+                                               1, 0, int(model.chunk_size), float(model.blender.scaling_i), float(model.blender.scaling_w), flags))
 
         for i in range(3):
             e2e_step(i)

@@ -78,10 +78,12 @@ void vsb_model_destroy(vsb_model* m);
 
 /* imgs_dev [F,3,H,W] fp32 in [0,1]; msgs_dev uint8 {0,1}: [F,nbits] (n_msgs == F) or [1,nbits] (n_msgs == 1);
  * imgs_w_dev [F,3,H,W]; preds_w_dev NULL or [F,unet_out_ch,H,W] (hmap * delta_up, before scaling_w);
- * step = 1 for image mode, else frames share the key frame f/step (videoseal.py:292-340). */
+ * step = 1 for image mode, else frames share the key frame f/step (videoseal.py:292-340);
+ * chunk_keys = the model's chunk_size (key frames per reference chunk, videoseal.py:300): it only changes the result in
+ * video_mode 'interpolate', where neighbouring key frames of ONE chunk are mixed (videoseal.py:101-113); 1..64 there. */
 int vsb_embed(vsb_model* m, const float* imgs_dev, const uint8_t* msgs_dev, int32_t n_msgs, float* imgs_w_dev,
-              float* preds_w_dev, int32_t F, int32_t H, int32_t W, int32_t step, int32_t video_mode, float scaling_i,
-              float scaling_w, int32_t flags, void* stream);
+              float* preds_w_dev, int32_t F, int32_t H, int32_t W, int32_t step, int32_t video_mode, int32_t chunk_keys,
+              float scaling_i, float scaling_w, int32_t flags, void* stream);
 
 /* x_dev [B, 3, S, S] RGB fp32 in [0,1] at processing size S = img_size (the Y extraction for yuv cards happens
  * inside, wam.py:168-172); delta_dev [B, unet_out_ch, S, S] */
@@ -98,7 +100,7 @@ int vsb_jnd_heatmaps(vsb_model* m, const float* imgs_dev, float* hmaps_dev, int3
 /* Host-buffer variants (pinned or pageable): copy in, run, copy out, synchronise. */
 int vsb_embed_host(vsb_model* m, const float* imgs_host, const uint8_t* msgs_host, int32_t n_msgs, float* imgs_w_host,
                    float* preds_w_host, int32_t F, int32_t H, int32_t W, int32_t step, int32_t video_mode,
-                   float scaling_i, float scaling_w, int32_t flags);
+                   int32_t chunk_keys, float scaling_i, float scaling_w, int32_t flags);
 int vsb_detect_host(vsb_model* m, const float* imgs_host, float* logits_host, int32_t F, int32_t H, int32_t W, int32_t flags);
 
 /* Streaming form of embed followed by detect of the watermarked frames, HOST (ideally pinned) buffers in and out: the frames are
@@ -106,8 +108,8 @@ int vsb_detect_host(vsb_model* m, const float* imgs_host, float* logits_host, in
  * (three internal streams).  This is how the reference's callers use the path on full-resolution video kept on the CPU
  * (evals/full.py:117-120, inference_streaming.py:83-107).  imgs_w_host [F,3,H,W], logits_host [F,1+nbits]. */
 int vsb_embed_detect_host(vsb_model* m, const float* imgs_host, const uint8_t* msgs_host, int32_t n_msgs, float* imgs_w_host,
-                          float* logits_host, int32_t F, int32_t H, int32_t W, int32_t step, int32_t video_mode, float scaling_i,
-                          float scaling_w, int32_t flags);
+                          float* logits_host, int32_t F, int32_t H, int32_t W, int32_t step, int32_t video_mode,
+                          int32_t chunk_keys, float scaling_i, float scaling_w, int32_t flags);
 
 /* number of kernels launched by this library since the last call with reset != 0 (bench.py's gpu_launches) */
 int64_t vsb_launch_count(int32_t reset);

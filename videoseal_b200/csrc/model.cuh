@@ -659,9 +659,16 @@ class Model {
     }
     int maxK4 = 0;
     for (int s = 0; s < 4; ++s) maxK4 = std::max(maxK4, 4 * d.ext_dims[s]);
-    float* stats = pl.pool.alloc_n<float>((size_t)B * maxK4);
-    float* scale = pl.pool.alloc_n<float>((size_t)B * maxK4);
-    VSB_CUDA(cudaMemset(stats, 0, (size_t)B * maxK4 * sizeof(float)));
+    for (int s = 1; s < 4; ++s) VSB_CHECK(d.ext_dims[s] >= d.ext_dims[s - 1], "extractor widths must not shrink along the trunk");
+    // GRN statistics ping-pong: block j's pwconv1 accumulates into stats_pp[j&1]; its apply pass clears stats_pp[(j+1)&1] over
+    // B*K_j floats, which covers what block j-1 left there because the widths never shrink along the trunk.  Both buffers are
+    // zeroed at the start of every run (the last block of the previous run leaves its statistics behind).
+    const size_t stats_n = (size_t)B * maxK4;
+    float* stats_all = pl.pool.alloc_n<float>(2 * stats_n);
+    float* stats_pp[2] = {stats_all, stats_all + stats_n};
+    int blk_counter = 0;
+    pl.steps.push_back(Step{[=](cudaStream_t st) { VSB_CUDA(cudaMemsetAsync(stats_all, 0, 2 * stats_n * sizeof(float), st)); }, 0,
+                            "cnx.grn_clear"});
     __half* x16 = nullptr;
     for (int s = 0; s < 4; ++s) {
       if (s > 0) {
@@ -725,23 +732,20 @@ class Model {
         {
           ConvGemmOp op; setup_tma_gemm(op, a, M, C, C);
           op.p.epi = EPI_AFFINE; op.p.act = ACT_GELU; op.p.bias = w.pw1.bias; op.p.out16 = g; op.p.ld_out16 = 4 * C;
+          float* stats = stats_pp[blk_counter & 1];
+          ++blk_counter;
           op.p.grn_stats = stats; op.p.rows_per_sample = rows_per_sample;
           add_conv(pl, op, w.pw1, "cnx.pwconv1." + std::to_string(C) + "@" + std::to_string(hs));
         }
         {
           const int K4 = 4 * C;
           float* gamma = w.gamma;
+          float* stats = stats_pp[(blk_counter - 1) & 1];
+          float* stats_next = stats_pp[blk_counter & 1];
           pl.steps.push_back(Step{[=](cudaStream_t st) {
-            grn_scale_kernel<<<B, 256, 0, st>>>(stats, gamma, K4, scale, K4);
-            VSB_CUDA(cudaGetLastError());
-          }, 1, "cnx.grn_scale"});
-        }
-        {
-          const int K4 = 4 * C;
-          pl.steps.push_back(Step{[=](cudaStream_t st) {
-            const long total = M * (K4 / 8);
-            const int grid = (int)std::min<long>((total + 255) / 256, 148L * 32);
-            grn_apply_kernel<<<grid, 256, 0, st>>>(g, M, K4, K4, scale, K4, rows_per_sample);
+            // enough row-slabs per sample to fill the GPU (~8 blocks per SM)
+            int slabs = std::max(1, std::min(rows_per_sample, (148 * 8 + B - 1) / B));
+            grn_apply_kernel<<<B * slabs, 256, K4 * sizeof(float), st>>>(g, rows_per_sample, K4, K4, stats, stats_next, gamma, slabs);
             VSB_CUDA(cudaGetLastError());
           }, 1, "cnx.grn_apply." + std::to_string(C) + "@" + std::to_string(hs)});
         }
@@ -820,7 +824,7 @@ class Model {
   cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
   std::vector<cudaEvent_t> ev_in, ev_cmp;
   void embed_detect_host(const float* imgs_h, const uint8_t* msgs_h, int n_msgs, float* imgs_w_h, float* logits_h, int F, int H, int W,
-                         int step, int video_mode, float scaling_i, float scaling_w, int flags) {
+                         int step, int video_mode, int chunk_keys, float scaling_i, float scaling_w, int flags) {
     check_ready();
     VSB_CUDA(cudaSetDevice(device));
     if (!s_in) {
@@ -835,8 +839,10 @@ class Model {
     float* lg = (float*)stage(2, (size_t)F * NO * sizeof(float));
     uint8_t* msgs = (uint8_t*)stage(3, (size_t)n_msgs * d.nbits + 256);
     // chunks of ~32 frames (multiples of `step` so that key-frame groups stay whole)
+    // (and of whole reference chunks in 'interpolate' mode, where neighbouring keys of one chunk are mixed)
     int ch = 32;
-    if (ch % step) ch = ((ch + step - 1) / step) * step;
+    const int unit = (video_mode == VSB_VIDEO_INTERPOLATE && step > 1) ? step * std::max(1, chunk_keys) : step;
+    if (ch % unit) ch = ((ch + unit - 1) / unit) * unit;
     const int nch = (F + ch - 1) / ch;
     while ((int)ev_in.size() < nch) {
       cudaEvent_t a, b;
@@ -851,8 +857,8 @@ class Model {
       VSB_CUDA(cudaEventRecord(ev_in[k], s_in));
       VSB_CUDA(cudaStreamWaitEvent(s_cmp, ev_in[k], 0));
       const uint8_t* mk = msgs + (n_msgs == 1 ? 0 : (size_t)f0 * d.nbits);
-      embed(imgs + (size_t)f0 * fpx, mk, n_msgs == 1 ? 1 : n, out + (size_t)f0 * fpx, nullptr, n, H, W, step, video_mode, scaling_i, scaling_w,
-            flags, s_cmp);
+      embed(imgs + (size_t)f0 * fpx, mk, n_msgs == 1 ? 1 : n, out + (size_t)f0 * fpx, nullptr, n, H, W, step, video_mode, chunk_keys, scaling_i,
+            scaling_w, flags, s_cmp);
       detect(out + (size_t)f0 * fpx, lg + (size_t)f0 * NO, n, H, W, flags & VSB_FLAG_RESIZE_NO_AA, s_cmp);
       VSB_CUDA(cudaEventRecord(ev_cmp[k], s_cmp));
       VSB_CUDA(cudaStreamWaitEvent(s_out, ev_cmp[k], 0));
@@ -887,11 +893,16 @@ class Model {
   }
 
   void embed(const float* imgs, const uint8_t* msgs, int n_msgs, float* imgs_w, float* preds_w, int F, int H, int W, int step,
-             int video_mode, float scaling_i, float scaling_w, int flags, cudaStream_t st) {
+             int video_mode, int chunk_keys, float scaling_i, float scaling_w, int flags, cudaStream_t st) {
     check_ready();
     VSB_CHECK(F > 0 && H > 0 && W > 0 && step >= 1, "bad embed shape");
     VSB_CHECK(n_msgs == 1 || (n_msgs == F && step == 1), "msgs must be [1,K], or [F,K] in image mode");
-    if (video_mode == VSB_VIDEO_INTERPOLATE) throw Error("video_mode='interpolate' is not implemented on the GPU path");
+    // 'interpolate' mixes neighbouring key frames inside one reference chunk (videoseal.py:300-331 chunks by chunk_size
+    // key frames; :101-113 interpolates within the chunk), so U-Net batches are whole chunks in that mode
+    const bool interp = (video_mode == VSB_VIDEO_INTERPOLATE) && step > 1;
+    if (interp) VSB_CHECK(chunk_keys >= 1 && chunk_keys <= kMaxBatch, "video_mode='interpolate' needs 1 <= chunk_size <= 64");
+    const int kbatch = interp ? (kMaxBatch / chunk_keys) * chunk_keys : kMaxBatch;
+    const int bint = interp ? chunk_keys : 0;
     const int S = d.img_size;
     const bool same = (H == S && W == S);
     const bool aa = !(flags & VSB_FLAG_RESIZE_NO_AA);
@@ -901,8 +912,8 @@ class Model {
     const long fstride = (long)3 * H * W;
     const int nkeys = (F + step - 1) / step;
     ResampleDev* up = same ? nullptr : get_resampler(S, S, H, W, aa);
-    for (int k0 = 0; k0 < nkeys; k0 += kMaxBatch) {
-      const int nk = std::min(kMaxBatch, nkeys - k0);
+    for (int k0 = 0; k0 < nkeys; k0 += kbatch) {
+      const int nk = std::min(kbatch, nkeys - k0);
       const int f0 = k0 * step, f1 = std::min(F, (k0 + nk) * step);
       Plan* pl = get_embed_plan(nk);
       const float* x = imgs + (size_t)f0 * fstride;
@@ -933,7 +944,7 @@ class Model {
         }
         lowres_buf = tmp.alloc_n<float>((size_t)nf * d.unet_out_ch * S * S);
         dim3 grid((S + kBlendTW - 1) / kBlendTW, (S + kBlendTH - 1) / kBlendTH, nf);
-        jnd_lowres_kernel<<<grid, 256, 0, st>>>(frames_res, delta, lowres_buf, S, S, d.unet_out_ch, step, balt);
+        jnd_lowres_kernel<<<grid, 256, 0, st>>>(frames_res, delta, lowres_buf, S, S, d.unet_out_ch, step, balt, bint);
         g_launches += 1;
         BlendParams bp;
         memset(&bp, 0, sizeof(bp));
@@ -952,6 +963,7 @@ class Model {
       bp.imgs = imgs + (size_t)f0 * fstride; bp.delta = delta; bp.imgs_w = imgs_w + (size_t)f0 * fstride;
       bp.preds_w = preds_w ? preds_w + (size_t)f0 * d.unet_out_ch * H * W : nullptr;
       bp.F = nf; bp.H = H; bp.W = W; bp.PH = S; bp.PW = S; bp.CD = d.unet_out_ch; bp.step = bstep; bp.alternate = balt;
+      bp.interp_chunk = bint;
       bp.use_jnd = use_jnd ? 1 : 0; bp.clamp = (flags & VSB_FLAG_CLAMP) ? 1 : 0; bp.identity_resample = same ? 1 : 0;
       bp.scaling_i = scaling_i; bp.scaling_w = scaling_w;
       if (up) bp.tab = up->tab;
@@ -977,7 +989,7 @@ class Model {
     std::vector<float> h((size_t)H * W, 1.0f);
     VSB_CUDA(cudaMemcpyAsync(ones, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, st));
     dim3 grid((W + kBlendTW - 1) / kBlendTW, (H + kBlendTH - 1) / kBlendTH, F);
-    jnd_lowres_kernel<<<grid, 256, 0, st>>>(imgs, ones, hmaps, H, W, 1, 1 << 30, 0);
+    jnd_lowres_kernel<<<grid, 256, 0, st>>>(imgs, ones, hmaps, H, W, 1, 1 << 30, 0, 0);
     g_launches += 1;
     VSB_CUDA(cudaGetLastError());
     VSB_CUDA(cudaStreamSynchronize(st));

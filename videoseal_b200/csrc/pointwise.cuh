@@ -141,12 +141,30 @@ __global__ void msg_embed_kernel(const uint8_t* __restrict__ msgs, const float* 
 struct BlendParams {
   const float* imgs; const float* delta; float* imgs_w; float* preds_w;
   int F, H, W, PH, PW, CD, step, alternate;
+  int interp_chunk;  // > 0: video_mode 'interpolate' with this many key frames per chunk (frame 0 starts a chunk)
   int use_jnd, clamp, identity_resample;
   float scaling_i, scaling_w;
   ResampleTab tab;  // delta (PH x PW) -> (H x W); unused when identity_resample
 };
 
 constexpr int kBlendTW = 128, kBlendTH = 8;
+
+// Which key-frame deltas feed frame f (models/videoseal.py:80-118).  repeat: key f/step.  alternate: key f/step on the
+// key frames, nothing in between.  interpolate: inside a chunk of `interp_chunk` keys, frames before the chunk's last key
+// mix key k and k+1 with alpha = 1 - (f % step)/(step-1) (torch.linspace(0,1,step)); from the last key on, that key alone.
+struct FrameKeys { int k0, k1; float a; bool has; };
+__device__ __forceinline__ FrameKeys frame_keys(int f, int F, int step, int alternate, int interp_chunk) {
+  FrameKeys r;
+  const int kf = f / step, ph = f - kf * step;
+  r.k0 = kf; r.k1 = kf; r.a = 1.f; r.has = !(alternate && ph != 0);
+  if (interp_chunk > 0) {
+    const int nkeys = (F + step - 1) / step;
+    const int c0 = (kf / interp_chunk) * interp_chunk;
+    const int nc = min(interp_chunk, nkeys - c0);
+    if (kf - c0 < nc - 1 && step > 1) { r.k1 = kf + 1; r.a = 1.f - (float)ph / (float)(step - 1); }
+  }
+  return r;
+}
 
 __device__ __forceinline__ float jnd_from_lum(const float (*lum)[kBlendTW + 4 + 1], int ly, int lx) {
   // lum holds L = 255 * Y with a 2-pixel zero halo; (ly, lx) index the centre pixel inside the halo tile
@@ -187,9 +205,9 @@ __global__ void __launch_bounds__(256) jnd_blend_kernel(BlendParams p) {
   const int tx = (threadIdx.x & 31) * 4, ty = threadIdx.x >> 5;
   const int gy = y0 + ty, gx = x0 + tx;
   if (gy >= p.H || gx >= p.W) return;
-  const int key = f / p.step;
-  const bool has_delta = !(p.alternate && (f % p.step) != 0);
-  const float* dl = p.delta + (long)key * p.CD * p.PH * p.PW;
+  const FrameKeys fk = frame_keys(f, p.F, p.step, p.alternate, p.interp_chunk);
+  const bool has_delta = fk.has;
+  const int nsrc = (fk.k1 != fk.k0 && fk.a != 1.f) ? 2 : 1;
   float hm[4], d[3][4];
   const int nvalid = min(4, p.W - gx);
 #pragma unroll
@@ -202,17 +220,21 @@ __global__ void __launch_bounds__(256) jnd_blend_kernel(BlendParams p) {
     for (int q = 0; q < 4; ++q) {
       float v = 0.f;
       if (has_delta && q < nvalid) {
-        const float* src = dl + (long)c * p.PH * p.PW;
-        if (p.identity_resample) {
-          v = __ldg(src + (long)gy * p.PW + gx + q);
-        } else {
-          const int ox = gx + q;
-          const int ys = p.tab.ystart[gy], yc = p.tab.ycnt[gy], xs = p.tab.xstart[ox], xc = p.tab.xcnt[ox];
-          for (int j = 0; j < yc; ++j) {
-            float racc = 0.f;
-            for (int i = 0; i < xc; ++i) racc += p.tab.xw[ox * p.tab.maxt_x + i] * __ldg(src + (long)(ys + j) * p.PW + xs + i);
-            v += p.tab.yw[gy * p.tab.maxt_y + j] * racc;
+        for (int s = 0; s < nsrc; ++s) {
+          const float* src = p.delta + ((long)(s ? fk.k1 : fk.k0) * p.CD + c) * p.PH * p.PW;
+          float vs = 0.f;
+          if (p.identity_resample) {
+            vs = __ldg(src + (long)gy * p.PW + gx + q);
+          } else {
+            const int ox = gx + q;
+            const int ys = p.tab.ystart[gy], yc = p.tab.ycnt[gy], xs = p.tab.xstart[ox], xc = p.tab.xcnt[ox];
+            for (int j = 0; j < yc; ++j) {
+              float racc = 0.f;
+              for (int i = 0; i < xc; ++i) racc += p.tab.xw[ox * p.tab.maxt_x + i] * __ldg(src + (long)(ys + j) * p.PW + xs + i);
+              vs += p.tab.yw[gy * p.tab.maxt_y + j] * racc;
+            }
           }
+          v += (nsrc == 1 ? 1.f : (s ? 1.f - fk.a : fk.a)) * vs;
         }
       }
       d[c][q] = v * hm[q];
@@ -251,7 +273,8 @@ __global__ void __launch_bounds__(256) jnd_blend_kernel(BlendParams p) {
 // low-resolution attenuation (wam.py:177-180): delta[k] *= hmap(imgs_res[k*step ... ]) is per FRAME in video mode, so this
 // kernel writes a per-frame attenuated delta:  out[f] = hmap(imgs_res[f]) * delta[f / step]   (all at PH x PW)
 __global__ void __launch_bounds__(256) jnd_lowres_kernel(const float* __restrict__ imgs_res, const float* __restrict__ delta,
-                                                         float* __restrict__ out, int PH, int PW, int CD, int step, int alternate) {
+                                                         float* __restrict__ out, int PH, int PW, int CD, int step, int alternate,
+                                                         int interp_chunk) {
   __shared__ float lum[kBlendTH + 4][kBlendTW + 4 + 1];
   const int f = blockIdx.z;
   const int x0 = blockIdx.x * kBlendTW, y0 = blockIdx.y * kBlendTH;
@@ -271,14 +294,18 @@ __global__ void __launch_bounds__(256) jnd_lowres_kernel(const float* __restrict
   const int tx = (threadIdx.x & 31) * 4, ty = threadIdx.x >> 5;
   const int gy = y0 + ty;
   if (gy >= PH) return;
-  const int key = f / step;
-  const bool has_delta = !(alternate && (f % step) != 0);
+  const FrameKeys fk = frame_keys(f, (int)gridDim.z, step, alternate, interp_chunk);
   for (int q = 0; q < 4; ++q) {
     const int gx = x0 + tx + q;
     if (gx >= PW) break;
     const float hm = jnd_from_lum(lum, ty + 2, tx + q + 2);
     for (int c = 0; c < CD; ++c) {
-      const float dv = has_delta ? delta[((long)key * CD + c) * plane + (long)gy * PW + gx] : 0.f;
+      const long o = (long)gy * PW + gx;
+      float dv = 0.f;
+      if (fk.has) {
+        dv = delta[((long)fk.k0 * CD + c) * plane + o];
+        if (fk.k1 != fk.k0) dv = fk.a * dv + (1.f - fk.a) * delta[((long)fk.k1 * CD + c) * plane + o];
+      }
       out[((long)f * CD + c) * plane + (long)gy * PW + gx] = hm * dv;
     }
   }
@@ -632,25 +659,51 @@ __global__ void __launch_bounds__(256) grn_scale_kernel(float* __restrict__ stat
   }
 }
 
-// K2d: apply the GRN multiplier in place: g[m, k] *= scale[m / rows_per_sample, k]  (fp16, 128-bit vectorised).  For all but
-// the first stage g fits in the 126 MB L2, so this pass mostly runs out of L2; pwconv2 is then a plain TMA-fed GEMM.
-__global__ void __launch_bounds__(256) grn_apply_kernel(__half* __restrict__ g, long M, int K, int ld, const float* __restrict__ scale,
-                                                        int ld_scale, int rows_per_sample) {
+// K2d: GRN (common.py:166-169) applied in place on the fp16 pwconv1 output, fused with the statistics -> multiplier step:
+//   Gx = sqrt(stats[b,k]);  Nx = Gx / (mean_k Gx + 1e-6);  g[m,k] *= gamma[k] * Nx + 1     (beta is folded into pwconv2's bias)
+// One block per (sample, row-slab); the per-sample mean is recomputed by every block (K <= 3072 values).  `stats_next` (the
+// ping-pong buffer the NEXT block's pwconv1 accumulates into) is cleared here.  For all but the first stage g fits in the
+// 126 MB L2, so this pass mostly runs out of L2; pwconv2 is then a plain TMA-fed GEMM.
+__global__ void __launch_bounds__(256) grn_apply_kernel(__half* __restrict__ g, int rows_per_sample, int K, int ld,
+                                                        const float* __restrict__ stats, float* __restrict__ stats_next,
+                                                        const float* __restrict__ gamma, int slabs) {
+  extern __shared__ float sc[];   // [K] multipliers of this sample
+  __shared__ float red[8];
+  __shared__ float mean_s;
+  const int b = blockIdx.x / slabs, slab = blockIdx.x - b * slabs;
+  const float* st = stats + (long)b * K;
+  float sum = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) { const float gx = sqrtf(st[k]); sc[k] = gx; sum += gx; }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    mean_s = t / (float)K;
+  }
+  __syncthreads();
+  const float inv = 1.0f / (mean_s + 1e-6f);
+  for (int k = threadIdx.x; k < K; k += blockDim.x) sc[k] = __ldg(gamma + k) * (sc[k] * inv) + 1.0f;
+  if (slab == 0) for (int k = threadIdx.x; k < K; k += blockDim.x) stats_next[(long)b * K + k] = 0.f;
+  __syncthreads();
   const int k8 = K >> 3;
-  const long total = M * k8;
-  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (long)gridDim.x * blockDim.x) {
+  const int r0 = (int)(((long)rows_per_sample * slab) / slabs), r1 = (int)(((long)rows_per_sample * (slab + 1)) / slabs);
+  const long total = (long)(r1 - r0) * k8;
+  __half* base = g + ((long)b * rows_per_sample + r0) * ld;
+  for (long i = threadIdx.x; i < total; i += blockDim.x) {
     const long m = i / k8;
     const int k = (int)(i - m * k8) * 8;
-    const float* sc = scale + (m / rows_per_sample) * ld_scale + k;
-    const float4 s0 = __ldg(reinterpret_cast<const float4*>(sc)), s1 = __ldg(reinterpret_cast<const float4*>(sc) + 1);
-    uint4* ptr = reinterpret_cast<uint4*>(g + m * ld + k);
+    uint4* ptr = reinterpret_cast<uint4*>(base + m * ld + k);
     uint4 v = *ptr;
     __half2* h = reinterpret_cast<__half2*>(&v);
-    float2 f;
-    f = __half22float2(h[0]); f.x *= s0.x; f.y *= s0.y; h[0] = __float22half2_rn(f);
-    f = __half22float2(h[1]); f.x *= s0.z; f.y *= s0.w; h[1] = __float22half2_rn(f);
-    f = __half22float2(h[2]); f.x *= s1.x; f.y *= s1.y; h[2] = __float22half2_rn(f);
-    f = __half22float2(h[3]); f.x *= s1.z; f.y *= s1.w; h[3] = __float22half2_rn(f);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float2 f = __half22float2(h[q]);
+      f.x *= sc[k + 2 * q]; f.y *= sc[k + 2 * q + 1];
+      h[q] = __float22half2_rn(f);
+    }
     *ptr = v;
   }
 }

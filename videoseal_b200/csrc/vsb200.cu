@@ -65,10 +65,12 @@ int vsb_model_finalize(vsb_model* m, int32_t device) {
 void vsb_model_destroy(vsb_model* m) { delete m; }
 
 int vsb_embed(vsb_model* m, const float* imgs, const uint8_t* msgs, int32_t n_msgs, float* imgs_w, float* preds_w, int32_t F, int32_t H,
-              int32_t W, int32_t step, int32_t video_mode, float scaling_i, float scaling_w, int32_t flags, void* stream) {
+              int32_t W, int32_t step, int32_t video_mode, int32_t chunk_keys, float scaling_i, float scaling_w, int32_t flags,
+              void* stream) {
   VSB_API_BEGIN
   VSB_CHECK(m && imgs && msgs && imgs_w, "null argument");
-  m->impl.embed(imgs, msgs, n_msgs, imgs_w, preds_w, F, H, W, step, video_mode, scaling_i, scaling_w, flags, (cudaStream_t)stream);
+  m->impl.embed(imgs, msgs, n_msgs, imgs_w, preds_w, F, H, W, step, video_mode, chunk_keys, scaling_i, scaling_w, flags,
+                (cudaStream_t)stream);
   return VSB_OK;
   VSB_API_END
 }
@@ -98,7 +100,8 @@ int vsb_jnd_heatmaps(vsb_model* m, const float* imgs, float* hmaps, int32_t F, i
 }
 
 int vsb_embed_host(vsb_model* m, const float* imgs_h, const uint8_t* msgs_h, int32_t n_msgs, float* imgs_w_h, float* preds_w_h, int32_t F,
-                   int32_t H, int32_t W, int32_t step, int32_t video_mode, float scaling_i, float scaling_w, int32_t flags) {
+                   int32_t H, int32_t W, int32_t step, int32_t video_mode, int32_t chunk_keys, float scaling_i, float scaling_w,
+                   int32_t flags) {
   VSB_API_BEGIN
   VSB_CHECK(m && imgs_h && msgs_h && imgs_w_h, "null argument");
   m->impl.check_ready();
@@ -112,7 +115,7 @@ int vsb_embed_host(vsb_model* m, const float* imgs_h, const uint8_t* msgs_h, int
   cudaStream_t st = 0;
   VSB_CUDA(cudaMemcpyAsync(imgs, imgs_h, n * sizeof(float), cudaMemcpyHostToDevice, st));
   VSB_CUDA(cudaMemcpyAsync(msgs, msgs_h, (size_t)n_msgs * m->impl.d.nbits, cudaMemcpyHostToDevice, st));
-  m->impl.embed(imgs, msgs, n_msgs, out, pw, F, H, W, step, video_mode, scaling_i, scaling_w, flags, st);
+  m->impl.embed(imgs, msgs, n_msgs, out, pw, F, H, W, step, video_mode, chunk_keys, scaling_i, scaling_w, flags, st);
   VSB_CUDA(cudaMemcpyAsync(imgs_w_h, out, n * sizeof(float), cudaMemcpyDeviceToHost, st));
   if (pw) VSB_CUDA(cudaMemcpyAsync(preds_w_h, pw, np * sizeof(float), cudaMemcpyDeviceToHost, st));
   VSB_CUDA(cudaStreamSynchronize(st));
@@ -139,10 +142,12 @@ int vsb_detect_host(vsb_model* m, const float* imgs_h, float* logits_h, int32_t 
 }
 
 int vsb_embed_detect_host(vsb_model* m, const float* imgs_h, const uint8_t* msgs_h, int32_t n_msgs, float* imgs_w_h, float* logits_h,
-                          int32_t F, int32_t H, int32_t W, int32_t step, int32_t video_mode, float scaling_i, float scaling_w, int32_t flags) {
+                          int32_t F, int32_t H, int32_t W, int32_t step, int32_t video_mode, int32_t chunk_keys, float scaling_i,
+                          float scaling_w, int32_t flags) {
   VSB_API_BEGIN
   VSB_CHECK(m && imgs_h && msgs_h && imgs_w_h && logits_h, "null argument");
-  m->impl.embed_detect_host(imgs_h, msgs_h, n_msgs, imgs_w_h, logits_h, F, H, W, step, video_mode, scaling_i, scaling_w, flags);
+  m->impl.embed_detect_host(imgs_h, msgs_h, n_msgs, imgs_w_h, logits_h, F, H, W, step, video_mode, chunk_keys, scaling_i, scaling_w,
+                            flags);
   return VSB_OK;
   VSB_API_END
 }

@@ -230,7 +230,7 @@ class Videoseal(nn.Module):
         _lib.check(_lib.lib().vsb_embed(
             self._handle(), x.data_ptr(), mm.data_ptr(), mm.shape[0], imgs_w.data_ptr(),
             preds_w.data_ptr() if preds_w is not None else None, F_, H, W, step, _lib.VIDEO_MODES[self.video_mode],
-            float(self.blender.scaling_i), float(self.blender.scaling_w), self._flags(interpolation, lowres_attenuation),
+            int(self.chunk_size), float(self.blender.scaling_i), float(self.blender.scaling_w), self._flags(interpolation, lowres_attenuation),
             self._stream()))
         if is_video:
             return {"imgs_w": imgs_w.to(imgs.device), "msgs": msgs[0:1].repeat(F_, 1)}
