@@ -8,7 +8,7 @@ import torch.nn.functional as F
 
 from videoseal_b200 import _lib
 
-LD_TMA, LD_GCONV, LD_GUPS, LD_GSCALE, LD_HALO = 0, 1, 2, 3, 4
+LD_TMA, LD_GCONV, LD_GUPS, LD_GSCALE, LD_HALO, LD_DIRECT = 0, 1, 2, 3, 4, 5
 
 CASES = {
     # name: dict(loader, B, IH, IW, C0, C1, R, S, stride, pad, pad_mode, N, extras...)
@@ -29,6 +29,16 @@ CASES = {
     "halo_bott":       dict(loader=LD_HALO, B=24, IH=32, IW=32, C0=384, N=384, R=3, S=3, pad=1, bias=True, act=1, resid16=True, out="f16"),
     "halo_outc":       dict(loader=LD_HALO, B=2, IH=128, IW=128, C0=16, N=16, R=3, S=3, pad=1, bias=True, act=1, resid16=True, n_out=1, out="none"),
     "halo_outc3":      dict(loader=LD_HALO, B=1, IH=64, IW=64, C0=64, N=64, R=3, S=3, pad=1, bias=True, act=1, resid16=True, n_out=3, out="none"),
+    # direct 3x3 (conv3_direct.cuh): ring of padded rows in 8-channel planes, one MMA per tap straight from the ring
+    "direct_c16_w64":  dict(loader=LD_DIRECT, B=2, IH=64, IW=64, C0=16, N=16, R=3, S=3, pad=1, bias=True, act=1, resid16=True, out="f16"),
+    "direct_c16_w256": dict(loader=LD_DIRECT, B=2, IH=24, IW=256, C0=16, N=16, R=3, S=3, pad=1, bias=True, act=1, resid16=True, out="f16"),
+    "direct_c32":      dict(loader=LD_DIRECT, B=3, IH=48, IW=128, C0=32, N=32, R=3, S=3, pad=1, bias=True, act=1, out="f16"),
+    "direct_c64":      dict(loader=LD_DIRECT, B=2, IH=64, IW=64, C0=64, N=64, R=3, S=3, pad=1, bias=True, act=1, resid16=True, out="f16"),
+    "direct_c32_n16":  dict(loader=LD_DIRECT, B=1, IH=32, IW=96, C0=32, N=16, R=3, S=3, pad=1, bias=True, act=1, out="f16"),
+    "direct_outc":     dict(loader=LD_DIRECT, B=2, IH=32, IW=256, C0=16, N=16, R=3, S=3, pad=1, bias=True, act=1, resid16=True, n_out=1, out="none"),
+    "direct_outc3":    dict(loader=LD_DIRECT, B=1, IH=64, IW=64, C0=64, N=64, R=3, S=3, pad=1, bias=True, act=1, resid16=True, n_out=3, out="none"),
+    "direct_ringwrap": dict(loader=LD_DIRECT, B=96, IH=128, IW=128, C0=16, N=16, R=3, S=3, pad=1, bias=True, act=1, resid16=True, out="f16"),
+    "direct_wrap_c64": dict(loader=LD_DIRECT, B=80, IH=64, IW=64, C0=64, N=64, R=3, S=3, pad=1, bias=True, act=1, out="f16"),
     "gups_c16":        dict(loader=LD_GUPS, B=1, IH=64, IW=64, C0=16, C1=16, N=16, R=3, S=3, epi=1, act=1, out="f16"),
     "gconv_s2":        dict(loader=LD_GCONV, B=2, IH=64, IW=64, C0=16, N=32, R=3, S=3, stride=2, pad=1, bias=True, out="f16"),
     "gconv_patch":     dict(loader=LD_GCONV, B=2, IH=16, IW=16, C0=96, N=192, R=2, S=2, stride=2, pad=0, bias=True, out="f32"),

@@ -1,0 +1,97 @@
+// Host side of conv3_direct.cuh: geometry, tensor map, shared-memory plan, launch.
+#pragma once
+#include "conv3_direct.cuh"
+#include "conv_gemm_host.cuh"
+
+namespace vsb {
+
+struct Conv3DirectOp {
+  Conv3DirectParams p;
+  int grid = 0;
+  size_t smem = 0;
+  Conv3DirectOp() { memset(&p, 0, sizeof(p)); }
+};
+
+// ring rows that fit next to the resident weights for a W-wide map (0 = channel counts not supported)
+inline int conv3_direct_ring_rows(int C, int N, int W) {
+  if (!((C == 16 || C == 32 || C == 64) && (N == 16 || N == 32 || N == 64))) return 0;
+  const int rw = (W + 2 + 7) / 8 * 8;
+  const uint32_t w_pad = ((uint32_t)((size_t)N * 9 * C * 2) + 1023u) & ~1023u;
+  const size_t budget = 227 * 1024 - 1024 /*alignment slack*/ - kD3HeaderBytes - w_pad;
+  int rows = (int)(budget / ((size_t)C * 2 * rw)) - (128 / rw + 1);
+  rows = std::min(rows, kD3MaxRing);
+  rows = std::min(rows, (kD3TileBars - 16) * 128 / rw);   // tiles in flight must stay below the tile_done barrier ring
+  return rows;
+}
+// W = 0: channel-count check only (weight packing time)
+inline bool conv3_direct_ok(int C, int N, int ld_in, int W = 0) {
+  static const bool off = getenv("VSB_NO_DIRECT") != nullptr;
+  if (off || ld_in != C) return false;
+  if (W == 0) return conv3_direct_ring_rows(C, N, 64) > 0;
+  return conv3_direct_ring_rows(C, N, W) >= 8;
+}
+
+// x: dense NHWC fp16 [B,H,W,C]; wpk: weights in core-matrix layout (pack_direct_weights_kernel), N*9*C halves
+inline void setup_conv3_direct(Conv3DirectOp& op, const __half* x, int B, int H, int W, int C, int N, const __half* wpk, int num_sms) {
+  Conv3DirectParams& p = op.p;
+  VSB_CHECK(conv3_direct_ring_rows(C, N, W) > 0, "direct conv3: unsupported channel counts");
+  p.B = B; p.H = H; p.W = W; p.C = C; p.N = N;
+  p.rw = (W + 2 + 7) / 8 * 8;
+  p.hp = H + 2;
+  const long positions = (long)B * p.hp * p.rw;
+  VSB_CHECK(positions + 3L * p.rw < (1L << 31) - 1024, "direct conv3: batch too large for 32-bit positions");
+  p.n_tiles = (int)((positions + 127) / 128);
+  p.mirror_rows = 128 / p.rw + 1;
+  p.w_bytes = (uint32_t)((size_t)N * 9 * C * 2);
+  const uint32_t w_pad = (p.w_bytes + 1023u) & ~1023u;
+  const int rows = conv3_direct_ring_rows(C, N, W);
+  VSB_CHECK(rows >= 8, "direct conv3: shared-memory ring too small");
+  p.ring_rows = rows;
+  p.plane_stride = (uint32_t)((size_t)(rows + p.mirror_rows) * p.rw * 16);
+  p.w_off = kD3HeaderBytes;
+  p.ring_off = kD3HeaderBytes + w_pad;
+  op.smem = 1024 + (size_t)p.ring_off + (size_t)(C / 8) * p.plane_stride;
+  p.acc_stages = kD3MaxAcc;      // 8 stages x N <= 64 columns
+  p.tmem_cols = kD3MaxAcc * N;   // 128 / 256 / 512: powers of two
+  p.idesc = (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(128 >> 4) << 24);
+  p.fd_rw = make_fastdiv(p.rw);
+  p.fd_hp = make_fastdiv(p.hp);
+  p.wpk = wpk;
+  static const bool swap = getenv("VSB_DIRECT_SWAP") != nullptr;
+  p.swap_lbo_sbo = swap ? 1 : 0;
+  p.x = x;
+  VSB_CHECK((reinterpret_cast<uintptr_t>(x) & 15) == 0, "direct conv3: input must be 16-byte aligned");
+  op.grid = std::min(num_sms, p.n_tiles);
+}
+
+template <int N, int KS>
+inline void launch_direct_nk(const Conv3DirectOp& op, cudaStream_t st) {
+  static bool attr = false;
+  if (!attr) {
+    VSB_CUDA(cudaFuncSetAttribute(conv3_direct_kernel<N, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr = true;
+  }
+  conv3_direct_kernel<N, KS><<<op.grid, kD3Threads, op.smem, st>>>(op.p);
+  VSB_CUDA(cudaGetLastError());
+}
+template <int N>
+inline void launch_direct_n(const Conv3DirectOp& op, cudaStream_t st) {
+  if (op.p.C == 16) launch_direct_nk<N, 1>(op, st);
+  else if (op.p.C == 32) launch_direct_nk<N, 2>(op, st);
+  else launch_direct_nk<N, 4>(op, st);
+}
+
+inline void launch_direct(const Conv3DirectOp& op, cudaStream_t st) {
+  VSB_CHECK(op.smem <= 227 * 1024, "direct conv3: shared-memory plan too large");
+  if (op.p.N == 16) launch_direct_n<16>(op, st);
+  else if (op.p.N == 32) launch_direct_n<32>(op, st);
+  else launch_direct_n<64>(op, st);
+}
+
+// [N][9*C] fp16 on the device -> a new buffer in the direct layout
+inline void pack_direct_weights(const __half* w, int N, int C, __half* out, cudaStream_t st) {
+  pack_direct_weights_kernel<<<32, 256, 0, st>>>(w, N, C, out);
+  VSB_CUDA(cudaGetLastError());
+}
+
+}  // namespace vsb

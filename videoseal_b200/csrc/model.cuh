@@ -10,6 +10,7 @@
 
 #include "../../include/vsb200.h"
 #include "conv_gemm_host.cuh"
+#include "conv3_direct_host.cuh"
 #include "pointwise.cuh"
 
 namespace vsb {
@@ -46,6 +47,7 @@ struct DevicePool {
 
 struct ConvW {          // packed conv / linear weights: fp16 [N][K] (K order r,s,c) + fp32 bias
   __half* w = nullptr;
+  __half* wd = nullptr;  // 3x3 convs eligible for conv3_direct.cuh: the same weights in its core-matrix layout
   float* bias = nullptr;
   int N = 0, K = 0;
 };
@@ -302,8 +304,15 @@ class Model {
     return C <= halo_max_c;
   }
   ConvW pack_conv3(const std::string& wkey, const std::vector<float>* out_scale, const std::vector<float>& bias) {
-    const int C = (int)get(wkey).shape[1];
-    return use_halo(C) ? pack_conv_halo(wkey, out_scale, bias, C, 0) : pack_conv(wkey, out_scale, bias);
+    const int C = (int)get(wkey).shape[1], N = (int)get(wkey).shape[0];
+    ConvW cw = use_halo(C) ? pack_conv_halo(wkey, out_scale, bias, C, 0) : pack_conv(wkey, out_scale, bias);
+    if (conv3_direct_ok(C, N, C)) {
+      ConvW plain = use_halo(C) ? pack_conv(wkey, out_scale, {}) : cw;   // [N][9*C], K order (r, s, c)
+      cw.wd = wpool.alloc_n<__half>((size_t)N * 9 * C);
+      pack_direct_weights(plain.w, N, C, cw.wd, 0);
+      VSB_CUDA(cudaStreamSynchronize(0));
+    }
+    return cw;
   }
   // eval-mode BatchNorm2d folded into the preceding bias-free conv: w' = w*g/sqrt(var+eps), b' = beta - mean*g/sqrt(var+eps)
   void bn_fold(const std::string& bn, std::vector<float>& scale, std::vector<float>& bias) const {
@@ -484,12 +493,25 @@ class Model {
       op.p.epi = EPI_AFFINE; op.p.act = ACT_NONE; op.p.bias = w.res.bias; op.p.out16 = r; op.p.ld_out16 = Cout;
       add_conv(pl, op, w.res, "unet.conv1x1." + std::to_string(Cin) + "-" + std::to_string(Cout) + "@" + std::to_string(H));
     }
-    {  // conv3 + BN + ReLU
+    const std::string sfx = "@" + std::to_string(H);
+    if (w.c1.wd && conv3_direct_ok(Cin, Cout, ldx, W)) {  // conv3 + BN + ReLU, narrow layers: straight from a ring of padded rows
+      Conv3DirectOp op; setup_conv3_direct(op, x, B, H, W, Cin, Cout, w.c1.wd, num_sms);
+      op.p.bias = w.c1.bias; op.p.out = h;
+      pl.steps.push_back(Step{[op](cudaStream_t st) { launch_direct(op, st); }, 1, "unet.conv3x3d." + std::to_string(Cin) + "-" + std::to_string(Cout) + sfx});
+    } else {  // conv3 + BN + ReLU
       ConvGemmOp op; setup_conv3(op, x, B, H, W, Cin, ldx);
       op.p.epi = EPI_AFFINE; op.p.act = ACT_RELU; op.p.bias = w.c1.bias; op.p.out16 = h; op.p.ld_out16 = Cout;
       add_conv(pl, op, w.c1, "unet.conv3x3." + std::to_string(Cin) + "-" + std::to_string(Cout) + "@" + std::to_string(H));
     }
-    {  // conv3 + BN + ReLU, + res
+    if (w.c2.wd && conv3_direct_ok(Cout, Cout, Cout, W) && (out == nullptr || ld_out == Cout)) {
+      Conv3DirectOp op; setup_conv3_direct(op, h, B, H, W, Cout, Cout, w.c2.wd, num_sms);
+      op.p.bias = w.c2.bias; op.p.resid = r; op.p.out = out;
+      if (fuse_outc) {
+        op.p.outc_w = outc_w; op.p.outc_b = outc_b; op.p.n_out = d.unet_out_ch; op.p.delta = pl.delta; op.p.outc_tanh = d.unet_last_tanh;
+      }
+      pl.steps.push_back(Step{[op](cudaStream_t st) { launch_direct(op, st); }, 1,
+                              std::string(fuse_outc ? "unet.conv3x3d+outc." : "unet.conv3x3d.") + std::to_string(Cout) + "-" + std::to_string(Cout) + sfx});
+    } else {  // conv3 + BN + ReLU, + res
       ConvGemmOp op; setup_conv3(op, h, B, H, W, Cout, Cout);
       op.p.epi = EPI_AFFINE; op.p.act = ACT_RELU; op.p.bias = w.c2.bias; op.p.resid16 = r; op.p.ld_res16 = Cout;
       if (fuse_outc) {
@@ -537,7 +559,13 @@ class Model {
     std::vector<__half*> skips;  // outputs of inc, downs[0..]
     std::vector<int> skip_ld;
     __half* x = pl.pool.alloc_n<__half>(M0 * z[0]);
-    {
+    if (inc_c2.wd && conv3_direct_ok(z[0], z[0], z[0], S)) {
+      Conv3DirectOp op; setup_conv3_direct(op, h1, B, S, S, z[0], z[0], inc_c2.wd, num_sms);
+      op.p.bias = inc_c2.bias; op.p.resid = r0; op.p.out = x;
+      pl.steps.push_back(Step{[op](cudaStream_t st) { launch_direct(op, st); }, 1,
+                              "unet.conv3x3d." + std::to_string(z[0]) + "-" + std::to_string(z[0]) + "@" + std::to_string(S)});
+      dbg(pl, "inc", x, 1, B, S, S, z[0], z[0]);
+    } else {
       ConvGemmOp op; setup_conv3(op, h1, B, S, S, z[0], z[0]);
       op.p.epi = EPI_AFFINE; op.p.act = ACT_RELU; op.p.bias = inc_c2.bias; op.p.resid16 = r0; op.p.ld_res16 = z[0];
       op.p.out16 = x; op.p.ld_out16 = z[0];
