@@ -97,7 +97,7 @@ def conv_flops(name: str, B: int) -> float:
         if kind == "unet.uptap1x1":
             cin, cout = (int(x) for x in dims.split("-"))
             return 2.0 * M * cout * cin
-        if kind == "unet.conv1x1":
+        if kind in ("unet.conv1x1", "unet.conv1x1d"):
             cin, cout = (int(x) for x in dims.split("-"))
             return 2.0 * M * cout * cin
         if kind == "cnx.down2x2s2":

@@ -37,6 +37,10 @@ CASES = {
     "direct_c32_n16":  dict(loader=LD_DIRECT, B=1, IH=32, IW=96, C0=32, N=16, R=3, S=3, pad=1, bias=True, act=1, out="f16"),
     "direct_outc":     dict(loader=LD_DIRECT, B=2, IH=32, IW=256, C0=16, N=16, R=3, S=3, pad=1, bias=True, act=1, resid16=True, n_out=1, out="none"),
     "direct_outc3":    dict(loader=LD_DIRECT, B=1, IH=64, IW=64, C0=64, N=64, R=3, S=3, pad=1, bias=True, act=1, resid16=True, n_out=3, out="none"),
+    "direct1_c16":     dict(loader=LD_DIRECT, B=2, IH=40, IW=256, C0=16, N=16, R=1, S=1, bias=True, out="f16"),
+    "direct1_c32":     dict(loader=LD_DIRECT, B=3, IH=128, IW=128, C0=32, N=32, R=1, S=1, bias=True, out="f16"),
+    "direct1_c64":     dict(loader=LD_DIRECT, B=70, IH=64, IW=64, C0=64, N=64, R=1, S=1, bias=True, out="f16"),
+    "direct1_wrap":    dict(loader=LD_DIRECT, B=96, IH=128, IW=128, C0=16, N=16, R=1, S=1, bias=True, act=1, out="f16"),
     "direct_ringwrap": dict(loader=LD_DIRECT, B=96, IH=128, IW=128, C0=16, N=16, R=3, S=3, pad=1, bias=True, act=1, resid16=True, out="f16"),
     "direct_wrap_c64": dict(loader=LD_DIRECT, B=80, IH=64, IW=64, C0=64, N=64, R=3, S=3, pad=1, bias=True, act=1, out="f16"),
     "gups_c16":        dict(loader=LD_GUPS, B=1, IH=64, IW=64, C0=16, C1=16, N=16, R=3, S=3, epi=1, act=1, out="f16"),

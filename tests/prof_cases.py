@@ -13,6 +13,7 @@ BIG = {
     "p_direct_c16": dict(loader=cc.LD_DIRECT, B=64, IH=256, IW=256, C0=16, N=16, R=3, S=3, pad=1, bias=True, act=1, resid16=True, out="f16"),
     "p_direct_c32": dict(loader=cc.LD_DIRECT, B=64, IH=128, IW=128, C0=32, N=32, R=3, S=3, pad=1, bias=True, act=1, resid16=True, out="f16"),
     "p_direct_c64": dict(loader=cc.LD_DIRECT, B=64, IH=64, IW=64, C0=64, N=64, R=3, S=3, pad=1, bias=True, act=1, resid16=True, out="f16"),
+    "p_direct1_c16": dict(loader=cc.LD_DIRECT, B=64, IH=256, IW=256, C0=16, N=16, R=1, S=1, bias=True, out="f16"),
     "p_halo3_c32":  dict(loader=cc.LD_HALO, B=64, IH=128, IW=128, C0=32, N=32, R=3, S=3, pad=1, bias=True, act=1, resid16=True, out="f16"),
     "p_conv3_c32":  dict(loader=cc.LD_TMA, B=64, IH=128, IW=128, C0=32, N=32, R=3, S=3, pad=1, bias=True, act=1, resid16=True, out="f16"),
     "p_halo3_c64":  dict(loader=cc.LD_HALO, B=64, IH=64, IW=64, C0=64, N=64, R=3, S=3, pad=1, bias=True, act=1, resid16=True, out="f16"),

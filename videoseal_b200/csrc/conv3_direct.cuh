@@ -31,8 +31,8 @@ constexpr int kD3Threads = 128 + kD3EpiSets * 128;
 constexpr int kD3HeaderBytes = 2048;
 
 struct Conv3DirectParams {
-  int B, H, W, C, N;
-  int rw, hp;               // linear row pitch in positions; H + 2
+  int B, H, W, C, N, R;     // R = 3 (3x3, zero pad 1) or 1 (1x1)
+  int rw, hp;               // linear row pitch in positions (>= W + R - 1, multiple of 8); H + R - 1
   int n_tiles;              // ceil(B*hp*rw / 128)
   int ring_rows, mirror_rows;
   int acc_stages, tmem_cols;
@@ -47,6 +47,7 @@ struct Conv3DirectParams {
   const float* bias;
   const __half* resid; __half* out;
   const float* outc_w; const float* outc_b; float* delta; int n_out, outc_tanh;
+  int relu;                 // 1: ReLU after the bias (before the residual)
 };
 
 struct D3Header {
@@ -67,11 +68,11 @@ __device__ __forceinline__ uint64_t make_smem_desc_ns(uint32_t saddr, uint32_t l
          (1ull << 46);
 }
 
-// [N][9*C] (k = (r*3+s)*C + c) fp16  ->  [tap][C/16][k-half][N/8][8 rows][8 halves]
-__global__ void pack_direct_weights_kernel(const __half* __restrict__ w, int N, int C, __half* __restrict__ out) {
-  const int total = N * 9 * C;
+// [N][T*C] (k = tap*C + c, T = 9 or 1 taps) fp16  ->  [tap][C/16][k-half][N/8][8 rows][8 halves]
+__global__ void pack_direct_weights_kernel(const __half* __restrict__ w, int N, int C, int T, __half* __restrict__ out) {
+  const int total = N * T * C;
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < total; i += gridDim.x * blockDim.x) {
-    const int n = i / (9 * C), k = i - n * 9 * C;
+    const int n = i / (T * C), k = i - n * T * C;
     const int tap = k / C, c = k - tap * C;
     const int kk = c >> 4, kh = (c >> 3) & 1, k8 = c & 7;
     const long o = ((((long)(tap * (C >> 4) + kk) * 2 + kh) * (N >> 3) + (n >> 3)) * 8 + (n & 7)) * 8 + k8;
@@ -79,7 +80,7 @@ __global__ void pack_direct_weights_kernel(const __half* __restrict__ w, int N, 
   }
 }
 
-template <int N, int KS>
+template <int N, int KS, int R>
 __global__ void __launch_bounds__(kD3Threads, 1) conv3_direct_kernel(const Conv3DirectParams p) {
   extern __shared__ uint8_t d3_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(d3_smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -95,7 +96,7 @@ __global__ void __launch_bounds__(kD3Threads, 1) conv3_direct_kernel(const Conv3
   const int nt = per + ((int)blockIdx.x < rem ? 1 : 0);
   const int t1 = t0 + nt;
   const int row_lo = p.fd_rw.div(128 * t0);
-  const int row_hi = p.fd_rw.div(128 * t1 + 1) + 2;   // last position read: 128*t1 - 1 + 2*rw + 2
+  const int row_hi = p.fd_rw.div(128 * t1 - 1 + (R - 1)) + (R - 1);   // last position read: 128*t1 - 1 + (R-1)*rw + (R-1)
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < kD3MaxRing; ++i) mbar_init(&hd->row_full[i], 32);   // 32 cp.async arrivals (one producer warp per row)
@@ -141,14 +142,15 @@ __global__ void __launch_bounds__(kD3Threads, 1) conv3_direct_kernel(const Conv3
         }
       }
       const int b = p.fd_hp.div(gi), yy = gi - b * p.hp;
-      const bool rvalid = b < p.B && yy >= 1 && yy <= p.H;
-      const __half* rowbase = p.x + ((long)b * p.H + (yy - 1)) * p.W * p.C;
+      constexpr int PAD = (R - 1) / 2;
+      const bool rvalid = b < p.B && yy >= PAD && yy < p.H + PAD;
+      const __half* rowbase = p.x + ((long)b * p.H + (yy - PAD)) * p.W * p.C;
       const bool mir = slot < p.mirror_rows;
       uint8_t* base0 = ring + (size_t)slot * rw * 16;
       for (int j = lane; j < nchunk; j += 32) {
         const int xx = j >> pshift, pl = j & (planes - 1);
-        const bool ok = rvalid && xx >= 1 && xx <= p.W;
-        const __half* src = ok ? rowbase + ((long)(xx - 1) * planes + pl) * 8 : p.x;
+        const bool ok = rvalid && xx >= PAD && xx < p.W + PAD;
+        const __half* src = ok ? rowbase + ((long)(xx - PAD) * planes + pl) * 8 : p.x;
         uint8_t* dst = base0 + (size_t)pl * p.plane_stride + (size_t)xx * 16;
         cp_async16_zfill(dst, src, ok ? 16u : 0u);
         if (mir) cp_async16_zfill(dst + (size_t)NR * rw * 16, src, ok ? 16u : 0u);
@@ -171,7 +173,7 @@ __global__ void __launch_bounds__(kD3Threads, 1) conv3_direct_kernel(const Conv3
       const uint32_t kk_step = (2u * p.plane_stride) >> 4;
       const int rows_total = row_hi - row_lo;
       int x0 = 128 * t0 - row_lo * rw, slot0 = 0;          // first output position of the tile: (ring slot, column)
-      int xn = x0 + 129, gn = 0;                            // last input position of tap (0, 2): row (relative), column
+      int xn = x0 + 127 + (R - 1), gn = 0;                  // last input position of tap (0, R-1): row (relative), column
       while (xn >= rw) { xn -= rw; ++gn; }
       int rows_conf = 0, rslot = 0;
       uint32_t rpar = 0;
@@ -184,7 +186,7 @@ __global__ void __launch_bounds__(kD3Threads, 1) conv3_direct_kernel(const Conv3
           while (xn >= rw) { xn -= rw; ++gn; }
           continue;
         }
-        const int need = min(rows_total, gn + 2);
+        const int need = min(rows_total, gn + (R - 1));
         while (rows_conf <= need) {
           mbar_wait(&hd->row_full[rslot], rpar);
           ++rows_conf;
@@ -199,13 +201,13 @@ __global__ void __launch_bounds__(kD3Threads, 1) conv3_direct_kernel(const Conv3
         int s2 = s1 + 1; if (s2 >= NR) s2 -= NR;
         const uint32_t arow[3] = {a_lo + (uint32_t)(slot0 * rw + x0), a_lo + (uint32_t)(s1 * rw + x0), a_lo + (uint32_t)(s2 * rw + x0)};
 #pragma unroll
-        for (int r = 0; r < 3; ++r) {
+        for (int r = 0; r < R; ++r) {
 #pragma unroll
-          for (int s = 0; s < 3; ++s) {
+          for (int s = 0; s < R; ++s) {
 #pragma unroll
             for (int kk = 0; kk < KS; ++kk) {
               const uint64_t adesc = a_hi | (uint64_t)(arow[r] + (uint32_t)s + (uint32_t)kk * kk_step);
-              const uint64_t bdesc = b_hi | (uint64_t)(b_lo + (uint32_t)(((r * 3 + s) * KS + kk) * 2 * N));
+              const uint64_t bdesc = b_hi | (uint64_t)(b_lo + (uint32_t)(((r * R + s) * KS + kk) * 2 * N));
               umma_f16_ss(d_addr, adesc, bdesc, p.idesc, (r | s | kk) != 0 ? 1u : 0u);
             }
           }
@@ -276,16 +278,17 @@ __global__ void __launch_bounds__(kD3Threads, 1) conv3_direct_kernel(const Conv3
       if (lane == 0) mbar_arrive(&hd->acc_empty[as]);
       if (valid) {
       float dot0 = 0.f, dot1 = 0.f, dot2 = 0.f;
+      const float lo = p.relu ? 0.f : -3.0e38f;
 #pragma unroll
       for (int c = 0; c < N / 16; ++c) {
         float f[16];
 #pragma unroll
         for (int u = 0; u < 4; ++u) {
           const float4 bq = *reinterpret_cast<const float4*>(&hd->bias[c * 16 + 4 * u]);
-          f[4 * u + 0] = fmaxf(__uint_as_float(v[c][4 * u + 0]) + bq.x, 0.f);
-          f[4 * u + 1] = fmaxf(__uint_as_float(v[c][4 * u + 1]) + bq.y, 0.f);
-          f[4 * u + 2] = fmaxf(__uint_as_float(v[c][4 * u + 2]) + bq.z, 0.f);
-          f[4 * u + 3] = fmaxf(__uint_as_float(v[c][4 * u + 3]) + bq.w, 0.f);
+          f[4 * u + 0] = fmaxf(__uint_as_float(v[c][4 * u + 0]) + bq.x, lo);
+          f[4 * u + 1] = fmaxf(__uint_as_float(v[c][4 * u + 1]) + bq.y, lo);
+          f[4 * u + 2] = fmaxf(__uint_as_float(v[c][4 * u + 2]) + bq.z, lo);
+          f[4 * u + 3] = fmaxf(__uint_as_float(v[c][4 * u + 3]) + bq.w, lo);
         }
         if (p.resid != nullptr) {
           __align__(16) __half h[16];

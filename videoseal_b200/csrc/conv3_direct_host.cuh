@@ -13,10 +13,10 @@ struct Conv3DirectOp {
 };
 
 // ring rows that fit next to the resident weights for a W-wide map (0 = channel counts not supported)
-inline int conv3_direct_ring_rows(int C, int N, int W) {
+inline int conv3_direct_ring_rows(int C, int N, int W, int R = 3) {
   if (!((C == 16 || C == 32 || C == 64) && (N == 16 || N == 32 || N == 64))) return 0;
-  const int rw = (W + 2 + 7) / 8 * 8;
-  const uint32_t w_pad = ((uint32_t)((size_t)N * 9 * C * 2) + 1023u) & ~1023u;
+  const int rw = (W + R - 1 + 7) / 8 * 8;
+  const uint32_t w_pad = ((uint32_t)((size_t)N * R * R * C * 2) + 1023u) & ~1023u;
   const size_t budget = 227 * 1024 - 1024 /*alignment slack*/ - kD3HeaderBytes - w_pad;
   int rows = (int)(budget / ((size_t)C * 2 * rw)) - (128 / rw + 1);
   rows = std::min(rows, kD3MaxRing);
@@ -24,27 +24,31 @@ inline int conv3_direct_ring_rows(int C, int N, int W) {
   return rows;
 }
 // W = 0: channel-count check only (weight packing time)
-inline bool conv3_direct_ok(int C, int N, int ld_in, int W = 0) {
+inline bool conv3_direct_ok(int C, int N, int ld_in, int W = 0, int R = 3) {
   static const bool off = getenv("VSB_NO_DIRECT") != nullptr;
-  if (off || ld_in != C) return false;
-  if (W == 0) return conv3_direct_ring_rows(C, N, 64) > 0;
-  return conv3_direct_ring_rows(C, N, W) >= 8;
+  static const bool off1 = getenv("VSB_NO_DIRECT1") != nullptr;
+  if (off || (R == 1 && off1) || ld_in != C) return false;
+  if (W == 0) return conv3_direct_ring_rows(C, N, 64, R) > 0;
+  return W % 8 == 0 && conv3_direct_ring_rows(C, N, W, R) >= 8;
 }
 
 // x: dense NHWC fp16 [B,H,W,C]; wpk: weights in core-matrix layout (pack_direct_weights_kernel), N*9*C halves
-inline void setup_conv3_direct(Conv3DirectOp& op, const __half* x, int B, int H, int W, int C, int N, const __half* wpk, int num_sms) {
+inline void setup_conv3_direct(Conv3DirectOp& op, const __half* x, int B, int H, int W, int C, int N, const __half* wpk, int num_sms,
+                               int R = 3) {
   Conv3DirectParams& p = op.p;
-  VSB_CHECK(conv3_direct_ring_rows(C, N, W) > 0, "direct conv3: unsupported channel counts");
-  p.B = B; p.H = H; p.W = W; p.C = C; p.N = N;
-  p.rw = (W + 2 + 7) / 8 * 8;
-  p.hp = H + 2;
+  VSB_CHECK(R == 3 || R == 1, "direct conv: 3x3 or 1x1 only");
+  VSB_CHECK(conv3_direct_ring_rows(C, N, W, R) > 0, "direct conv3: unsupported channel counts");
+  p.B = B; p.H = H; p.W = W; p.C = C; p.N = N; p.R = R;
+  p.relu = 1;
+  p.rw = (W + R - 1 + 7) / 8 * 8;
+  p.hp = H + R - 1;
   const long positions = (long)B * p.hp * p.rw;
   VSB_CHECK(positions + 3L * p.rw < (1L << 31) - 1024, "direct conv3: batch too large for 32-bit positions");
   p.n_tiles = (int)((positions + 127) / 128);
   p.mirror_rows = 128 / p.rw + 1;
-  p.w_bytes = (uint32_t)((size_t)N * 9 * C * 2);
+  p.w_bytes = (uint32_t)((size_t)N * R * R * C * 2);
   const uint32_t w_pad = (p.w_bytes + 1023u) & ~1023u;
-  const int rows = conv3_direct_ring_rows(C, N, W);
+  const int rows = conv3_direct_ring_rows(C, N, W, R);
   VSB_CHECK(rows >= 8, "direct conv3: shared-memory ring too small");
   p.ring_rows = rows;
   p.plane_stride = (uint32_t)((size_t)(rows + p.mirror_rows) * p.rw * 16);
@@ -64,15 +68,20 @@ inline void setup_conv3_direct(Conv3DirectOp& op, const __half* x, int B, int H,
   op.grid = std::min(num_sms, p.n_tiles);
 }
 
-template <int N, int KS>
-inline void launch_direct_nk(const Conv3DirectOp& op, cudaStream_t st) {
+template <int N, int KS, int R>
+inline void launch_direct_nkr(const Conv3DirectOp& op, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    VSB_CUDA(cudaFuncSetAttribute(conv3_direct_kernel<N, KS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VSB_CUDA(cudaFuncSetAttribute(conv3_direct_kernel<N, KS, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
-  conv3_direct_kernel<N, KS><<<op.grid, kD3Threads, op.smem, st>>>(op.p);
+  conv3_direct_kernel<N, KS, R><<<op.grid, kD3Threads, op.smem, st>>>(op.p);
   VSB_CUDA(cudaGetLastError());
+}
+template <int N, int KS>
+inline void launch_direct_nk(const Conv3DirectOp& op, cudaStream_t st) {
+  if (op.p.R == 3) launch_direct_nkr<N, KS, 3>(op, st);
+  else launch_direct_nkr<N, KS, 1>(op, st);
 }
 template <int N>
 inline void launch_direct_n(const Conv3DirectOp& op, cudaStream_t st) {
@@ -89,8 +98,8 @@ inline void launch_direct(const Conv3DirectOp& op, cudaStream_t st) {
 }
 
 // [N][9*C] fp16 on the device -> a new buffer in the direct layout
-inline void pack_direct_weights(const __half* w, int N, int C, __half* out, cudaStream_t st) {
-  pack_direct_weights_kernel<<<32, 256, 0, st>>>(w, N, C, out);
+inline void pack_direct_weights(const __half* w, int N, int C, __half* out, cudaStream_t st, int T = 9) {
+  pack_direct_weights_kernel<<<32, 256, 0, st>>>(w, N, C, T, out);
   VSB_CUDA(cudaGetLastError());
 }
 

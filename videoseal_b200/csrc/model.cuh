@@ -333,6 +333,11 @@ class Model {
     bn_fold(key + ".double_conv.4", s, b);
     rb.c2 = pack_conv3(key + ".double_conv.3.weight", &s, b);
     rb.res = pack_conv(key + ".res_conv.weight", nullptr, get(key + ".res_conv.bias").data);
+    if (conv3_direct_ok(rb.res.K, rb.res.N, rb.res.K, 0, 1)) {   // narrow 1x1: same ring kernel with a single tap
+      rb.res.wd = wpool.alloc_n<__half>((size_t)rb.res.N * rb.res.K);
+      pack_direct_weights(rb.res.w, rb.res.N, rb.res.K, rb.res.wd, 0, 1);
+      VSB_CUDA(cudaStreamSynchronize(0));
+    }
     return rb;
   }
 
@@ -488,7 +493,12 @@ class Model {
     __half* r = pl.pool.alloc_n<__half>(M * Cout);
     __half* h = pl.pool.alloc_n<__half>(M * Cout);
     if (!out && !fuse_outc) { out = pl.pool.alloc_n<__half>(M * Cout); ld_out = Cout; }
-    {  // res 1x1
+    if (w.res.wd && conv3_direct_ok(Cin, Cout, ldx, W, 1)) {  // res 1x1, narrow layers
+      Conv3DirectOp op; setup_conv3_direct(op, x, B, H, W, Cin, Cout, w.res.wd, num_sms, 1);
+      op.p.bias = w.res.bias; op.p.out = r; op.p.relu = 0;
+      pl.steps.push_back(Step{[op](cudaStream_t st) { launch_direct(op, st); }, 1,
+                              "unet.conv1x1d." + std::to_string(Cin) + "-" + std::to_string(Cout) + "@" + std::to_string(H)});
+    } else {  // res 1x1
       ConvGemmOp op; setup_tma_conv(op, x, B, H, W, Cin, ldx, 1, 1, 0);
       op.p.epi = EPI_AFFINE; op.p.act = ACT_NONE; op.p.bias = w.res.bias; op.p.out16 = r; op.p.ld_out16 = Cout;
       add_conv(pl, op, w.res, "unet.conv1x1." + std::to_string(Cin) + "-" + std::to_string(Cout) + "@" + std::to_string(H));
@@ -752,8 +762,12 @@ class Model {
             for (int s2 = 1; s2 <= 4; s2 *= 2) if ((s2 * C2) % 32 == 0 && s2 * C2 <= 512) { spb = s2; break; }
             if (spb * C2 > 512) throw Error("dwconv7: C/2 > 512 threads is not implemented (unsupported chunky extractor width)");
             const long blocks = (nstrips + spb - 1) / spb;
-            dwconv7_ln_kernel<<<(unsigned)blocks, spb * C2, (size_t)spb * kDwStrip * Cc * sizeof(float), st>>>(
-                xin, B, H, H, Cc, Cc, dww, dwb, lw, lb, a, Cc, spb, nstrips);
+            const size_t smem_s = (size_t)spb * kDwStrip * Cc * sizeof(float);
+            const int kp = (Cc + 63) / 64;
+#define VSB_DW(KP) dwconv7_ln_kernel<KP><<<(unsigned)blocks, spb * C2, smem_s, st>>>(xin, B, H, H, Cc, Cc, dww, dwb, lw, lb, a, Cc, spb, nstrips)
+            if (kp <= 2) VSB_DW(2); else if (kp <= 3) VSB_DW(3); else if (kp <= 6) VSB_DW(6); else if (kp <= 12) VSB_DW(12);
+            else if (kp <= 16) VSB_DW(16); else throw Error("dwconv7: more than 1024 channels is not implemented");
+#undef VSB_DW
             VSB_CUDA(cudaGetLastError());
           }, 1, "cnx.dwconv7_ln." + std::to_string(C) + "@" + std::to_string(hs)});
         }

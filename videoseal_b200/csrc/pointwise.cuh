@@ -362,16 +362,20 @@ __global__ void __launch_bounds__(256) ups_gather_ln_kernel(const __half* __rest
         const uint4 v01 = __ldg(reinterpret_cast<const uint4*>(base + ((long)ya[r] * IW + xb[s]) * ldy));
         const uint4 v10 = __ldg(reinterpret_cast<const uint4*>(base + ((long)yb[r] * IW + xa[s]) * ldy));
         const uint4 v11 = __ldg(reinterpret_cast<const uint4*>(base + ((long)yb[r] * IW + xb[s]) * ldy));
-        const float w00 = wy[r] * wx[s], w01 = wy[r] * (1.f - wx[s]), w10 = (1.f - wy[r]) * wx[s], w11 = (1.f - wy[r]) * (1.f - wx[s]);
+        // the 4-corner bilinear mix of one tap runs in packed half precision (weights 1/16, 3/16, 9/16 are exact, the
+        // operands are fp16 already); the 9 taps accumulate in fp32
+        const __half2 w00 = __float2half2_rn(wy[r] * wx[s]), w01 = __float2half2_rn(wy[r] * (1.f - wx[s]));
+        const __half2 w10 = __float2half2_rn((1.f - wy[r]) * wx[s]), w11 = __float2half2_rn((1.f - wy[r]) * (1.f - wx[s]));
         const __half2* p00 = reinterpret_cast<const __half2*>(&v00);
         const __half2* p01 = reinterpret_cast<const __half2*>(&v01);
         const __half2* p10 = reinterpret_cast<const __half2*>(&v10);
         const __half2* p11 = reinterpret_cast<const __half2*>(&v11);
 #pragma unroll
         for (int k = 0; k < 4; ++k) {
-          const float2 a = __half22float2(p00[k]), bq = __half22float2(p01[k]), cq = __half22float2(p10[k]), d = __half22float2(p11[k]);
-          acc[2 * k] += w00 * a.x + w01 * bq.x + w10 * cq.x + w11 * d.x;
-          acc[2 * k + 1] += w00 * a.y + w01 * bq.y + w10 * cq.y + w11 * d.y;
+          const __half2 t = __hfma2(w00, p00[k], __hfma2(w01, p01[k], __hfma2(w10, p10[k], __hmul2(w11, p11[k]))));
+          const float2 f = __half22float2(t);
+          acc[2 * k] += f.x;
+          acc[2 * k + 1] += f.y;
         }
       }
     }
@@ -444,7 +448,9 @@ __global__ void __launch_bounds__(256) stem_ln_kernel(const float* __restrict__ 
 // a channel pair and slides over the 7 x (strip+6) input window; pre-LN results go to smem, then LN per pixel by warps.
 constexpr int kDwStrip = 8;
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }   // Blackwell packed fp32 FMA
-// blockDim.x = spb * C/2 threads: `spb` strips per block so that every warp is full
+// blockDim.x = spb * C/2 threads: `spb` strips per block so that every warp is full.  KP = ceil(C / 64): channel pairs per
+// lane in the LayerNorm stage (values stay in registers between the mean and the variance pass).
+template <int KP>
 __global__ void __launch_bounds__(768) dwconv7_ln_kernel(const float* __restrict__ x, int B, int H, int W, int C, int ldx,
                                                          const float* __restrict__ wdw /*[49][C]*/, const float* __restrict__ bdw,
                                                          const float* __restrict__ lnw, const float* __restrict__ lnb,
@@ -454,13 +460,14 @@ __global__ void __launch_bounds__(768) dwconv7_ln_kernel(const float* __restrict
   const int C2 = C >> 1;
   const int ls = threadIdx.x / C2;                 // local strip
   const int cp = threadIdx.x - ls * C2;            // channel pair
-  const long strip = (long)blockIdx.x * spb + ls;
-  const bool active = (ls < spb) && (strip < nstrips);
+  // (32-bit index math throughout: the 64-bit div/mod this replaced was ~30 % of the kernel's instructions)
+  const unsigned strip = blockIdx.x * (unsigned)spb + (unsigned)ls;
+  const bool active = (ls < spb) && (strip < (unsigned)nstrips);
   int sx = 0, oy = 0, b = 0, ox0 = 0;
   if (active) {
-    sx = (int)(strip % strips_x);
-    const long t = strip / strips_x;
-    oy = (int)(t % H); b = (int)(t / H);
+    const unsigned t = strip / (unsigned)strips_x;
+    sx = (int)(strip - t * (unsigned)strips_x);
+    b = (int)(t / (unsigned)H); oy = (int)(t - (unsigned)b * (unsigned)H);
     ox0 = sx * kDwStrip;
     const int c = cp * 2;
     float2 acc[kDwStrip];
@@ -494,29 +501,43 @@ __global__ void __launch_bounds__(768) dwconv7_ln_kernel(const float* __restrict
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
   for (int item = warp; item < spb * kDwStrip; item += nwarps) {
     const int l2 = item / kDwStrip, i = item - l2 * kDwStrip;
-    const long st2 = (long)blockIdx.x * spb + l2;
-    if (st2 >= nstrips) continue;
-    const int sx2 = (int)(st2 % strips_x);
-    const long t2 = st2 / strips_x;
-    const int oy2 = (int)(t2 % H), b2 = (int)(t2 / H);
+    const unsigned st2 = blockIdx.x * (unsigned)spb + (unsigned)l2;
+    if (st2 >= (unsigned)nstrips) continue;
+    const unsigned t2 = st2 / (unsigned)strips_x;
+    const int sx2 = (int)(st2 - t2 * (unsigned)strips_x);
+    const int b2 = (int)(t2 / (unsigned)H), oy2 = (int)(t2 - (unsigned)b2 * (unsigned)H);
     const int ox = sx2 * kDwStrip + i;
     if (ox >= W) continue;
-    const float* pr = pre + ((size_t)l2 * kDwStrip + i) * C;
+    const float2* pr2 = reinterpret_cast<const float2*>(pre + ((size_t)l2 * kDwStrip + i) * C);
+    float2 vv[KP];
     float sum = 0.f;
-    for (int c = lane; c < C; c += 32) sum += pr[c];
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      const int c2 = lane + 32 * k;
+      vv[k] = c2 < C2 ? pr2[c2] : make_float2(0.f, 0.f);
+      sum += vv[k].x + vv[k].y;
+    }
 #pragma unroll
     for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     const float mean = sum / (float)C;
     float var = 0.f;
-    for (int c = lane; c < C; c += 32) { const float d = pr[c] - mean; var += d * d; }
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      if (lane + 32 * k < C2) { const float dx = vv[k].x - mean, dy = vv[k].y - mean; var += dx * dx + dy * dy; }
+    }
 #pragma unroll
     for (int o = 16; o; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
     const float rstd = 1.0f / sqrtf(var / (float)C + 1e-6f);
     __half* dst = out + (((long)b2 * H + oy2) * W + ox) * ld_out;
-    for (int c = lane * 2; c < C; c += 64) {
-      const float a = (pr[c] - mean) * rstd * __ldg(lnw + c) + __ldg(lnb + c);
-      const float bq = (pr[c + 1] - mean) * rstd * __ldg(lnw + c + 1) + __ldg(lnb + c + 1);
-      *reinterpret_cast<__half2*>(dst + c) = __floats2half2_rn(a, bq);
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      const int c2 = lane + 32 * k;
+      if (c2 < C2) {
+        const float2 g = __ldg(reinterpret_cast<const float2*>(lnw) + c2), bt = __ldg(reinterpret_cast<const float2*>(lnb) + c2);
+        const float a = (vv[k].x - mean) * rstd * g.x + bt.x;
+        const float bq = (vv[k].y - mean) * rstd * g.y + bt.y;
+        *reinterpret_cast<__half2*>(dst + 2 * c2) = __floats2half2_rn(a, bq);
+      }
     }
   }
 }
@@ -690,12 +711,14 @@ __global__ void __launch_bounds__(256) grn_apply_kernel(__half* __restrict__ g, 
   __syncthreads();
   const int k8 = K >> 3;
   const int r0 = (int)(((long)rows_per_sample * slab) / slabs), r1 = (int)(((long)rows_per_sample * (slab + 1)) / slabs);
-  const long total = (long)(r1 - r0) * k8;
   __half* base = g + ((long)b * rows_per_sample + r0) * ld;
-  for (long i = threadIdx.x; i < total; i += blockDim.x) {
-    const long m = i / k8;
-    const int k = (int)(i - m * k8) * 8;
-    uint4* ptr = reinterpret_cast<uint4*>(base + m * ld + k);
+  // thread -> (row m, 16-byte column chunk kc), advanced incrementally (no division in the loop)
+  const int dm = (int)blockDim.x / k8, dk = (int)blockDim.x - dm * k8;
+  int m = (int)threadIdx.x / k8, kc = (int)threadIdx.x - m * k8;
+  const int nrows = r1 - r0;
+  while (m < nrows) {
+    const int k = kc * 8;
+    uint4* ptr = reinterpret_cast<uint4*>(base + (long)m * ld + k);
     uint4 v = *ptr;
     __half2* h = reinterpret_cast<__half2*>(&v);
 #pragma unroll
@@ -705,6 +728,8 @@ __global__ void __launch_bounds__(256) grn_apply_kernel(__half* __restrict__ g, 
       h[q] = __float22half2_rn(f);
     }
     *ptr = v;
+    m += dm; kc += dk;
+    if (kc >= k8) { kc -= k8; ++m; }
   }
 }
 

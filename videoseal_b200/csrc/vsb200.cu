@@ -197,13 +197,15 @@ int vsb_debug_conv(const vsb_conv_test* t, void* stream) {
   }
   if (t->loader == 5) {
     // direct 3x3 conv (conv3_direct.cuh): weights arrive as [N][9*C0] and are re-packed here
-    VSB_CHECK(t->R == 3 && t->S == 3 && t->stride == 1 && t->pad == 1 && t->C1 == 0, "direct conv3: 3x3 stride 1 pad 1 only");
+    VSB_CHECK(((t->R == 3 && t->S == 3 && t->pad == 1) || (t->R == 1 && t->S == 1 && t->pad == 0)) && t->stride == 1 && t->C1 == 0,
+              "direct conv: 3x3 pad 1 or 1x1, stride 1");
     // (one scratch buffer, never freed: test-only path; the small pack kernel runs on every call)
     static __half* wpk = nullptr;
     if (wpk == nullptr) VSB_CUDA(cudaMalloc(&wpk, (size_t)64 * 9 * 64 * sizeof(__half)));
-    pack_direct_weights((const __half*)t->weights, t->N, t->C0, wpk, (cudaStream_t)stream);
+    pack_direct_weights((const __half*)t->weights, t->N, t->C0, wpk, (cudaStream_t)stream, t->R * t->S);
     Conv3DirectOp dop;
-    setup_conv3_direct(dop, (const __half*)t->src0, t->B, t->IH, t->IW, t->C0, t->N, wpk, num_sms);
+    setup_conv3_direct(dop, (const __half*)t->src0, t->B, t->IH, t->IW, t->C0, t->N, wpk, num_sms, t->R);
+    dop.p.relu = t->act == ACT_RELU ? 1 : 0;
     dop.p.bias = t->bias; dop.p.resid = (const __half*)t->resid16; dop.p.out = (__half*)t->out16;
     dop.p.outc_w = t->outc_w; dop.p.outc_b = t->outc_b; dop.p.n_out = t->n_out; dop.p.delta = t->delta; dop.p.outc_tanh = 1;
     launch_direct(dop, (cudaStream_t)stream);
