@@ -763,6 +763,14 @@ class Model {
             if (spb * C2 > 512) throw Error("dwconv7: C/2 > 512 threads is not implemented (unsupported chunky extractor width)");
             const long blocks = (nstrips + spb - 1) / spb;
             const size_t smem_s = (size_t)spb * kDwStrip * Cc * sizeof(float);
+            static const bool generic_dw = getenv("VSB_DW_GENERIC") != nullptr;
+#define VSB_DWC(CC) dwconv7_ln_c_kernel<CC><<<(unsigned)blocks, spb * C2, smem_s, st>>>(xin, B, H, H, dww, dwb, lw, lb, a, Cc, spb, (int)nstrips)
+            if (!generic_dw && (Cc == 96 || Cc == 192 || Cc == 384 || Cc == 768)) {
+              if (Cc == 96) VSB_DWC(96); else if (Cc == 192) VSB_DWC(192); else if (Cc == 384) VSB_DWC(384); else VSB_DWC(768);
+              VSB_CUDA(cudaGetLastError());
+              return;
+            }
+#undef VSB_DWC
             const int kp = (Cc + 63) / 64;
 #define VSB_DW(KP) dwconv7_ln_kernel<KP><<<(unsigned)blocks, spb * C2, smem_s, st>>>(xin, B, H, H, Cc, Cc, dww, dwb, lw, lb, a, Cc, spb, nstrips)
             if (kp <= 2) VSB_DW(2); else if (kp <= 3) VSB_DW(3); else if (kp <= 6) VSB_DW(6); else if (kp <= 12) VSB_DW(12);

@@ -542,6 +542,125 @@ __global__ void __launch_bounds__(768) dwconv7_ln_kernel(const float* __restrict
   }
 }
 
+// K4, fixed-width variant used for the ConvNeXt trunk widths (96/192/384/768).  Same mapping as above, but written around
+// the instruction count: the generic kernel spent 91 % of its 4300 instructions per thread on 64-bit address arithmetic,
+// bounds tests and the divergence bookkeeping of branchy conditional loads (profiles/r1_history.md).  Here C is a template
+// constant, so every input and weight load is `base + immediate`; rows advance by one pointer add; interior strips take a
+// path with no predicates at all and edge strips use a single predicated load per tap column (inline PTX, no branches).
+template <int OFF>
+__device__ __forceinline__ float2 ldg_f2_pred(const float* p, unsigned pred) {
+  float2 v;
+  asm("{\n\t.reg .pred q;\n\tsetp.ne.u32 q, %3, 0;\n\tmov.f32 %0, 0f00000000;\n\tmov.f32 %1, 0f00000000;\n\t"
+      "@q ld.global.nc.v2.f32 {%0, %1}, [%2+%4];\n\t}"
+      : "=f"(v.x), "=f"(v.y)
+      : "l"(p), "r"(pred), "n"(OFF));
+  return v;
+}
+template <int C, int U, bool EDGE>
+struct DwCol {
+  static __device__ __forceinline__ void run(const float* prow, unsigned cmask, const float2 (&wr)[7], float2 (&acc)[kDwStrip]) {
+    float2 v;
+    if (EDGE) v = ldg_f2_pred<U * C * 4>(prow, cmask & (1u << U));
+    else v = __ldg(reinterpret_cast<const float2*>(prow + U * C));
+#pragma unroll
+    for (int s2 = 0; s2 < 7; ++s2) {
+      const int i = U - s2;  // output pixel index within the strip
+      if (i >= 0 && i < kDwStrip) acc[i] = ffma2(v, wr[s2], acc[i]);
+    }
+    DwCol<C, U + 1, EDGE>::run(prow, cmask, wr, acc);
+  }
+};
+template <int C, bool EDGE>
+struct DwCol<C, kDwStrip + 6, EDGE> {
+  static __device__ __forceinline__ void run(const float*, unsigned, const float2 (&)[7], float2 (&)[kDwStrip]) {}
+};
+
+template <int C>
+__global__ void __launch_bounds__(768) dwconv7_ln_c_kernel(const float* __restrict__ x, int B, int H, int W,
+                                                           const float* __restrict__ wdw /*[49][C]*/, const float* __restrict__ bdw,
+                                                           const float* __restrict__ lnw, const float* __restrict__ lnb,
+                                                           __half* __restrict__ out, int ld_out, int spb, int nstrips) {
+  constexpr int C2 = C / 2, KP = (C + 63) / 64;
+  extern __shared__ float pre[];  // [spb][kDwStrip][C]
+  const int strips_x = (W + kDwStrip - 1) / kDwStrip;
+  const int ls = threadIdx.x / C2;                 // local strip
+  const int cp = threadIdx.x - ls * C2;            // channel pair
+  const unsigned strip = blockIdx.x * (unsigned)spb + (unsigned)ls;
+  if (ls < spb && strip < (unsigned)nstrips) {
+    const unsigned t = strip / (unsigned)strips_x;
+    const int sx = (int)(strip - t * (unsigned)strips_x);
+    const int b = (int)(t / (unsigned)H), oy = (int)(t - (unsigned)b * (unsigned)H);
+    const int ox0 = sx * kDwStrip;
+    const int c = cp * 2;
+    float2 acc[kDwStrip];
+    const float2 bb = __ldg(reinterpret_cast<const float2*>(bdw + c));
+#pragma unroll
+    for (int i = 0; i < kDwStrip; ++i) acc[i] = bb;
+    unsigned cmask = 0;
+#pragma unroll
+    for (int u = 0; u < kDwStrip + 6; ++u) cmask |= ((unsigned)(ox0 + u - 3) < (unsigned)W) ? (1u << u) : 0u;
+    const bool interior = cmask == (1u << (kDwStrip + 6)) - 1u;
+    const long rowpitch = (long)W * C;
+    // (oy - 3, ox0 - 3): may lie outside the image; only dereferenced where the masks allow
+    const float* prow = x + (((long)b * H + oy) * W + ox0) * C + c - 3 * rowpitch - 3 * C;
+    const float* wrow = wdw + c;
+#pragma unroll 1
+    for (int r = 0; r < 7; ++r, prow += rowpitch, wrow += 7 * C) {
+      if ((unsigned)(oy + r - 3) >= (unsigned)H) continue;
+      float2 wr[7];
+#pragma unroll
+      for (int s2 = 0; s2 < 7; ++s2) wr[s2] = __ldg(reinterpret_cast<const float2*>(wrow + s2 * C));
+      if (interior) DwCol<C, 0, false>::run(prow, cmask, wr, acc);
+      else DwCol<C, 0, true>::run(prow, cmask, wr, acc);
+    }
+    float* pr = pre + (size_t)ls * kDwStrip * C;
+#pragma unroll
+    for (int i = 0; i < kDwStrip; ++i) *reinterpret_cast<float2*>(pr + i * C + c) = acc[i];
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int item = warp; item < spb * kDwStrip; item += nwarps) {
+    const int l2 = item / kDwStrip, i = item - l2 * kDwStrip;
+    const unsigned st2 = blockIdx.x * (unsigned)spb + (unsigned)l2;
+    if (st2 >= (unsigned)nstrips) continue;
+    const unsigned t2 = st2 / (unsigned)strips_x;
+    const int sx2 = (int)(st2 - t2 * (unsigned)strips_x);
+    const int ox = sx2 * kDwStrip + i;
+    if (ox >= W) continue;
+    const float2* pr2 = reinterpret_cast<const float2*>(pre + ((size_t)l2 * kDwStrip + i) * C);
+    float2 vv[KP];
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      const int c2 = lane + 32 * k;
+      vv[k] = c2 < C2 ? pr2[c2] : make_float2(0.f, 0.f);
+      sum += vv[k].x + vv[k].y;
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum * (1.0f / (float)C);
+    float var = 0.f;
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      if (lane + 32 * k < C2) { const float dx = vv[k].x - mean, dy = vv[k].y - mean; var += dx * dx + dy * dy; }
+    }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+    const float rstd = 1.0f / sqrtf(var / (float)C + 1e-6f);
+    __half* dst = out + ((long)t2 * W + ox) * ld_out;   // t2 = b*H + oy
+#pragma unroll
+    for (int k = 0; k < KP; ++k) {
+      const int c2 = lane + 32 * k;
+      if (c2 < C2) {
+        const float2 g = __ldg(reinterpret_cast<const float2*>(lnw) + c2), bt = __ldg(reinterpret_cast<const float2*>(lnb) + c2);
+        const float a = (vv[k].x - mean) * rstd * g.x + bt.x;
+        const float bq = (vv[k].y - mean) * rstd * g.y + bt.y;
+        *reinterpret_cast<__half2*>(dst + 2 * c2) = __floats2half2_rn(a, bq);
+      }
+    }
+  }
+}
+
 // K4 (tiled): depthwise 7x7 + channels-last LayerNorm with the input staged in shared memory.
 // One block = a kDwTH x TW (4 x 16 or 4 x 8) tile of output pixels of one image.  The C channels are processed in chunks of
 // kDwCC = 96: the (4+6) x (TW+6) x 96 fp32 input window is loaded ONCE (coalesced, zero-filled outside the image) and every
