@@ -75,6 +75,8 @@ struct ConvGemmParams {
   int C0, C1, ld0, ld1, IH, IW, OH, OW, stride, pad_mode /*0 zero, 1 reflect*/, Ktot;
   const float* a_scale;  // LD_GATHER_SCALE: [num_samples, ld_scale] fp32
   int rows_per_sample, ld_scale;
+  int b_sample_rows;              // > 0: per-sample weights [samples][N][K] (GRN folded into pwconv2); = N
+  FastDiv fd_tps;                 // M tiles per sample
   // ---- epilogue
   int epi, act;
   const float* bias;     // [N] or null
@@ -299,6 +301,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           }
         } else if (LOADER == LD_TMA) {
           int tap_r = 0, tap_s = 0, cblk = 0;
+          const int brow = n_tile * p.block_n + (p.b_sample_rows ? p.fd_tps.div(m_tile) * p.b_sample_rows : 0);
           for (int kb = 0; kb < p.num_kb; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1u);
             uint8_t* sa = tiles + (size_t)stage * p.stage_bytes;
@@ -311,7 +314,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               if (p.c0_blocks == 0 || kb < p.c0_blocks) tma_load_2d(&tmA, &full_bar[stage], sa, kb * p.kblk, m_tile * kBlockM);
               else tma_load_2d(&tmA2, &full_bar[stage], sa, (kb - p.c0_blocks) * p.kblk, m_tile * kBlockM);
             }
-            if (!p.b_resident) tma_load_2d(&tmB, &full_bar[stage], sa + p.a_stage_bytes, kb * p.kblk, n_tile * p.block_n);
+            if (!p.b_resident) tma_load_2d(&tmB, &full_bar[stage], sa + p.a_stage_bytes, kb * p.kblk, brow);
             if (++stage == p.stages) { stage = 0; phase ^= 1u; }
           }
         } else if (!p.b_resident) {  // gather loaders: weights only

@@ -77,6 +77,7 @@ struct ConvGemmOp {
   ConvGemmParams p;
   CUtensorMap tmA, tmA2, tmB;
   int grid = 0, threads = 0;
+  int w_samples = 1;   // > 1: weights are [w_samples][N][K], sample = row / rows_per_sample (finalize_op)
   size_t smem = 0;
   const char* name = "";
   ConvGemmOp() { memset(&p, 0, sizeof(p)); memset(&tmA, 0, sizeof(tmA)); memset(&tmA2, 0, sizeof(tmA2)); memset(&tmB, 0, sizeof(tmB)); }
@@ -140,7 +141,7 @@ inline void finalize_op(ConvGemmOp& op, const __half* W, int N, int Kw, int ldw,
   const size_t u_bytes = op.loader == LD_HALO_UPS ? (((size_t)kHaloH * kHaloW * p.cc * 2 + 1023) & ~size_t(1023)) : 0;
   // resident weights: one N tile, whole K slab <= 48 KB -> loaded once per CTA instead of once per tile
   const size_t bslab = (size_t)p.num_kb * p.b_stage_bytes;
-  p.b_resident = (p.n_tiles == 1 && bslab <= 48 * 1024) ? 1 : 0;
+  p.b_resident = (p.n_tiles == 1 && bslab <= 48 * 1024 && op.w_samples == 1) ? 1 : 0;
   if (getenv("VSB_NO_BRES")) p.b_resident = 0;
   const size_t bres_bytes = p.b_resident ? bslab : 0;
   if (p.b_resident) p.stage_bytes = p.a_stage_bytes;
@@ -158,7 +159,13 @@ inline void finalize_op(ConvGemmOp& op, const __half* W, int N, int Kw, int ldw,
   p.idesc = (1u << 4) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
   if (p.epi == EPI_LN || p.outc_w) VSB_CHECK(p.n_tiles == 1 && N <= 256, "LN / fused-outc epilogues need the full row in one tile");
   // weights: dims (K, N)
-  uint64_t dims[2] = {(uint64_t)Kw, (uint64_t)N};
+  if (op.w_samples > 1) {
+    VSB_CHECK(op.loader == LD_TMA && !p.a_is_conv && p.rows_per_sample > 0 && p.rows_per_sample % kBlockM == 0 && N % p.block_n == 0,
+              "per-sample weights: plain GEMM with whole tiles per sample only");
+    p.b_sample_rows = N;
+    p.fd_tps = make_fastdiv(p.rows_per_sample / kBlockM);
+  }
+  uint64_t dims[2] = {(uint64_t)Kw, (uint64_t)N * (uint64_t)op.w_samples};
   uint64_t strides[1] = {(uint64_t)ldw * 2};
   uint32_t box[2] = {(uint32_t)p.kblk, (uint32_t)p.block_n};
   encode_map(&op.tmB, W, 2, dims, strides, box, p.kblk);

@@ -471,8 +471,8 @@ class Model {
   static void dbg(Plan& pl, const std::string& name, const void* p, int dtype, int64_t B, int64_t H, int64_t W, int64_t C, int64_t ld) {
     pl.dbg[name] = DebugTensor{p, dtype, {B, H, W, C}, ld};
   }
-  void add_conv(Plan& pl, ConvGemmOp op, const ConvW& w, const std::string& name, int block_n = 0) {
-    finalize_op(op, w.w, w.N, w.K, w.K, num_sms, block_n);
+  void add_conv(Plan& pl, ConvGemmOp op, const ConvW& w, const std::string& name, int block_n = 0, const __half* w_override = nullptr) {
+    finalize_op(op, w_override ? w_override : w.w, w.N, w.K, w.K, num_sms, block_n);
     pl.steps.push_back(Step{[op](cudaStream_t st) { launch(op, st); }, 1, name});
   }
   // 3x3 stride-1 zero-padded conv: on-chip im2col from a shared-memory halo tile (input crosses L2->SM once) up to
@@ -735,6 +735,11 @@ class Model {
       const int rows_per_sample = hs * hs;
       __half* a = pl.pool.alloc_n<__half>(M * C);
       __half* g = pl.pool.alloc_n<__half>(M * 4 * C);
+      // GRN multiplier: folded into per-sample pwconv2 weights where a sample has many more rows than W2 has output
+      // channels (stages 0-1 of the tiny trunk), applied to g in place otherwise
+      static const bool no_wscale = getenv("VSB_NO_WSCALE") != nullptr;
+      const bool wscale = !no_wscale && 4 * C <= rows_per_sample && rows_per_sample % kBlockM == 0 && C % 16 == 0;
+      __half* w2s = wscale ? pl.pool.alloc_n<__half>((size_t)B * C * 4 * C) : nullptr;
       for (int jb = 0; jb < d.ext_depths[s]; ++jb) {
         const CnBlockW& w = cn[s][jb];
         {
@@ -792,22 +797,34 @@ class Model {
           float* gamma = w.gamma;
           float* stats = stats_pp[(blk_counter - 1) & 1];
           float* stats_next = stats_pp[blk_counter & 1];
+          if (wscale) {
+            // GRN multiplier folded into per-sample copies of W2 (pointwise.cuh K2e): no pass over g at all
+            const __half* w2 = w.pw2.w;
+            __half* w2s_ = w2s;
+            const int Nn = C;
+            pl.steps.push_back(Step{[=](cudaStream_t st) {
+              grn_scale_weights_kernel<<<dim3(B, 4), 256, K4 * sizeof(float), st>>>(stats, stats_next, gamma, w2, w2s_, Nn, K4);
+              VSB_CUDA(cudaGetLastError());
+            }, 1, "cnx.grn_wscale." + std::to_string(C) + "@" + std::to_string(hs)});
+          } else {
           pl.steps.push_back(Step{[=](cudaStream_t st) {
             // enough row-slabs per sample to fill the GPU (~8 blocks per SM)
             int slabs = std::max(1, std::min(rows_per_sample, (148 * 8 + B - 1) / B));
             grn_apply_kernel<<<B * slabs, 256, K4 * sizeof(float), st>>>(g, rows_per_sample, K4, K4, stats, stats_next, gamma, slabs);
             VSB_CUDA(cudaGetLastError());
           }, 1, "cnx.grn_apply." + std::to_string(C) + "@" + std::to_string(hs)});
+          }
         }
         {
           ConvGemmOp op; setup_tma_gemm(op, g, M, 4 * C, 4 * C);
           op.p.epi = EPI_AFFINE; op.p.act = ACT_NONE; op.p.bias = w.pw2.bias; op.p.resid32 = x; op.p.ld_res32 = C;
           op.p.out32 = x; op.p.ld_out32 = C;  // in place: each element is read and written by the same thread
+          if (wscale) { op.w_samples = B; op.p.rows_per_sample = rows_per_sample; }
           if (s == 3 && jb == d.ext_depths[s] - 1) {
             x16 = pl.pool.alloc_n<__half>(M * C);
             op.p.out16 = x16; op.p.ld_out16 = C;
           }
-          add_conv(pl, op, w.pw2, "cnx.pwconv2." + std::to_string(C) + "@" + std::to_string(hs));
+          add_conv(pl, op, w.pw2, "cnx.pwconv2." + std::to_string(C) + "@" + std::to_string(hs), 0, wscale ? w2s : nullptr);
         }
         if (jb == 0) { dbg(pl, "s" + std::to_string(s) + "b0_a", a, 1, B, hs, hs, C, C); dbg(pl, "s" + std::to_string(s) + "b0_g", g, 1, B, hs, hs, 4 * C, 4 * C); }
       }

@@ -852,6 +852,54 @@ __global__ void __launch_bounds__(256) grn_apply_kernel(__half* __restrict__ g, 
   }
 }
 
+// K2e: GRN folded into the NEXT GEMM's weights instead of the activations (stages where C_out << rows per sample):
+//   pwconv2(g * s[b,:]) = (W2 * diag(s[b,:])) g,   s[b,k] = gamma[k] * Gx[b,k] / (mean_k Gx[b,:] + 1e-6) + 1
+// so each sample gets its own fp16 copy of W2 [N][K] (64 x 72 KB at stage 0) and the 200 MB activation tensor is neither
+// re-read nor re-written.  grid (samples, splits); `stats_next` is cleared like grn_apply_kernel does.
+__global__ void __launch_bounds__(256) grn_scale_weights_kernel(const float* __restrict__ stats, float* __restrict__ stats_next,
+                                                                const float* __restrict__ gamma, const __half* __restrict__ w,
+                                                                __half* __restrict__ out, int N, int K) {
+  extern __shared__ float sc[];   // [K]
+  __shared__ float red[8];
+  __shared__ float mean_s;
+  const int b = blockIdx.x;
+  const float* st = stats + (long)b * K;
+  float sum = 0.f;
+  for (int k = threadIdx.x; k < K; k += blockDim.x) { const float gx = sqrtf(st[k]); sc[k] = gx; sum += gx; }
+#pragma unroll
+  for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float t = 0.f;
+    for (int i = 0; i < (int)(blockDim.x >> 5); ++i) t += red[i];
+    mean_s = t / (float)K;
+  }
+  __syncthreads();
+  const float inv = 1.0f / (mean_s + 1e-6f);
+  for (int k = threadIdx.x; k < K; k += blockDim.x) sc[k] = __ldg(gamma + k) * (sc[k] * inv) + 1.0f;
+  if (blockIdx.y == 0) for (int k = threadIdx.x; k < K; k += blockDim.x) stats_next[(long)b * K + k] = 0.f;
+  __syncthreads();
+  const int k8 = K >> 3;
+  const int n0 = (int)(((long)N * blockIdx.y) / gridDim.y), n1 = (int)(((long)N * (blockIdx.y + 1)) / gridDim.y);
+  const int dm = (int)blockDim.x / k8, dk = (int)blockDim.x - dm * k8;
+  int n = n0 + (int)threadIdx.x / k8, kc = (int)threadIdx.x % k8;
+  while (n < n1) {
+    const int k = kc * 8;
+    uint4 v = __ldg(reinterpret_cast<const uint4*>(w + (long)n * K + k));
+    __half2* h = reinterpret_cast<__half2*>(&v);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      float2 f = __half22float2(h[q]);
+      f.x *= sc[k + 2 * q]; f.y *= sc[k + 2 * q + 1];
+      h[q] = __float22half2_rn(f);
+    }
+    *reinterpret_cast<uint4*>(out + ((long)b * N + n) * K + k) = v;
+    n += dm; kc += dk;
+    if (kc >= k8) { kc -= k8; ++n; }
+  }
+}
+
 // K9a: stem im2col: x = 2*img-1 (extractor.py:25) patches of the k4 conv (stride s, no padding) -> fp16 [M, 64] rows
 // (k = c*16 + r*4 + t for k < 48, zero for 48..63) for the tensor-core stem GEMM.  One thread per (pixel, channel c).
 __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restrict__ imgs, int B, int H, int W, int OH, int OW, int stride,
