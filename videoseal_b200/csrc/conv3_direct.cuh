@@ -48,6 +48,10 @@ struct Conv3DirectParams {
   const __half* resid; __half* out;
   const float* outc_w; const float* outc_b; float* delta; int n_out, outc_tanh;
   int relu;                 // 1: ReLU after the bias (before the residual)
+  // up-conv phase mode (UP template flag): second source for the virtual channel concat [x | x2] (planes0 planes come
+  // from x), replicate instead of zero padding, epilogue = per-phase LayerNorm + ReLU + pixel shuffle to [B,2H,2W,16]
+  const __half* x2; int planes0; int replicate;
+  const float* ln_w; const float* ln_b; float ln_eps;
 };
 
 struct D3Header {
@@ -80,7 +84,7 @@ __global__ void pack_direct_weights_kernel(const __half* __restrict__ w, int N, 
   }
 }
 
-template <int N, int KS, int R>
+template <int N, int KS, int R, bool UP>
 __global__ void __launch_bounds__(kD3Threads, 1) conv3_direct_kernel(const Conv3DirectParams p) {
   extern __shared__ uint8_t d3_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(d3_smem_raw) + 1023) & ~(uintptr_t)1023);
@@ -112,6 +116,7 @@ __global__ void __launch_bounds__(kD3Threads, 1) conv3_direct_kernel(const Conv3
     if (threadIdx.x < N) {
       hd->bias[threadIdx.x] = p.bias ? __ldg(p.bias + threadIdx.x) : 0.f;
       for (int o = 0; o < 3; ++o) hd->ocw[o][threadIdx.x] = (p.outc_w && o < p.n_out) ? __ldg(p.outc_w + o * N + threadIdx.x) : 0.f;
+      if (UP && threadIdx.x < 16) { hd->ocw[0][threadIdx.x] = __ldg(p.ln_w + threadIdx.x); hd->ocw[1][threadIdx.x] = __ldg(p.ln_b + threadIdx.x); }
     }
   }
   fence_proxy_async_smem();   // weights were written through the generic proxy, tcgen05.mma reads them through the async proxy
@@ -127,7 +132,6 @@ __global__ void __launch_bounds__(kD3Threads, 1) conv3_direct_kernel(const Conv3
     // bandwidth, then bounds the kernel: measured 20 G lines/s chip-wide, profiles/r1_history.md.)
     const int pw = warp >> 1;
     const int planes = p.C >> 3, pshift = planes == 2 ? 1 : (planes == 4 ? 2 : 3);
-    const int nchunk = rw * planes;
     int tiles_conf = 0;
     int slot = pw;   // NR >= 8 > 2 producers
     for (int k = pw; k <= row_hi - row_lo && nt > 0; k += 2, slot = slot + 2 >= NR ? slot + 2 - NR : slot + 2) {
@@ -143,17 +147,38 @@ __global__ void __launch_bounds__(kD3Threads, 1) conv3_direct_kernel(const Conv3
       }
       const int b = p.fd_hp.div(gi), yy = gi - b * p.hp;
       constexpr int PAD = (R - 1) / 2;
-      const bool rvalid = b < p.B && yy >= PAD && yy < p.H + PAD;
-      const __half* rowbase = p.x + ((long)b * p.H + (yy - PAD)) * p.W * p.C;
       const bool mir = slot < p.mirror_rows;
       uint8_t* base0 = ring + (size_t)slot * rw * 16;
-      for (int j = lane; j < nchunk; j += 32) {
-        const int xx = j >> pshift, pl = j & (planes - 1);
-        const bool ok = rvalid && xx >= PAD && xx < p.W + PAD;
-        const __half* src = ok ? rowbase + ((long)(xx - PAD) * planes + pl) * 8 : p.x;
-        uint8_t* dst = base0 + (size_t)pl * p.plane_stride + (size_t)xx * 16;
-        cp_async16_zfill(dst, src, ok ? 16u : 0u);
-        if (mir) cp_async16_zfill(dst + (size_t)NR * rw * 16, src, ok ? 16u : 0u);
+      // each lane keeps one plane and walks the positions (32 / planes of them per warp pass): the per-copy address math is
+      // one 32-bit multiply-add on a per-row lane pointer
+      const int pl = lane & (planes - 1), xstep = 32 >> pshift;
+      uint8_t* lane_dst = base0 + (size_t)pl * p.plane_stride;
+      if (UP) {
+        // two sources (virtual concat along channels), replicate padding: clamp the coordinates instead of zero-filling
+        const bool rvalid = b < p.B;
+        const int yc = min(max(yy - PAD, 0), p.H - 1);
+        const int planes1 = planes - p.planes0;
+        const bool first = pl < p.planes0;
+        const int lstride = (first ? p.planes0 : planes1) * 8;
+        const __half* lane_src = first ? p.x + ((long)b * p.H + yc) * p.W * (p.planes0 * 8) + pl * 8
+                                       : p.x2 + ((long)b * p.H + yc) * p.W * (planes1 * 8) + (pl - p.planes0) * 8;
+        for (int xx = lane >> pshift; xx < rw; xx += xstep) {
+          const int xc = min(max(xx - PAD, 0), p.W - 1);
+          const __half* src = rvalid ? lane_src + xc * lstride : p.x;
+          uint8_t* dst = lane_dst + xx * 16;
+          cp_async16_zfill(dst, src, rvalid ? 16u : 0u);
+          if (mir) cp_async16_zfill(dst + (size_t)NR * rw * 16, src, rvalid ? 16u : 0u);
+        }
+      } else {
+        const bool rvalid = b < p.B && yy >= PAD && yy < p.H + PAD;
+        const __half* lane_src = p.x + ((long)b * p.H + (yy - PAD)) * p.W * p.C + pl * 8 - PAD * p.C;
+        for (int xx = lane >> pshift; xx < rw; xx += xstep) {
+          const bool ok = rvalid && (unsigned)(xx - PAD) < (unsigned)p.W;
+          const __half* src = ok ? lane_src + xx * p.C : p.x;
+          uint8_t* dst = lane_dst + xx * 16;
+          cp_async16_zfill(dst, src, ok ? 16u : 0u);
+          if (mir) cp_async16_zfill(dst + (size_t)NR * rw * 16, src, ok ? 16u : 0u);
+        }
       }
       cp_async_mbar_arrive_noinc(&hd->row_full[slot]);
     }
@@ -276,7 +301,35 @@ __global__ void __launch_bounds__(kD3Threads, 1) conv3_direct_kernel(const Conv3
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(&hd->acc_empty[as]);
-      if (valid) {
+      if (UP) {
+        // accumulator columns = (phase py*2+px, co): per phase a LayerNorm over the 16 channels (biased variance,
+        // modules/common.py:150-155), ReLU, and the pixel shuffle to (2y+py, 2x+px)
+        if (valid) {
+#pragma unroll
+          for (int c = 0; c < N / 16; ++c) {
+            float f[16];
+            float sum = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { f[j] = __uint_as_float(v[c][j]); sum += f[j]; }
+            const float mean = sum * (1.f / 16.f);
+            float var = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { const float dd = f[j] - mean; var += dd * dd; }
+            const float rstd = 1.0f / sqrtf(var * (1.f / 16.f) + p.ln_eps);
+            __align__(16) __half2 h2[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float a = fmaxf((f[2 * j] - mean) * rstd * hd->ocw[0][2 * j] + hd->ocw[1][2 * j], 0.f);
+              const float bb = fmaxf((f[2 * j + 1] - mean) * rstd * hd->ocw[0][2 * j + 1] + hd->ocw[1][2 * j + 1], 0.f);
+              h2[j] = __floats2half2_rn(fminf(a, 65504.f), fminf(bb, 65504.f));
+            }
+            const long opix = ((long)b * 2 * p.H + 2 * y + (c >> 1)) * (2 * p.W) + 2 * x + (c & 1);
+            uint4* op = reinterpret_cast<uint4*>(p.out + opix * 16);
+            op[0] = reinterpret_cast<const uint4*>(h2)[0];
+            op[1] = reinterpret_cast<const uint4*>(h2)[1];
+          }
+        }
+      } else if (valid) {
       float dot0 = 0.f, dot1 = 0.f, dot2 = 0.f;
       const float lo = p.relu ? 0.f : -3.0e38f;
 #pragma unroll

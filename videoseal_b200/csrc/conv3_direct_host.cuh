@@ -23,13 +23,19 @@ inline int conv3_direct_ring_rows(int C, int N, int W, int R = 3) {
   rows = std::min(rows, (kD3TileBars - 16) * 128 / rw);   // tiles in flight must stay below the tile_done barrier ring
   return rows;
 }
+// Fewest ring rows that cannot deadlock: a tile touches ceil(129/rw) + R rows at once, the producer refills a slot only after
+// the tiles that read its previous row are done, and the issuers run in order; two more rows keep loads ahead of the MMAs.
+inline int conv3_direct_min_rows(int W, int R = 3) {
+  const int rw = (W + R - 1 + 7) / 8 * 8;
+  return (129 + rw - 1) / rw + R + 2;
+}
 // W = 0: channel-count check only (weight packing time)
 inline bool conv3_direct_ok(int C, int N, int ld_in, int W = 0, int R = 3) {
   static const bool off = getenv("VSB_NO_DIRECT") != nullptr;
   static const bool off1 = getenv("VSB_NO_DIRECT1") != nullptr;
   if (off || (R == 1 && off1) || ld_in != C) return false;
   if (W == 0) return conv3_direct_ring_rows(C, N, 64, R) > 0;
-  return W % 8 == 0 && conv3_direct_ring_rows(C, N, W, R) >= 8;
+  return W % 8 == 0 && conv3_direct_ring_rows(C, N, W, R) >= conv3_direct_min_rows(W, R);
 }
 
 // x: dense NHWC fp16 [B,H,W,C]; wpk: weights in core-matrix layout (pack_direct_weights_kernel), N*9*C halves
@@ -49,7 +55,7 @@ inline void setup_conv3_direct(Conv3DirectOp& op, const __half* x, int B, int H,
   p.w_bytes = (uint32_t)((size_t)N * R * R * C * 2);
   const uint32_t w_pad = (p.w_bytes + 1023u) & ~1023u;
   const int rows = conv3_direct_ring_rows(C, N, W, R);
-  VSB_CHECK(rows >= 8, "direct conv3: shared-memory ring too small");
+  VSB_CHECK(rows >= conv3_direct_min_rows(W, R), "direct conv3: shared-memory ring too small");
   p.ring_rows = rows;
   p.plane_stride = (uint32_t)((size_t)(rows + p.mirror_rows) * p.rw * 16);
   p.w_off = kD3HeaderBytes;
@@ -68,14 +74,14 @@ inline void setup_conv3_direct(Conv3DirectOp& op, const __half* x, int B, int H,
   op.grid = std::min(num_sms, p.n_tiles);
 }
 
-template <int N, int KS, int R>
+template <int N, int KS, int R, bool UP = false>
 inline void launch_direct_nkr(const Conv3DirectOp& op, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    VSB_CUDA(cudaFuncSetAttribute(conv3_direct_kernel<N, KS, R>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VSB_CUDA(cudaFuncSetAttribute(conv3_direct_kernel<N, KS, R, UP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
-  conv3_direct_kernel<N, KS, R><<<op.grid, kD3Threads, op.smem, st>>>(op.p);
+  conv3_direct_kernel<N, KS, R, UP><<<op.grid, kD3Threads, op.smem, st>>>(op.p);
   VSB_CUDA(cudaGetLastError());
 }
 template <int N, int KS>
@@ -92,9 +98,29 @@ inline void launch_direct_n(const Conv3DirectOp& op, cudaStream_t st) {
 
 inline void launch_direct(const Conv3DirectOp& op, cudaStream_t st) {
   VSB_CHECK(op.smem <= 227 * 1024, "direct conv3: shared-memory plan too large");
+  if (op.p.x2 != nullptr) {   // up-conv phase mode: 64 input channels (two sources), 4 phases x 16 output channels
+    VSB_CHECK(op.p.N == 64 && op.p.C == 64 && op.p.R == 3, "up-phase direct conv: C = 64, N = 4 x 16 only");
+    launch_direct_nkr<64, 4, 3, true>(op, st);
+    return;
+  }
   if (op.p.N == 16) launch_direct_n<16>(op, st);
   else if (op.p.N == 32) launch_direct_n<32>(op, st);
   else launch_direct_n<64>(op, st);
+}
+
+// UBlock up-conv (bilinear x2 -> reflect pad -> conv3x3 -> LN -> ReLU, modules/common.py:45-52 + unet.py:187-190) as ONE 3x3 conv
+// on the LOW-resolution grid with 4 x 16 output columns (one group per output phase (oy&1, ox&1)) and replicate padding:
+// away from the image border the bilinear weights depend only on the phase, so they fold into the conv weights
+// (Model::pack_upconv_phase).  The outermost output rows/columns (reflect padding of the up-sampled map) do not follow the
+// phase pattern and are recomputed exactly by up_border_fix_kernel afterwards.
+inline void setup_up_phase_direct(Conv3DirectOp& op, const __half* x0, int C0, const __half* x1, int C1, int B, int H, int W,
+                                  const __half* wpk, const float* ln_w, const float* ln_b, float eps, __half* out, int num_sms) {
+  VSB_CHECK(C0 % 8 == 0 && C1 % 8 == 0 && C0 + C1 == 64, "up-phase direct conv: 64 input channels in two sources");
+  setup_conv3_direct(op, x0, B, H, W, 64, 64, wpk, num_sms, 3);
+  op.p.x2 = x1; op.p.planes0 = C0 / 8; op.p.replicate = 1;
+  op.p.ln_w = ln_w; op.p.ln_b = ln_b; op.p.ln_eps = eps;
+  op.p.out = out; op.p.relu = 0;
+  VSB_CHECK((reinterpret_cast<uintptr_t>(x1) & 15) == 0, "direct conv3: input must be 16-byte aligned");
 }
 
 // [N][9*C] fp16 on the device -> a new buffer in the direct layout

@@ -186,6 +186,8 @@ class Model {
   std::vector<ResBlockW> down_rb, bott_rb, up_rb;
   std::vector<ConvW> up_conv;
   std::vector<float*> up_lnw, up_lnb;
+  std::vector<__half*> up_phase_w;   // per level: phase-folded weights (direct layout) or nullptr
+  std::vector<float*> up_border_w;   // per level: fp32 taps [9][Cout][Ct] for the border fix-up, or nullptr
   float *outc_w = nullptr, *outc_b = nullptr;
   float* msg_table = nullptr;
   // extractor
@@ -295,6 +297,35 @@ class Model {
     cw.w = wpool.upload(to_half(p));
     return cw;
   }
+  // the same up-conv folded for the phase path (conv3_direct_host.cuh, setup_up_phase_direct): rows n = (py*2+px)*Cout + co,
+  // K = (ey*3+ex)*Ct + c over the 3x3 LOW-resolution neighbourhood; g[phase][d][e] = weight of low-res offset e-1 in tap d of
+  // an output row of that phase (bilinear x2, align_corners=False).  Also the plain fp32 taps for the border fix-up kernel.
+  void pack_upconv_phase(const std::string& wkey, const std::vector<float>& in_scale, __half** wd_out, float** wk_out) {
+    const HostTensor& w = get(wkey);
+    const int Co = (int)w.shape[0], Ct = (int)w.shape[1];
+    static const float g[2][3][3] = {{{.75f, .25f, 0.f}, {.25f, .75f, 0.f}, {0.f, .75f, .25f}},
+                                     {{.25f, .75f, 0.f}, {0.f, .75f, .25f}, {0.f, .25f, .75f}}};
+    std::vector<float> p((size_t)4 * Co * 9 * Ct, 0.f), wk((size_t)9 * Co * Ct);
+    for (int co = 0; co < Co; ++co)
+      for (int c = 0; c < Ct; ++c)
+        for (int dy = 0; dy < 3; ++dy)
+          for (int dx = 0; dx < 3; ++dx) {
+            const float kv = w.data[(((size_t)co * Ct + c) * 3 + dy) * 3 + dx] * in_scale[c];
+            wk[((size_t)(dy * 3 + dx) * Co + co) * Ct + c] = kv;
+            for (int py = 0; py < 2; ++py)
+              for (int px = 0; px < 2; ++px)
+                for (int ey = 0; ey < 3; ++ey)
+                  for (int ex = 0; ex < 3; ++ex) {
+                    const float cf = g[py][dy][ey] * g[px][dx][ex];
+                    if (cf != 0.f) p[((size_t)((py * 2 + px) * Co + co) * 9 + (ey * 3 + ex)) * Ct + c] += kv * cf;
+                  }
+          }
+    __half* plain = wpool.upload(to_half(p));
+    *wd_out = wpool.alloc_n<__half>(p.size());
+    pack_direct_weights(plain, 4 * Co, Ct, *wd_out, 0, 9);
+    VSB_CUDA(cudaStreamSynchronize(0));
+    *wk_out = wpool.upload(wk);
+  }
   int halo_max_c = -1;
   bool use_halo(int C) {
     if (halo_max_c < 0) {
@@ -391,6 +422,10 @@ class Model {
         std::vector<float> in_scale(2 * zz[ii + 1], 1.0f);
         for (int c = zz[ii + 1]; c < 2 * zz[ii + 1]; ++c) in_scale[c] = 0.70710678118654752440f;
         up_conv.push_back(pack_upconv_taps(U + ".up.upsample_block.2.weight", in_scale));
+        __half* pw = nullptr; float* bw = nullptr;
+        if (zz[ii] == 16 && 2 * zz[ii + 1] == 64 && conv3_direct_ok(64, 64, 64, 0, 3) && !getenv("VSB_NO_UPPHASE"))
+          pack_upconv_phase(U + ".up.upsample_block.2.weight", in_scale, &pw, &bw);
+        up_phase_w.push_back(pw); up_border_w.push_back(bw);
         up_lnw.push_back(wpool.upload(get(U + ".up.upsample_block.3.weight").data));
         up_lnb.push_back(wpool.upload(get(U + ".up.upsample_block.3.bias").data));
         up_rb.push_back(pack_resblock(U + ".conv"));
@@ -633,7 +668,23 @@ class Model {
       const int ho = hs * 2;
       const long Mo = (long)B * ho * ho;
       __half* u = pl.pool.alloc_n<__half>(Mo * Cout);
-      {
+      if (up_phase_w[j] && ldx == Cin && ld_skip == Cin && conv3_direct_ok(64, 64, 64, hs, 3)) {
+        // one tensor-core conv on the low-resolution grid (bilinear weights folded per output phase) + exact border pixels
+        Conv3DirectOp op;
+        setup_up_phase_direct(op, x, Cin, skip, Cin, B, hs, hs, up_phase_w[j], up_lnw[j], up_lnb[j], 1e-6f, u, num_sms);
+        pl.steps.push_back(Step{[op](cudaStream_t st) { launch_direct(op, st); }, 1,
+                                "unet.upphase." + std::to_string(2 * Cin) + "-" + std::to_string(Cout) + "@" + std::to_string(ho)});
+        const __half *x0 = x, *x1 = skip;
+        const int IH = hs, Ci = Cin;
+        const float *wk = up_border_w[j], *lw = up_lnw[j], *lb = up_lnb[j];
+        pl.steps.push_back(Step{[=](cudaStream_t st) {
+          const long nb = (long)B * (2 * (2 * IH) + 2 * (2 * IH - 2));
+          static bool attr = false;
+          if (!attr) { VSB_CUDA(cudaFuncSetAttribute(up_border_fix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUpFixSmem)); attr = true; }
+          up_border_fix_kernel<<<(unsigned)((nb + kUpFixPPB - 1) / kUpFixPPB), 256, kUpFixSmem, st>>>(x0, Ci, x1, Ci, B, IH, IH, wk, lw, lb, 1e-6f, u);
+          VSB_CUDA(cudaGetLastError());
+        }, 1, "unet.upborder." + std::to_string(Cout) + "@" + std::to_string(ho)});
+      } else {
         // channel mixing first, at low resolution: y[b,i,j, tap*Cout + co] = sum_c W[co,c,tap] * [x | skip/sqrt2][b,i,j,c]
         const long Mi = (long)B * hs * hs;
         __half* ytap = pl.pool.alloc_n<__half>(Mi * 9 * Cout);
@@ -651,8 +702,8 @@ class Model {
           ups_gather_ln_kernel<<<(unsigned)std::min<long>(blocks, 148L * 32), 256, 0, st>>>(ytap, B, IH, IH, Cc, lw, lb, 1e-6f, u, Cc);
           VSB_CUDA(cudaGetLastError());
         }, 1, "unet.upgather." + std::to_string(Cout) + "@" + std::to_string(ho)});
-        dbg(pl, "up" + std::to_string(j) + "_conv", u, 1, B, ho, ho, Cout, Cout);
       }
+      dbg(pl, "up" + std::to_string(j) + "_conv", u, 1, B, ho, ho, Cout, Cout);
       const bool last = (ii == 0);
       x = add_resblock(pl, "up" + std::to_string(j), up_rb[j], u, B, ho, ho, Cout, Cout, nullptr, 0, /*fuse_outc=*/last);
       ldx = Cout; hs = ho;

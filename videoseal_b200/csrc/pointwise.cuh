@@ -400,6 +400,103 @@ __global__ void __launch_bounds__(256) ups_gather_ln_kernel(const __half* __rest
   }
 }
 
+// K3b: exact border pixels of the UBlock up-conv for the phase-folded tensor-core path (conv3_direct_host.cuh,
+// setup_up_phase_direct): the outermost rows/columns of the 2H x 2W output see the reflect padding of the up-sampled map,
+// which breaks the per-phase weight pattern.  One block = 8 border pixels x 16 output channels; the 9 bilinear-sampled
+// input vectors of a pixel (64 channels, two sources) are staged in shared memory, then each thread does its 576 MACs in
+// fp32 and the 16 threads of a pixel finish with LayerNorm + ReLU.  wk: fp32 [9][16][64] (input scale folded).
+constexpr int kUpFixPPB = 16;   // border pixels per block (x 16 output channels = 256 threads)
+constexpr size_t kUpFixSmem = (size_t)(9 * 16 * 16 * 4 + kUpFixPPB * 9 * 64) * sizeof(float);
+__global__ void __launch_bounds__(256) up_border_fix_kernel(const __half* __restrict__ x0, int C0, const __half* __restrict__ x1, int C1,
+                                                            int B, int IH, int IW, const float* __restrict__ wk,
+                                                            const float* __restrict__ lnw, const float* __restrict__ lnb, float eps,
+                                                            __half* __restrict__ out) {
+  constexpr int PPB = kUpFixPPB, CT = 64;
+  extern __shared__ __align__(16) float upfix_smem[];
+  float* Ws = upfix_smem;                     // [tap][c4][co][4]: conflict-free float4 reads across the 16 co threads
+  float* U = upfix_smem + 9 * 16 * 16 * 4;    // [PPB][9][CT]
+  const int OH = 2 * IH, OW = 2 * IW;
+  const int per_img = 2 * OW + 2 * (OH - 2);
+  const int total = B * per_img;              // < 2^31: B * 4 * 2W
+  const int q0 = (int)blockIdx.x * PPB;
+  auto decode = [&](int q, int& b, int& oy, int& ox) {
+    b = q / per_img;
+    int r = q - b * per_img;
+    if (r < OW) { oy = 0; ox = r; }
+    else if (r < 2 * OW) { oy = OH - 1; ox = r - OW; }
+    else { r -= 2 * OW; const int side = r / (OH - 2); oy = 1 + r - side * (OH - 2); ox = side ? OW - 1 : 0; }
+  };
+  // weights wk [tap][co][c] -> Ws [tap][c4][co][4]
+  for (int i = threadIdx.x; i < 9 * 16 * 16; i += 256) {
+    const int c4 = i & 15, co = (i >> 4) & 15, tap = i >> 8;
+    const float4 w4 = __ldg(reinterpret_cast<const float4*>(wk + ((long)tap * 16 + co) * CT) + c4);
+    *reinterpret_cast<float4*>(Ws + (((tap * 16 + c4) * 16 + co) << 2)) = w4;
+  }
+  for (int it = threadIdx.x; it < PPB * 9 * 16; it += 256) {
+    const int g4 = it & 15, tap = (it >> 4) % 9, pp = it / 144;
+    const int q = q0 + pp;
+    float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (q < total) {
+      int b, oy, ox;
+      decode(q, b, oy, ox);
+      const int r = tap / 3, s2 = tap - r * 3;
+      int u = oy + r - 1;
+      if (u < 0) u = -u;
+      if (u >= OH) u = 2 * OH - 2 - u;
+      int v = ox + s2 - 1;
+      if (v < 0) v = -v;
+      if (v >= OW) v = 2 * OW - 2 - v;
+      int ya, yb, xa, xb; float wy, wx;
+      { const int i = u >> 1; if (u & 1) { ya = i; yb = min(i + 1, IH - 1); wy = 0.75f; } else { ya = max(i - 1, 0); yb = i; wy = 0.25f; } }
+      { const int i = v >> 1; if (v & 1) { xa = i; xb = min(i + 1, IW - 1); wx = 0.75f; } else { xa = max(i - 1, 0); xb = i; wx = 0.25f; } }
+      const int c = g4 * 4;
+      const __half* src = c < C0 ? x0 + c : x1 + (c - C0);
+      const int ld = c < C0 ? C0 : C1;
+      auto ld4 = [&](int yy, int xx) {
+        const uint2 raw = __ldg(reinterpret_cast<const uint2*>(src + (((long)b * IH + yy) * IW + xx) * ld));
+        const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&raw.x)), hi = __half22float2(*reinterpret_cast<const __half2*>(&raw.y));
+        return make_float4(lo.x, lo.y, hi.x, hi.y);
+      };
+      const float4 a = ld4(ya, xa), bq = ld4(ya, xb), cq = ld4(yb, xa), d = ld4(yb, xb);
+      const float w00 = wy * wx, w01 = wy * (1.f - wx), w10 = (1.f - wy) * wx, w11 = (1.f - wy) * (1.f - wx);
+      val.x = w00 * a.x + w01 * bq.x + w10 * cq.x + w11 * d.x;
+      val.y = w00 * a.y + w01 * bq.y + w10 * cq.y + w11 * d.y;
+      val.z = w00 * a.z + w01 * bq.z + w10 * cq.z + w11 * d.z;
+      val.w = w00 * a.w + w01 * bq.w + w10 * cq.w + w11 * d.w;
+    }
+    *reinterpret_cast<float4*>(U + ((pp * 9 + tap) * CT + g4 * 4)) = val;
+  }
+  __syncthreads();
+  const int pp = threadIdx.x >> 4, co = threadIdx.x & 15;
+  float acc = 0.f;
+#pragma unroll 1
+  for (int tap = 0; tap < 9; ++tap) {
+    const float4* up = reinterpret_cast<const float4*>(U + (pp * 9 + tap) * CT);
+    const float4* wp = reinterpret_cast<const float4*>(Ws + ((tap * 16 * 16 + co) << 2));
+#pragma unroll
+    for (int c4 = 0; c4 < CT / 4; ++c4) {
+      const float4 u4 = up[c4];
+      const float4 w4 = wp[c4 * 16];
+      acc += u4.x * w4.x + u4.y * w4.y + u4.z * w4.z + u4.w * w4.w;
+    }
+  }
+  float sum = acc;
+#pragma unroll
+  for (int o = 8; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+  const float mean = sum * (1.f / 16.f);
+  const float dv = acc - mean;
+  float var = dv * dv;
+#pragma unroll
+  for (int o = 8; o; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+  const float rstd = 1.0f / sqrtf(var * (1.f / 16.f) + eps);
+  const int q = q0 + pp;
+  if (q < total) {
+    int b, oy, ox;
+    decode(q, b, oy, ox);
+    out[(((long)b * OH + oy) * OW + ox) * 16 + co] = __float2half_rn(fmaxf(dv * rstd * __ldg(lnw + co) + __ldg(lnb + co), 0.f));
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K9: ConvNeXt stem: x = 2*img-1 (extractor.py:25); conv k4 stride s (no padding) + bias; channels-first LN eps 1e-6
 // (convnext.py:108-111).  imgs [B,3,H,W] fp32 -> out NHWC fp32 [B,OH,OW,C] (row pitch ld).  One warp per output pixel.
