@@ -322,6 +322,30 @@ def run_ours(args):
                "h2d_bytes_per_step": B * 3 * S * S * 4 + B * K, "d2h_bytes_per_step": B * 3 * S * S * 4 + B * (1 + K) * 4,
                "path": "vsb_embed_detect_host: pinned host frames in, watermarked frames + logits out, 32-frame chunks, "
                        "copies overlapped with compute on 3 streams; timed by host wall clock around the synchronous calls"}
+        # the streaming caller's RGB24 form of the same call (inference_streaming.py): uint8 HWC frames over PCIe,
+        # conversions on the GPU; the detector sees the re-quantised frames.  Reported next to the fp32-API number, not instead.
+        u_in = [torch.randint(0, 256, (B, S, S, 3), dtype=torch.uint8, generator=g).pin_memory() for _ in range(2)]
+        u_out = torch.empty(B, S, S, 3, dtype=torch.uint8).pin_memory()
+
+        def u8_step(i):
+            _lib.check(L.vsb_frames_host_u8(h, u_in[i % 2].data_ptr(), h_msgs.data_ptr(), B, u_out.data_ptr(), h_log.data_ptr(), B, S, S,
+                                            1, 0, int(model.chunk_size), float(model.blender.scaling_i), float(model.blender.scaling_w), flags))
+
+        for i in range(3):
+            u8_step(i)
+        sync_all()
+        t0 = time.perf_counter()
+        for i in range(n_e2e):
+            u8_step(i)
+        sync_all()
+        u_ms = (time.perf_counter() - t0) * 1000.0
+        if world > 1:
+            t = torch.tensor([u_ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            u_ms = t.item()
+        e2e["u8_frames"] = {"value": world * B * n_e2e / (u_ms / 1000.0), "unit": "frames/s",
+                            "h2d_bytes_per_step": B * 3 * S * S + B * K, "d2h_bytes_per_step": B * 3 * S * S + B * (1 + K) * 4,
+                            "path": "vsb_frames_host_u8: RGB24 frames in and out, uint8<->float on the GPU"}
 
     # ---- per-kernel profile (CUDA events around every plan step) -> roofline of the dominant kernel
     roofline, table = None, []

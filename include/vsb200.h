@@ -111,6 +111,16 @@ int vsb_embed_detect_host(vsb_model* m, const float* imgs_host, const uint8_t* m
                           float* logits_host, int32_t F, int32_t H, int32_t W, int32_t step, int32_t video_mode,
                           int32_t chunk_keys, float scaling_i, float scaling_w, int32_t flags);
 
+/* The streaming caller's form (inference_streaming.py:23-33 embed_video_clip, :116-124 detect_video_clip): RGB24 frames
+ * [F,H,W,3] uint8 on the host, converted on the GPU (x = u8 / 255; u8 = (uint8) trunc(imgs_w * 255)) so that PCIe carries one byte
+ * per sample instead of four; same chunked three-stream overlap as vsb_embed_detect_host.
+ *   frames_w_host != NULL, logits_host == NULL : embed only            (embed_video_clip)
+ *   frames_w_host == NULL, logits_host != NULL : detect the input      (detect_video_clip; msgs_host may be NULL)
+ *   both != NULL                               : embed, then detect the re-quantised watermarked frames */
+int vsb_frames_host_u8(vsb_model* m, const uint8_t* frames_host, const uint8_t* msgs_host, int32_t n_msgs, uint8_t* frames_w_host,
+                       float* logits_host, int32_t F, int32_t H, int32_t W, int32_t step, int32_t video_mode, int32_t chunk_keys,
+                       float scaling_i, float scaling_w, int32_t flags);
+
 /* number of kernels launched by this library since the last call with reset != 0 (bench.py's gpu_launches) */
 int64_t vsb_launch_count(int32_t reset);
 

@@ -304,3 +304,38 @@ def test_streaming_host_entry_matches_device_path(v1):
                                                 _lib.FLAG_CLAMP))
     assert torch.equal(out, ref["imgs_w"].cpu())
     assert (logits - ref_log).abs().max().item() <= 1e-3 * ref_log.abs().max().item()
+
+
+def test_u8_streaming_clip_entry(v1):
+    """the streaming CLI's embed_video_clip / detect_video_clip (inference_streaming.py:23-33,116-124) on RGB24
+    frames: bit-identical to the same arithmetic through the fp32 API, within one grey level of the oracle."""
+    import numpy as np
+    from videoseal_b200.streaming import detect_video_clip, embed_detect_video_clip, embed_video_clip
+    model, orc, spec = v1
+    g = torch.Generator().manual_seed(13)
+    clip = torch.randint(0, 256, (37, 200, 264, 3), dtype=torch.uint8, generator=g).numpy()   # 2 chunks (32 + 5), ragged last key
+    msgs = torch.randint(0, 2, (1, spec["nbits"]), generator=g)
+    old = (model.step_size, orc.step_size)
+    try:
+        model.step_size = orc.step_size = 4
+        out = embed_video_clip(model, clip, msgs)
+        assert out.dtype == np.uint8 and out.shape == clip.shape
+        x = torch.tensor(clip, dtype=torch.float32).permute(0, 3, 1, 2) / 255.0
+        ref32 = model.embed(x.cuda(), msgs, is_video=True, lowres_attenuation=True)["imgs_w"]
+        ref_u8 = (ref32 * 255.0).byte().permute(0, 2, 3, 1).cpu().numpy()
+        assert np.array_equal(out, ref_u8)
+        with torch.no_grad():
+            o = orc.embed(x, msgs, is_video=True, lowres_attenuation=True)["imgs_w"]
+        o_u8 = (o * 255.0).byte().permute(0, 2, 3, 1).numpy()
+        diff = np.abs(out.astype(np.int16) - o_u8.astype(np.int16))
+        assert diff.max() <= 1 and (diff != 0).mean() < 0.01, (diff.max(), (diff != 0).mean())
+        bits = detect_video_clip(model, out)
+        xq = torch.tensor(out, dtype=torch.float32).permute(0, 3, 1, 2) / 255.0
+        ref_det = model.detect(xq.cuda(), is_video=True)["preds"][:, 1:].cpu()
+        assert bits.shape == (37, spec["nbits"])
+        assert (bits - ref_det).abs().max().item() <= 1e-3 * ref_det.abs().max().item()
+        out2, preds2, _ = embed_detect_video_clip(model, clip, msgs)
+        assert np.array_equal(out2, out)
+        assert (preds2[:, 1:] - bits).abs().max().item() <= 1e-3 * ref_det.abs().max().item()
+    finally:
+        model.step_size, orc.step_size = old

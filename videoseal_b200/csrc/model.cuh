@@ -202,7 +202,7 @@ class Model {
 
   // grow-only device staging for the host-buffer entry points (no cudaMalloc on the steady-state path)
   struct Staging { void* p = nullptr; size_t cap = 0; };
-  Staging staging[4];
+  Staging staging[6];
   void* stage(int slot, size_t bytes) {
     Staging& s = staging[slot];
     if (bytes > s.cap) {
@@ -982,6 +982,69 @@ class Model {
       VSB_CUDA(cudaStreamWaitEvent(s_out, ev_cmp[k], 0));
       VSB_CUDA(cudaMemcpyAsync(imgs_w_h + (size_t)f0 * fpx, out + (size_t)f0 * fpx, (size_t)n * fpx * sizeof(float), cudaMemcpyDeviceToHost, s_out));
       VSB_CUDA(cudaMemcpyAsync(logits_h + (size_t)f0 * NO, lg + (size_t)f0 * NO, (size_t)n * NO * sizeof(float), cudaMemcpyDeviceToHost, s_out));
+    }
+    VSB_CUDA(cudaStreamSynchronize(s_out));
+  }
+
+  // ---- the same streaming scheme with RGB24 frames [F,H,W,3] uint8 on the host (inference_streaming.py:23-33,116-124):
+  // out_h == nullptr -> detect only (logits of the input frames); logits_h == nullptr -> embed only; both -> the logits are
+  // those of the re-quantised watermarked frames, which is what the reference's detect pass reads back from the encoder
+  void frames_host_u8(const uint8_t* in_h, const uint8_t* msgs_h, int n_msgs, uint8_t* out_h, float* logits_h, int F, int H, int W,
+                      int step, int video_mode, int chunk_keys, float scaling_i, float scaling_w, int flags) {
+    check_ready();
+    VSB_CUDA(cudaSetDevice(device));
+    if (!s_in) {
+      VSB_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+      VSB_CUDA(cudaStreamCreateWithFlags(&s_cmp, cudaStreamNonBlocking));
+      VSB_CUDA(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+    }
+    const bool do_embed = out_h != nullptr, do_detect = logits_h != nullptr;
+    VSB_CHECK(do_embed || do_detect, "nothing to do");
+    const size_t fpx = (size_t)3 * H * W;
+    const long plane = (long)H * W;
+    const int NO = 1 + d.nbits;
+    float* imgs = (float*)stage(0, (size_t)F * fpx * sizeof(float));
+    float* out = do_embed ? (float*)stage(1, (size_t)F * fpx * sizeof(float)) : nullptr;
+    float* lg = do_detect ? (float*)stage(2, (size_t)F * NO * sizeof(float)) : nullptr;
+    uint8_t* msgs = do_embed ? (uint8_t*)stage(3, (size_t)n_msgs * d.nbits + 256) : nullptr;
+    uint8_t* in8 = (uint8_t*)stage(4, (size_t)F * fpx);
+    uint8_t* out8 = do_embed ? (uint8_t*)stage(5, (size_t)F * fpx) : nullptr;
+    int ch = kMaxBatch;   // one-byte samples: the exposed first/last copies are short, so full 64-frame batches win
+    const int unit = (video_mode == VSB_VIDEO_INTERPOLATE && step > 1) ? step * std::max(1, chunk_keys) : step;
+    if (ch % unit) ch = ((ch + unit - 1) / unit) * unit;
+    const int nch = (F + ch - 1) / ch;
+    while ((int)ev_in.size() < nch) {
+      cudaEvent_t a, b;
+      VSB_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
+      VSB_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
+      ev_in.push_back(a); ev_cmp.push_back(b);
+    }
+    if (do_embed) VSB_CUDA(cudaMemcpyAsync(msgs, msgs_h, (size_t)n_msgs * d.nbits, cudaMemcpyHostToDevice, s_in));
+    for (int k = 0; k < nch; ++k) {
+      const int f0 = k * ch, n = std::min(ch, F - f0);
+      VSB_CUDA(cudaMemcpyAsync(in8 + (size_t)f0 * fpx, in_h + (size_t)f0 * fpx, (size_t)n * fpx, cudaMemcpyHostToDevice, s_in));
+      VSB_CUDA(cudaEventRecord(ev_in[k], s_in));
+      VSB_CUDA(cudaStreamWaitEvent(s_cmp, ev_in[k], 0));
+      const long npx = (long)n * plane;
+      const unsigned blocks = (unsigned)std::min<long>((npx + 255) / 256, 148L * 16);
+      u8hwc_to_f32chw_kernel<<<blocks, 256, 0, s_cmp>>>(in8 + (size_t)f0 * fpx, imgs + (size_t)f0 * fpx, npx, plane);
+      g_launches += 1;
+      const float* det_in = imgs + (size_t)f0 * fpx;
+      if (do_embed) {
+        const uint8_t* mk = msgs + (n_msgs == 1 ? 0 : (size_t)f0 * d.nbits);
+        embed(imgs + (size_t)f0 * fpx, mk, n_msgs == 1 ? 1 : n, out + (size_t)f0 * fpx, nullptr, n, H, W, step, video_mode, chunk_keys,
+              scaling_i, scaling_w, flags, s_cmp);
+        f32chw_to_u8hwc_kernel<<<blocks, 256, 0, s_cmp>>>(out + (size_t)f0 * fpx, out8 + (size_t)f0 * fpx,
+                                                          do_detect ? out + (size_t)f0 * fpx : nullptr, npx, plane);
+        g_launches += 1;
+        det_in = out + (size_t)f0 * fpx;
+      }
+      if (do_detect) detect(det_in, lg + (size_t)f0 * NO, n, H, W, flags & VSB_FLAG_RESIZE_NO_AA, s_cmp);
+      VSB_CUDA(cudaGetLastError());
+      VSB_CUDA(cudaEventRecord(ev_cmp[k], s_cmp));
+      VSB_CUDA(cudaStreamWaitEvent(s_out, ev_cmp[k], 0));
+      if (do_embed) VSB_CUDA(cudaMemcpyAsync(out_h + (size_t)f0 * fpx, out8 + (size_t)f0 * fpx, (size_t)n * fpx, cudaMemcpyDeviceToHost, s_out));
+      if (do_detect) VSB_CUDA(cudaMemcpyAsync(logits_h + (size_t)f0 * NO, lg + (size_t)f0 * NO, (size_t)n * NO * sizeof(float), cudaMemcpyDeviceToHost, s_out));
     }
     VSB_CUDA(cudaStreamSynchronize(s_out));
   }

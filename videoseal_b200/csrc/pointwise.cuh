@@ -497,6 +497,38 @@ __global__ void __launch_bounds__(256) up_border_fix_kernel(const __half* __rest
   }
 }
 
+// K10: uint8 frame I/O around the path (inference_streaming.py:26,31,118): the streaming caller holds RGB24
+// frames [F,H,W,3] uint8; moving those over PCIe instead of fp32 planes is 4x less traffic each way.
+//   in : x[f,c,y,x] = float(u8[f,y,x,c]) / 255                               (torch: tensor(clip).permute(0,3,1,2) / 255.0)
+//   out: u8[f,y,x,c] = (uint8) trunc(imgs_w * 255)  and  imgs_q = float(u8) / 255   ((imgs_w * 255.0).byte(); the detector
+//        of the streaming pipeline sees the re-quantised frames)
+__global__ void __launch_bounds__(256) u8hwc_to_f32chw_kernel(const uint8_t* __restrict__ src, float* __restrict__ dst, long npix_total,
+                                                              long plane) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < npix_total; i += (long)gridDim.x * blockDim.x) {
+    const long f = i / plane, o = i - f * plane;
+    const uint8_t* s = src + i * 3;
+    float* d = dst + f * 3 * plane + o;
+    d[0] = __fdiv_rn((float)s[0], 255.f);
+    d[plane] = __fdiv_rn((float)s[1], 255.f);
+    d[2 * plane] = __fdiv_rn((float)s[2], 255.f);
+  }
+}
+__global__ void __launch_bounds__(256) f32chw_to_u8hwc_kernel(const float* __restrict__ src, uint8_t* __restrict__ dst, float* __restrict__ requant,
+                                                              long npix_total, long plane) {
+  for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < npix_total; i += (long)gridDim.x * blockDim.x) {
+    const long f = i / plane, o = i - f * plane;
+    const float* s = src + f * 3 * plane + o;
+    uint8_t* d = dst + i * 3;
+#pragma unroll
+    for (int c = 0; c < 3; ++c) {
+      const float v = __fmul_rn(s[c * plane], 255.f);
+      const int q = min(max((int)v, 0), 255);   // .byte(): truncation toward zero; inputs are clamped to [0, 1] by the blend
+      d[c] = (uint8_t)q;
+      if (requant != nullptr) requant[f * 3 * plane + o + c * plane] = __fdiv_rn((float)q, 255.f);
+    }
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // K9: ConvNeXt stem: x = 2*img-1 (extractor.py:25); conv k4 stride s (no padding) + bias; channels-first LN eps 1e-6
 // (convnext.py:108-111).  imgs [B,3,H,W] fp32 -> out NHWC fp32 [B,OH,OW,C] (row pitch ld).  One warp per output pixel.

@@ -152,6 +152,18 @@ int vsb_embed_detect_host(vsb_model* m, const float* imgs_h, const uint8_t* msgs
   VSB_API_END
 }
 
+int vsb_frames_host_u8(vsb_model* m, const uint8_t* frames_h, const uint8_t* msgs_h, int32_t n_msgs, uint8_t* frames_w_h, float* logits_h,
+                       int32_t F, int32_t H, int32_t W, int32_t step, int32_t video_mode, int32_t chunk_keys, float scaling_i,
+                       float scaling_w, int32_t flags) {
+  VSB_API_BEGIN
+  VSB_CHECK(m && frames_h && (frames_w_h || logits_h) && (msgs_h || !frames_w_h), "null argument");
+  VSB_CHECK(F > 0 && H > 0 && W > 0 && step >= 1, "bad shape");
+  m->impl.frames_host_u8(frames_h, msgs_h, n_msgs, frames_w_h, logits_h, F, H, W, step, video_mode, chunk_keys, scaling_i, scaling_w,
+                         flags);
+  return VSB_OK;
+  VSB_API_END
+}
+
 int64_t vsb_launch_count(int32_t reset) {
   const int64_t v = g_launches;
   if (reset) g_launches = 0;
