@@ -1,4 +1,4 @@
 timeout 600 python -m pytest tests -m gpu -x -q 2>&1 | tail -4
-timeout 300 python bench.py --steps 20 --warmup 3 --no-cpu-baseline 2>gpurun_out/bench_err.log | tail -1 | python -c "
+timeout 300 python bench.py --steps 10 --warmup 3 --no-cpu-baseline --profile-out gpurun_out/prof_dwc.json 2>gpurun_out/bench_err.log | tail -1 | python -c "
 import json,sys
-d=json.loads(sys.stdin.read()); print({k:d[k] for k in ('value','ms_per_step','e2e','gpu_launches','clocks')}); print(d['roofline'])"
+d=json.loads(sys.stdin.read()); print({k:d[k] for k in ('value','ms_per_step','gpu_launches')}); print(d['e2e']['value'], d['e2e']['u8_frames']['value'])"

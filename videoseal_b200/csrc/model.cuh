@@ -681,7 +681,7 @@ class Model {
           const long nb = (long)B * (2 * (2 * IH) + 2 * (2 * IH - 2));
           static bool attr = false;
           if (!attr) { VSB_CUDA(cudaFuncSetAttribute(up_border_fix_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kUpFixSmem)); attr = true; }
-          up_border_fix_kernel<<<(unsigned)((nb + kUpFixPPB - 1) / kUpFixPPB), 256, kUpFixSmem, st>>>(x0, Ci, x1, Ci, B, IH, IH, wk, lw, lb, 1e-6f, u);
+          up_border_fix_kernel<<<(unsigned)std::min<long>((nb + kUpFixPPB - 1) / kUpFixPPB, 148L * 3), 256, kUpFixSmem, st>>>(x0, Ci, x1, Ci, B, IH, IH, wk, lw, lb, 1e-6f, u);
           VSB_CUDA(cudaGetLastError());
         }, 1, "unet.upborder." + std::to_string(Cout) + "@" + std::to_string(ho)});
       } else {
@@ -820,9 +820,17 @@ class Model {
             const long blocks = (nstrips + spb - 1) / spb;
             const size_t smem_s = (size_t)spb * kDwStrip * Cc * sizeof(float);
             static const bool generic_dw = getenv("VSB_DW_GENERIC") != nullptr;
-#define VSB_DWC(CC) dwconv7_ln_c_kernel<CC><<<(unsigned)blocks, spb * C2, smem_s, st>>>(xin, B, H, H, dww, dwb, lw, lb, a, Cc, spb, (int)nstrips)
+#define VSB_DWC(CC, ST, FR, SPB, NST) dwconv7_ln_c_kernel<CC, ST, FR><<<(unsigned)(((NST) + (SPB) - 1) / (SPB)), (SPB) * (CC) / 2, \
+    (size_t)(SPB) * (ST) * (CC) * sizeof(float), st>>>(xin, B, H, H, dww, dwb, lw, lb, a, Cc, SPB, (int)(NST))
             if (!generic_dw && (Cc == 96 || Cc == 192 || Cc == 384 || Cc == 768)) {
-              if (Cc == 96) VSB_DWC(96); else if (Cc == 192) VSB_DWC(192); else if (Cc == 384) VSB_DWC(384); else VSB_DWC(768);
+              // narrow maps: one strip = the whole row, so no column is ever out of the image
+              const long nrows = (long)B * H;
+              if (Cc == 384 && H == 16) VSB_DWC(384, 16, true, 1, nrows);
+              else if (Cc == 768 && H == 8) VSB_DWC(768, 8, true, 1, nrows);
+              else if (Cc == 96) VSB_DWC(96, 8, false, spb, nstrips);
+              else if (Cc == 192) VSB_DWC(192, 8, false, spb, nstrips);
+              else if (Cc == 384) VSB_DWC(384, 8, false, spb, nstrips);
+              else VSB_DWC(768, 8, false, spb, nstrips);
               VSB_CUDA(cudaGetLastError());
               return;
             }

@@ -418,7 +418,6 @@ __global__ void __launch_bounds__(256) up_border_fix_kernel(const __half* __rest
   const int OH = 2 * IH, OW = 2 * IW;
   const int per_img = 2 * OW + 2 * (OH - 2);
   const int total = B * per_img;              // < 2^31: B * 4 * 2W
-  const int q0 = (int)blockIdx.x * PPB;
   auto decode = [&](int q, int& b, int& oy, int& ox) {
     b = q / per_img;
     int r = q - b * per_img;
@@ -432,6 +431,9 @@ __global__ void __launch_bounds__(256) up_border_fix_kernel(const __half* __rest
     const float4 w4 = __ldg(reinterpret_cast<const float4*>(wk + ((long)tap * 16 + co) * CT) + c4);
     *reinterpret_cast<float4*>(Ws + (((tap * 16 + c4) * 16 + co) << 2)) = w4;
   }
+  // the block keeps its weights and walks over groups of PPB border pixels
+  for (int q0 = (int)blockIdx.x * PPB; q0 < total; q0 += (int)gridDim.x * PPB) {
+  __syncthreads();   // U of the previous group has been consumed (and Ws is complete on the first pass)
   for (int it = threadIdx.x; it < PPB * 9 * 16; it += 256) {
     const int g4 = it & 15, tap = (it >> 4) % 9, pp = it / 144;
     const int q = q0 + pp;
@@ -495,6 +497,7 @@ __global__ void __launch_bounds__(256) up_border_fix_kernel(const __half* __rest
     decode(q, b, oy, ox);
     out[(((long)b * OH + oy) * OW + ox) * 16 + co] = __float2half_rn(fmaxf(dv * rstd * __ldg(lnw + co) + __ldg(lnb + co), 0.f));
   }
+  }  // pixel groups
 }
 
 // K10: uint8 frame I/O around the path (inference_streaming.py:26,31,118): the streaming caller holds RGB24
@@ -685,33 +688,37 @@ __device__ __forceinline__ float2 ldg_f2_pred(const float* p, unsigned pred) {
       : "l"(p), "r"(pred), "n"(OFF));
   return v;
 }
-template <int C, int U, bool EDGE>
+// MODE 0: interior strip (no predicates), 1: edge strip (predicated loads), 2: the strip is the whole row (W == STRIP): the
+// out-of-image columns are dropped at compile time
+template <int C, int STRIP, int U, int MODE>
 struct DwCol {
-  static __device__ __forceinline__ void run(const float* prow, unsigned cmask, const float2 (&wr)[7], float2 (&acc)[kDwStrip]) {
+  static __device__ __forceinline__ void run(const float* prow, unsigned cmask, const float2 (&wr)[7], float2 (&acc)[STRIP]) {
+    if (MODE != 2 || (U >= 3 && U < STRIP + 3)) {
     float2 v;
-    if (EDGE) v = ldg_f2_pred<U * C * 4>(prow, cmask & (1u << U));
+    if (MODE == 1) v = ldg_f2_pred<U * C * 4>(prow, cmask & (1u << U));
     else v = __ldg(reinterpret_cast<const float2*>(prow + U * C));
 #pragma unroll
     for (int s2 = 0; s2 < 7; ++s2) {
       const int i = U - s2;  // output pixel index within the strip
-      if (i >= 0 && i < kDwStrip) acc[i] = ffma2(v, wr[s2], acc[i]);
+      if (i >= 0 && i < STRIP) acc[i] = ffma2(v, wr[s2], acc[i]);
     }
-    DwCol<C, U + 1, EDGE>::run(prow, cmask, wr, acc);
+    }
+    DwCol<C, STRIP, U + 1, MODE>::run(prow, cmask, wr, acc);
   }
 };
-template <int C, bool EDGE>
-struct DwCol<C, kDwStrip + 6, EDGE> {
-  static __device__ __forceinline__ void run(const float*, unsigned, const float2 (&)[7], float2 (&)[kDwStrip]) {}
+template <int C, int STRIP, int MODE>
+struct DwCol<C, STRIP, STRIP + 6, MODE> {
+  static __device__ __forceinline__ void run(const float*, unsigned, const float2 (&)[7], float2 (&)[STRIP]) {}
 };
 
-template <int C>
+template <int C, int STRIP, bool FULLROW>
 __global__ void __launch_bounds__(768) dwconv7_ln_c_kernel(const float* __restrict__ x, int B, int H, int W,
                                                            const float* __restrict__ wdw /*[49][C]*/, const float* __restrict__ bdw,
                                                            const float* __restrict__ lnw, const float* __restrict__ lnb,
                                                            __half* __restrict__ out, int ld_out, int spb, int nstrips) {
   constexpr int C2 = C / 2, KP = (C + 63) / 64;
-  extern __shared__ float pre[];  // [spb][kDwStrip][C]
-  const int strips_x = (W + kDwStrip - 1) / kDwStrip;
+  extern __shared__ float pre[];  // [spb][STRIP][C]
+  const int strips_x = (W + STRIP - 1) / STRIP;
   const int ls = threadIdx.x / C2;                 // local strip
   const int cp = threadIdx.x - ls * C2;            // channel pair
   const unsigned strip = blockIdx.x * (unsigned)spb + (unsigned)ls;
@@ -719,16 +726,16 @@ __global__ void __launch_bounds__(768) dwconv7_ln_c_kernel(const float* __restri
     const unsigned t = strip / (unsigned)strips_x;
     const int sx = (int)(strip - t * (unsigned)strips_x);
     const int b = (int)(t / (unsigned)H), oy = (int)(t - (unsigned)b * (unsigned)H);
-    const int ox0 = sx * kDwStrip;
+    const int ox0 = sx * STRIP;
     const int c = cp * 2;
-    float2 acc[kDwStrip];
+    float2 acc[STRIP];
     const float2 bb = __ldg(reinterpret_cast<const float2*>(bdw + c));
 #pragma unroll
-    for (int i = 0; i < kDwStrip; ++i) acc[i] = bb;
+    for (int i = 0; i < STRIP; ++i) acc[i] = bb;
     unsigned cmask = 0;
 #pragma unroll
-    for (int u = 0; u < kDwStrip + 6; ++u) cmask |= ((unsigned)(ox0 + u - 3) < (unsigned)W) ? (1u << u) : 0u;
-    const bool interior = cmask == (1u << (kDwStrip + 6)) - 1u;
+    for (int u = 0; u < STRIP + 6; ++u) cmask |= ((unsigned)(ox0 + u - 3) < (unsigned)W) ? (1u << u) : 0u;
+    const bool interior = cmask == (1u << (STRIP + 6)) - 1u;
     const long rowpitch = (long)W * C;
     // (oy - 3, ox0 - 3): may lie outside the image; only dereferenced where the masks allow
     const float* prow = x + (((long)b * H + oy) * W + ox0) * C + c - 3 * rowpitch - 3 * C;
@@ -739,24 +746,25 @@ __global__ void __launch_bounds__(768) dwconv7_ln_c_kernel(const float* __restri
       float2 wr[7];
 #pragma unroll
       for (int s2 = 0; s2 < 7; ++s2) wr[s2] = __ldg(reinterpret_cast<const float2*>(wrow + s2 * C));
-      if (interior) DwCol<C, 0, false>::run(prow, cmask, wr, acc);
-      else DwCol<C, 0, true>::run(prow, cmask, wr, acc);
+      if (FULLROW) DwCol<C, STRIP, 0, 2>::run(prow, cmask, wr, acc);
+      else if (interior) DwCol<C, STRIP, 0, 0>::run(prow, cmask, wr, acc);
+      else DwCol<C, STRIP, 0, 1>::run(prow, cmask, wr, acc);
     }
-    float* pr = pre + (size_t)ls * kDwStrip * C;
+    float* pr = pre + (size_t)ls * STRIP * C;
 #pragma unroll
-    for (int i = 0; i < kDwStrip; ++i) *reinterpret_cast<float2*>(pr + i * C + c) = acc[i];
+    for (int i = 0; i < STRIP; ++i) *reinterpret_cast<float2*>(pr + i * C + c) = acc[i];
   }
   __syncthreads();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int item = warp; item < spb * kDwStrip; item += nwarps) {
-    const int l2 = item / kDwStrip, i = item - l2 * kDwStrip;
+  for (int item = warp; item < spb * STRIP; item += nwarps) {
+    const int l2 = item / STRIP, i = item - l2 * STRIP;
     const unsigned st2 = blockIdx.x * (unsigned)spb + (unsigned)l2;
     if (st2 >= (unsigned)nstrips) continue;
     const unsigned t2 = st2 / (unsigned)strips_x;
     const int sx2 = (int)(st2 - t2 * (unsigned)strips_x);
-    const int ox = sx2 * kDwStrip + i;
+    const int ox = sx2 * STRIP + i;
     if (ox >= W) continue;
-    const float2* pr2 = reinterpret_cast<const float2*>(pre + ((size_t)l2 * kDwStrip + i) * C);
+    const float2* pr2 = reinterpret_cast<const float2*>(pre + ((size_t)l2 * STRIP + i) * C);
     float2 vv[KP];
     float sum = 0.f;
 #pragma unroll
