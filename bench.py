@@ -91,7 +91,7 @@ def conv_flops(name: str, B: int) -> float:
         dims, hs = rest.split("@")
         h = int(hs)
         M = B * h * h
-        if kind in ("unet.conv3x3", "unet.conv3x3+outc", "unet.conv3x3d", "unet.conv3x3d+outc", "unet.down3x3s2", "unet.up3x3"):
+        if kind in ("unet.conv3x3", "unet.conv3x3+outc", "unet.conv3x3d", "unet.conv3x3d+outc", "unet.down3x3s2", "unet.down3x3s2d", "unet.up3x3"):
             cin, cout = (int(x) for x in dims.split("-"))
             return 2.0 * M * cout * 9 * cin
         if kind == "unet.uptap1x1":

@@ -52,6 +52,7 @@ struct Conv3DirectParams {
   // from x), replicate instead of zero padding, epilogue = per-phase LayerNorm + ReLU + pixel shuffle to [B,2H,2W,16]
   const __half* x2; int planes0; int replicate;
   const float* ln_w; const float* ln_b; float ln_eps;
+  int s2d;                  // stride-2 mode (S2): x is [B,2H,2W,C/4]
 };
 
 struct D3Header {
@@ -84,8 +85,12 @@ __global__ void pack_direct_weights_kernel(const __half* __restrict__ w, int N, 
   }
 }
 
-template <int N, int KS, int R, bool UP>
+// MODE 0: plain conv; MODE 1 ("UP"): phase-folded up-conv (two sources, replicate padding, LN + pixel-shuffle epilogue);
+// MODE 2 ("S2"): stride-2 3x3 conv, pad 1, as a 2x2-tap conv over the space-to-depth view of the input (C = 4*C_in planes
+// gathered by the producers straight from the [B,2H,2W,C_in] tensor; taps with an offset of +1 have no weights and are skipped)
+template <int N, int KS, int R, int MODE>
 __global__ void __launch_bounds__(kD3Threads, 1) conv3_direct_kernel(const Conv3DirectParams p) {
+  constexpr bool UP = MODE == 1, S2 = MODE == 2;
   extern __shared__ uint8_t d3_smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(d3_smem_raw) + 1023) & ~(uintptr_t)1023);
   D3Header* hd = reinterpret_cast<D3Header*>(smem);
@@ -169,6 +174,19 @@ __global__ void __launch_bounds__(kD3Threads, 1) conv3_direct_kernel(const Conv3
           cp_async16_zfill(dst, src, rvalid ? 16u : 0u);
           if (mir) cp_async16_zfill(dst + (size_t)NR * rw * 16, src, rvalid ? 16u : 0u);
         }
+      } else if (S2) {
+        // plane = (dy, dx, 8-channel group) of the 2x2 input block under low-res position (Y, X) = (yy - 1, xx - 1)
+        const int cin = p.C >> 2, pc = cin >> 3;
+        const int sub = pl / pc, c8 = pl - sub * pc, dy = sub >> 1, dx = sub & 1;
+        const bool rvalid = b < p.B && yy >= PAD && yy < p.H + PAD;
+        const __half* lane_src = p.x + (((long)b * 2 * p.H + 2 * (yy - PAD) + dy) * (2 * p.W) + dx) * cin + c8 * 8 - PAD * 2 * cin;
+        for (int xx = lane >> pshift; xx < rw; xx += xstep) {
+          const bool ok = rvalid && (unsigned)(xx - PAD) < (unsigned)p.W;
+          const __half* src = ok ? lane_src + xx * 2 * cin : p.x;
+          uint8_t* dst = lane_dst + xx * 16;
+          cp_async16_zfill(dst, src, ok ? 16u : 0u);
+          if (mir) cp_async16_zfill(dst + (size_t)NR * rw * 16, src, ok ? 16u : 0u);
+        }
       } else {
         const bool rvalid = b < p.B && yy >= PAD && yy < p.H + PAD;
         const __half* lane_src = p.x + ((long)b * p.H + (yy - PAD)) * p.W * p.C + pl * 8 - PAD * p.C;
@@ -226,9 +244,9 @@ __global__ void __launch_bounds__(kD3Threads, 1) conv3_direct_kernel(const Conv3
         int s2 = s1 + 1; if (s2 >= NR) s2 -= NR;
         const uint32_t arow[3] = {a_lo + (uint32_t)(slot0 * rw + x0), a_lo + (uint32_t)(s1 * rw + x0), a_lo + (uint32_t)(s2 * rw + x0)};
 #pragma unroll
-        for (int r = 0; r < R; ++r) {
+        for (int r = 0; r < (S2 ? 2 : R); ++r) {
 #pragma unroll
-          for (int s = 0; s < R; ++s) {
+          for (int s = 0; s < (S2 ? 2 : R); ++s) {
 #pragma unroll
             for (int kk = 0; kk < KS; ++kk) {
               const uint64_t adesc = a_hi | (uint64_t)(arow[r] + (uint32_t)s + (uint32_t)kk * kk_step);

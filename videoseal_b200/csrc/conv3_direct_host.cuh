@@ -74,14 +74,14 @@ inline void setup_conv3_direct(Conv3DirectOp& op, const __half* x, int B, int H,
   op.grid = std::min(num_sms, p.n_tiles);
 }
 
-template <int N, int KS, int R, bool UP = false>
+template <int N, int KS, int R, int MODE = 0>
 inline void launch_direct_nkr(const Conv3DirectOp& op, cudaStream_t st) {
   static bool attr = false;
   if (!attr) {
-    VSB_CUDA(cudaFuncSetAttribute(conv3_direct_kernel<N, KS, R, UP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    VSB_CUDA(cudaFuncSetAttribute(conv3_direct_kernel<N, KS, R, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
-  conv3_direct_kernel<N, KS, R, UP><<<op.grid, kD3Threads, op.smem, st>>>(op.p);
+  conv3_direct_kernel<N, KS, R, MODE><<<op.grid, kD3Threads, op.smem, st>>>(op.p);
   VSB_CUDA(cudaGetLastError());
 }
 template <int N, int KS>
@@ -100,7 +100,12 @@ inline void launch_direct(const Conv3DirectOp& op, cudaStream_t st) {
   VSB_CHECK(op.smem <= 227 * 1024, "direct conv3: shared-memory plan too large");
   if (op.p.x2 != nullptr) {   // up-conv phase mode: 64 input channels (two sources), 4 phases x 16 output channels
     VSB_CHECK(op.p.N == 64 && op.p.C == 64 && op.p.R == 3, "up-phase direct conv: C = 64, N = 4 x 16 only");
-    launch_direct_nkr<64, 4, 3, true>(op, st);
+    launch_direct_nkr<64, 4, 3, 1>(op, st);
+    return;
+  }
+  if (op.p.s2d) {             // stride-2 conv through the space-to-depth view: C = 4 x 16 input channels, 32 outputs
+    VSB_CHECK(op.p.N == 32 && op.p.C == 64 && op.p.R == 3, "stride-2 direct conv: 16 -> 32 channels only");
+    launch_direct_nkr<32, 4, 3, 2>(op, st);
     return;
   }
   if (op.p.N == 16) launch_direct_n<16>(op, st);
@@ -121,6 +126,15 @@ inline void setup_up_phase_direct(Conv3DirectOp& op, const __half* x0, int C0, c
   op.p.ln_w = ln_w; op.p.ln_b = ln_b; op.p.ln_eps = eps;
   op.p.out = out; op.p.relu = 0;
   VSB_CHECK((reinterpret_cast<uintptr_t>(x1) & 15) == 0, "direct conv3: input must be 16-byte aligned");
+}
+
+// DBlock.down (unet.py:75: 3x3, stride 2, pad 1, bias) on x [B,2H,2W,Cin] -> [B,H,W,N]: output (Y,X), tap r reads input row
+// 2Y + r - 1 = row (Y-1, dy=1), (Y, dy=0), (Y, dy=1) of the space-to-depth view, i.e. a conv with offsets {-1, 0} only.
+// wpk: weights re-indexed to [N][(ey,ex)][(dy,dx,c)] (Model::pack_down_s2d) in the direct layout.
+inline void setup_down_s2d_direct(Conv3DirectOp& op, const __half* x, int Cin, int B, int H, int W, int N, const __half* wpk,
+                                  const float* bias, __half* out, int num_sms) {
+  setup_conv3_direct(op, x, B, H, W, 4 * Cin, N, wpk, num_sms, 3);
+  op.p.s2d = 1; op.p.bias = bias; op.p.out = out; op.p.relu = 0;
 }
 
 // [N][9*C] fp16 on the device -> a new buffer in the direct layout

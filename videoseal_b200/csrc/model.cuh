@@ -326,6 +326,24 @@ class Model {
     VSB_CUDA(cudaStreamSynchronize(0));
     *wk_out = wpool.upload(wk);
   }
+  // DBlock.down weights [N][Cin][3][3] re-indexed for the space-to-depth ring conv (conv3_direct_host.cuh,
+  // setup_down_s2d_direct): K = (ey*3+ex)*4Cin + (dy*2+dx)*Cin + c with tap r -> (ey, dy) = (0,1), (1,0), (1,1)
+  __half* pack_down_s2d(const std::string& wkey) {
+    const HostTensor& w = get(wkey);
+    const int N = (int)w.shape[0], Ci = (int)w.shape[1], Cs = 4 * Ci;
+    static const int E[3] = {0, 1, 1}, D[3] = {1, 0, 1};
+    std::vector<float> p((size_t)N * 9 * Cs, 0.f);
+    for (int n = 0; n < N; ++n)
+      for (int c = 0; c < Ci; ++c)
+        for (int r = 0; r < 3; ++r)
+          for (int s2 = 0; s2 < 3; ++s2)
+            p[((size_t)n * 9 + (E[r] * 3 + E[s2])) * Cs + (D[r] * 2 + D[s2]) * Ci + c] = w.data[(((size_t)n * Ci + c) * 3 + r) * 3 + s2];
+    __half* plain = wpool.upload(to_half(p));
+    __half* wd = wpool.alloc_n<__half>(p.size());
+    pack_direct_weights(plain, N, Cs, wd, 0, 9);
+    VSB_CUDA(cudaStreamSynchronize(0));
+    return wd;
+  }
   int halo_max_c = -1;
   bool use_halo(int C) {
     if (halo_max_c < 0) {
@@ -409,6 +427,8 @@ class Model {
     }
     for (int i = 0; i < L - 1; ++i) {
       down_conv.push_back(pack_conv(P + "downs." + std::to_string(i) + ".down.weight", nullptr, get(P + "downs." + std::to_string(i) + ".down.bias").data));
+      if (z[i] == 16 && z[i + 1] == 32 && conv3_direct_ok(64, 32, 64, 0, 3) && !getenv("VSB_NO_S2D"))
+        down_conv.back().wd = pack_down_s2d(P + "downs." + std::to_string(i) + ".down.weight");
       down_rb.push_back(pack_resblock(P + "downs." + std::to_string(i) + ".conv"));
     }
     for (int i = 0; i < d.unet_num_blocks; ++i) bott_rb.push_back(pack_resblock(P + "bottleneck.model." + std::to_string(i)));
@@ -624,7 +644,12 @@ class Model {
       const int ho = hs / 2;
       const long Mo = (long)B * ho * ho;
       __half* dn = pl.pool.alloc_n<__half>(Mo * z[i + 1]);
-      {
+      if (down_conv[i].wd && ldx == z[i] && hs % 2 == 0 && conv3_direct_ok(4 * z[i], z[i + 1], 4 * z[i], ho, 3)) {
+        Conv3DirectOp op;
+        setup_down_s2d_direct(op, x, z[i], B, ho, ho, z[i + 1], down_conv[i].wd, down_conv[i].bias, dn, num_sms);
+        pl.steps.push_back(Step{[op](cudaStream_t st) { launch_direct(op, st); }, 1,
+                                "unet.down3x3s2d." + std::to_string(z[i]) + "-" + std::to_string(z[i + 1]) + "@" + std::to_string(ho)});
+      } else {
         ConvGemmOp op;
         setup_gather_conv(op, LD_GATHER_CONV, x, z[i], ldx, nullptr, 0, 0, B, hs, hs, ho, ho, 3, 3, 2, 1, 0);
         op.p.epi = EPI_AFFINE; op.p.act = ACT_NONE; op.p.bias = down_conv[i].bias; op.p.out16 = dn; op.p.ld_out16 = z[i + 1];
