@@ -527,6 +527,11 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             p.fd_rps.div(m_tile * kBlockM + q * 32) == p.fd_rps.div(m_tile * kBlockM + q * 32 + 31) &&
             (m_tile * kBlockM + q * 32 + 31) < p.M;
         float* grn_row = grn_uniform ? p.grn_stats + (long)p.fd_rps.div(m_tile * kBlockM + q * 32) * p.N : nullptr;
+        // whole tile, fp16 output only, no residual / fused 1x1, statistics (if any) uniform per warp
+        const bool whole = (m_tile + 1) * kBlockM <= p.M && n0 + p.block_n <= p.N && p.out16 != nullptr && p.out32 == nullptr &&
+                           p.outc_w == nullptr && (p.ld_out16 & 7) == 0;
+        const bool lean = ACT == ACT_GELU ? (whole && !has_res && (p.grn_stats == nullptr || grn_uniform))
+                                          : (whole && p.grn_stats == nullptr && (!has_res || (p.resid16 != nullptr && res_fast)));
         uint32_t vnext[16];
         if (half < nchunks) tmem_ld16_issue(trow + half * 16, vnext);
         for (int ch = half; ch < nchunks; ch += kEpiSplit) {
@@ -537,6 +542,89 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(vnext[j]);
           if (ch + kEpiSplit < nchunks) tmem_ld16_issue(trow + c + 16 * kEpiSplit, vnext);   // overlaps the math below
           const int n = n0 + c;
+          if (ACT == ACT_GELU && lean) {
+            // pwconv1 on whole tiles (every shipped card): bias + GELU + fp16 store + GRN column statistics and nothing
+            // else.  The generic chunk body below costs ~490 instructions per 16 elements, 45 % of them guards and
+            // index arithmetic for tails, residuals and the other epilogue variants (profiles/r1_history.md).
+            const float4* sb4 = reinterpret_cast<const float4*>(sb + c);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float4 bq = sb4[u];
+              v[4 * u + 0] += bq.x; v[4 * u + 1] += bq.y; v[4 * u + 2] += bq.z; v[4 * u + 3] += bq.w;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) gelu_erf2(v[j], v[j + 1]);
+            {
+              __align__(16) __half2 h[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j) h[j] = __floats2half2_rn(fminf(v[2 * j], 65504.f), fminf(v[2 * j + 1], 65504.f));
+              uint4* o = reinterpret_cast<uint4*>(p.out16 + m * p.ld_out16 + n);
+              o[0] = reinterpret_cast<const uint4*>(h)[0];
+              o[1] = reinterpret_cast<const uint4*>(h)[1];
+            }
+            if (grn_row != nullptr) {
+              float sq[16];
+#pragma unroll
+              for (int j = 0; j < 16; ++j) sq[j] = v[j] * v[j];
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                const float send = (lane & 16) ? sq[i] : sq[i + 8];
+                const float keep = (lane & 16) ? sq[i + 8] : sq[i];
+                sq[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+              }
+#pragma unroll
+              for (int i = 0; i < 4; ++i) {
+                const float send = (lane & 8) ? sq[i] : sq[i + 4];
+                const float keep = (lane & 8) ? sq[i + 4] : sq[i];
+                sq[i] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+              }
+#pragma unroll
+              for (int i = 0; i < 2; ++i) {
+                const float send = (lane & 4) ? sq[i] : sq[i + 2];
+                const float keep = (lane & 4) ? sq[i + 2] : sq[i];
+                sq[i] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+              }
+              {
+                const float send = (lane & 2) ? sq[0] : sq[1];
+                const float keep = (lane & 2) ? sq[1] : sq[0];
+                sq[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+              }
+              sq[0] += __shfl_xor_sync(0xffffffffu, sq[0], 1);
+              if ((lane & 1) == 0) atomicAdd(grn_row + n + ((lane >> 1) & 15), sq[0]);
+            }
+            continue;
+          }
+          if (ACT != ACT_GELU && lean) {
+            // whole-tile conv / GEMM with an fp16 output: bias, ReLU, optional fp16 residual from the prefetch ring, store
+            const float4* sb4 = reinterpret_cast<const float4*>(sb + c);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float4 bq = sb4[u];
+              v[4 * u + 0] += bq.x; v[4 * u + 1] += bq.y; v[4 * u + 2] += bq.z; v[4 * u + 3] += bq.w;
+            }
+            if (ACT == ACT_RELU) {
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] = fmaxf(v[j], 0.f);
+            }
+            if (has_res) {
+              __align__(16) __half h[16];
+              reinterpret_cast<uint4*>(h)[0] = *reinterpret_cast<const uint4*>(rb_ + ((size_t)(2 * ch) * 128 + row) * 16);
+              reinterpret_cast<uint4*>(h)[1] = *reinterpret_cast<const uint4*>(rb_ + ((size_t)(2 * ch + 1) * 128 + row) * 16);
+#pragma unroll
+              for (int j = 0; j < 16; ++j) v[j] += __half2float(h[j]);
+            }
+            __align__(16) __half2 h2[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              float a = fminf(v[2 * j], 65504.f), b2 = fminf(v[2 * j + 1], 65504.f);
+              if (ACT == ACT_NONE || has_res) { a = fmaxf(a, -65504.f); b2 = fmaxf(b2, -65504.f); }
+              h2[j] = __floats2half2_rn(a, b2);
+            }
+            uint4* o = reinterpret_cast<uint4*>(p.out16 + m * p.ld_out16 + n);
+            o[0] = reinterpret_cast<const uint4*>(h2)[0];
+            o[1] = reinterpret_cast<const uint4*>(h2)[1];
+            continue;
+          }
           if (n >= p.N) continue;  // uniform across the warp
           const int nval = min(16, p.N - n);   // 16 on every full chunk (all shipped tiny/pixelseal layers)
           {
