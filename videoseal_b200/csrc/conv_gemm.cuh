@@ -530,6 +530,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         // whole tile, fp16 output only, no residual / fused 1x1, statistics (if any) uniform per warp
         const bool whole = (m_tile + 1) * kBlockM <= p.M && n0 + p.block_n <= p.N && p.out16 != nullptr && p.out32 == nullptr &&
                            p.outc_w == nullptr && (p.ld_out16 & 7) == 0;
+        const bool lean32 = ACT == ACT_NONE && (m_tile + 1) * kBlockM <= p.M && n0 + p.block_n <= p.N && p.out32 != nullptr &&
+                            p.outc_w == nullptr && p.grn_stats == nullptr && p.resid32 != nullptr && res_fast && (p.ld_out32 & 3) == 0 &&
+                            (p.out16 == nullptr || (p.ld_out16 & 7) == 0);
         const bool lean = ACT == ACT_GELU ? (whole && !has_res && (p.grn_stats == nullptr || grn_uniform))
                                           : (whole && p.grn_stats == nullptr && (!has_res || (p.resid16 != nullptr && res_fast)));
         uint32_t vnext[16];
@@ -591,6 +594,28 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
               sq[0] += __shfl_xor_sync(0xffffffffu, sq[0], 1);
               if ((lane & 1) == 0) atomicAdd(grn_row + n + ((lane >> 1) & 15), sq[0]);
+            }
+            continue;
+          }
+          if (ACT == ACT_NONE && lean32) {
+            // pwconv2 on whole tiles: bias + fp32 residual stream from the prefetch ring, updated in place (+ fp16 copy)
+            const float4* sb4 = reinterpret_cast<const float4*>(sb + c);
+            float4* o = reinterpret_cast<float4*>(p.out32 + m * p.ld_out32 + n);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float4 bq = sb4[u];
+              const float4 t = *reinterpret_cast<const float4*>(rb_ + ((size_t)(4 * ch + u) * 128 + row) * 16);
+              v[4 * u + 0] += bq.x + t.x; v[4 * u + 1] += bq.y + t.y; v[4 * u + 2] += bq.z + t.z; v[4 * u + 3] += bq.w + t.w;
+              o[u] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+            }
+            if (p.out16 != nullptr) {
+              __align__(16) __half2 h2[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                h2[j] = __floats2half2_rn(fminf(fmaxf(v[2 * j], -65504.f), 65504.f), fminf(fmaxf(v[2 * j + 1], -65504.f), 65504.f));
+              uint4* o16 = reinterpret_cast<uint4*>(p.out16 + m * p.ld_out16 + n);
+              o16[0] = reinterpret_cast<const uint4*>(h2)[0];
+              o16[1] = reinterpret_cast<const uint4*>(h2)[1];
             }
             continue;
           }

@@ -845,17 +845,22 @@ class Model {
             const long blocks = (nstrips + spb - 1) / spb;
             const size_t smem_s = (size_t)spb * kDwStrip * Cc * sizeof(float);
             static const bool generic_dw = getenv("VSB_DW_GENERIC") != nullptr;
-#define VSB_DWC(CC, ST, FR, SPB, NST) dwconv7_ln_c_kernel<CC, ST, FR><<<(unsigned)(((NST) + (SPB) - 1) / (SPB)), (SPB) * (CC) / 2, \
-    (size_t)(SPB) * (ST) * (CC) * sizeof(float), st>>>(xin, B, H, H, dww, dwb, lw, lb, a, Cc, SPB, (int)(NST))
+#define VSB_DWC(CC, ST, FR, SPB, NGR, RPB) dwconv7_ln_c_kernel<CC, ST, FR><<<(unsigned)(((NGR) + (SPB) - 1) / (SPB)), (SPB) * (CC) / 2, \
+    (size_t)(SPB) * (ST) * (CC) * sizeof(float), st>>>(xin, B, H, H, dww, dwb, lw, lb, a, Cc, SPB, (int)(NGR), RPB)
             if (!generic_dw && (Cc == 96 || Cc == 192 || Cc == 384 || Cc == 768)) {
+              // rows per block: 1.  Walking 2-4 consecutive rows per block (L1 reuse of the 7-row input window) was measured
+              // SLOWER (96@64: 148 -> 228 us, 192@32: 58 -> 87 us): the kernel is latency-bound and fewer, longer blocks with
+              // two block barriers per row hide less of it; VSB_DW_RPB re-enables the experiment
+              int rpb = 1;
+              if (const char* e = getenv("VSB_DW_RPB")) { const int r2 = atoi(e); if (r2 > 0 && H % r2 == 0) rpb = r2; }
               // narrow maps: one strip = the whole row, so no column is ever out of the image
               const long nrows = (long)B * H;
-              if (Cc == 384 && H == 16) VSB_DWC(384, 16, true, 1, nrows);
-              else if (Cc == 768 && H == 8) VSB_DWC(768, 8, true, 1, nrows);
-              else if (Cc == 96) VSB_DWC(96, 8, false, spb, nstrips);
-              else if (Cc == 192) VSB_DWC(192, 8, false, spb, nstrips);
-              else if (Cc == 384) VSB_DWC(384, 8, false, spb, nstrips);
-              else VSB_DWC(768, 8, false, spb, nstrips);
+              if (Cc == 384 && H == 16) VSB_DWC(384, 16, true, 1, nrows, 1);
+              else if (Cc == 768 && H == 8) VSB_DWC(768, 8, true, 1, nrows, 1);
+              else if (Cc == 96) VSB_DWC(96, 8, false, spb, nstrips / rpb, rpb);
+              else if (Cc == 192) VSB_DWC(192, 8, false, spb, nstrips / rpb, rpb);
+              else if (Cc == 384) VSB_DWC(384, 8, false, spb, nstrips / rpb, rpb);
+              else VSB_DWC(768, 8, false, spb, nstrips / rpb, rpb);
               VSB_CUDA(cudaGetLastError());
               return;
             }
