@@ -146,6 +146,9 @@ typedef struct vsb_conv_test {
   const float* ln_w; const float* ln_b;
   const float* outc_w; const float* outc_b; int32_t n_out;
   void* out16; float* out32; float* delta; float* grn_stats;
+  int32_t ld0;               /* pixel pitch of src0 in elements (0 = C0): widths that are not multiples of 8 live in padded rows */
+  int32_t ldw;               /* row pitch of the weights (0 = K) */
+  int32_t ld_out;            /* row pitch of out16 / out32 / resid32 (0 = N) */
 } vsb_conv_test;
 int vsb_debug_conv(const vsb_conv_test* t, void* stream);
 

@@ -172,8 +172,39 @@ def synth_state_dict(spec: dict, seed: int = 0) -> Dict[str, Tensor]:
         conv(D + "output_upscaling.0.upsample_block.2", dims[-1], dims[-1], 3, False)
         affine(D + "output_upscaling.0.upsample_block.3", dims[-1])
         linear(D + "linear", 1 + spec["nbits"], dims[-1])
+    elif spec["ext_kind"] == "sam":
+        # modules/vit.py:14-143 (ImageEncoderViT), :146-210 (Block), :302-353 (Attention), :494-525 (PatchEmbed)
+        v = spec["vit"]
+        E, depth, heads = int(v["embed_dim"]), int(v["depth"]), int(v["num_heads"])
+        ps, oc = int(v["patch_size"]), int(v["out_chans"])
+        grid = spec["img_size"] // ps
+        hd = E // heads
+        Q = "detector.image_encoder."
+        conv(Q + "patch_embed.proj", E, 3, ps, True)
+        sd[Q + "pos_embed"] = 0.02 * torch.randn(1, grid, grid, E, generator=g)
+        for i in range(depth):
+            B = Q + f"blocks.{i}."
+            ws = 0 if i in list(v["global_attn_indexes"]) else int(v["window_size"])
+            n = grid if ws == 0 else ws
+            affine(B + "norm1", E)
+            linear(B + "attn.qkv", 3 * E, E)
+            linear(B + "attn.proj", E, E)
+            if v.get("use_rel_pos", False):      # zero-initialised in the reference; randomised so the term is exercised
+                sd[B + "attn.rel_pos_h"] = 0.02 * torch.randn(2 * n - 1, hd, generator=g)
+                sd[B + "attn.rel_pos_w"] = 0.02 * torch.randn(2 * n - 1, hd, generator=g)
+            affine(B + "norm2", E)
+            linear(B + "mlp.lin1", int(E * float(v["mlp_ratio"])), E)
+            linear(B + "mlp.lin2", E, int(E * float(v["mlp_ratio"])))
+        conv(Q + "neck.0", oc, E, 1, False)
+        affine(Q + "neck.1", oc)
+        conv(Q + "neck.2", oc, oc, 3, False)
+        affine(Q + "neck.3", oc)
+        D = "detector.pixel_decoder."
+        conv(D + "output_upscaling.0.upsample_block.2", oc, oc, 3, False)
+        affine(D + "output_upscaling.0.upsample_block.3", oc)
+        linear(D + "linear", 1 + spec["nbits"], oc)
     else:
-        raise NotImplementedError("synthetic checkpoints: only convnext extractors")
+        raise NotImplementedError("synthetic checkpoints: only convnext / sam extractors")
     sd["rgb2yuv.M"] = torch.tensor([[0.299, 0.587, 0.114], [-0.14713, -0.28886, 0.436],
                                     [0.615, -0.51499, -0.10001]], dtype=torch.float32)
     return sd
@@ -323,6 +354,91 @@ def convnext_extractor_forward(sd, spec, x: Tensor, taps: Optional[dict] = None)
     return F.linear(x, sd[D + "linear.weight"], sd[D + "linear.bias"])  # no sigmoid (all cards)
 
 
+def _vit_rel_pos(q_size: int, k_size: int, rel_pos: Tensor) -> Tensor:
+    """modules/vit.py:398-428 get_rel_pos"""
+    max_rel = int(2 * max(q_size, k_size) - 1)
+    if rel_pos.shape[0] != max_rel:
+        rp = F.interpolate(rel_pos.reshape(1, rel_pos.shape[0], -1).permute(0, 2, 1), size=max_rel, mode="linear")
+        rp = rp.reshape(-1, max_rel).permute(1, 0)
+    else:
+        rp = rel_pos
+    qc = torch.arange(q_size)[:, None] * max(k_size / q_size, 1.0)
+    kc = torch.arange(k_size)[None, :] * max(q_size / k_size, 1.0)
+    rel = (qc - kc) + (k_size - 1) * max(q_size / k_size, 1.0)
+    return rp[rel.long()]
+
+
+def _vit_attention(sd, key: str, x: Tensor, heads: int, use_rel_pos: bool) -> Tensor:
+    """modules/vit.py:302-353 Attention.forward + :431-470 add_decomposed_rel_pos; x: [B, H, W, C]"""
+    B, H, W, C = x.shape
+    qkv = F.linear(x, sd[key + "qkv.weight"], sd[key + "qkv.bias"]).reshape(B, H * W, 3, heads, -1).permute(2, 0, 3, 1, 4)
+    q, k, v = qkv.reshape(3, B * heads, H * W, -1).unbind(0)
+    scale = (C // heads) ** -0.5
+    attn = (q * scale) @ k.transpose(-2, -1)
+    if use_rel_pos:
+        Rh = _vit_rel_pos(H, H, sd[key + "rel_pos_h"])
+        Rw = _vit_rel_pos(W, W, sd[key + "rel_pos_w"])
+        r_q = q.reshape(B * heads, H, W, -1)
+        rel_h = torch.einsum("bhwc,hkc->bhwk", r_q, Rh)
+        rel_w = torch.einsum("bhwc,wkc->bhwk", r_q, Rw)
+        attn = (attn.view(B * heads, H, W, H, W) + rel_h[:, :, :, :, None] + rel_w[:, :, :, None, :]).view(B * heads, H * W, H * W)
+    attn = attn.softmax(dim=-1)
+    x = (attn @ v).view(B, heads, H, W, -1).permute(0, 2, 3, 1, 4).reshape(B, H, W, -1)
+    return F.linear(x, sd[key + "proj.weight"], sd[key + "proj.bias"])
+
+
+def _vit_block(sd, key: str, x: Tensor, heads: int, window: int, use_rel_pos: bool) -> Tensor:
+    """modules/vit.py:146-210 Block.forward with window_partition / window_unpartition (:356-395); nn.LayerNorm eps 1e-5"""
+    C = x.shape[-1]
+    shortcut = x
+    x = F.layer_norm(x, (C,), sd[key + "norm1.weight"], sd[key + "norm1.bias"], 1e-5)
+    if window > 0:
+        B, H, W, _ = x.shape
+        ph, pw = (window - H % window) % window, (window - W % window) % window
+        if ph or pw:
+            x = F.pad(x, (0, 0, 0, pw, 0, ph))
+        Hp, Wp = H + ph, W + pw
+        x = x.view(B, Hp // window, window, Wp // window, window, C).permute(0, 1, 3, 2, 4, 5).contiguous().view(-1, window, window, C)
+    x = _vit_attention(sd, key + "attn.", x, heads, use_rel_pos)
+    if window > 0:
+        x = x.view(B, Hp // window, Wp // window, window, window, -1).permute(0, 1, 3, 2, 4, 5).contiguous().view(B, Hp, Wp, -1)
+        if Hp > H or Wp > W:
+            x = x[:, :H, :W, :].contiguous()
+    x = shortcut + x
+    h = F.layer_norm(x, (C,), sd[key + "norm2.weight"], sd[key + "norm2.bias"], 1e-5)
+    h = F.linear(F.gelu(F.linear(h, sd[key + "mlp.lin1.weight"], sd[key + "mlp.lin1.bias"])),
+                 sd[key + "mlp.lin2.weight"], sd[key + "mlp.lin2.bias"])              # common.py:112-125 MLPBlock
+    return x + h
+
+
+def sam_extractor_forward(sd, spec, x: Tensor, taps: Optional[dict] = None) -> Tensor:
+    """models/extractor.py:41-69 SegmentationExtractor; modules/vit.py:111-143 ImageEncoderViT.forward;
+    modules/pixel_decoder.py:61-83"""
+    v = spec["vit"]
+    Q = "detector.image_encoder."
+    ps = int(v["patch_size"])
+    x = x * 2 - 1                                                      # extractor.py:25,64
+    x = F.conv2d(x, sd[Q + "patch_embed.proj.weight"], sd[Q + "patch_embed.proj.bias"], stride=ps).permute(0, 2, 3, 1)
+    x = x + sd[Q + "pos_embed"]
+    glob = [int(i) for i in v["global_attn_indexes"]]
+    for i in range(int(v["depth"])):
+        x = _vit_block(sd, Q + f"blocks.{i}.", x, int(v["num_heads"]), 0 if i in glob else int(v["window_size"]),
+                       bool(v.get("use_rel_pos", False)))
+        if taps is not None:
+            taps[f"blk{i}"] = x
+    x = x.permute(0, 3, 1, 2).contiguous()
+    x = F.conv2d(x, sd[Q + "neck.0.weight"], None)                      # neck: 1x1, LN, 3x3 pad 1, LN (vit.py:90-109)
+    x = layernorm_cf(x, sd[Q + "neck.1.weight"], sd[Q + "neck.1.bias"])
+    x = F.conv2d(x, sd[Q + "neck.2.weight"], None, padding=1)
+    x = layernorm_cf(x, sd[Q + "neck.3.weight"], sd[Q + "neck.3.bias"])
+    D = "detector.pixel_decoder."
+    x = F.pad(x, (1, 1, 1, 1), mode="reflect")                          # Upsample(up_factor=1): identity + reflect pad
+    x = F.conv2d(x, sd[D + "output_upscaling.0.upsample_block.2.weight"], None)
+    x = layernorm_cf(x, sd[D + "output_upscaling.0.upsample_block.3.weight"], sd[D + "output_upscaling.0.upsample_block.3.bias"])
+    x = F.gelu(x).mean(dim=[-2, -1])
+    return F.linear(x, sd[D + "linear.weight"], sd[D + "linear.bias"])
+
+
 def rgb_to_y(x: Tensor) -> Tensor:
     """data/transforms.py:15-27 RGB2YUV, row 0 only (wam.py:168-172)"""
     M = torch.tensor([[0.299, 0.587, 0.114], [-0.14713, -0.28886, 0.436], [0.615, -0.51499, -0.10001]], dtype=torch.float32)
@@ -403,6 +519,8 @@ class OracleModel:
         return unet_forward(self.sd, self.spec, x, msgs, taps)
 
     def detector(self, imgs_res: Tensor, taps=None) -> Tensor:
+        if self.spec["ext_kind"] == "sam":
+            return sam_extractor_forward(self.sd, self.spec, imgs_res, taps)
         return convnext_extractor_forward(self.sd, self.spec, imgs_res, taps)
 
     def heatmaps(self, imgs: Tensor) -> Tensor:

@@ -53,6 +53,10 @@ CASES = {
     "gscale":          dict(loader=LD_GSCALE, B=2, IH=8, IW=8, C0=384, N=96, R=1, S=1, bias=True, resid32=True, scale=True, rps=64, out="f32"),
     "gelu_grn":        dict(loader=LD_TMA, B=1, IH=1, IW=512, C0=96, N=384, R=1, S=1, bias=True, act=2, grn=True, rps=256, out="f16"),
     "gelu_grn_rag":    dict(loader=LD_TMA, B=1, IH=1, IW=450, C0=96, N=384, R=1, S=1, bias=True, act=2, grn=True, rps=225, out="f16"),
+    # chunkyseal's proportional trunk: widths 362 / 724 / 1448 (not multiples of 8 / 16) in rows padded to 8 elements, odd maps
+    "chunky_pw1":      dict(loader=LD_TMA, B=1, IH=1, IW=1922, C0=362, ld0=368, ldw=368, N=1448, R=1, S=1, bias=True, act=2, grn=True, rps=961, out="f16"),
+    "chunky_pw2":      dict(loader=LD_TMA, B=1, IH=1, IW=1922, C0=1448, N=362, ld_out=368, R=1, S=1, bias=True, resid32=True, out="f32"),
+    "chunky_ds":       dict(loader=LD_GCONV, B=2, IH=31, IW=31, C0=368, N=724, ld_out=728, R=2, S=2, stride=2, pad=0, bias=True, out="f32"),
 }
 
 
@@ -123,6 +127,7 @@ def run_case(name, seed=0, verbose=False, time_iters=0):
     R, S = cfg["R"], cfg["S"]
     Ct = C0 + C1
     K = R * S * Ct
+    ld0, ldw, ld_out = cfg.get("ld0", 0), cfg.get("ldw", 0), cfg.get("ld_out", 0)
     x0 = (torch.randn(B, IH, IW, C0, generator=g)).half().to(dev)
     x1 = (torch.randn(B, IH, IW, C1, generator=g)).half().to(dev) if C1 else None
     w = (torch.randn(N, R, S, Ct, generator=g) / math.sqrt(K)).half().to(dev)
@@ -145,6 +150,16 @@ def run_case(name, seed=0, verbose=False, time_iters=0):
     out32 = None
     if cfg["out"] == "f32":
         out32 = resid32.clone() if resid32 is not None else torch.full((B, OH, OW, N), float("nan"), device=dev)
+    # padded pitches: the operands live in wider rows whose pad columns hold a sentinel the kernel must neither read nor write
+    SENT = 1000.0
+    x0_p = w_p = out32_p = None
+    if ld0:
+        x0_p = torch.full((B, IH, IW, ld0), SENT, dtype=torch.float16, device=dev)
+        x0_p[..., :C0] = x0
+    if ld_out:
+        assert out32 is not None
+        out32_p = torch.full((B, OH, OW, ld_out), SENT, device=dev)
+        out32_p[..., :N] = out32
     n_out = cfg.get("n_out", 0)
     outc_w = (torch.randn(n_out, N, generator=g) / math.sqrt(N)).to(dev) if n_out else None
     outc_b = (0.1 * torch.randn(n_out, generator=g)).to(dev) if n_out else None
@@ -157,8 +172,15 @@ def run_case(name, seed=0, verbose=False, time_iters=0):
     t.R, t.S, t.stride, t.pad, t.pad_mode = R, S, cfg.get("stride", 1), cfg.get("pad", 0), cfg.get("pad_mode", 0)
     t.N, t.epi, t.act, t.rows_per_sample, t.block_n = N, cfg.get("epi", 0), cfg.get("act", 0), cfg.get("rps", 0), cfg.get("block_n", 0)
     w_dev = halo_layout(w, C0, C1) if ld in (LD_GUPS, LD_HALO) else w
-    t.src0, t.src1, t.weights = _ptr(x0), _ptr(x1), _ptr(w_dev)
+    if ldw:
+        w_p = torch.full((N, ldw), SENT, dtype=torch.float16, device=dev)
+        w_p[:, :K] = w.reshape(N, K)
+        w_dev = w_p
+    t.ld0, t.ldw, t.ld_out = ld0, ldw, ld_out
+    t.src0, t.src1, t.weights = _ptr(x0_p if ld0 else x0), _ptr(x1), _ptr(w_dev)
     t.bias, t.resid16 = _ptr(bias), _ptr(resid16)
+    if ld_out:
+        out32_true, out32 = out32, out32_p
     t.resid32 = _ptr(out32) if resid32 is not None else None     # in place, like the ConvNeXt residual stream
     t.a_scale, t.ln_w, t.ln_b = _ptr(scale), _ptr(lnw), _ptr(lnb)
     t.outc_w, t.outc_b, t.n_out = _ptr(outc_w), _ptr(outc_b), n_out
@@ -186,6 +208,9 @@ def run_case(name, seed=0, verbose=False, time_iters=0):
     resid = resid16 if resid16 is not None else resid32
     ref, pre = reference(cfg, x0, x1, w, bias, resid, scale, lnw, lnb)
     res = {}
+    if ld_out:
+        res["pad_untouched"] = bool((out32[..., N:] == SENT).all())
+        out32 = out32[..., :N]
     if timing is not None:
         res["us"] = timing
         res["tflops"] = 2.0 * M * N * K / (timing * 1e-6) / 1e12
@@ -197,7 +222,7 @@ def run_case(name, seed=0, verbose=False, time_iters=0):
         res["out_ref_max"] = scale_ref
         res["nan"] = int(torch.isnan(got).sum().item())
         tol = 2e-2 * max(1.0, scale_ref) if out16 is not None else 5e-3 * max(1.0, scale_ref)
-        res["ok"] = bool(res["nan"] == 0 and res["out_maxerr"] <= tol)
+        res["ok"] = bool(res["nan"] == 0 and res["out_maxerr"] <= tol and res.get("pad_untouched", True))
         if verbose and not res["ok"]:
             e = torch.nan_to_num(err, nan=1e9)
             res["err_by_col"] = e.amax(dim=(0, 2, 3))[: min(N, 64)].tolist()

@@ -249,7 +249,7 @@ def test_against_reference_golden(card, v1, px):
     rel, flips, _ = logits_ok(det, c["preds"])
     assert rel <= LOGIT_RTOL and flips == 0, (rel, flips)
     assert (restate.psnr(out["imgs_w"].cpu(), imgs) - c["psnr"]).abs().max().item() < 0.01
-    c = gold["cases"]["vid10"]
+    c = gold["cases"]["vid"]
     g = torch.Generator().manual_seed(c["gen_seed"])
     vid = torch.rand(c["F"], 3, c["H"], c["W"], generator=g)
     msgs = torch.randint(0, 2, (1, spec["nbits"]), generator=g)

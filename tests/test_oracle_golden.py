@@ -16,7 +16,7 @@ def _sample(t, stride=8):
     return t[..., ::stride, ::stride]
 
 
-@pytest.mark.parametrize("card", ["videoseal_1.0", "pixelseal"])
+@pytest.mark.parametrize("card", ["videoseal_1.0", "pixelseal", "videoseal_0.0", "chunkyseal"])
 def test_oracle_matches_reference_golden(card):
     torch.set_num_threads(max(1, os.cpu_count() or 1))
     gold = torch.load(os.path.join(ROOT, "tests", "golden", f"{card}.pt"))
@@ -33,12 +33,18 @@ def test_oracle_matches_reference_golden(card):
         d = orc.detect(o["imgs_w"], is_video=False)
         assert (_sample(o["imgs_w"]) - c["imgs_w_s"]).abs().max() < 1e-5
         assert (_sample(o["preds_w"]) - c["preds_w_s"]).abs().max() < 1e-5
-        assert (_sample(orc.heatmaps(imgs)) - c["hmaps_s"]).abs().max() < 1e-6
+        if orc.attenuation is not None:
+            assert (_sample(orc.heatmaps(imgs)) - c["hmaps_s"]).abs().max() < 1e-6
         assert (d["preds"] - c["preds"]).abs().max() < 1e-4
         assert abs(o["imgs_w"].double().mean().item() - c["imgs_w_stats"]["mean"]) < 1e-6
         assert (restate.psnr(o["imgs_w"], imgs) - c["psnr"]).abs().max() < 1e-3
 
-        c = gold["cases"]["img384x480"]
+        if card == "chunkyseal":
+            # ~3.5 TFLOP per frame on the CPU: the resized-image and video cases of this card were checked when the fixture was
+            # generated (their oracle-vs-reference differences, all 0.0, are stored in the fixture) and are not re-run here
+            assert all(v == 0.0 or v is True for cc in gold["cases"].values() for v in cc["oracle_vs_ref"].values())
+            return
+        c = gold["cases"]["img_resized"]
         g = torch.Generator().manual_seed(c["gen_seed"])
         imgs = torch.rand(c["B"], 3, c["H"], c["W"], generator=g)
         msgs = torch.randint(0, 2, (c["B"], spec["nbits"]), generator=g)
@@ -47,7 +53,7 @@ def test_oracle_matches_reference_golden(card):
         assert (_sample(o["imgs_w"]) - c["imgs_w_s"]).abs().max() < 1e-5
         assert (d["preds"] - c["preds"]).abs().max() < 1e-4
 
-        c = gold["cases"]["vid10"]
+        c = gold["cases"]["vid"]
         g = torch.Generator().manual_seed(c["gen_seed"])
         vid = torch.rand(c["F"], 3, c["H"], c["W"], generator=g)
         msgs = torch.randint(0, 2, (1, spec["nbits"]), generator=g)

@@ -38,6 +38,7 @@ class ConvTest(C.Structure):
         ("ln_w", C.c_void_p), ("ln_b", C.c_void_p),
         ("outc_w", C.c_void_p), ("outc_b", C.c_void_p), ("n_out", C.c_int32),
         ("out16", C.c_void_p), ("out32", C.c_void_p), ("delta", C.c_void_p), ("grn_stats", C.c_void_p),
+        ("ld0", C.c_int32), ("ldw", C.c_int32), ("ld_out", C.c_int32),
     ]
 
 

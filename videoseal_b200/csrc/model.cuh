@@ -50,6 +50,7 @@ struct ConvW {          // packed conv / linear weights: fp16 [N][K] (K order r,
   __half* wd = nullptr;  // 3x3 convs eligible for conv3_direct.cuh: the same weights in its core-matrix layout
   float* bias = nullptr;
   int N = 0, K = 0;
+  int ld = 0;            // row pitch of `w` in elements (0 = K): rows are padded to a multiple of 8 (16-byte TMA strides)
 };
 
 struct DebugTensor { const void* ptr; int dtype; /*0 f32, 1 f16*/ int64_t shape[4]; int64_t ld; };
@@ -192,6 +193,7 @@ class Model {
   float* msg_table = nullptr;
   // extractor
   __half* stem_w16 = nullptr;
+  float* stem_wk = nullptr;   // widths > 256 (chunkyseal): fp32 [48][C0] for the CUDA-core stem kernel
   float *stem_b = nullptr, *stem_lnw = nullptr, *stem_lnb = nullptr;
   struct DsW { float* lnw; float* lnb; ConvW conv; };
   std::vector<DsW> ds;
@@ -239,13 +241,18 @@ class Model {
     return h;
   }
   // conv weight [N][C][R][S] (+ per-output-channel scale, + per-input-channel scale) -> [N][R][S][C]
+  // pad_taps: every tap's channel run is zero-padded to a multiple of 8 (gather loaders move 16-byte channel chunks; the
+  // activation buffer then has the same padded pixel pitch with ZERO pad channels).  Rows are padded to a multiple of 8
+  // elements either way (a no-op for every width of the tiny / pixelseal cards).
   ConvW pack_conv(const std::string& wkey, const std::vector<float>* out_scale, const std::vector<float>& bias,
-                  const std::vector<float>* in_scale = nullptr) {
+                  const std::vector<float>* in_scale = nullptr, bool pad_taps = false) {
     const HostTensor& w = get(wkey);
     VSB_CHECK(w.shape.size() == 4 || w.shape.size() == 2, "conv weight rank");
     const int N = (int)w.shape[0], C = (int)w.shape[1];
     const int R = w.shape.size() == 4 ? (int)w.shape[2] : 1, S = w.shape.size() == 4 ? (int)w.shape[3] : 1;
-    std::vector<float> p((size_t)N * R * S * C);
+    const int Cp = pad_taps ? (C + 7) / 8 * 8 : C;
+    const int K = R * S * Cp, ld = (K + 7) / 8 * 8;
+    std::vector<float> p((size_t)N * ld, 0.f);
     for (int n = 0; n < N; ++n)
       for (int c = 0; c < C; ++c)
         for (int r = 0; r < R; ++r)
@@ -253,10 +260,10 @@ class Model {
             float v = w.data[(((size_t)n * C + c) * R + r) * S + s];
             if (out_scale) v *= (*out_scale)[n];
             if (in_scale) v *= (*in_scale)[c];
-            p[(((size_t)n * R + r) * S + s) * C + c] = v;
+            p[(size_t)n * ld + ((size_t)r * S + s) * Cp + c] = v;
           }
     ConvW cw;
-    cw.N = N; cw.K = R * S * C;
+    cw.N = N; cw.K = K; cw.ld = ld;
     cw.w = wpool.upload(to_half(p));
     cw.bias = bias.empty() ? nullptr : wpool.upload(bias);
     return cw;
@@ -465,9 +472,15 @@ class Model {
       const HostTensor& w = get(Q + "downsample_layers.0.0.weight");  // [C0][3][4][4]
       const int C0 = d.ext_dims[0];
       VSB_CHECK((int)w.shape[0] == C0 && w.shape[1] == 3 && w.shape[2] == 4, "stem shape");
-      std::vector<float> t((size_t)C0 * 64, 0.f);   // GEMM operand [C0][64], K = (c, r, t) zero-padded 48 -> 64
-      for (int c = 0; c < C0; ++c) for (int k = 0; k < 48; ++k) t[(size_t)c * 64 + k] = w.data[(size_t)c * 48 + k];
-      stem_w16 = wpool.upload(to_half(t));
+      if (C0 <= 256) {   // tensor-core stem GEMM with the LayerNorm fused in the epilogue (needs the whole row in one N tile)
+        std::vector<float> t((size_t)C0 * 64, 0.f);   // GEMM operand [C0][64], K = (c, r, t) zero-padded 48 -> 64
+        for (int c = 0; c < C0; ++c) for (int k = 0; k < 48; ++k) t[(size_t)c * 64 + k] = w.data[(size_t)c * 48 + k];
+        stem_w16 = wpool.upload(to_half(t));
+      } else {           // stem_ln_kernel: [48][C0]
+        std::vector<float> t((size_t)48 * C0);
+        for (int c = 0; c < C0; ++c) for (int k = 0; k < 48; ++k) t[(size_t)k * C0 + c] = w.data[(size_t)c * 48 + k];
+        stem_wk = wpool.upload(t);
+      }
       stem_b = wpool.upload(get(Q + "downsample_layers.0.0.bias").data);
       stem_lnw = wpool.upload(get(Q + "downsample_layers.0.1.weight").data);
       stem_lnb = wpool.upload(get(Q + "downsample_layers.0.1.bias").data);
@@ -477,13 +490,13 @@ class Model {
       const std::string K = Q + "downsample_layers." + std::to_string(i);
       w.lnw = wpool.upload(get(K + ".0.weight").data);
       w.lnb = wpool.upload(get(K + ".0.bias").data);
-      w.conv = pack_conv(K + ".1.weight", nullptr, get(K + ".1.bias").data);
+      w.conv = pack_conv(K + ".1.weight", nullptr, get(K + ".1.bias").data, nullptr, /*pad_taps=*/true);
       ds.push_back(w);
     }
     cn.resize(4);
     for (int s = 0; s < 4; ++s) {
       const int C = d.ext_dims[s];
-      VSB_CHECK(C % 8 == 0 || true, "dims");
+      VSB_CHECK(C % 2 == 0, "extractor widths must be even (channel pairs in the depthwise kernel)");
       for (int j = 0; j < d.ext_depths[s]; ++j) {
         const std::string B = Q + "stages." + std::to_string(s) + "." + std::to_string(j) + ".";
         CnBlockW w;
@@ -510,7 +523,7 @@ class Model {
     }
     {
       const std::string D = "detector.pixel_decoder.";
-      head_conv = pack_conv(D + "output_upscaling.0.upsample_block.2.weight", nullptr, {});
+      head_conv = pack_conv(D + "output_upscaling.0.upsample_block.2.weight", nullptr, {}, nullptr, /*pad_taps=*/true);
       head_lnw = wpool.upload(get(D + "output_upscaling.0.upsample_block.3.weight").data);
       head_lnb = wpool.upload(get(D + "output_upscaling.0.upsample_block.3.bias").data);
       const HostTensor& lw = get(D + "linear.weight");
@@ -527,7 +540,7 @@ class Model {
     pl.dbg[name] = DebugTensor{p, dtype, {B, H, W, C}, ld};
   }
   void add_conv(Plan& pl, ConvGemmOp op, const ConvW& w, const std::string& name, int block_n = 0, const __half* w_override = nullptr) {
-    finalize_op(op, w_override ? w_override : w.w, w.N, w.K, w.K, num_sms, block_n);
+    finalize_op(op, w_override ? w_override : w.w, w.N, w.K, w.ld ? w.ld : w.K, num_sms, block_n);
     pl.steps.push_back(Step{[op](cudaStream_t st) { launch(op, st); }, 1, name});
   }
   // 3x3 stride-1 zero-padded conv: on-chip im2col from a shared-memory halo tile (input crosses L2->SM once) up to
@@ -720,11 +733,15 @@ class Model {
         // then bilinear x2 + reflect pad + 3x3 tap sum + LayerNorm + ReLU (CUDA cores, memory-bound)
         const int IH = hs, Cc = Cout;
         float *lw = up_lnw[j], *lb = up_lnb[j];
-        VSB_CHECK(Cc % 8 == 0 && Cc / 8 <= 32 && ((Cc / 8) & (Cc / 8 - 1)) == 0, "up conv: C_out must be 8 * 2^k <= 256");
+        const int vpt = Cc <= 256 ? 1 : 2;            // 16-byte channel vectors per thread (chunkyseal's first up-conv: 512 channels)
+        const int gthreads = Cc / (8 * vpt);          // threads per output pixel
+        VSB_CHECK(Cc % (8 * vpt) == 0 && gthreads <= 32 && (gthreads & (gthreads - 1)) == 0, "up conv: C_out must be 8 * 2^k <= 512");
         pl.steps.push_back(Step{[=](cudaStream_t st) {
-          const int ppb = 256 / (Cc / 8);
+          const int ppb = 256 / gthreads;
           const long blocks = (Mo + ppb - 1) / ppb;
-          ups_gather_ln_kernel<<<(unsigned)std::min<long>(blocks, 148L * 32), 256, 0, st>>>(ytap, B, IH, IH, Cc, lw, lb, 1e-6f, u, Cc);
+          const unsigned grid = (unsigned)std::min<long>(blocks, 148L * 32);
+          if (vpt == 1) ups_gather_ln_kernel<1><<<grid, 256, 0, st>>>(ytap, B, IH, IH, Cc, lw, lb, 1e-6f, u, Cc);
+          else ups_gather_ln_kernel<2><<<grid, 256, 0, st>>>(ytap, B, IH, IH, Cc, lw, lb, 1e-6f, u, Cc);
           VSB_CUDA(cudaGetLastError());
         }, 1, "unet.upgather." + std::to_string(Cout) + "@" + std::to_string(ho)});
       }
@@ -751,8 +768,24 @@ class Model {
     const int st_ = d.ext_stem_stride;
     int hs = (S - 4) / st_ + 1;
     int C = d.ext_dims[0];
-    float* x = pl.pool.alloc_n<float>((size_t)B * hs * hs * C);
-    {
+    // pixel pitch of every NHWC buffer of the trunk: the width rounded up to 8 channels (16-byte fp16 rows for TMA / vector
+    // access; the proportional chunkyseal widths 362 / 724 are not multiples of 8).  Pad channels are never read through a
+    // TMA map (its K extent is the true width); the buffers the gather loaders read are zeroed once below.
+    auto pitch = [](int c) { return (c + 7) / 8 * 8; };
+    int Cp = pitch(C);
+    float* x = pl.pool.alloc_n<float>((size_t)B * hs * hs * Cp);
+    if (stem_wk != nullptr) {
+      // widths > 256: CUDA-core stem conv + LayerNorm (one warp per output pixel); the fused-LN GEMM epilogue needs N <= 256
+      const int OH = hs, Cc = C, ldo = Cp;
+      float *wk = stem_wk, *sb = stem_b, *lw = stem_lnw, *lb = stem_lnb;
+      pl.steps.push_back(Step{[=](cudaStream_t st) {
+        const long npix = (long)B * OH * OH;
+        const int grid = (int)std::min<long>((npix + 7) / 8, 148L * 16);
+        stem_ln_kernel<<<grid, 256, (size_t)8 * (48 + Cc) * sizeof(float), st>>>(plp->in_imgs, B, S, S, OH, OH, st_, wk, sb, lw, lb, Cc, x, ldo);
+        VSB_CUDA(cudaGetLastError());
+      }, 1, "cnx.stem_ln." + std::to_string(C) + "@" + std::to_string(hs)});
+      dbg(pl, "ds0", x, 0, B, hs, hs, C, Cp);
+    } else {
       // stem (convnext.py:108-111): im2col of the k4 patches (x = 2*img-1 folded) -> tensor-core GEMM [M,64]x[64,C0] with the
       // conv bias and the channels-first LayerNorm fused into the epilogue, fp32 NHWC output (the residual stream)
       const int OH = hs;
@@ -766,10 +799,10 @@ class Model {
       }, 1, "cnx.stem_im2col"});
       ConvGemmOp op; setup_tma_gemm(op, patches, M, 64, 64);
       op.p.epi = EPI_LN; op.p.act = ACT_NONE; op.p.bias = stem_b; op.p.ln_w = stem_lnw; op.p.ln_b = stem_lnb; op.p.ln_eps = 1e-6f;
-      op.p.out32 = x; op.p.ld_out32 = C;
+      op.p.out32 = x; op.p.ld_out32 = Cp;
       ConvW sw; sw.w = stem_w16; sw.N = C; sw.K = 64; sw.bias = stem_b;
       add_conv(pl, op, sw, "cnx.stem_gemm." + std::to_string(C) + "@" + std::to_string(hs));
-      dbg(pl, "ds0", x, 0, B, hs, hs, C, C);
+      dbg(pl, "ds0", x, 0, B, hs, hs, C, Cp);
     }
     int maxK4 = 0;
     for (int s = 0; s < 4; ++s) maxK4 = std::max(maxK4, 4 * d.ext_dims[s]);
@@ -786,31 +819,33 @@ class Model {
     __half* x16 = nullptr;
     for (int s = 0; s < 4; ++s) {
       if (s > 0) {
-        const int Cp = d.ext_dims[s - 1], Cn = d.ext_dims[s];
+        const int Cv = d.ext_dims[s - 1], Cvp = Cp, Cn = d.ext_dims[s], Cnp = pitch(Cn);
         const long Mp = (long)B * hs * hs;
-        __half* xn = pl.pool.alloc_n<__half>(Mp * Cp);
+        __half* xn = pl.pool.alloc_n<__half>(Mp * Cvp);
+        if (Cvp != Cv) VSB_CUDA(cudaMemset(xn, 0, (size_t)Mp * Cvp * sizeof(__half)));   // pad channels stay zero: ln_rows writes [0, Cv)
         {
           float *lw = ds[s - 1].lnw, *lb = ds[s - 1].lnb;
           const float* xin = x;
           pl.steps.push_back(Step{[=](cudaStream_t st) {
             const int grid = (int)std::min<long>((Mp + 7) / 8, 148L * 16);
-            ln_rows_kernel<<<grid, 256, 0, st>>>(xin, Mp, Cp, Cp, lw, lb, 1e-6f, xn, Cp);
+            ln_rows_kernel<<<grid, 256, 0, st>>>(xin, Mp, Cv, Cvp, lw, lb, 1e-6f, xn, Cvp);
             VSB_CUDA(cudaGetLastError());
           }, 1, "cnx.ln_rows"});
         }
-        const int ho = (hs - 2) / 2 + 1;
-        float* xo = pl.pool.alloc_n<float>((size_t)B * ho * ho * Cn);
+        const int ho = (hs - 2) / 2 + 1;   // odd maps (127, 63, 31): the last row / column is dropped, like nn.Conv2d k2 s2
+        float* xo = pl.pool.alloc_n<float>((size_t)B * ho * ho * Cnp);
         ConvGemmOp op;
-        setup_gather_conv(op, LD_GATHER_CONV, xn, Cp, Cp, nullptr, 0, 0, B, hs, hs, ho, ho, 2, 2, 2, 0, 0);
-        op.p.epi = EPI_AFFINE; op.p.act = ACT_NONE; op.p.bias = ds[s - 1].conv.bias; op.p.out32 = xo; op.p.ld_out32 = Cn;
-        add_conv(pl, op, ds[s - 1].conv, "cnx.down2x2s2." + std::to_string(Cp) + "-" + std::to_string(Cn) + "@" + std::to_string(ho));
-        x = xo; hs = ho; C = Cn;
-        dbg(pl, "ds" + std::to_string(s), x, 0, B, hs, hs, C, C);
+        // K order (r, s, c) with c over the PADDED width: matches pack_conv(..., pad_taps)
+        setup_gather_conv(op, LD_GATHER_CONV, xn, Cvp, Cvp, nullptr, 0, 0, B, hs, hs, ho, ho, 2, 2, 2, 0, 0);
+        op.p.epi = EPI_AFFINE; op.p.act = ACT_NONE; op.p.bias = ds[s - 1].conv.bias; op.p.out32 = xo; op.p.ld_out32 = Cnp;
+        add_conv(pl, op, ds[s - 1].conv, "cnx.down2x2s2." + std::to_string(Cv) + "-" + std::to_string(Cn) + "@" + std::to_string(ho));
+        x = xo; hs = ho; C = Cn; Cp = Cnp;
+        dbg(pl, "ds" + std::to_string(s), x, 0, B, hs, hs, C, Cp);
       }
       const long M = (long)B * hs * hs;
       const int rows_per_sample = hs * hs;
-      __half* a = pl.pool.alloc_n<__half>(M * C);
-      __half* g = pl.pool.alloc_n<__half>(M * 4 * C);
+      __half* a = pl.pool.alloc_n<__half>(M * Cp);
+      __half* g = pl.pool.alloc_n<__half>(M * 4 * C);   // 4C is a multiple of 8 for every even width
       // GRN multiplier: folded into per-sample pwconv2 weights where a sample has many more rows than W2 has output
       // channels (stages 0-1 of the tiny trunk), applied to g in place otherwise
       static const bool no_wscale = getenv("VSB_NO_WSCALE") != nullptr;
@@ -819,10 +854,22 @@ class Model {
       for (int jb = 0; jb < d.ext_depths[s]; ++jb) {
         const CnBlockW& w = cn[s][jb];
         {
-          const int H = hs, Cc = C;
+          const int H = hs, Cc = C, ldc = Cp;
           const float* xin = x;
           float *dww = w.dww, *dwb = w.dwb, *lw = w.lnw, *lb = w.lnb;
           pl.steps.push_back(Step{[=](cudaStream_t st) {
+            if (!(Cc == 96 || Cc == 192 || Cc == 384 || Cc == 768) || getenv("VSB_DW_WIDE")) {
+              // any even width / odd map size (chunkyseal's proportional trunk): threads loop over the channel pairs
+              const long nstrips = (long)B * H * ((H + kDwStrip - 1) / kDwStrip);
+              const int threads = std::min(512, (Cc / 2 + 31) / 32 * 32);
+              const size_t smem_w = (size_t)kDwStrip * Cc * sizeof(float);
+              static bool attr = false;
+              if (!attr) { VSB_CUDA(cudaFuncSetAttribute(dwconv7_ln_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+              if (smem_w > 200 * 1024) throw Error("dwconv7: more than 6400 channels is not implemented");
+              dwconv7_ln_wide_kernel<<<(unsigned)nstrips, threads, smem_w, st>>>(xin, B, H, H, Cc, ldc, dww, dwb, lw, lb, a, ldc);
+              VSB_CUDA(cudaGetLastError());
+              return;
+            }
             // experimental tiled kernel (input window staged in smem), VSB_DW_TILED=1: measured no faster than the strip kernel
             // (both are latency-bound per block, profiles/r1_history.md), kept for round-2 work
             const int TW = (H % 16 == 0) ? 16 : ((H % 8 == 0) ? 8 : 0);
@@ -874,7 +921,7 @@ class Model {
           }, 1, "cnx.dwconv7_ln." + std::to_string(C) + "@" + std::to_string(hs)});
         }
         {
-          ConvGemmOp op; setup_tma_gemm(op, a, M, C, C);
+          ConvGemmOp op; setup_tma_gemm(op, a, M, C, Cp);
           op.p.epi = EPI_AFFINE; op.p.act = ACT_GELU; op.p.bias = w.pw1.bias; op.p.out16 = g; op.p.ld_out16 = 4 * C;
           float* stats = stats_pp[blk_counter & 1];
           ++blk_counter;
@@ -906,34 +953,35 @@ class Model {
         }
         {
           ConvGemmOp op; setup_tma_gemm(op, g, M, 4 * C, 4 * C);
-          op.p.epi = EPI_AFFINE; op.p.act = ACT_NONE; op.p.bias = w.pw2.bias; op.p.resid32 = x; op.p.ld_res32 = C;
-          op.p.out32 = x; op.p.ld_out32 = C;  // in place: each element is read and written by the same thread
+          op.p.epi = EPI_AFFINE; op.p.act = ACT_NONE; op.p.bias = w.pw2.bias; op.p.resid32 = x; op.p.ld_res32 = Cp;
+          op.p.out32 = x; op.p.ld_out32 = Cp;  // in place: each element is read and written by the same thread
           if (wscale) { op.w_samples = B; op.p.rows_per_sample = rows_per_sample; }
           if (s == 3 && jb == d.ext_depths[s] - 1) {
-            x16 = pl.pool.alloc_n<__half>(M * C);
-            op.p.out16 = x16; op.p.ld_out16 = C;
+            x16 = pl.pool.alloc_n<__half>(M * Cp);
+            if (Cp != C) VSB_CUDA(cudaMemset(x16, 0, (size_t)M * Cp * sizeof(__half)));   // the head conv's gather reads the pad channels
+            op.p.out16 = x16; op.p.ld_out16 = Cp;
           }
           add_conv(pl, op, w.pw2, "cnx.pwconv2." + std::to_string(C) + "@" + std::to_string(hs), 0, wscale ? w2s : nullptr);
         }
-        if (jb == 0) { dbg(pl, "s" + std::to_string(s) + "b0_a", a, 1, B, hs, hs, C, C); dbg(pl, "s" + std::to_string(s) + "b0_g", g, 1, B, hs, hs, 4 * C, 4 * C); }
+        if (jb == 0) { dbg(pl, "s" + std::to_string(s) + "b0_a", a, 1, B, hs, hs, C, Cp); dbg(pl, "s" + std::to_string(s) + "b0_g", g, 1, B, hs, hs, 4 * C, 4 * C); }
       }
-      dbg(pl, "stage" + std::to_string(s), x, 0, B, hs, hs, C, C);
+      dbg(pl, "stage" + std::to_string(s), x, 0, B, hs, hs, C, Cp);
     }
     // ---- head (pixel_decoder.py:61-83)
     {
       const long M = (long)B * hs * hs;
-      float* y = pl.pool.alloc_n<float>(M * C);
+      float* y = pl.pool.alloc_n<float>(M * Cp);
       ConvGemmOp op;
-      setup_gather_conv(op, LD_GATHER_CONV, x16, C, C, nullptr, 0, 0, B, hs, hs, hs, hs, 3, 3, 1, 1, 1);
-      op.p.epi = EPI_AFFINE; op.p.act = ACT_NONE; op.p.out32 = y; op.p.ld_out32 = C;
+      setup_gather_conv(op, LD_GATHER_CONV, x16, Cp, Cp, nullptr, 0, 0, B, hs, hs, hs, hs, 3, 3, 1, 1, 1);
+      op.p.epi = EPI_AFFINE; op.p.act = ACT_NONE; op.p.out32 = y; op.p.ld_out32 = Cp;
       add_conv(pl, op, head_conv, "cnx.head3x3." + std::to_string(C) + "@" + std::to_string(hs));
-      dbg(pl, "head_conv", y, 0, B, hs, hs, C, C);
+      dbg(pl, "head_conv", y, 0, B, hs, hs, C, Cp);
       float* pooled = pl.pool.alloc_n<float>((size_t)B * C);
-      const int P = hs * hs, Cc = C, NO = 1 + d.nbits;
+      const int P = hs * hs, Cc = C, ldy = Cp, NO = 1 + d.nbits;
       float *lw = head_lnw, *lb = head_lnb, *hw = head_lw, *hb = head_lb;
       float* logits = pl.logits;
       pl.steps.push_back(Step{[=](cudaStream_t st) {
-        head_pool_kernel<<<B, 256, Cc * sizeof(float), st>>>(y, P, Cc, Cc, lw, lb, pooled);
+        head_pool_kernel<<<B, 256, Cc * sizeof(float), st>>>(y, P, Cc, ldy, lw, lb, pooled);
         const int grid = (int)(((long)B * NO + 7) / 8);
         head_linear_kernel<<<grid, 256, 0, st>>>(pooled, hw, hb, B, Cc, NO, logits);
         VSB_CUDA(cudaGetLastError());

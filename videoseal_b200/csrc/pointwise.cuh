@@ -318,10 +318,13 @@ __global__ void __launch_bounds__(256) jnd_lowres_kernel(const float* __restrict
 // (4x fewer MACs than convolving the up-sampled map, no im2col), and this kernel does the cheap spatial part
 //   out[b,oy,ox,co] = act(LN_c( sum_{r,s} bilinear_x2( y[.., (3r+s)*C + co] )(reflect(oy+r-1), reflect(ox+s-1)) ))
 // One group of C/8 threads per output pixel (8 channels = one 16-byte load per thread and tap corner).
+// VPT = 16-byte channel vectors per thread: C = 8 * VPT * G with G <= 32 threads per pixel (C <= 256: VPT 1; chunkyseal's
+// 512-channel first up-conv: VPT 2); thread lane_g owns the vectors lane_g + G*j.
+template <int VPT>
 __global__ void __launch_bounds__(256) ups_gather_ln_kernel(const __half* __restrict__ y, int B, int IH, int IW, int C,
                                                             const float* __restrict__ lnw, const float* __restrict__ lnb, float eps,
                                                             __half* __restrict__ out, int ld_out) {
-  const int G = C >> 3;                       // threads per pixel (power of two, <= 32)
+  const int G = C / (8 * VPT);                // threads per pixel (power of two, <= 32)
   const int OH = 2 * IH, OW = 2 * IW;
   const long npix = (long)B * OH * OW;
   const int ppb = 256 / G;                    // pixels per block
@@ -349,54 +352,60 @@ __global__ void __launch_bounds__(256) ups_gather_ln_kernel(const __half* __rest
       if (v & 1) { xa[r] = jx; xb[r] = min(jx + 1, IW - 1); wx[r] = 0.75f; }
       else       { xa[r] = max(jx - 1, 0); xb[r] = jx; wx[r] = 0.25f; }
     }
-    float acc[8];
+    float acc[8 * VPT];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) acc[k] = 0.f;
+    for (int k = 0; k < 8 * VPT; ++k) acc[k] = 0.f;
     const __half* yb_ = y + (long)b * IH * IW * ldy + lane_g * 8;
 #pragma unroll
     for (int r = 0; r < 3; ++r) {
 #pragma unroll
       for (int s = 0; s < 3; ++s) {
-        const __half* base = yb_ + (r * 3 + s) * C;
-        const uint4 v00 = __ldg(reinterpret_cast<const uint4*>(base + ((long)ya[r] * IW + xa[s]) * ldy));
-        const uint4 v01 = __ldg(reinterpret_cast<const uint4*>(base + ((long)ya[r] * IW + xb[s]) * ldy));
-        const uint4 v10 = __ldg(reinterpret_cast<const uint4*>(base + ((long)yb[r] * IW + xa[s]) * ldy));
-        const uint4 v11 = __ldg(reinterpret_cast<const uint4*>(base + ((long)yb[r] * IW + xb[s]) * ldy));
         // the 4-corner bilinear mix of one tap runs in packed half precision (weights 1/16, 3/16, 9/16 are exact, the
         // operands are fp16 already); the 9 taps accumulate in fp32
         const __half2 w00 = __float2half2_rn(wy[r] * wx[s]), w01 = __float2half2_rn(wy[r] * (1.f - wx[s]));
         const __half2 w10 = __float2half2_rn((1.f - wy[r]) * wx[s]), w11 = __float2half2_rn((1.f - wy[r]) * (1.f - wx[s]));
-        const __half2* p00 = reinterpret_cast<const __half2*>(&v00);
-        const __half2* p01 = reinterpret_cast<const __half2*>(&v01);
-        const __half2* p10 = reinterpret_cast<const __half2*>(&v10);
-        const __half2* p11 = reinterpret_cast<const __half2*>(&v11);
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const __half2 t = __hfma2(w00, p00[k], __hfma2(w01, p01[k], __hfma2(w10, p10[k], __hmul2(w11, p11[k]))));
-          const float2 f = __half22float2(t);
-          acc[2 * k] += f.x;
-          acc[2 * k + 1] += f.y;
+        for (int j = 0; j < VPT; ++j) {
+          const __half* base = yb_ + (r * 3 + s) * C + j * G * 8;
+          const uint4 v00 = __ldg(reinterpret_cast<const uint4*>(base + ((long)ya[r] * IW + xa[s]) * ldy));
+          const uint4 v01 = __ldg(reinterpret_cast<const uint4*>(base + ((long)ya[r] * IW + xb[s]) * ldy));
+          const uint4 v10 = __ldg(reinterpret_cast<const uint4*>(base + ((long)yb[r] * IW + xa[s]) * ldy));
+          const uint4 v11 = __ldg(reinterpret_cast<const uint4*>(base + ((long)yb[r] * IW + xb[s]) * ldy));
+          const __half2* p00 = reinterpret_cast<const __half2*>(&v00);
+          const __half2* p01 = reinterpret_cast<const __half2*>(&v01);
+          const __half2* p10 = reinterpret_cast<const __half2*>(&v10);
+          const __half2* p11 = reinterpret_cast<const __half2*>(&v11);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const __half2 t = __hfma2(w00, p00[k], __hfma2(w01, p01[k], __hfma2(w10, p10[k], __hmul2(w11, p11[k]))));
+            const float2 f = __half22float2(t);
+            acc[8 * j + 2 * k] += f.x;
+            acc[8 * j + 2 * k + 1] += f.y;
+          }
         }
       }
     }
     // channels-first LayerNorm over the C channels of this pixel (biased variance) + ReLU
     float sum = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) sum += acc[k];
+    for (int k = 0; k < 8 * VPT; ++k) sum += acc[k];
     for (int o = G >> 1; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
     const float mean = sum / (float)C;
     float var = 0.f;
 #pragma unroll
-    for (int k = 0; k < 8; ++k) { const float d = acc[k] - mean; var += d * d; }
+    for (int k = 0; k < 8 * VPT; ++k) { const float d = acc[k] - mean; var += d * d; }
     for (int o = G >> 1; o; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
     const float rstd = 1.0f / sqrtf(var / (float)C + eps);
-    __align__(16) __half h[8];
 #pragma unroll
-    for (int k = 0; k < 8; ++k) {
-      const int c = lane_g * 8 + k;
-      h[k] = __float2half_rn(fmaxf((acc[k] - mean) * rstd * __ldg(lnw + c) + __ldg(lnb + c), 0.f));
+    for (int j = 0; j < VPT; ++j) {
+      __align__(16) __half h[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int c = (lane_g + j * G) * 8 + k;
+        h[k] = __float2half_rn(fmaxf((acc[8 * j + k] - mean) * rstd * __ldg(lnw + c) + __ldg(lnb + c), 0.f));
+      }
+      *reinterpret_cast<uint4*>(out + pix * ld_out + (lane_g + j * G) * 8) = *reinterpret_cast<const uint4*>(h);
     }
-    *reinterpret_cast<uint4*>(out + pix * ld_out + lane_g * 8) = *reinterpret_cast<const uint4*>(h);
   }
 }
 
@@ -670,6 +679,75 @@ __global__ void __launch_bounds__(768) dwconv7_ln_kernel(const float* __restrict
         const float bq = (vv[k].y - mean) * rstd * g.y + bt.y;
         *reinterpret_cast<__half2*>(dst + 2 * c2) = __floats2half2_rn(a, bq);
       }
+    }
+  }
+}
+
+// K4 for arbitrary (even) widths, used for the proportional chunkyseal trunk (362 / 724 / 1448 / 2896 channels on 127 / 63 / 31 /
+// 15 pixel maps): one block per strip of kDwStrip output pixels; the threads LOOP over the channel pairs (C/2 may exceed the
+// block size) and the LayerNorm stage re-reads the pre-LN strip from shared memory instead of holding it in registers.
+__global__ void __launch_bounds__(512) dwconv7_ln_wide_kernel(const float* __restrict__ x, int B, int H, int W, int C, int ldx,
+                                                              const float* __restrict__ wdw /*[49][C]*/, const float* __restrict__ bdw,
+                                                              const float* __restrict__ lnw, const float* __restrict__ lnb,
+                                                              __half* __restrict__ out, int ld_out) {
+  extern __shared__ float pre[];  // [kDwStrip][C]
+  const int strips_x = (W + kDwStrip - 1) / kDwStrip;
+  const int C2 = C >> 1;
+  const unsigned strip = blockIdx.x;
+  const unsigned t = strip / (unsigned)strips_x;
+  const int sx = (int)(strip - t * (unsigned)strips_x);
+  const int b = (int)(t / (unsigned)H), oy = (int)(t - (unsigned)b * (unsigned)H);
+  const int ox0 = sx * kDwStrip;
+  for (int cp = threadIdx.x; cp < C2; cp += blockDim.x) {
+    const int c = cp * 2;
+    float2 acc[kDwStrip];
+    const float2 bb = __ldg(reinterpret_cast<const float2*>(bdw + c));
+#pragma unroll
+    for (int i = 0; i < kDwStrip; ++i) acc[i] = bb;
+    for (int r = 0; r < 7; ++r) {
+      const int iy = oy + r - 3;
+      if (iy < 0 || iy >= H) continue;
+      float2 wr[7];
+#pragma unroll
+      for (int s2 = 0; s2 < 7; ++s2) wr[s2] = __ldg(reinterpret_cast<const float2*>(wdw + (r * 7 + s2) * C + c));
+      const float* rowp = x + (((long)b * H + iy) * W) * ldx + c;
+#pragma unroll
+      for (int u = 0; u < kDwStrip + 6; ++u) {
+        const int ix = ox0 + u - 3;
+        float2 v = make_float2(0.f, 0.f);
+        if (ix >= 0 && ix < W) v = __ldg(reinterpret_cast<const float2*>(rowp + (long)ix * ldx));
+#pragma unroll
+        for (int s2 = 0; s2 < 7; ++s2) {
+          const int i = u - s2;  // output pixel index within the strip
+          if (i >= 0 && i < kDwStrip) acc[i] = ffma2(v, wr[s2], acc[i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int i = 0; i < kDwStrip; ++i) { pre[i * C + c] = acc[i].x; pre[i * C + c + 1] = acc[i].y; }
+  }
+  __syncthreads();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
+  for (int i = warp; i < kDwStrip; i += nwarps) {   // one warp per output pixel of the strip
+    const int ox = ox0 + i;
+    if (ox >= W) continue;
+    const float* pr = pre + (size_t)i * C;
+    float sum = 0.f;
+    for (int c = lane; c < C; c += 32) sum += pr[c];
+#pragma unroll
+    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / (float)C;
+    float var = 0.f;
+    for (int c = lane; c < C; c += 32) { const float d = pr[c] - mean; var += d * d; }
+#pragma unroll
+    for (int o = 16; o; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+    const float rstd = 1.0f / sqrtf(var / (float)C + 1e-6f);
+    __half* dst = out + (((long)b * H + oy) * W + ox) * ld_out;
+    for (int c2 = lane; c2 < C2; c2 += 32) {
+      const float2 g = __ldg(reinterpret_cast<const float2*>(lnw) + c2), bt = __ldg(reinterpret_cast<const float2*>(lnb) + c2);
+      const float a = (pr[2 * c2] - mean) * rstd * g.x + bt.x;
+      const float bq = (pr[2 * c2 + 1] - mean) * rstd * g.y + bt.y;
+      *reinterpret_cast<__half2*>(dst + 2 * c2) = __floats2half2_rn(a, bq);
     }
   }
 }

@@ -229,14 +229,15 @@ int vsb_debug_conv(const vsb_conv_test* t, void* stream) {
   int K = t->R * t->S * Ct;
   if (t->loader == LD_HALO_UPS || t->loader == LD_HALO_CONV3) K = halo_kpad(t->C0, t->C1);  // weights in halo layout
   int OH, OW;
+  const int ld0 = t->ld0 ? t->ld0 : t->C0, ld_out = t->ld_out ? t->ld_out : t->N;
   if (t->loader == LD_TMA) {
     OH = t->IH; OW = t->IW;
-    if (t->IH == 1 && t->R == 1) setup_tma_gemm(op, (const __half*)t->src0, (long)t->B * t->IW, t->C0, t->C0);
-    else setup_tma_conv(op, (const __half*)t->src0, t->B, t->IH, t->IW, t->C0, t->C0, t->R, t->S, t->pad);
+    if (t->IH == 1 && t->R == 1) setup_tma_gemm(op, (const __half*)t->src0, (long)t->B * t->IW, t->C0, ld0);
+    else setup_tma_conv(op, (const __half*)t->src0, t->B, t->IH, t->IW, t->C0, ld0, t->R, t->S, t->pad);
   } else if (t->loader == LD_GATHER_CONV) {
     OH = (t->IH + 2 * t->pad - t->R) / t->stride + 1;
     OW = (t->IW + 2 * t->pad - t->S) / t->stride + 1;
-    setup_gather_conv(op, LD_GATHER_CONV, (const __half*)t->src0, t->C0, t->C0, (const __half*)t->src1, t->C1, t->C1, t->B, t->IH, t->IW, OH, OW,
+    setup_gather_conv(op, LD_GATHER_CONV, (const __half*)t->src0, t->C0, ld0, (const __half*)t->src1, t->C1, t->C1, t->B, t->IH, t->IW, OH, OW,
                       t->R, t->S, t->stride, t->pad, t->pad_mode);
   } else if (t->loader == LD_HALO_UPS) {
     OH = 2 * t->IH; OW = 2 * t->IW;
@@ -251,14 +252,14 @@ int vsb_debug_conv(const vsb_conv_test* t, void* stream) {
   ConvGemmParams& p = op.p;
   p.epi = t->epi; p.act = t->act; p.bias = t->bias;
   p.resid16 = (const __half*)t->resid16; p.ld_res16 = t->N;
-  p.resid32 = t->resid32; p.ld_res32 = t->N;
-  p.out16 = (__half*)t->out16; p.ld_out16 = t->N;
-  p.out32 = t->out32; p.ld_out32 = t->N;
+  p.resid32 = t->resid32; p.ld_res32 = ld_out;
+  p.out16 = (__half*)t->out16; p.ld_out16 = ld_out;
+  p.out32 = t->out32; p.ld_out32 = ld_out;
   p.ln_w = t->ln_w; p.ln_b = t->ln_b; p.ln_eps = 1e-6f;
   p.outc_w = t->outc_w; p.outc_b = t->outc_b; p.n_out = t->n_out; p.delta = t->delta; p.hw = OH * OW; p.outc_tanh = 1;
   p.grn_stats = t->grn_stats;
   if (t->rows_per_sample) p.rows_per_sample = t->rows_per_sample;
-  finalize_op(op, (const __half*)t->weights, t->N, K, K, num_sms, t->block_n);
+  finalize_op(op, (const __half*)t->weights, t->N, K, t->ldw ? t->ldw : K, num_sms, t->block_n);
   launch(op, (cudaStream_t)stream);
   g_launches += 1;
   return VSB_OK;
