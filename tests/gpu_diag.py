@@ -21,14 +21,16 @@ def one_case(name):
 def net_walk(card):
     import torch
     from tests.util import make_model_pair
-    model, orc, spec = make_model_pair(card, device="cuda:0")
+    tiny = None
+    if card.endswith(":tiny"):      # chunkyseal:tiny = every width / map size of the card, reduced depth (tests/test_e2e_gpu.py)
+        card, tiny = card[:-5], {"num_blocks": 1, "depths": [1, 1, 2, 1]}
+    model, orc, spec = make_model_pair(card, device="cuda:0", tiny=tiny)
     g = torch.Generator().manual_seed(0)
     B = 2
     imgs = torch.rand(B, 3, 256, 256, generator=g)
     msgs = torch.randint(0, 2, (B, spec["nbits"]), generator=g)
     taps = {}
     ref_delta = orc.embedder(imgs, msgs, taps)
-    out = model.embed(imgs.cuda(), msgs, is_video=False)
     rows = []
 
     def cmp(name, ref_nchw):
@@ -49,19 +51,27 @@ def net_walk(card):
         rows.append({"tensor": name, "maxerr": err.max().item(), "ref_absmax": ref.abs().max().item(),
                      "meanerr": err.mean().item(), "nan": int(torch.isnan(g_).sum())})
 
-    nd = len(spec["unet"]["mults"]) - 1
-    for i in range(nd - 1):
-        cmp(f"down{i}", taps[f"down{i}"])
-    for i in range(spec["unet"]["num_blocks"]):
-        cmp(f"bott{i}", taps[f"bott{i}"])
-    for j in range(nd):
-        cmp(f"up{j}_conv", taps[f"up{j}_conv"])
-        if j < nd - 1:
-            cmp(f"up{j}", taps[f"up{j}"])
-    cmp("delta", ref_delta)
     ref = orc.embed(imgs, msgs, is_video=False)
-    rows.append({"tensor": "imgs_w", "maxerr": (out["imgs_w"].cpu() - ref["imgs_w"]).abs().max().item()})
-    rows.append({"tensor": "preds_w", "maxerr": (out["preds_w"].cpu() - ref["preds_w"]).abs().max().item()})
+    try:
+        out = model.embed(imgs.cuda(), msgs, is_video=False)
+        torch.cuda.synchronize()
+        nd = len(spec["unet"]["mults"]) - 1
+        for i in range(nd - 1):
+            cmp(f"down{i}", taps[f"down{i}"])
+        for i in range(spec["unet"]["num_blocks"]):
+            cmp(f"bott{i}", taps[f"bott{i}"])
+        for j in range(nd):
+            cmp(f"up{j}_conv", taps[f"up{j}_conv"])
+            if j < nd - 1:
+                cmp(f"up{j}", taps[f"up{j}"])
+        cmp("delta", ref_delta)
+        rows.append({"tensor": "imgs_w", "maxerr": (out["imgs_w"].cpu() - ref["imgs_w"]).abs().max().item()})
+        rows.append({"tensor": "preds_w", "maxerr": (out["preds_w"].cpu() - ref["preds_w"]).abs().max().item()})
+    except Exception as e:   # keep going: the extractor walk below does not depend on the embedder
+        rows.append({"tensor": "embed", "error": repr(e)[:1500]})
+    for r in rows:
+        print("RESULT " + json.dumps({"card": card, **r}), flush=True)
+    rows.clear()
     # extractor on the ORACLE's watermarked image so errors do not compound
     taps = {}
     ref_logits = orc.detector(ref["imgs_w"], taps)
@@ -69,6 +79,16 @@ def net_walk(card):
     for s in range(4):
         cmp(f"ds{s}", taps[f"ds{s}"])
         cmp(f"stage{s}", taps[f"stage{s}"])
+    # first block of every stage, its LayerNorm'd dwconv output and its GELU output (oracle recomputed from the stage input)
+    import torch.nn.functional as F
+    for s in range(4):
+        key = f"detector.convnext.stages.{s}.0."
+        xin = taps[f"ds{s}"]
+        C = xin.shape[1]
+        a = F.conv2d(xin, orc.sd[key + "dwconv.weight"], orc.sd[key + "dwconv.bias"], padding=3, groups=C).permute(0, 2, 3, 1)
+        a = F.layer_norm(a, (C,), orc.sd[key + "norm.weight"], orc.sd[key + "norm.bias"], 1e-6)
+        cmp(f"s{s}b0_a", a.permute(0, 3, 1, 2))
+        cmp(f"s{s}b0_g", F.gelu(F.linear(a, orc.sd[key + "pwconv1.weight"], orc.sd[key + "pwconv1.bias"])).permute(0, 3, 1, 2))
     err = (got_logits - ref_logits).abs()
     rows.append({"tensor": "logits", "maxerr": err.max().item(), "ref_absmax": ref_logits.abs().max().item(),
                  "bit_mismatch": int(((got_logits[:, 1:] > 0) != (ref_logits[:, 1:] > 0)).sum())})
@@ -85,6 +105,10 @@ def main():
     from tests.conv_cases import CASES
     cases = list(CASES)
     skip_net = "--skip-net" in args
+    net_card = "videoseal_1.0"
+    for i, a in enumerate(args):
+        if a == "--net-card":
+            net_card = args[i + 1]
     for i, a in enumerate(args):
         if a == "--cases":
             cases = args[i + 1].split(",")
@@ -108,7 +132,7 @@ def main():
     for c in cases:
         run(["--one", c], c, 180)
     if not skip_net:
-        run(["--net", "videoseal_1.0"], "net:videoseal_1.0", 600)
+        run(["--net", net_card], "net:" + net_card, 600)
 
 
 if __name__ == "__main__":

@@ -339,3 +339,43 @@ def test_u8_streaming_clip_entry(v1):
         assert (preds2[:, 1:] - bits).abs().max().item() <= 1e-3 * ref_det.abs().max().item()
     finally:
         model.step_size, orc.step_size = old
+
+
+# ---------------------------------------------------------------------------------------------------------------------
+# chunkyseal (BASELINE configs[4]): RGB in/out U-Net with 4x the widths (bottleneck 2560 channels), 1024-bit message,
+# proportional ConvNeXt trunk (362 / 724 / 1448 / 2896 channels: not multiples of 8 / 16; stem stride 2 -> odd maps 127 / 63 / 31 /
+# 15).  The parity case keeps every WIDTH and map size of the card but cuts the depth (1 bottleneck block, trunk depths
+# [1,1,2,1]) so that the synthetic checkpoint is 0.35 G parameters instead of 1.75 G and the CPU oracle finishes in seconds.
+CHUNKY_TINY = {"num_blocks": 1, "depths": [1, 1, 2, 1]}
+
+
+@pytest.fixture(scope="module")
+def ck():
+    return make_model_pair("chunkyseal", tiny=CHUNKY_TINY)
+
+
+def test_chunkyseal_widths_image_256(ck):
+    _img_case(ck, 2, 256, 256, seed=21)
+
+
+def test_chunkyseal_widths_resized_and_video(ck):
+    model, orc, spec = ck
+    _img_case(ck, 1, 200, 312, seed=22)
+    g = torch.Generator().manual_seed(23)
+    vid = torch.rand(5, 3, 272, 304, generator=g)
+    msgs = torch.randint(0, 2, (1, spec["nbits"]), generator=g)
+    old = (model.chunk_size, model.step_size, orc.chunk_size, orc.step_size)
+    try:
+        model.chunk_size = orc.chunk_size = 2
+        model.step_size = orc.step_size = 4
+        with torch.no_grad():
+            ref = orc.embed(vid, msgs, is_video=True)
+            ref_det = orc.detect(ref["imgs_w"], is_video=True)["preds"]
+        out = model.embed(vid.cuda(), msgs, is_video=True)
+        assert (out["imgs_w"].cpu() - ref["imgs_w"]).abs().max().item() <= PIX_TOL
+        det = model.detect(out["imgs_w"], is_video=True)["preds"].cpu()
+        rel, flips, _ = logits_ok(det, ref_det)
+        assert rel <= LOGIT_RTOL and flips == 0, (rel, flips)
+        assert (model.extract_message(out["imgs_w"]).cpu() == orc.extract_message(ref["imgs_w"])).all()
+    finally:
+        model.chunk_size, model.step_size, orc.chunk_size, orc.step_size = old

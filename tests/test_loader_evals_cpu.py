@@ -1,0 +1,117 @@
+"""Host-side logic that needs no GPU: raw-training-checkpoint loading (utils/cfg.py:50-85,156-178 of the
+reference), the metrics of the evaluation slice (8(f)4, evals/metrics.py) and the speed tester's bookkeeping."""
+import argparse
+import math
+
+import pytest
+import torch
+
+from oracle import restate
+from tests.util import load_card, tmpdir
+import videoseal_b200
+from videoseal_b200 import cfg as vcfg
+from videoseal_b200.evals import metrics, speed
+
+
+def _training_ckpt(card_name, emb_model, ext_model, as_namespace=False):
+    card = load_card(card_name)
+    spec = restate.spec_from_card(card)
+    args = dict(card["args"])
+    args.update({"embedder_config": "configs/embedder.yaml", "extractor_config": "configs/extractor.yaml",
+                 "embedder_model": emb_model, "extractor_model": ext_model, "lr": 1e-4, "epochs": 3})
+    path = tmpdir() / f"train_{card_name}_{int(as_namespace)}.pth"
+    # a small stand-in state dict is enough: load_state_dict keeps what it is given, nothing is finalised without a GPU
+    sd = {"embedder.unet.outc.bias": torch.zeros(spec["unet"]["out_channels"])}
+    torch.save({"args": argparse.Namespace(**args) if as_namespace else args, "model": sd, "epoch": 3}, path)
+    return path, card
+
+
+@pytest.mark.parametrize("card_name,emb,ext", [("videoseal_1.0", "unet_small2_yuv_quant", "convnext_tiny"),
+                                               ("pixelseal", "unet_base_yuv_quant", "convnext_tiny"),
+                                               ("chunkyseal", "unet_sweep_3", "convnext_sweep_3_prop_stride2")])
+def test_training_checkpoint_resolves_to_the_cards_architecture(card_name, emb, ext):
+    path, card = _training_ckpt(card_name, emb, ext)
+    got = vcfg.spec_from_card(vcfg.get_config_from_checkpoint(path))
+    want = vcfg.spec_from_card(card)
+    assert got == want
+    model = vcfg.setup_model_from_checkpoint(str(path))
+    assert model.spec == want and "embedder.unet.outc.bias" in model.state_dict()
+
+
+def test_training_checkpoint_args_as_namespace_and_card_name_passthrough():
+    path, card = _training_ckpt("videoseal_1.0", "unet_small2_yuv_quant", "convnext_tiny", as_namespace=True)
+    assert vcfg.spec_from_card(vcfg.get_config_from_checkpoint(path)) == vcfg.spec_from_card(card)
+    with pytest.raises(NotImplementedError):
+        vcfg.setup_model_from_checkpoint("baseline/hidden")
+    with pytest.raises(FileNotFoundError):
+        vcfg.setup_model_from_checkpoint("no_such_card")
+    from videoseal_b200.utils.cfg import setup_model_from_checkpoint as alias   # the reference's import path
+    assert alias is vcfg.setup_model_from_checkpoint
+
+
+def test_unknown_preset_is_rejected_at_load_time():
+    path, _ = _training_ckpt("videoseal_1.0", "unet_small2_yuv_quant", "sam_small")
+    with pytest.raises(NotImplementedError):
+        vcfg.get_config_from_checkpoint(path)
+
+
+def test_videoseal_0_0_card_is_rejected_by_the_product_loader():
+    """configs[0] runs on the reference's CPU path only (oracle); the B200 package has no ViT extractor and no CPU fallback"""
+    with pytest.raises(NotImplementedError):
+        vcfg.spec_from_card(load_card("videoseal_0.0"))
+
+
+def test_metrics_match_the_oracle_and_closed_forms():
+    g = torch.Generator().manual_seed(0)
+    x = torch.rand(3, 3, 32, 40, generator=g)
+    y = (x + 0.01 * torch.randn(3, 3, 32, 40, generator=g)).clamp(0, 1)
+    assert torch.allclose(metrics.psnr(y, x), restate.psnr(y, x))
+    assert metrics.psnr(y, x, is_video=True).ndim == 0
+    mse = ((255 * (y - x)) ** 2).mean().item()
+    assert metrics.psnr(y, x, is_video=True).item() == pytest.approx(20 * math.log10(255) - 10 * math.log10(mse), abs=1e-4)
+    assert metrics.linf(y, x).item() == pytest.approx(255 * (y - x).abs().max().item())
+    logits = torch.tensor([[9.0, 1.0, -1.0, 2.0, -3.0], [0.0, -1.0, -1.0, -2.0, 3.0]])
+    msgs = torch.tensor([[1, 0, 1, 0], [1, 1, 0, 0]])
+    acc = metrics.bit_accuracy(logits[:, 1:], msgs)
+    assert acc.tolist() == [1.0, 0.25]
+    assert torch.equal(acc, restate.bit_accuracy(logits, msgs))
+    pv = metrics.pvalue(logits[:, 1:], msgs)
+    assert pv[0].item() == pytest.approx(0.5 ** 4) and pv[1].item() == pytest.approx(1 - 0.5 ** 4)
+    cap = metrics.capacity(logits[:, 1:], msgs)
+    assert cap[0].item() == pytest.approx(4.0)
+    assert cap[1].item() == pytest.approx(4 * (1 + 0.25 * math.log2(0.25) + 0.75 * math.log2(0.75)))
+    pix = torch.zeros(1, 2, 4, 4)
+    pix[0, 0] = 1.0
+    pix[0, 1, :1] = 1.0    # 4 of 16 pixels vote 1 -> bit 0
+    assert metrics.bit_accuracy(pix, torch.tensor([[1, 0]])).item() == 1.0
+
+
+class _FakeModel:
+    def __init__(self):
+        self.calls = []
+
+    def embed(self, imgs, is_video=True, interpolation=None, lowres_attenuation=False):
+        self.calls.append(("embed", tuple(imgs.shape), is_video, lowres_attenuation))
+        return {"imgs_w": imgs}
+
+    def detect(self, imgs, is_video=True):
+        self.calls.append(("detect", tuple(imgs.shape), is_video))
+        return {"preds": torch.zeros(len(imgs), 5)}
+
+    def extract_message(self, imgs, aggregation="avg", interpolation=None):
+        self.calls.append(("extract", tuple(imgs.shape), aggregation))
+        return torch.zeros(1, 4, dtype=torch.bool)
+
+
+def test_speed_tester_bookkeeping_matches_the_reference_semantics():
+    m = _FakeModel()
+    items = list(speed.synthetic_items(2, True, 10, 16, 24, "cpu"))
+    res = speed.SpeedTester("cpu").test_speed(m, items, is_video=True, num_frames=8, num_runs=2, warmup_runs=1)
+    # per item: 1 warm-up (embed + extract) + 2 timed embeds + 2 timed extracts, all on the first 8 frames
+    assert len(m.calls) == 2 * (2 + 2 + 2) and all(c[1][0] == 8 for c in m.calls)
+    assert res["image_shape"] == ["10x16x24", "10x16x24"] and len(res["embedding_time"]) == 2
+    assert res["avg_embedding_ms_per_frame"] == pytest.approx(res["avg_embedding_time"] / 8 * 1000)
+    m2 = _FakeModel()
+    res2 = speed.SpeedTester("cpu").test_speed(m2, list(speed.synthetic_items(1, False, 1, 16, 16, "cpu")), is_video=False)
+    assert m2.calls[0] == ("embed", (1, 3, 16, 16), False, False) and m2.calls[1][0] == "detect"
+    assert "avg_embedding_ms_per_frame" not in res2

@@ -123,6 +123,53 @@ def setup_model(card: dict, ckpt_path):
     return model
 
 
+def _plain(o):
+    """checkpoint['args'] may be a dict, an argparse.Namespace or an OmegaConf container saved by the training script"""
+    if hasattr(o, "items"):
+        return {str(k): _plain(v) for k, v in o.items()}
+    if hasattr(o, "__dict__") and not isinstance(o, (str, bytes)):
+        return {str(k): _plain(v) for k, v in vars(o).items()}
+    if isinstance(o, (list, tuple)):
+        return [_plain(v) for v in o]
+    return o
+
+
+def get_config_from_checkpoint(ckpt_path) -> dict:
+    """utils/cfg.py:50-85 of the reference: a raw training checkpoint carries its `args`; the embedder / extractor
+    hyper-parameters are the presets named by args.embedder_model / args.extractor_model in the YAML files named by
+    args.embedder_config / args.extractor_config (cwd first, then this package).  Returns a card-shaped dict."""
+    try:
+        checkpoint = torch.load(ckpt_path, map_location="cpu", weights_only=True)
+    except Exception:   # args saved as a Namespace / DictConfig object need the full unpickler
+        checkpoint = torch.load(ckpt_path, map_location="cpu", weights_only=False)
+    if "args" not in checkpoint:
+        raise KeyError(f"{ckpt_path} holds no 'args': not a training checkpoint (use a model card for released weights)")
+    args = _plain(checkpoint["args"])
+    if not isinstance(args, dict):
+        raise Exception("Expected logfile to contain params dictionary.")
+    emb_cfg = yaml.safe_load(open(resolve_config_path(args.get("embedder_config", "configs/embedder.yaml"))))
+    ext_cfg = yaml.safe_load(open(resolve_config_path(args.get("extractor_config", "configs/extractor.yaml"))))
+    emb_model = args.get("embedder_model") or emb_cfg["model"]
+    ext_model = args.get("extractor_model") or ext_cfg["model"]
+    for name, cfg_, kind in ((emb_model, emb_cfg, "embedder"), (ext_model, ext_cfg, "extractor")):
+        if name not in cfg_:
+            raise NotImplementedError(f"{kind} preset '{name}' is not on the B200 hot path (known: "
+                                      f"{', '.join(k for k in cfg_ if k != 'model')})")
+    return {"checkpoint_path": str(ckpt_path), "args": args,
+            "embedder": {"model": emb_model, "params": emb_cfg[emb_model]},
+            "extractor": {"model": ext_model, "params": ext_cfg[ext_model]}}
+
+
+def setup_model_from_checkpoint(ckpt_path) -> "Videoseal":
+    """utils/cfg.py:156-178 of the reference: a model-card name, or the path of a raw training checkpoint (.pth)."""
+    ckpt_path = str(ckpt_path)
+    if "baseline" in ckpt_path:
+        raise NotImplementedError("baseline watermarkers (videoseal/models/baselines.py) are outside the B200 hot path")
+    if not ckpt_path.endswith(".pth") and "/" not in ckpt_path:
+        return setup_model_from_model_card(ckpt_path)
+    return setup_model(get_config_from_checkpoint(ckpt_path), ckpt_path)
+
+
 def setup_model_from_model_card(model_card) -> "Videoseal":
     """`videoseal.load()`: card name (looked up in ./videoseal/cards, then in this package's cards/) or a Path to a YAML."""
     if model_card == "videoseal":
