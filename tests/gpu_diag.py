@@ -129,6 +129,8 @@ def main():
             log.write(l + "\n")
             log.flush()
 
+    if "--no-cases" in args:
+        cases = []
     for c in cases:
         run(["--one", c], c, 180)
     if not skip_net:

@@ -822,7 +822,10 @@ class Model {
         const int Cv = d.ext_dims[s - 1], Cvp = Cp, Cn = d.ext_dims[s], Cnp = pitch(Cn);
         const long Mp = (long)B * hs * hs;
         __half* xn = pl.pool.alloc_n<__half>(Mp * Cvp);
-        if (Cvp != Cv) VSB_CUDA(cudaMemset(xn, 0, (size_t)Mp * Cvp * sizeof(__half)));   // pad channels stay zero: ln_rows writes [0, Cv)
+        if (Cvp != Cv) {   // pad channels stay zero: ln_rows writes [0, Cv)
+          VSB_CUDA(cudaMemset(xn, 0, (size_t)Mp * Cvp * sizeof(__half)));
+          VSB_CUDA(cudaDeviceSynchronize());   // the plan runs on the caller's stream, which need not be ordered after stream 0
+        }
         {
           float *lw = ds[s - 1].lnw, *lb = ds[s - 1].lnb;
           const float* xin = x;
@@ -958,7 +961,10 @@ class Model {
           if (wscale) { op.w_samples = B; op.p.rows_per_sample = rows_per_sample; }
           if (s == 3 && jb == d.ext_depths[s] - 1) {
             x16 = pl.pool.alloc_n<__half>(M * Cp);
-            if (Cp != C) VSB_CUDA(cudaMemset(x16, 0, (size_t)M * Cp * sizeof(__half)));   // the head conv's gather reads the pad channels
+            if (Cp != C) {   // the head conv's gather reads the pad channels
+              VSB_CUDA(cudaMemset(x16, 0, (size_t)M * Cp * sizeof(__half)));
+              VSB_CUDA(cudaDeviceSynchronize());
+            }
             op.p.out16 = x16; op.p.ld_out16 = Cp;
           }
           add_conv(pl, op, w.pw2, "cnx.pwconv2." + std::to_string(C) + "@" + std::to_string(hs), 0, wscale ? w2s : nullptr);
