@@ -84,13 +84,14 @@ class ClockSampler:
         return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def conv_flops(name: str, B: int) -> float:
-    """algorithmic FLOPs (2*MAC) of one launch of a named plan step, from its shape tag (model.cuh step names)"""
+def conv_flops(name: str, B: int, B_unet: int = 0) -> float:
+    """algorithmic FLOPs (2*MAC) of one launch of a named plan step, from its shape tag (model.cuh step names).
+    B_unet: frames that go through the U-Net (key frames only in video mode); the extractor sees all B frames."""
     try:
         kind, rest = name.rsplit(".", 1)
         dims, hs = rest.split("@")
         h = int(hs)
-        M = B * h * h
+        M = (B_unet if (B_unet and kind.startswith("unet.")) else B) * h * h
         if kind in ("unet.conv3x3", "unet.conv3x3+outc", "unet.conv3x3d", "unet.conv3x3d+outc", "unet.down3x3s2", "unet.down3x3s2d", "unet.up3x3"):
             cin, cout = (int(x) for x in dims.split("-"))
             return 2.0 * M * cout * 9 * cin
@@ -246,6 +247,7 @@ def run_ours(args):
 
     vid = bool(args.video)
     msgs_v = msgs[:1]
+    n_keys = (B + model.step_size - 1) // model.step_size if vid else B   # frames that go through the U-Net per step
 
     def step_local(i):
         out = model.embed(imgs[i % NB], msgs_v if vid else msgs, is_video=vid)
@@ -362,7 +364,7 @@ def run_ours(args):
         for line in buf.value.decode().splitlines():
             name, tms, cnt = line.split("\t")
             tms, cnt = float(tms), int(cnt)
-            fl = conv_flops(name, B)
+            fl = conv_flops(name, B, n_keys)
             table.append({"name": name, "ms_per_step": tms / 3, "launches_per_step": cnt // 3, "avg_us": 1000 * tms / cnt,
                           "tflops": (fl / (tms / cnt * 1e-3) / 1e12) if fl else None})
             tot += tms / 3
@@ -398,7 +400,7 @@ def run_ours(args):
                                    f"batch {B} x 3x{S}x{S} per GPU" + (" (BASELINE configs[1])" if (B, S, vid, args.card) == (64, 256, False, "videoseal_1.0") else ""),
                        "card": args.card, "batch_per_gpu": B, "size": S, "parallelism": f"dp{world} (frames sharded, weak scaling)",
                        "l2": f"{NB} rotating input batches ({NB * B * 3 * S * S * 4 / 1e6:.0f} MB > 126 MB L2); activations per step >> L2"},
-            "step_tflops": (fe + fd) * world * B * args.steps / (ms / 1000.0) / 1e12,
+            "step_tflops": (fe * n_keys + fd * B) * world * args.steps / (ms / 1000.0) / 1e12,
             "clocks": clocks, "e2e": e2e, "gpu_launches": launches, "roofline": roofline, "cpu_baseline": cpu,
             "top_kernels": [{k: (round(v, 4) if isinstance(v, float) else v) for k, v in r.items()} for r in table[:8]],
         }
