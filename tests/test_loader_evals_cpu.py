@@ -90,7 +90,7 @@ class _FakeModel:
     def __init__(self):
         self.calls = []
 
-    def embed(self, imgs, is_video=True, interpolation=None, lowres_attenuation=False):
+    def embed(self, imgs, msgs=None, is_video=True, interpolation=None, lowres_attenuation=False):
         self.calls.append(("embed", tuple(imgs.shape), is_video, lowres_attenuation))
         return {"imgs_w": imgs}
 
@@ -115,3 +115,29 @@ def test_speed_tester_bookkeeping_matches_the_reference_semantics():
     res2 = speed.SpeedTester("cpu").test_speed(m2, list(speed.synthetic_items(1, False, 1, 16, 16, "cpu")), is_video=False)
     assert m2.calls[0] == ("embed", (1, 3, 16, 16), False, False) and m2.calls[1][0] == "detect"
     assert "avg_embedding_ms_per_frame" not in res2
+
+
+def test_tensor_api_facade_forwards_to_the_model():
+    """docs/torchscript.md surface: tuple / tensor returns, attribute plumbing, attenuation switch"""
+    from videoseal_b200 import jit
+
+    class M(_FakeModel):
+        def __init__(self):
+            super().__init__()
+            self.blender = argparse.Namespace(scaling_w=0.2, scaling_i=1.0)
+            self.img_size, self.clamp, self.chunk_size, self.step_size, self.video_mode = 256, True, 32, 4, "repeat"
+            self.attenuation = "jnd_1_1"
+
+    m = M()
+    t = jit.TensorAPI(m)
+    x = torch.rand(2, 3, 16, 16)
+    img_w, preds = t(x, torch.zeros(2, 4))
+    assert img_w.shape == x.shape and preds.shape == (2, 5)
+    assert m.calls[0] == ("embed", (2, 3, 16, 16), False, True)          # lowres attenuation on by default, like the artefact
+    assert t.chunk_size == 16 and m.chunk_size == 16
+    t.scaling_w, t.step_size, t.video_mode, t.do_attenuation = 0.5, 8, "interpolate", False
+    assert m.blender.scaling_w == 0.5 and m.step_size == 8 and m.video_mode == "interpolate" and m.attenuation is None
+    t.do_attenuation = True
+    assert m.attenuation == "jnd_1_1" and t.do_attenuation
+    bits = t.detect_video_and_aggregate(x, aggregation="squared_avg")
+    assert bits.dtype == torch.float32 and m.calls[-1] == ("extract", (2, 3, 16, 16), "squared_avg")
