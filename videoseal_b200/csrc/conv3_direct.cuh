@@ -128,6 +128,9 @@ __global__ void __launch_bounds__(kD3Threads, 1) conv3_direct_kernel(const Conv3
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // (PDL builds) so far only weights / bias / LN parameters were read: the resident-weight copy overlaps the predecessor's tail
+  pdl_launch_dependents();
+  pdl_wait();
   const uint32_t tmem_base = hd->tmem_base;
 
   if (warp == 0 || warp == 2) {

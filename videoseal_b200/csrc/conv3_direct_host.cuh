@@ -81,7 +81,11 @@ inline void launch_direct_nkr(const Conv3DirectOp& op, cudaStream_t st) {
     VSB_CUDA(cudaFuncSetAttribute(conv3_direct_kernel<N, KS, R, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr = true;
   }
+#ifdef VSB_PDL
+  launch_pdl(conv3_direct_kernel<N, KS, R, MODE>, dim3(op.grid), dim3(kD3Threads), op.smem, st, op.p);
+#else
   conv3_direct_kernel<N, KS, R, MODE><<<op.grid, kD3Threads, op.smem, st>>>(op.p);
+#endif
   VSB_CUDA(cudaGetLastError());
 }
 template <int N, int KS>

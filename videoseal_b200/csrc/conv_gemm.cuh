@@ -249,6 +249,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
+  // (PDL builds) nothing above reads or writes a tensor produced by an earlier kernel: only parameters and weights
+  pdl_launch_dependents();
+  pdl_wait();
   const uint32_t tmem_base = *tmem_ptr_smem;
   const uint32_t row_bytes = (uint32_t)p.kblk * 2u;
 

@@ -335,6 +335,23 @@ inline void setup_gather_scale(ConvGemmOp& op, const __half* G, long M, int K, i
   p.num_kb = (K + 63) / 64;
 }
 
+#ifdef VSB_PDL
+// launch with programmatic stream serialization: the kernel may begin while its predecessor drains and synchronises
+// itself with pdl_wait() (ptx.cuh).  VSB_NO_PDL=1 falls back to classic launches at run time (A/B in one build).
+template <class... KArgs, class... Args>
+inline void launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args&&... args) {
+  static const bool off = getenv("VSB_NO_PDL") != nullptr;
+  cudaLaunchConfig_t cfg;
+  memset(&cfg, 0, sizeof(cfg));
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = off ? 0 : 1;
+  VSB_CUDA(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
+}
+#endif
+
 template <int LOADER, int ACT>
 inline void launch_one(const ConvGemmOp& op, cudaStream_t st) {
   static bool attr_set = false;
@@ -342,7 +359,11 @@ inline void launch_one(const ConvGemmOp& op, cudaStream_t st) {
     VSB_CUDA(cudaFuncSetAttribute(conv_gemm_kernel<LOADER, ACT>, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
     attr_set = true;
   }
+#ifdef VSB_PDL
+  launch_pdl(conv_gemm_kernel<LOADER, ACT>, dim3(op.grid), dim3(op.threads), op.smem, st, op.tmA, op.tmA2, op.tmB, op.p);
+#else
   conv_gemm_kernel<LOADER, ACT><<<op.grid, op.threads, op.smem, st>>>(op.tmA, op.tmA2, op.tmB, op.p);
+#endif
 }
 
 // instantiated (loader, activation) pairs: only what the networks need, to bound compile time
