@@ -151,6 +151,10 @@ typedef struct vsb_conv_test {
   int32_t ld_out;            /* row pitch of out16 / out32 / resid32 (0 = N) */
 } vsb_conv_test;
 int vsb_debug_conv(const vsb_conv_test* t, void* stream);
+/* host-only (no GPU needed): the separable table the resize kernels use along one axis of length `in` -> `out`, i.e. the library's
+ * restatement of ATen's bilinear (anti-aliased or plain, align_corners=False) index/weight computation behind F.interpolate
+ * (wam.py:163,184,224).  start / cnt: [out]; weights: [out * maxt] row-major, capacity in floats.  Returns maxt, or < 0. */
+int vsb_debug_resample_table(int32_t in, int32_t out, int32_t antialias, int32_t* start, int32_t* cnt, float* weights, int64_t capacity);
 
 #ifdef __cplusplus
 }

@@ -66,3 +66,32 @@ def test_unsupported_card_features_raise_at_load():
     c["extractor"]["model"] = "sam_small"
     with pytest.raises(NotImplementedError):
         cfg.spec_from_card(c)
+
+
+@pytest.mark.parametrize("n_in,n_out,aa", [(768, 256, True), (300, 256, True), (480, 256, True), (257, 256, True), (200, 256, True),
+                                            (256, 768, True), (256, 768, False), (256, 300, False), (17, 256, False), (1080, 256, False)])
+def test_resample_tables_match_aten_interpolate(built_lib, n_in, n_out, aa):
+    """the host-built separable tables of the resize kernels (model.cuh:make_resample) against F.interpolate applied to the
+    identity: every output sample's tap positions and weights (wam.py:163,184,224 call sites; bilinear, align_corners=False)"""
+    import ctypes as C
+    import numpy as np
+    import torch.nn.functional as F
+    start = np.zeros(n_out, dtype=np.int32)
+    cnt = np.zeros(n_out, dtype=np.int32)
+    cap = n_out * 64
+    w = np.zeros(cap, dtype=np.float32)
+    maxt = built_lib.vsb_debug_resample_table(n_in, n_out, int(aa), start.ctypes.data, cnt.ctypes.data, w.ctypes.data, cap)
+    assert maxt > 0, built_lib.vsb_last_error()
+    w = w[: n_out * maxt].reshape(n_out, maxt)
+    op = np.zeros((n_out, n_in), dtype=np.float64)
+    for o in range(n_out):
+        assert 0 <= start[o] and start[o] + cnt[o] <= n_in and 1 <= cnt[o] <= maxt
+        op[o, start[o]:start[o] + cnt[o]] = w[o, :cnt[o]]
+    eye = torch.eye(n_in, dtype=torch.float32).reshape(1, n_in, 1, n_in)          # n_in "channels", each a one-hot row of width n_in
+    ref = F.interpolate(eye, size=(1, n_out), mode="bilinear", align_corners=False, antialias=aa)
+    ref = ref.reshape(n_in, n_out).t().double().numpy()
+    # up-scaling with antialias=True: ATen routes it through its anti-aliasing code (triangle filter of support 1 == plain bilinear
+    # mathematically), whose source coordinate is rounded once more than the plain kernel's: one float ulp of a coordinate < 256
+    tol = 8e-6 if (aa and n_out > n_in) else 2e-6
+    assert np.abs(op - ref).max() < tol
+    assert np.allclose(op.sum(1), 1.0, atol=1e-5)

@@ -147,7 +147,8 @@ inline ResampleHost make_resample(int in, int out, bool antialias) {
     t.start.resize(out); t.cnt.resize(out); t.w.assign((size_t)out * 2, 0.f);
     for (int i = 0; i < out; ++i) {
       // area_pixel_compute_source_index(scale, dst, align_corners=false, cubic=false)
-      float src = (float)scale * (i + 0.5f) - 0.5f;
+      // single rounding (fused multiply-add), like the vectorised ATen CPU kernel and the CUDA one
+      float src = std::fmaf((float)scale, i + 0.5f, -0.5f);
       if (src < 0.f) src = 0.f;
       int x0 = (int)src; if (x0 > in - 1) x0 = in - 1;
       const int x1 = x0 + ((x0 < in - 1) ? 1 : 0);

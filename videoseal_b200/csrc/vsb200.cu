@@ -266,6 +266,20 @@ int vsb_debug_conv(const vsb_conv_test* t, void* stream) {
   VSB_API_END
 }
 
+int vsb_debug_resample_table(int32_t in, int32_t out, int32_t antialias, int32_t* start, int32_t* cnt, float* weights, int64_t capacity) {
+  try {
+    VSB_CHECK(in > 0 && out > 0 && start && cnt && weights, "bad argument");
+    const ResampleHost t = make_resample(in, out, antialias != 0);
+    VSB_CHECK(capacity >= (int64_t)out * t.maxt, "weights buffer too small");
+    for (int i = 0; i < out; ++i) { start[i] = t.start[i]; cnt[i] = t.cnt[i]; }
+    for (size_t i = 0; i < t.w.size(); ++i) weights[i] = t.w[i];
+    return t.maxt;
+  } catch (const std::exception& e) {
+    g_err = e.what();
+    return -1;
+  }
+}
+
 }  // extern "C"
 
 // ---- per-step profile (bench.py roofline leg): enable, run some steps, then read "name\ttotal_ms\tcount\n" lines
