@@ -862,6 +862,21 @@ class Model {
           const float* xin = x;
           float *dww = w.dww, *dwb = w.dwb, *lw = w.lnw, *lb = w.lnb;
           pl.steps.push_back(Step{[=](cudaStream_t st) {
+#ifdef VSB_EXP
+            // experimental build only: register-rolling kernel (pointwise.cuh K4 v2), opt in with VSB_DW2=1
+            static const bool dw2 = getenv("VSB_DW2") != nullptr;
+            if (dw2 && ldc == Cc && (Cc == 96 || Cc == 192)) {
+              const int R = (H >= 64 && H % 16 == 0) ? 16 : 8;
+              const int NS = Cc == 96 ? 2 : 1;
+              if (H % R == 0 && H % (4 * NS) == 0) {
+                const unsigned blocks = (unsigned)((long)B * (H / R) * (H / (4 * NS)));
+                if (Cc == 96) dwconv7_ln_roll_kernel<96, 2><<<blocks, 96, 0, st>>>(xin, B, H, H, dww, dwb, lw, lb, a, R);
+                else dwconv7_ln_roll_kernel<192, 1><<<blocks, 96, 0, st>>>(xin, B, H, H, dww, dwb, lw, lb, a, R);
+                VSB_CUDA(cudaGetLastError());
+                return;
+              }
+            }
+#endif
             if (!(Cc == 96 || Cc == 192 || Cc == 384 || Cc == 768) || getenv("VSB_DW_WIDE")) {
               // any even width / odd map size (chunkyseal's proportional trunk): threads loop over the channel pairs
               const long nstrips = (long)B * H * ((H + kDwStrip - 1) / kDwStrip);

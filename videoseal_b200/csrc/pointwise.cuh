@@ -9,6 +9,7 @@
 //   K2c grn_scale_kernel       GRN statistics -> per-(sample, channel) multiplier
 //   K8  head_pool_kernel / head_linear_kernel   LN + GELU + spatial mean, then Linear(C -> 1 + nbits)
 #pragma once
+#include <type_traits>
 #include "ptx.cuh"
 
 namespace vsb {
@@ -975,6 +976,170 @@ __global__ void __launch_bounds__(384) dwconv7_ln_tiled_kernel(const float* __re
     }
   }
 }
+
+#ifdef VSB_EXP
+// K4 v2 (experimental build only, -DVSB_EXP; opt in at run time with VSB_DW2=1): depthwise 7x7 + LayerNorm with a REGISTER-ROLLING
+// walk down the rows.  Motivation (profiles/r1_cnx_kernels_ncu.md): the strip kernel above re-loads a 7 x 14 pixel window for
+// every 8-pixel strip (98 loads for 392 packed FMAs per thread), runs at 37 % occupancy with a long-scoreboard stall on 40 % of
+// the samples and executes 93 M warp instructions for 19 M FFMA2.  Here a thread owns one channel pair and a strip of 4 output
+// columns and walks R output rows: its 49 weights stay in registers, every input row (10 pixels) is loaded ONCE and feeds the 7
+// output rows it overlaps (7 x 4 accumulators in a statically rotated register ring: slot = (row phase + j + 1) mod 7), the next
+// row's pixels are prefetched while the current ones are used, and the LayerNorm statistics of a finished row are reduced with a
+// halving butterfly over 16-lane segments + one block barrier per row (double-buffered partial sums), one-pass variance.
+// Block = NS strips x C/2 channel pairs (C/2 is a multiple of 16, so a 16-lane segment never straddles two strips); grid =
+// B x (H/R) x (W/(4 NS)).  Requires H % R == 0, W % (4 NS) == 0, x and out dense (pixel pitch C).
+template <int C, int NS, bool EDGE>
+__device__ __forceinline__ void dw2_load_row(const float* __restrict__ rowp, int x0, int W, float2 (&v)[10]) {
+  // rowp -> channel pair of pixel (iy, x0 - 3); pixels outside the image read as zero (only strips at the left / right border)
+#pragma unroll
+  for (int u = 0; u < 10; ++u) {
+    if (!EDGE || (unsigned)(x0 - 3 + u) < (unsigned)W) v[u] = __ldg(reinterpret_cast<const float2*>(rowp + u * C));
+    else v[u] = make_float2(0.f, 0.f);
+  }
+}
+
+template <int C, int NS>
+__global__ void __launch_bounds__((C / 2) * NS, 2) dwconv7_ln_roll_kernel(const float* __restrict__ x, int B, int H, int W,
+                                                                          const float* __restrict__ wdw /*[49][C]*/,
+                                                                          const float* __restrict__ bdw, const float* __restrict__ lnw,
+                                                                          const float* __restrict__ lnb, __half* __restrict__ out, int R) {
+  constexpr int C2 = C / 2, KSEG = C2 / 16;          // 16-lane segments per strip
+  __shared__ __align__(16) float part[2][NS][KSEG][8];   // per-segment partial sums {sum, sumsq} x 4 pixels, double-buffered
+  const int s = threadIdx.x / C2, cp = threadIdx.x - s * C2, c = cp * 2;
+  const int lane = threadIdx.x & 31, seg = cp >> 4;
+  const int cgroups = W / (4 * NS), rgroups = H / R;
+  const int cg = blockIdx.x % cgroups;
+  const int t = blockIdx.x / cgroups;
+  const int rg = t % rgroups, b = t / rgroups;
+  const int x0 = (cg * NS + s) * 4, y0 = rg * R;
+  const bool edge = (x0 < 3) || (x0 + 7 > W);
+
+  float2 wt[49];
+#pragma unroll
+  for (int k = 0; k < 49; ++k) wt[k] = __ldg(reinterpret_cast<const float2*>(wdw + k * C + c));
+  const float2 bias = __ldg(reinterpret_cast<const float2*>(bdw + c));
+  const float2 lg = __ldg(reinterpret_cast<const float2*>(lnw + c)), lb = __ldg(reinterpret_cast<const float2*>(lnb + c));
+
+  float2 acc[7][4];
+  float2 cur[10], nxt[10];
+  const long rowpitch = (long)W * C;
+  // pixel (y0 - 3, x0 - 3): outside the image at the borders, only dereferenced where the row / column tests allow
+  const float* rowp = x + (((long)b * H + y0) * W + x0) * C + c - 3 * rowpitch - 3 * C;
+  const int nsteps = R + 6;                          // input rows y0 - 3 ... y0 + R + 2
+  int emitted = 0;                                   // rows emitted so far -> partial-sum buffer parity
+
+  // prefetch input row 0
+#pragma unroll
+  for (int u = 0; u < 10; ++u) nxt[u] = make_float2(0.f, 0.f);
+  if ((unsigned)(y0 - 3) < (unsigned)H) {
+    if (edge) dw2_load_row<C, NS, true>(rowp, x0, W, nxt); else dw2_load_row<C, NS, false>(rowp, x0, W, nxt);
+  }
+
+  // one step = one input row i (iy = y0 - 3 + i); PH = i mod 7 is a compile-time constant inside the 7-fold unrolled body so that
+  // every accumulator index below is static.  Output row o = i + j - 6 (kernel row 6 - j) lives in slot (PH + j + 1) % 7.
+  auto step = [&](auto ph_tag, int i) {
+    constexpr int PH = decltype(ph_tag)::value;
+    const int iy = y0 - 3 + i;
+    const bool rowok = (unsigned)iy < (unsigned)H;
+#pragma unroll
+    for (int u = 0; u < 10; ++u) cur[u] = nxt[u];
+    if (i + 1 < nsteps && (unsigned)(iy + 1) < (unsigned)H) {   // prefetch the next input row while this one is consumed
+      const float* np = rowp + (long)(i + 1) * rowpitch;
+      if (edge) dw2_load_row<C, NS, true>(np, x0, W, nxt); else dw2_load_row<C, NS, false>(np, x0, W, nxt);
+    }
+    {   // j = 6: output row o = i starts here (kernel row 0): initialise its slot
+      constexpr int SL = (PH + 7) % 7;
+      if (rowok && i < R) {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) {
+          acc[SL][p] = ffma2(cur[p], wt[0], bias);
+#pragma unroll
+          for (int q = 1; q < 7; ++q) acc[SL][p] = ffma2(cur[p + q], wt[q], acc[SL][p]);
+        }
+      } else {
+#pragma unroll
+        for (int p = 0; p < 4; ++p) acc[SL][p] = bias;
+      }
+    }
+    if (rowok) {
+#pragma unroll
+      for (int j = 0; j < 6; ++j) {                  // output rows o = i + j - 6, kernel row 6 - j
+        const int o = i + j - 6;
+        if (o >= 0 && o < R) {
+#pragma unroll
+          for (int p = 0; p < 4; ++p)
+#pragma unroll
+            for (int q = 0; q < 7; ++q) acc[(PH + j + 1) % 7][p] = ffma2(cur[p + q], wt[(6 - j) * 7 + q], acc[(PH + j + 1) % 7][p]);
+        }
+      }
+    }
+    const int o = i - 6;                             // j = 0: this output row has now seen its last input row
+    if (o >= 0) {
+      constexpr int SL = (PH + 1) % 7;
+      float v[8];
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const float2 a = acc[SL][p];
+        v[2 * p] = a.x + a.y;
+        v[2 * p + 1] = fmaf(a.x, a.x, a.y * a.y);
+      }
+      // halving butterfly over the 16 lanes of the segment: 8 values -> lane (l & 15) ends with value index
+      // ((l >> 3) & 1) * 4 + ((l >> 2) & 1) * 2 + ((l >> 1) & 1), summed over the 16 lanes
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        const float send = (lane & 8) ? v[k] : v[k + 4];
+        const float keep = (lane & 8) ? v[k + 4] : v[k];
+        v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+      }
+#pragma unroll
+      for (int k = 0; k < 2; ++k) {
+        const float send = (lane & 4) ? v[k] : v[k + 2];
+        const float keep = (lane & 4) ? v[k + 2] : v[k];
+        v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+      }
+      {
+        const float send = (lane & 2) ? v[0] : v[1];
+        const float keep = (lane & 2) ? v[1] : v[0];
+        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
+      }
+      v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
+      const int buf = emitted & 1;
+      if ((lane & 1) == 0) part[buf][s][seg][((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1)] = v[0];
+      __syncthreads();     // one barrier per emitted row: the other buffer is only rewritten after the NEXT barrier
+      float tot[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) tot[k] = 0.f;
+#pragma unroll
+      for (int g = 0; g < KSEG; ++g) {
+        const float4 t0 = *reinterpret_cast<const float4*>(&part[buf][s][g][0]);
+        const float4 t1 = *reinterpret_cast<const float4*>(&part[buf][s][g][4]);
+        tot[0] += t0.x; tot[1] += t0.y; tot[2] += t0.z; tot[3] += t0.w;
+        tot[4] += t1.x; tot[5] += t1.y; tot[6] += t1.z; tot[7] += t1.w;
+      }
+      __half* dst = out + (((long)b * H + (y0 + o)) * W + x0) * C + c;
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const float mean = tot[2 * p] * (1.0f / (float)C);
+        const float var = fmaxf(tot[2 * p + 1] * (1.0f / (float)C) - mean * mean, 0.f);
+        const float rstd = rsqrtf(var + 1e-6f);
+        const float sx = rstd * lg.x, sy = rstd * lg.y;
+        const float2 a = acc[SL][p];
+        *reinterpret_cast<__half2*>(dst + p * C) = __floats2half2_rn(fmaf(a.x, sx, fmaf(-mean, sx, lb.x)), fmaf(a.y, sy, fmaf(-mean, sy, lb.y)));
+      }
+      ++emitted;
+    }
+  };
+  for (int i0 = 0; i0 < nsteps; i0 += 7) {
+    if (i0 + 0 < nsteps) step(std::integral_constant<int, 0>{}, i0 + 0);
+    if (i0 + 1 < nsteps) step(std::integral_constant<int, 1>{}, i0 + 1);
+    if (i0 + 2 < nsteps) step(std::integral_constant<int, 2>{}, i0 + 2);
+    if (i0 + 3 < nsteps) step(std::integral_constant<int, 3>{}, i0 + 3);
+    if (i0 + 4 < nsteps) step(std::integral_constant<int, 4>{}, i0 + 4);
+    if (i0 + 5 < nsteps) step(std::integral_constant<int, 5>{}, i0 + 5);
+    if (i0 + 6 < nsteps) step(std::integral_constant<int, 6>{}, i0 + 6);
+  }
+}
+#endif  // VSB_EXP
 
 // K4b: per-row LayerNorm over C (biased variance, eps) of fp32 rows -> fp16 rows.  One warp per row.
 __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ x, long M, int C, int ldx, const float* __restrict__ w,
