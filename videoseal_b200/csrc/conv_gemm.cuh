@@ -553,6 +553,28 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             // else.  The generic chunk body below costs ~490 instructions per 16 elements, 45 % of them guards and
             // index arithmetic for tails, residuals and the other epilogue variants (profiles/r1_history.md).
             const float4* sb4 = reinterpret_cast<const float4*>(sb + c);
+#ifdef VSB_EXP
+            // experimental build: packed fp32 bias add, one saturating F2FP per pair instead of two FMNMX + F2FP, packed squares
+            // (profiles/r1_cnx_kernels_ncu.md: this epilogue is issue-bound at 26 thread instructions per element)
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float4 bq = sb4[u];
+              const float2 a = __fadd2_rn(make_float2(v[4 * u + 0], v[4 * u + 1]), make_float2(bq.x, bq.y));
+              const float2 b = __fadd2_rn(make_float2(v[4 * u + 2], v[4 * u + 3]), make_float2(bq.z, bq.w));
+              v[4 * u + 0] = a.x; v[4 * u + 1] = a.y; v[4 * u + 2] = b.x; v[4 * u + 3] = b.y;
+            }
+#pragma unroll
+            for (int j = 0; j < 16; j += 2) gelu_erf2(v[j], v[j + 1]);
+            {
+              uint32_t h[8];
+#pragma unroll
+              for (int j = 0; j < 8; ++j)
+                asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[j]) : "f"(v[2 * j + 1]), "f"(v[2 * j]));   // {hi, lo}
+              uint4* o = reinterpret_cast<uint4*>(p.out16 + m * p.ld_out16 + n);
+              o[0] = make_uint4(h[0], h[1], h[2], h[3]);
+              o[1] = make_uint4(h[4], h[5], h[6], h[7]);
+            }
+#else
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               const float4 bq = sb4[u];
@@ -568,10 +590,19 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               o[0] = reinterpret_cast<const uint4*>(h)[0];
               o[1] = reinterpret_cast<const uint4*>(h)[1];
             }
+#endif
             if (grn_row != nullptr) {
               float sq[16];
+#ifdef VSB_EXP
+#pragma unroll
+              for (int j = 0; j < 16; j += 2) {
+                const float2 t2 = __fmul2_rn(make_float2(v[j], v[j + 1]), make_float2(v[j], v[j + 1]));
+                sq[j] = t2.x; sq[j + 1] = t2.y;
+              }
+#else
 #pragma unroll
               for (int j = 0; j < 16; ++j) sq[j] = v[j] * v[j];
+#endif
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const float send = (lane & 16) ? sq[i] : sq[i + 8];
