@@ -131,6 +131,36 @@ def main(cards=None):
             "imgs_w_s": sample(r["imgs_w"]), "preds": d["preds"].clone(), "extract": em.clone(),
             "imgs_w_stats": stats(r["imgs_w"]), "oracle_vs_ref": errs,
         }
+        # case D (cards with an attenuation, cheap ones only): the other video modes, low-resolution attenuation, and every
+        # extract_message aggregation (videoseal.py:80-118, wam.py:177-180, videoseal.py:390-428)
+        if ref.attenuation is not None and card_name != "chunkyseal":
+            g = torch.Generator().manual_seed(3)
+            vid = torch.rand(11, 3, 288, 272, generator=g)
+            msgs = torch.randint(0, 2, (1, spec["nbits"]), generator=g)
+            ref.chunk_size, orc.chunk_size = 2, 2
+            ref.step_size, orc.step_size = 4, 4
+            dcase = {"gen_seed": 3, "F": 11, "H": 288, "W": 272, "chunk_size": 2, "step_size": 4, "modes": {}}
+            for mode in ("alternate", "interpolate", "repeat"):
+                for lowres in (False, True):
+                    ref.video_mode, orc.video_mode = mode, mode
+                    with torch.no_grad():
+                        r = ref.embed(vid, msgs, is_video=True, lowres_attenuation=lowres)
+                        o = orc.embed(vid, msgs, is_video=True, lowres_attenuation=lowres)
+                    e = (r["imgs_w"] - o["imgs_w"]).abs().max().item()
+                    print(card_name, "D", mode, "lowres" if lowres else "fullres", e)
+                    assert e < 1e-6, (mode, lowres, e)
+                    dcase["modes"][f"{mode}/{int(lowres)}"] = {"imgs_w_s": sample(r["imgs_w"]), "imgs_w_stats": stats(r["imgs_w"]), "err": e}
+            ref.video_mode, orc.video_mode = "repeat", "repeat"
+            with torch.no_grad():
+                r = ref.embed(vid, msgs, is_video=True)
+                aggs = {}
+                for agg in ("avg", "squared_avg", "l1norm_avg", "l2norm_avg"):
+                    a_ref = ref.extract_message(r["imgs_w"], aggregation=agg)
+                    a_orc = orc.extract_message(r["imgs_w"], aggregation=agg)
+                    assert (a_ref == a_orc).all(), agg
+                    aggs[agg] = a_ref.clone()
+            dcase["aggregations"] = aggs
+            out["cases"]["vid_modes"] = dcase
         path = os.path.join(ROOT, "tests", "golden", card_name + ".pt")
         torch.save(out, path)
         print(card_name, "->", path, os.path.getsize(path) // 1024, "KiB", f"{time.time()-t0:.1f}s")

@@ -71,3 +71,29 @@ def test_video_mode_and_metrics_restatements():
     assert restate.apply_video_mode(p, 10, 4, "alternate").flatten().tolist() == [1, 0, 0, 0, 2, 0, 0, 0, 3, 0]
     preds = torch.tensor([[0.0, 1.0, -1.0, 2.0]])
     assert restate.bit_accuracy(preds, torch.tensor([[1, 0, 0]])).item() == pytest.approx(2 / 3)
+
+
+@pytest.mark.parametrize("card", ["videoseal_1.0", "pixelseal"])
+def test_oracle_video_modes_lowres_and_aggregations_match_reference_golden(card):
+    """`alternate` / `interpolate` / `repeat` x lowres_attenuation and the extract_message aggregations, against
+    fixtures generated from the unmodified reference (oracle/make_golden.py case D; agreement was bit-exact at generation)"""
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", f"{card}.pt"))
+    spec = restate.spec_from_card(load_card(card))
+    orc = restate.OracleModel(spec, restate.synth_state_dict(spec, seed=gold["seed"]))
+    c = gold["cases"]["vid_modes"]
+    g = torch.Generator().manual_seed(c["gen_seed"])
+    vid = torch.rand(c["F"], 3, c["H"], c["W"], generator=g)
+    msgs = torch.randint(0, 2, (1, spec["nbits"]), generator=g)
+    orc.chunk_size, orc.step_size = c["chunk_size"], c["step_size"]
+    with torch.no_grad():
+        for key, ref in c["modes"].items():
+            mode, lowres = key.split("/")
+            orc.video_mode = mode
+            o = orc.embed(vid, msgs, is_video=True, lowres_attenuation=bool(int(lowres)))
+            assert (_sample(o["imgs_w"]) - ref["imgs_w_s"]).abs().max() < 1e-5, key
+            assert abs(o["imgs_w"].double().mean().item() - ref["imgs_w_stats"]["mean"]) < 1e-6, key
+        orc.video_mode = "repeat"
+        o = orc.embed(vid, msgs, is_video=True)
+        for agg, ref in c["aggregations"].items():
+            assert (orc.extract_message(o["imgs_w"], aggregation=agg) == ref).all(), agg
