@@ -160,6 +160,15 @@ def main(cards=None):
                     assert (a_ref == a_orc).all(), agg
                     aggs[agg] = a_ref.clone()
             dcase["aggregations"] = aggs
+            # image mode with low-resolution attenuation (wam.py:177-180) and a non-default interpolation (antialias off)
+            with torch.no_grad():
+                nointerp = {"mode": "bilinear", "align_corners": False, "antialias": False}
+                r = ref.embed(vid[:2], msgs.repeat(2, 1), is_video=False, lowres_attenuation=True, interpolation=nointerp)
+                o = orc.embed(vid[:2], msgs.repeat(2, 1), is_video=False, lowres_attenuation=True, interpolation=nointerp)
+            e = max((r["imgs_w"] - o["imgs_w"]).abs().max().item(), (r["preds_w"] - o["preds_w"]).abs().max().item())
+            print(card_name, "D image lowres no-aa", e)
+            assert e < 1e-6, e
+            dcase["img_lowres_noaa"] = {"imgs_w_s": sample(r["imgs_w"]), "preds_w_s": sample(r["preds_w"]), "err": e}
             out["cases"]["vid_modes"] = dcase
         path = os.path.join(ROOT, "tests", "golden", card_name + ".pt")
         torch.save(out, path)
