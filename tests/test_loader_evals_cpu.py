@@ -141,3 +141,51 @@ def test_tensor_api_facade_forwards_to_the_model():
     assert m.attenuation == "jnd_1_1" and t.do_attenuation
     bits = t.detect_video_and_aggregate(x, aggregation="squared_avg")
     assert bits.dtype == torch.float32 and m.calls[-1] == ("extract", (2, 3, 16, 16), "squared_avg")
+
+
+def test_streaming_loops_chunking_tail_and_thread_plumbing():
+    """outer loops of the streaming CLI (inference_streaming.py:83-107,146-162) on in-memory RGB24 streams with stand-in clip functions"""
+    import io
+    import numpy as np
+    from videoseal_b200 import streaming
+    W, H, F_, CH = 6, 4, 11, 4
+    rng = np.random.default_rng(0)
+    frames = rng.integers(0, 256, (F_, H, W, 3), dtype=np.uint8)
+    chunks = list(streaming.iter_rawvideo_chunks(io.BytesIO(frames.tobytes()), W, H, CH))
+    assert [len(c) for c in chunks] == [4, 4, 3] and np.array_equal(np.concatenate(chunks), frames)
+    assert list(streaming.iter_rawvideo_chunks(io.BytesIO(b""), W, H, CH)) == []
+
+    class M:
+        def get_random_msg(self):
+            return torch.tensor([[1, 0, 1]])
+
+    seen = []
+
+    def fake_embed(model, clip, msgs):
+        seen.append(len(clip))
+        return 255 - clip
+
+    dst = io.BytesIO()
+    msgs = streaming.embed_stream(M(), io.BytesIO(frames.tobytes()), dst, W, H, CH, clip_fn=fake_embed)
+    assert msgs.tolist() == [[1, 0, 1]] and seen == [4, 4, 3]
+    assert np.array_equal(np.frombuffer(dst.getvalue(), np.uint8).reshape(F_, H, W, 3), 255 - frames)      # order and tail preserved
+
+    def fake_detect(model, clip):
+        return torch.from_numpy(clip.reshape(len(clip), -1)[:, :3].astype(np.float32))
+
+    soft = streaming.detect_stream(M(), io.BytesIO(frames.tobytes()), W, H, CH, clip_fn=fake_detect)       # full chunks only, like the reference
+    assert torch.allclose(soft, torch.from_numpy(frames[:8].reshape(8, -1)[:, :3].astype(np.float32)).mean(0))
+    soft_all = streaming.detect_stream(M(), io.BytesIO(frames.tobytes()), W, H, CH, include_tail=True, clip_fn=fake_detect)
+    assert torch.allclose(soft_all, torch.from_numpy(frames.reshape(F_, -1)[:, :3].astype(np.float32)).mean(0))
+    with pytest.raises(ValueError):
+        streaming.detect_stream(M(), io.BytesIO(frames[:3].tobytes()), W, H, CH, clip_fn=fake_detect)
+
+    def boom(model, clip, msgs):
+        raise RuntimeError("clip failed")
+
+    with pytest.raises(RuntimeError, match="clip failed"):
+        streaming.embed_stream(M(), io.BytesIO(frames.tobytes()), io.BytesIO(), W, H, CH, clip_fn=boom)
+    import shutil
+    if shutil.which("ffmpeg") is None:
+        with pytest.raises(RuntimeError, match="ffmpeg"):
+            streaming.embed_video(M(), "in.mp4", "out.mp4", 8)
