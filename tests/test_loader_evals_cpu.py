@@ -189,3 +189,35 @@ def test_streaming_loops_chunking_tail_and_thread_plumbing():
     if shutil.which("ffmpeg") is None:
         with pytest.raises(RuntimeError, match="ffmpeg"):
             streaming.embed_video(M(), "in.mp4", "out.mp4", 8)
+
+
+def test_full_evaluation_slice_columns_and_values(tmp_path):
+    """evals/full.py identity slice: the reference's column names, perfect decoding of a stand-in model that embeds nothing
+    and returns the message as logits"""
+    from videoseal_b200.evals import full
+
+    class M:
+        def __init__(self):
+            self.msg = torch.tensor([[1, 0, 1, 1, 0, 0, 1, 0]])
+
+        def embed(self, imgs, msgs=None, is_video=True, interpolation=None, lowres_attenuation=False):
+            n = imgs.shape[0]
+            return {"imgs_w": (imgs + 0.01).clamp(0, 1), "msgs": self.msg.repeat(n, 1)}
+
+        def detect(self, imgs, is_video=True):
+            z = self.msg.float() * 2 - 1
+            return {"preds": torch.cat([torch.zeros(len(imgs), 1), z.repeat(len(imgs), 1)], 1)}
+
+        def extract_message(self, imgs, aggregation="avg", interpolation=None):
+            return self.msg.bool()
+
+    items = list(speed.synthetic_items(2, True, 6, 16, 16, "cpu"))
+    rows = full.evaluate(M(), items, True, str(tmp_path), num_frames=4)
+    assert [r["iteration"] for r in rows] == [0, 1] and rows[0]["t"] == 6
+    assert rows[0]["bit_acc_Identity_0"] == 1.0 and rows[0]["capacity_Identity_0"] == pytest.approx(8.0)
+    assert rows[0]["pvalue_Identity_0"] == pytest.approx(0.5 ** 8) and rows[0]["log_pvalue_Identity_0"] == pytest.approx(8 * math.log10(2))
+    assert 39.0 < rows[0]["psnr"] < 41.0                                  # +0.01 everywhere (minus clamping) ~ 40 dB
+    lines = open(tmp_path / "metrics.csv").read().strip().splitlines()
+    assert lines[0].split(",")[:5] == ["iteration", "t", "h", "w", "embed_time"] and len(lines) == 3
+    rows_img = full.evaluate(M(), list(speed.synthetic_items(1, False, 1, 16, 16, "cpu")), False, str(tmp_path / "img"))
+    assert rows_img[0]["bit_acc_Identity_0"] == 1.0 and rows_img[0]["t"] == 1
