@@ -9,6 +9,7 @@
 4. writes small fixtures to tests/golden/<card>.pt: full logits, strided samples + global
    statistics of the image-sized outputs, so the fixtures stay small.
 """
+import math
 import os
 import sys
 import time
@@ -36,6 +37,23 @@ def stats(t: torch.Tensor) -> dict:
     t = t.double()
     return {"mean": t.mean().item(), "absmean": t.abs().mean().item(), "std": t.std().item(),
             "min": t.min().item(), "max": t.max().item()}
+
+
+def structured_image(h: int, w: int, seed: int = 5) -> torch.Tensor:
+    """Deterministic [1,3,h,w] image with natural-image-like statistics for the JND branches the uniform-noise cases never reach:
+    near-black and near-white flat regions (background luminance far below / above 127), smooth gradients (zero contrast
+    masking), hard edges and fine texture (large Sobel responses).  Procedural on purpose: no reference asset is copied."""
+    g = torch.Generator().manual_seed(seed)
+    yy, xx = torch.meshgrid(torch.linspace(0, 1, h), torch.linspace(0, 1, w), indexing="ij")
+    base = 0.5 + 0.45 * torch.sin(2.3 * math.pi * xx + 0.7) * torch.cos(1.7 * math.pi * yy)
+    img = torch.stack([base, 0.5 + 0.45 * torch.sin(3.1 * math.pi * yy), 0.5 + 0.4 * torch.cos(2.0 * math.pi * (xx + yy))])
+    img[:, : h // 5, : w // 4] = 0.01                                   # dark flat block
+    img[:, -h // 5:, -w // 3:] = 0.99                                   # bright flat block
+    disc = ((yy - 0.55) ** 2 + (xx - 0.35) ** 2) < 0.03
+    img[:, disc] = torch.tensor([0.95, 0.9, 0.2])[:, None]              # saturated disc with a hard edge
+    img[:, h // 2: h // 2 + h // 6, w // 2: w // 2 + w // 5] = (torch.rand(3, h // 6, w // 5, generator=g) > 0.5).float()   # binary texture
+    img = img + 0.02 * torch.randn(3, h, w, generator=g)
+    return img.clamp(0, 1).unsqueeze(0)
 
 
 def main(cards=None):
@@ -170,6 +188,23 @@ def main(cards=None):
             assert e < 1e-6, e
             dcase["img_lowres_noaa"] = {"imgs_w_s": sample(r["imgs_w"]), "preds_w_s": sample(r["preds_w"]), "err": e}
             out["cases"]["vid_modes"] = dcase
+        # case E: structured image (dark / bright flats, gradients, edges, texture), image mode at a non-processing size
+        if ref.attenuation is not None and card_name != "chunkyseal":
+            imgs = structured_image(352, 416)
+            g = torch.Generator().manual_seed(6)
+            msgs = torch.randint(0, 2, (1, spec["nbits"]), generator=g)
+            with torch.no_grad():
+                r = ref.embed(imgs, msgs, is_video=False)
+                d = ref.detect(r["imgs_w"], is_video=False)
+                o = orc.embed(imgs, msgs, is_video=False)
+                od = orc.detect(o["imgs_w"], is_video=False)
+                hm = ref.attenuation.heatmaps(imgs)
+            errs = {"imgs_w": (r["imgs_w"] - o["imgs_w"]).abs().max().item(), "preds": (d["preds"] - od["preds"]).abs().max().item(),
+                    "hmaps": (hm - orc.heatmaps(imgs)).abs().max().item()}
+            print(card_name, "E", errs, "hmap range", hm.min().item(), hm.max().item())
+            assert errs["imgs_w"] < 1e-6 and errs["preds"] < 1e-5 and errs["hmaps"] < 1e-7, errs
+            out["cases"]["structured"] = {"H": 352, "W": 416, "msg_seed": 6, "imgs_w_s": sample(r["imgs_w"], 4), "hmaps_s": sample(hm, 4),
+                                          "preds": d["preds"].clone(), "hmaps_stats": stats(hm), "oracle_vs_ref": errs}
         path = os.path.join(ROOT, "tests", "golden", card_name + ".pt")
         torch.save(out, path)
         print(card_name, "->", path, os.path.getsize(path) // 1024, "KiB", f"{time.time()-t0:.1f}s")

@@ -379,3 +379,23 @@ def test_chunkyseal_widths_resized_and_video(ck):
         assert (model.extract_message(out["imgs_w"]).cpu() == orc.extract_message(ref["imgs_w"])).all()
     finally:
         model.chunk_size, model.step_size, orc.chunk_size, orc.step_size = old
+
+
+@pytest.mark.parametrize("card", ["videoseal_1.0", "pixelseal"])
+def test_structured_image_against_reference_golden(card, v1, px):
+    """natural-image-like statistics (dark / bright flats, gradients, hard edges, binary texture): the JND heat-map spans
+    6e-5 .. 0.127 here; fixture from the unmodified reference (oracle/make_golden.py case E)"""
+    from oracle.make_golden import structured_image
+    model, orc, spec = v1 if card == "videoseal_1.0" else px
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", f"{card}.pt"))
+    c = gold["cases"]["structured"]
+    imgs = structured_image(c["H"], c["W"])
+    msgs = torch.randint(0, 2, (1, spec["nbits"]), generator=torch.Generator().manual_seed(c["msg_seed"]))
+    hm = model.attenuation.heatmaps(imgs.cuda()).cpu() if hasattr(model.attenuation, "heatmaps") else None
+    if hm is not None:
+        assert (hm[..., ::4, ::4] - c["hmaps_s"]).abs().max().item() <= 1e-5
+    out = model.embed(imgs.cuda(), msgs, is_video=False)
+    assert (out["imgs_w"].cpu()[..., ::4, ::4] - c["imgs_w_s"]).abs().max().item() <= PIX_TOL
+    det = model.detect(out["imgs_w"], is_video=False)["preds"].cpu()
+    rel, flips, _ = logits_ok(det, c["preds"])
+    assert rel <= LOGIT_RTOL and flips == 0, (rel, flips)

@@ -101,3 +101,24 @@ def test_oracle_video_modes_lowres_and_aggregations_match_reference_golden(card)
         o = orc.embed(vid, msgs, is_video=True)
         for agg, ref in c["aggregations"].items():
             assert (orc.extract_message(o["imgs_w"], aggregation=agg) == ref).all(), agg
+
+
+@pytest.mark.parametrize("card", ["videoseal_1.0", "pixelseal"])
+def test_oracle_structured_image_matches_reference_golden(card):
+    """JND branches that uniform noise never reaches (near-black / near-white flats, zero-gradient regions, hard edges):
+    heat-map range 6e-5 .. 0.127 instead of 0.005 .. 0.117 (oracle/make_golden.py case E)"""
+    from oracle.make_golden import structured_image
+    gold = torch.load(os.path.join(ROOT, "tests", "golden", f"{card}.pt"))
+    spec = restate.spec_from_card(load_card(card))
+    orc = restate.OracleModel(spec, restate.synth_state_dict(spec, seed=gold["seed"]))
+    c = gold["cases"]["structured"]
+    imgs = structured_image(c["H"], c["W"])
+    msgs = torch.randint(0, 2, (1, spec["nbits"]), generator=torch.Generator().manual_seed(c["msg_seed"]))
+    with torch.no_grad():
+        o = orc.embed(imgs, msgs, is_video=False)
+        d = orc.detect(o["imgs_w"], is_video=False)
+        hm = orc.heatmaps(imgs)
+    assert (hm[..., ::4, ::4] - c["hmaps_s"]).abs().max() < 1e-7
+    assert hm.min().item() < 1e-3 and hm.max().item() > 0.12
+    assert (o["imgs_w"][..., ::4, ::4] - c["imgs_w_s"]).abs().max() < 1e-5
+    assert (d["preds"] - c["preds"]).abs().max() < 1e-4
