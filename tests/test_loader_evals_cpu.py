@@ -2,6 +2,7 @@
 reference), the metrics of the evaluation slice (8(f)4, evals/metrics.py) and the speed tester's bookkeeping."""
 import argparse
 import math
+import os
 
 import pytest
 import torch
@@ -221,3 +222,56 @@ def test_full_evaluation_slice_columns_and_values(tmp_path):
     assert lines[0].split(",")[:5] == ["iteration", "t", "h", "w", "embed_time"] and len(lines) == 3
     rows_img = full.evaluate(M(), list(speed.synthetic_items(1, False, 1, 16, 16, "cpu")), False, str(tmp_path / "img"))
     assert rows_img[0]["bit_acc_Identity_0"] == 1.0 and rows_img[0]["t"] == 1
+
+
+def test_checkpoint_loader_never_falls_back_to_the_full_unpickler(tmp_path):
+    """a checkpoint the safe unpickler rejects must raise, not execute"""
+    import pickle
+    from videoseal_b200 import cfg
+
+    class Boom:
+        def __reduce__(self):
+            return (os.system, ("echo pwned > %s" % (tmp_path / "pwned"),))
+
+    p = tmp_path / "evil.pth"
+    torch.save({"args": Boom(), "model": {}}, p)
+    with pytest.raises((pickle.UnpicklingError, RuntimeError, Exception)) as ei:
+        cfg.get_config_from_checkpoint(str(p))
+    assert not (tmp_path / "pwned").exists(), "the malicious reducer ran"
+    assert "pwned" not in str(ei.value) or True
+
+
+def test_embed_stream_surfaces_a_dead_writer_instead_of_deadlocking():
+    """the encoder side dies on its 2nd (slow) write while the output queue is full"""
+    import io
+    import threading
+    import time
+    import numpy as np
+    from videoseal_b200 import streaming
+
+    w, h, cs, n = 8, 8, 2, 40
+    src = io.BytesIO(np.zeros((n, h, w, 3), np.uint8).tobytes())
+
+    class Dst:
+        def __init__(self):
+            self.n = 0
+
+        def write(self, b):
+            self.n += 1
+            if self.n >= 2:
+                time.sleep(0.3)
+                raise BrokenPipeError("encoder went away")
+
+    done = {}
+
+    def run():
+        try:
+            streaming.embed_stream(None, src, Dst(), w, h, cs, msgs=torch.zeros(1, 4), prefetch=1, clip_fn=lambda m, c, ms: c)
+        except BaseException as e:
+            done["err"] = e
+
+    t = threading.Thread(target=run, daemon=True)
+    t.start()
+    t.join(timeout=20)
+    assert not t.is_alive(), "embed_stream deadlocked on a full queue with a dead writer"
+    assert isinstance(done.get("err"), BrokenPipeError)

@@ -138,10 +138,12 @@ def get_config_from_checkpoint(ckpt_path) -> dict:
     """utils/cfg.py:50-85 of the reference: a raw training checkpoint carries its `args`; the embedder / extractor
     hyper-parameters are the presets named by args.embedder_model / args.extractor_model in the YAML files named by
     args.embedder_config / args.extractor_config (cwd first, then this package).  Returns a card-shaped dict."""
-    try:
+    # the safe unpickler only, like the reference (utils/cfg.py:62,148): a checkpoint is untrusted input.  Training scripts save
+    # `args` as an argparse.Namespace, which is allow-listed for the duration of the load (a plain attribute bag, no code);
+    # anything else the safe unpickler rejects (e.g. an OmegaConf container) is an error, never a silent full-pickle retry.
+    import argparse
+    with torch.serialization.safe_globals([argparse.Namespace]):
         checkpoint = torch.load(ckpt_path, map_location="cpu", weights_only=True)
-    except Exception:   # args saved as a Namespace / DictConfig object need the full unpickler
-        checkpoint = torch.load(ckpt_path, map_location="cpu", weights_only=False)
     if "args" not in checkpoint:
         raise KeyError(f"{ckpt_path} holds no 'args': not a training checkpoint (use a model card for released weights)")
     args = _plain(checkpoint["args"])

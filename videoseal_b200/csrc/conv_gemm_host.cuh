@@ -9,8 +9,11 @@
 
 namespace vsb {
 
+// status codes of include/vsb200.h (static_assert-ed equal in vsb200.cu): every throw site names its code, the C ABI returns it
+enum : int { kErrInvalid = -1, kErrUnsupported = -2, kErrCuda = -3, kErrState = -4 };
 struct Error : std::runtime_error {
-  using std::runtime_error::runtime_error;
+  int code;
+  explicit Error(const std::string& m, int c = kErrInvalid) : std::runtime_error(m), code(c) {}
 };
 
 #define VSB_CHECK(cond, msg)                                                                      \
@@ -22,7 +25,7 @@ struct Error : std::runtime_error {
   do {                                                                                            \
     cudaError_t _e = (expr);                                                                      \
     if (_e != cudaSuccess)                                                                        \
-      throw ::vsb::Error(std::string("CUDA error ") + cudaGetErrorString(_e) + " in " #expr " at " __FILE__ ":" + std::to_string(__LINE__)); \
+      throw ::vsb::Error(std::string("CUDA error ") + cudaGetErrorString(_e) + " in " #expr " at " __FILE__ ":" + std::to_string(__LINE__), ::vsb::kErrCuda); \
   } while (0)
 
 typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
@@ -378,19 +381,19 @@ inline void launch(const ConvGemmOp& op, cudaStream_t st) {
     case LD_GATHER_CONV:
       if (a == ACT_NONE) launch_one<LD_GATHER_CONV, ACT_NONE>(op, st);
       else if (a == ACT_RELU) launch_one<LD_GATHER_CONV, ACT_RELU>(op, st);
-      else throw Error("gather conv: unsupported activation");
+      else throw Error("gather conv: unsupported activation", kErrUnsupported);
       break;
     case LD_HALO_UPS:
       if (a == ACT_RELU) launch_one<LD_HALO_UPS, ACT_RELU>(op, st);
-      else throw Error("halo ups: unsupported activation");
+      else throw Error("halo ups: unsupported activation", kErrUnsupported);
       break;
     case LD_HALO_CONV3:
       if (a == ACT_RELU) launch_one<LD_HALO_CONV3, ACT_RELU>(op, st);
-      else throw Error("halo conv3: unsupported activation");
+      else throw Error("halo conv3: unsupported activation", kErrUnsupported);
       break;
     case LD_GATHER_SCALE:
       if (a == ACT_NONE) launch_one<LD_GATHER_SCALE, ACT_NONE>(op, st);
-      else throw Error("gather scale: unsupported activation");
+      else throw Error("gather scale: unsupported activation", kErrUnsupported);
       break;
     default: throw Error("bad loader");
   }

@@ -5,6 +5,7 @@
 #include <functional>
 #include <map>
 #include <memory>
+#include <mutex>
 #include <string>
 #include <vector>
 
@@ -12,6 +13,7 @@
 #include "conv_gemm_host.cuh"
 #include "conv3_direct_host.cuh"
 #include "pointwise.cuh"
+#include "resize_blend.cuh"
 
 namespace vsb {
 
@@ -164,10 +166,26 @@ inline ResampleHost make_resample(int in, int out, bool antialias) {
 struct ResampleDev {
   DevicePool pool;
   ResampleTab tab;
+  // geometry of resize_sep_kernel for this (in -> out) pair: output rows per block, input rows per staging round, the largest
+  // number of input rows one block touches, dynamic shared memory
+  int toy = 8, gstage = 1, rin_max = 1;
+  size_t smem = 0;
   ResampleDev(int ih, int iw, int oh, int ow, bool aa) {
     ResampleHost y = make_resample(ih, oh, aa), x = make_resample(iw, ow, aa);
     tab.ystart = pool.upload(y.start); tab.ycnt = pool.upload(y.cnt); tab.yw = pool.upload(y.w); tab.maxt_y = y.maxt;
     tab.xstart = pool.upload(x.start); tab.xcnt = pool.upload(x.cnt); tab.xw = pool.upload(x.w); tab.maxt_x = x.maxt;
+    const int iwp = (iw + 3) & ~3;
+    gstage = std::max(1, std::min(8, (24 * 1024) / (iwp * 4)));
+    for (toy = 8; toy >= 1; toy >>= 1) {
+      rin_max = 1;
+      for (int o0 = 0; o0 < oh; o0 += toy) {
+        const int o1 = std::min(oh, o0 + toy) - 1;
+        rin_max = std::max(rin_max, y.start[o1] + y.cnt[o1] - y.start[o0]);
+      }
+      smem = ((size_t)rin_max * ow + (size_t)gstage * iwp) * sizeof(float);
+      if (smem <= 100 * 1024 || toy == 1) break;
+    }
+    if (smem > 200 * 1024) throw Error("resize: image too wide for the shared-memory resample kernel (not implemented)", kErrUnsupported);
   }
 };
 
@@ -177,6 +195,7 @@ class Model {
   std::map<std::string, HostTensor> sd;
   bool finalized = false;
   int device = -1, num_sms = 0;
+  std::recursive_mutex mu;   // serialises the C entry points of one handle (vsb200.cu VSB_MODEL_SCOPE)
   DevicePool wpool;
   static constexpr int kMaxBatch = 64;
 
@@ -205,7 +224,7 @@ class Model {
 
   // grow-only device staging for the host-buffer entry points (no cudaMalloc on the steady-state path)
   struct Staging { void* p = nullptr; size_t cap = 0; };
-  Staging staging[6];
+  Staging staging[8];   // 0-5: host entry points; 6-7: low-resolution attenuation scratch
   void* stage(int slot, size_t bytes) {
     Staging& s = staging[slot];
     if (bytes > s.cap) {
@@ -231,7 +250,7 @@ class Model {
 
   const HostTensor& get(const std::string& k) const {
     auto it = sd.find(k);
-    if (it == sd.end()) throw Error("missing checkpoint tensor: " + k);
+    if (it == sd.end()) throw Error("missing checkpoint tensor: " + k, kErrState);
     return it->second;
   }
 
@@ -399,16 +418,16 @@ class Model {
   }
 
   void finalize(int dev) {
-    VSB_CHECK(!finalized, "already finalized");
+    if (finalized) throw Error("model already finalized", kErrState);
     int count = 0;
-    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) throw Error("no CUDA device: libvsb200 has no CPU fallback");
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count == 0) throw Error("no CUDA device: libvsb200 has no CPU fallback", kErrCuda);
     VSB_CUDA(cudaSetDevice(dev));
     cudaDeviceProp prop;
     VSB_CUDA(cudaGetDeviceProperties(&prop, dev));
-    if (prop.major != 10) throw Error("libvsb200 is built for sm_100a only (found sm_" + std::to_string(prop.major) + std::to_string(prop.minor) + ")");
+    if (prop.major != 10) throw Error("libvsb200 is built for sm_100a only (found sm_" + std::to_string(prop.major) + std::to_string(prop.minor) + ")", kErrUnsupported);
     device = dev;
     num_sms = prop.multiProcessorCount;
-    if (d.unet_act != 0 || d.unet_norm != 0) throw Error("unsupported card: only BatchNorm+ReLU U-Nets are implemented on the GPU path");
+    if (d.unet_act != 0 || d.unet_norm != 0) throw Error("unsupported card: only BatchNorm+ReLU U-Nets are implemented on the GPU path", kErrUnsupported);
     VSB_CHECK(d.unet_levels >= 2 && d.unet_levels <= 6, "unet levels");
     VSB_CHECK(d.unet_in_ch == 1 || d.unet_in_ch == 3, "unet in_channels must be 1 or 3");
     VSB_CHECK(d.unet_out_ch >= 1 && d.unet_out_ch <= 3, "unet out_channels must be <= 3");
@@ -884,7 +903,7 @@ class Model {
               const size_t smem_w = (size_t)kDwStrip * Cc * sizeof(float);
               static bool attr = false;
               if (!attr) { VSB_CUDA(cudaFuncSetAttribute(dwconv7_ln_wide_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
-              if (smem_w > 200 * 1024) throw Error("dwconv7: more than 6400 channels is not implemented");
+              if (smem_w > 200 * 1024) throw Error("dwconv7: more than 6400 channels is not implemented", kErrUnsupported);
               dwconv7_ln_wide_kernel<<<(unsigned)nstrips, threads, smem_w, st>>>(xin, B, H, H, Cc, ldc, dww, dwb, lw, lb, a, ldc);
               VSB_CUDA(cudaGetLastError());
               return;
@@ -907,7 +926,7 @@ class Model {
             const int C2 = Cc / 2;
             int spb = 1;
             for (int s2 = 1; s2 <= 4; s2 *= 2) if ((s2 * C2) % 32 == 0 && s2 * C2 <= 512) { spb = s2; break; }
-            if (spb * C2 > 512) throw Error("dwconv7: C/2 > 512 threads is not implemented (unsupported chunky extractor width)");
+            if (spb * C2 > 512) throw Error("dwconv7: C/2 > 512 threads is not implemented (unsupported chunky extractor width)", kErrUnsupported);
             const long blocks = (nstrips + spb - 1) / spb;
             const size_t smem_s = (size_t)spb * kDwStrip * Cc * sizeof(float);
             static const bool generic_dw = getenv("VSB_DW_GENERIC") != nullptr;
@@ -934,7 +953,7 @@ class Model {
             const int kp = (Cc + 63) / 64;
 #define VSB_DW(KP) dwconv7_ln_kernel<KP><<<(unsigned)blocks, spb * C2, smem_s, st>>>(xin, B, H, H, Cc, Cc, dww, dwb, lw, lb, a, Cc, spb, nstrips)
             if (kp <= 2) VSB_DW(2); else if (kp <= 3) VSB_DW(3); else if (kp <= 6) VSB_DW(6); else if (kp <= 12) VSB_DW(12);
-            else if (kp <= 16) VSB_DW(16); else throw Error("dwconv7: more than 1024 channels is not implemented");
+            else if (kp <= 16) VSB_DW(16); else throw Error("dwconv7: more than 1024 channels is not implemented", kErrUnsupported);
 #undef VSB_DW
             VSB_CUDA(cudaGetLastError());
           }, 1, "cnx.dwconv7_ln." + std::to_string(C) + "@" + std::to_string(hs)});
@@ -1024,27 +1043,45 @@ class Model {
     return ret;
   }
 
-  // gather `n` frames that are `frame_stride` floats apart and resample them to S x S
+  // per-call CUDA-event scope for the launches outside the plans (bench.py roofline leg: vsb_profile_enable)
+  template <class Fn> static void prof_scope(const std::string& name, cudaStream_t st, int launches, Fn&& fn) {
+    if (!g_profile.enabled) { fn(); g_launches += launches; return; }
+    cudaEvent_t a, b;
+    cudaEventCreate(&a); cudaEventCreate(&b);
+    cudaEventRecord(a, st);
+    fn();
+    cudaEventRecord(b, st);
+    g_launches += launches;
+    g_profile.pending.push_back({name, {a, b}});
+  }
+
+  // resample `n` frames that are `frame_stride` floats apart to S x S (one launch, also for strided key frames)
   void resize_frames(const float* src, long frame_stride, int n, int H, int W, float* dst, bool aa, cudaStream_t st) {
     const int S = d.img_size;
     ResampleDev* r = get_resampler(H, W, S, S, aa);
-    if (frame_stride == (long)3 * H * W) {
-      const long total = (long)n * 3 * S * S;
-      const int grid = (int)std::min<long>((total + 255) / 256, 148L * 32);
-      resample_kernel<<<grid, 256, 0, st>>>(src, dst, n * 3, H, W, S, S, r->tab);
-      g_launches += 1;
-    } else {
-      for (int i = 0; i < n; ++i) {
-        const long total = (long)3 * S * S;
-        const int grid = (int)std::min<long>((total + 255) / 256, 148L * 32);
-        resample_kernel<<<grid, 256, 0, st>>>(src + (long)i * frame_stride, dst + (long)i * 3 * S * S, 3, H, W, S, S, r->tab);
-        g_launches += 1;
-      }
+    const int vec = (W % 4 == 0) && (reinterpret_cast<uintptr_t>(src) % 16 == 0) && (frame_stride % 4 == 0);
+    if (n > 16384) {   // gridDim.y limit: split very long frame ranges
+      for (int i = 0; i < n; i += 16384)
+        resize_frames(src + (long)i * frame_stride, frame_stride, std::min(16384, n - i), H, W, dst + (size_t)i * 3 * S * S, aa, st);
+      return;
     }
+    const dim3 grid((S + r->toy - 1) / r->toy, n * 3);
+    static bool attr = false;
+    if (!attr) {
+      VSB_CUDA(cudaFuncSetAttribute(resize_sep_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      VSB_CUDA(cudaFuncSetAttribute(resize_sep_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      VSB_CUDA(cudaFuncSetAttribute(resize_sep_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr = true;
+    }
+    prof_scope("pw.resize." + std::to_string(H) + "x" + std::to_string(W) + "@" + std::to_string(n), st, 1, [&] {
+      if (r->tab.maxt_x <= 2) resize_sep_kernel<2><<<grid, 256, r->smem, st>>>(src, frame_stride, dst, H, W, S, S, r->tab, r->toy, r->gstage, r->rin_max, vec);
+      else if (r->tab.maxt_x <= 8) resize_sep_kernel<8><<<grid, 256, r->smem, st>>>(src, frame_stride, dst, H, W, S, S, r->tab, r->toy, r->gstage, r->rin_max, vec);
+      else resize_sep_kernel<0><<<grid, 256, r->smem, st>>>(src, frame_stride, dst, H, W, S, S, r->tab, r->toy, r->gstage, r->rin_max, vec);
+    });
     VSB_CUDA(cudaGetLastError());
   }
 
-  void check_ready() const { if (!finalized) throw Error("model not finalized"); }
+  void check_ready() const { if (!finalized) throw Error("model not finalized", kErrState); }
 
   // ---- streaming host path: embed + detect of HOST frames with the PCIe copies overlapped with compute
   cudaStream_t s_in = nullptr, s_cmp = nullptr, s_out = nullptr;
@@ -1052,7 +1089,6 @@ class Model {
   void embed_detect_host(const float* imgs_h, const uint8_t* msgs_h, int n_msgs, float* imgs_w_h, float* logits_h, int F, int H, int W,
                          int step, int video_mode, int chunk_keys, float scaling_i, float scaling_w, int flags) {
     check_ready();
-    VSB_CUDA(cudaSetDevice(device));
     if (!s_in) {
       VSB_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
       VSB_CUDA(cudaStreamCreateWithFlags(&s_cmp, cudaStreamNonBlocking));
@@ -1064,32 +1100,43 @@ class Model {
     float* out = (float*)stage(1, (size_t)F * fpx * sizeof(float));
     float* lg = (float*)stage(2, (size_t)F * NO * sizeof(float));
     uint8_t* msgs = (uint8_t*)stage(3, (size_t)n_msgs * d.nbits + 256);
-    // chunks of ~32 frames (multiples of `step` so that key-frame groups stay whole)
-    // (and of whole reference chunks in 'interpolate' mode, where neighbouring keys of one chunk are mixed)
-    int ch = 32;
+    // Pipeline (three streams): frames travel in SLICES of ~32 (multiples of `step`, and of whole reference chunks in
+    // 'interpolate' mode where neighbouring keys of one chunk are mixed, so that key-frame groups stay whole); embed() runs per
+    // slice as soon as its copy has landed, the D2H of a slice's watermarked frames starts as soon as its embed() is done and
+    // runs under the following compute; detect() runs once per GROUP of two slices (64 frames: full-size extractor batches).
+    // Exposed copies: the first slice in and the last group's logits out.
+    int sl = 32;
     const int unit = (video_mode == VSB_VIDEO_INTERPOLATE && step > 1) ? step * std::max(1, chunk_keys) : step;
-    if (ch % unit) ch = ((ch + unit - 1) / unit) * unit;
-    const int nch = (F + ch - 1) / ch;
-    while ((int)ev_in.size() < nch) {
+    if (sl % unit) sl = ((sl + unit - 1) / unit) * unit;
+    const int nsl = (F + sl - 1) / sl;
+    while ((int)ev_in.size() < nsl + 1) {
       cudaEvent_t a, b;
       VSB_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
       VSB_CUDA(cudaEventCreateWithFlags(&b, cudaEventDisableTiming));
       ev_in.push_back(a); ev_cmp.push_back(b);
     }
     VSB_CUDA(cudaMemcpyAsync(msgs, msgs_h, (size_t)n_msgs * d.nbits, cudaMemcpyHostToDevice, s_in));
-    for (int k = 0; k < nch; ++k) {
-      const int f0 = k * ch, n = std::min(ch, F - f0);
+    for (int k = 0; k < nsl; ++k) {       // all input copies are queued up front: s_in runs ahead of the compute
+      const int f0 = k * sl, n = std::min(sl, F - f0);
       VSB_CUDA(cudaMemcpyAsync(imgs + (size_t)f0 * fpx, imgs_h + (size_t)f0 * fpx, (size_t)n * fpx * sizeof(float), cudaMemcpyHostToDevice, s_in));
       VSB_CUDA(cudaEventRecord(ev_in[k], s_in));
+    }
+    for (int k = 0; k < nsl; ++k) {
+      const int f0 = k * sl, n = std::min(sl, F - f0);
       VSB_CUDA(cudaStreamWaitEvent(s_cmp, ev_in[k], 0));
       const uint8_t* mk = msgs + (n_msgs == 1 ? 0 : (size_t)f0 * d.nbits);
       embed(imgs + (size_t)f0 * fpx, mk, n_msgs == 1 ? 1 : n, out + (size_t)f0 * fpx, nullptr, n, H, W, step, video_mode, chunk_keys, scaling_i,
             scaling_w, flags, s_cmp);
-      detect(out + (size_t)f0 * fpx, lg + (size_t)f0 * NO, n, H, W, flags & VSB_FLAG_RESIZE_NO_AA, s_cmp);
       VSB_CUDA(cudaEventRecord(ev_cmp[k], s_cmp));
       VSB_CUDA(cudaStreamWaitEvent(s_out, ev_cmp[k], 0));
       VSB_CUDA(cudaMemcpyAsync(imgs_w_h + (size_t)f0 * fpx, out + (size_t)f0 * fpx, (size_t)n * fpx * sizeof(float), cudaMemcpyDeviceToHost, s_out));
-      VSB_CUDA(cudaMemcpyAsync(logits_h + (size_t)f0 * NO, lg + (size_t)f0 * NO, (size_t)n * NO * sizeof(float), cudaMemcpyDeviceToHost, s_out));
+      if ((k & 1) == 1 || k == nsl - 1) {   // a group is complete: detect its frames in one batch
+        const int g0 = (k & ~1) * sl, gn = std::min(F, (k + 1) * sl) - g0;
+        detect(out + (size_t)g0 * fpx, lg + (size_t)g0 * NO, gn, H, W, flags & VSB_FLAG_RESIZE_NO_AA, s_cmp);
+        VSB_CUDA(cudaEventRecord(ev_cmp[nsl], s_cmp));
+        VSB_CUDA(cudaStreamWaitEvent(s_out, ev_cmp[nsl], 0));
+        VSB_CUDA(cudaMemcpyAsync(logits_h + (size_t)g0 * NO, lg + (size_t)g0 * NO, (size_t)gn * NO * sizeof(float), cudaMemcpyDeviceToHost, s_out));
+      }
     }
     VSB_CUDA(cudaStreamSynchronize(s_out));
   }
@@ -1100,7 +1147,6 @@ class Model {
   void frames_host_u8(const uint8_t* in_h, const uint8_t* msgs_h, int n_msgs, uint8_t* out_h, float* logits_h, int F, int H, int W,
                       int step, int video_mode, int chunk_keys, float scaling_i, float scaling_w, int flags) {
     check_ready();
-    VSB_CUDA(cudaSetDevice(device));
     if (!s_in) {
       VSB_CUDA(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
       VSB_CUDA(cudaStreamCreateWithFlags(&s_cmp, cudaStreamNonBlocking));
@@ -1196,7 +1242,7 @@ class Model {
     const bool same = (H == S && W == S);
     const bool aa = !(flags & VSB_FLAG_RESIZE_NO_AA);
     const bool use_jnd = !(flags & VSB_FLAG_NO_ATTENUATION) && d.jnd_in_ch != 0;
-    if (use_jnd && !(d.jnd_in_ch == 1 && d.jnd_out_ch == 1)) throw Error("only the jnd_1_1 attenuation is implemented on the GPU path");
+    if (use_jnd && !(d.jnd_in_ch == 1 && d.jnd_out_ch == 1)) throw Error("only the jnd_1_1 attenuation is implemented on the GPU path", kErrUnsupported);
     const bool lowres = use_jnd && (flags & VSB_FLAG_LOWRES_ATTN);
     const long fstride = (long)3 * H * W;
     const int nkeys = (F + step - 1) / step;
@@ -1204,12 +1250,22 @@ class Model {
     for (int k0 = 0; k0 < nkeys; k0 += kbatch) {
       const int nk = std::min(kbatch, nkeys - k0);
       const int f0 = k0 * step, f1 = std::min(F, (k0 + nk) * step);
+      const int nf = f1 - f0;
       Plan* pl = get_embed_plan(nk);
       const float* x = imgs + (size_t)f0 * fstride;
+      // low-resolution attenuation needs EVERY frame of the chunk at processing size (wam.py:177-180, videoseal.py:321-324):
+      // resample them once into a grow-only scratch buffer of the model (no allocation or synchronisation on the steady-state
+      // path) and take the key frames from there
+      const float* frames_res = x;
+      if (lowres && !same) {
+        float* fr = (float*)stage(6, (size_t)nf * 3 * S * S * sizeof(float));
+        resize_frames(x, fstride, nf, H, W, fr, aa, st);
+        frames_res = fr;
+      }
       if (!same || step != 1) {
-        // key frames -> contiguous processing-size RGB batch (resize_frames handles the frame stride)
-        if (same) {
-          VSB_CUDA(cudaMemcpy2DAsync(pl->x_res, (size_t)3 * S * S * sizeof(float), x, (size_t)step * fstride * sizeof(float),
+        // key frames -> contiguous processing-size RGB batch
+        if (same || lowres) {
+          VSB_CUDA(cudaMemcpy2DAsync(pl->x_res, (size_t)3 * S * S * sizeof(float), frames_res, (size_t)step * 3 * S * S * sizeof(float),
                                      (size_t)3 * S * S * sizeof(float), nk, cudaMemcpyDeviceToDevice, st));
         } else {
           resize_frames(x, (long)step * fstride, nk, H, W, pl->x_res, aa, st);
@@ -1218,70 +1274,62 @@ class Model {
       }
       run_unet(x, msgs + (n_msgs == 1 ? 0 : (size_t)k0 * d.nbits), n_msgs == 1 ? 0 : d.nbits, nk, st);
       const float* delta = pl->delta;
-      int bstep = step, balt = (video_mode == VSB_VIDEO_ALTERNATE) ? 1 : 0;
-      float* lowres_buf = nullptr;
-      const int nf = f1 - f0;
-      if (lowres) {
-        // hmaps at processing resolution on every frame of the chunk (wam.py:177-180, videoseal.py:321-324)
-        float* fr = nullptr;
-        DevicePool tmp;  // freed after the stream is synchronised below
-        const float* frames_res = imgs + (size_t)f0 * fstride;
-        if (!same) {
-          fr = tmp.alloc_n<float>((size_t)nf * 3 * S * S);
-          resize_frames(imgs + (size_t)f0 * fstride, fstride, nf, H, W, fr, aa, st);
-          frames_res = fr;
-        }
-        lowres_buf = tmp.alloc_n<float>((size_t)nf * d.unet_out_ch * S * S);
-        dim3 grid((S + kBlendTW - 1) / kBlendTW, (S + kBlendTH - 1) / kBlendTH, nf);
-        jnd_lowres_kernel<<<grid, 256, 0, st>>>(frames_res, delta, lowres_buf, S, S, d.unet_out_ch, step, balt, bint);
-        g_launches += 1;
-        BlendParams bp;
-        memset(&bp, 0, sizeof(bp));
-        bp.imgs = imgs + (size_t)f0 * fstride; bp.delta = lowres_buf; bp.imgs_w = imgs_w + (size_t)f0 * fstride;
-        bp.preds_w = preds_w ? preds_w + (size_t)f0 * d.unet_out_ch * H * W : nullptr;
-        bp.F = nf; bp.H = H; bp.W = W; bp.PH = S; bp.PW = S; bp.CD = d.unet_out_ch; bp.step = 1; bp.alternate = 0;
-        bp.use_jnd = 0; bp.clamp = (flags & VSB_FLAG_CLAMP) ? 1 : 0; bp.identity_resample = same ? 1 : 0;
-        bp.scaling_i = scaling_i; bp.scaling_w = scaling_w;
-        if (up) bp.tab = up->tab;
-        launch_blend(bp, st);
-        VSB_CUDA(cudaStreamSynchronize(st));  // tmp buffers die here (lowres path is not the throughput path)
-        continue;
-      }
+      const int balt = (video_mode == VSB_VIDEO_ALTERNATE) ? 1 : 0;
       BlendParams bp;
       memset(&bp, 0, sizeof(bp));
-      bp.imgs = imgs + (size_t)f0 * fstride; bp.delta = delta; bp.imgs_w = imgs_w + (size_t)f0 * fstride;
+      bp.imgs = imgs + (size_t)f0 * fstride; bp.imgs_w = imgs_w + (size_t)f0 * fstride;
       bp.preds_w = preds_w ? preds_w + (size_t)f0 * d.unet_out_ch * H * W : nullptr;
-      bp.F = nf; bp.H = H; bp.W = W; bp.PH = S; bp.PW = S; bp.CD = d.unet_out_ch; bp.step = bstep; bp.alternate = balt;
-      bp.interp_chunk = bint;
-      bp.use_jnd = use_jnd ? 1 : 0; bp.clamp = (flags & VSB_FLAG_CLAMP) ? 1 : 0; bp.identity_resample = same ? 1 : 0;
+      bp.F = nf; bp.H = H; bp.W = W; bp.PH = S; bp.PW = S; bp.CD = d.unet_out_ch;
+      bp.clamp = (flags & VSB_FLAG_CLAMP) ? 1 : 0; bp.identity_resample = same ? 1 : 0;
       bp.scaling_i = scaling_i; bp.scaling_w = scaling_w;
       if (up) bp.tab = up->tab;
+      if (lowres) {
+        // per-frame attenuated delta at processing size: out[f] = hmap(frames_res[f]) * delta(keys of f); then a plain blend
+        float* lowres_buf = (float*)stage(7, (size_t)nf * d.unet_out_ch * S * S * sizeof(float));
+        VSB_CHECK(nf <= 65535, "too many frames per key-frame batch");
+        dim3 grid((S + kBlendTW - 1) / kBlendTW, (S + kBlendTH - 1) / kBlendTH, nf);
+        const int CD = d.unet_out_ch;
+        prof_scope("pw.jnd_lowres@" + std::to_string(nf), st, 1,
+                   [&] { jnd_lowres_kernel<<<grid, 256, 0, st>>>(frames_res, delta, lowres_buf, S, S, CD, step, balt, bint); });
+        VSB_CUDA(cudaGetLastError());
+        bp.delta = lowres_buf; bp.step = 1; bp.alternate = 0; bp.interp_chunk = 0; bp.use_jnd = 0;
+      } else {
+        bp.delta = delta; bp.step = step; bp.alternate = balt; bp.interp_chunk = bint; bp.use_jnd = use_jnd ? 1 : 0;
+      }
       launch_blend(bp, st);
     }
   }
 
   static void launch_blend(const BlendParams& bp, cudaStream_t st) {
-    dim3 grid((bp.W + kBlendTW - 1) / kBlendTW, (bp.H + kBlendTH - 1) / kBlendTH, bp.F);
+    VSB_CHECK(bp.F <= 65535, "too many frames per blend launch");
+    dim3 grid((bp.W + kB2TW - 1) / kB2TW, (bp.H + kB2TH - 1) / kB2TH, bp.F);
     const bool vec = (bp.W % 4 == 0) && ((reinterpret_cast<uintptr_t>(bp.imgs) | reinterpret_cast<uintptr_t>(bp.imgs_w) |
                                           reinterpret_cast<uintptr_t>(bp.preds_w)) % 16 == 0);
-    if (vec) jnd_blend_kernel<4><<<grid, 256, 0, st>>>(bp);
-    else jnd_blend_kernel<1><<<grid, 256, 0, st>>>(bp);
-    g_launches += 1;
+    // delta read in place, or through <= 2 taps per axis (plain bilinear up-scale: every input at least as large as the processing size)
+    const bool fastup = bp.identity_resample || (bp.tab.maxt_x <= 2 && bp.tab.maxt_y <= 2);
+    static bool attr = false;
+    if (!attr) {
+      VSB_CUDA(cudaFuncSetAttribute(jnd_blend2_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kB2Smem));
+      VSB_CUDA(cudaFuncSetAttribute(jnd_blend2_kernel<4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kB2Smem));
+      VSB_CUDA(cudaFuncSetAttribute(jnd_blend2_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kB2Smem));
+      VSB_CUDA(cudaFuncSetAttribute(jnd_blend2_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kB2Smem));
+      attr = true;
+    }
+    prof_scope(std::string(bp.use_jnd ? "pw.jnd_blend." : "pw.blend.") + std::to_string(bp.H) + "x" + std::to_string(bp.W) + "@" + std::to_string(bp.F) +
+                   (bp.preds_w ? "+preds" : ""), st, 1, [&] {
+      if (vec) { if (fastup) jnd_blend2_kernel<4, 1><<<grid, 256, kB2Smem, st>>>(bp); else jnd_blend2_kernel<4, 0><<<grid, 256, kB2Smem, st>>>(bp); }
+      else     { if (fastup) jnd_blend2_kernel<1, 1><<<grid, 256, kB2Smem, st>>>(bp); else jnd_blend2_kernel<1, 0><<<grid, 256, kB2Smem, st>>>(bp); }
+    });
     VSB_CUDA(cudaGetLastError());
   }
 
   void jnd_heatmaps(const float* imgs, float* hmaps, int F, int H, int W, cudaStream_t st) {
-    // heat-map only: blend kernel with a constant delta of 1 would need an extra buffer; reuse jnd_lowres_kernel:
-    // out[f] = hmap(imgs[f]) * delta[f/step] with delta == 1
-    DevicePool tmp;
-    float* ones = tmp.alloc_n<float>((size_t)H * W);
-    std::vector<float> h((size_t)H * W, 1.0f);
-    VSB_CUDA(cudaMemcpyAsync(ones, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice, st));
+    // heat-map only (operator seam, modules/jnd.py:80-108): jnd_lowres_kernel with delta == nullptr writes hmap * 1
+    VSB_CHECK(F <= 65535, "too many frames");
     dim3 grid((W + kBlendTW - 1) / kBlendTW, (H + kBlendTH - 1) / kBlendTH, F);
-    jnd_lowres_kernel<<<grid, 256, 0, st>>>(imgs, ones, hmaps, H, W, 1, 1 << 30, 0, 0);
+    jnd_lowres_kernel<<<grid, 256, 0, st>>>(imgs, nullptr, hmaps, H, W, 1, 1, 0, 0);
     g_launches += 1;
     VSB_CUDA(cudaGetLastError());
-    VSB_CUDA(cudaStreamSynchronize(st));
   }
 
   void detect(const float* imgs, float* logits, int F, int H, int W, int flags, cudaStream_t st) {

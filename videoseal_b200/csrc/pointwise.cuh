@@ -25,27 +25,7 @@ struct ResampleTab {
   int maxt_y, maxt_x;
 };
 
-// in: [N, C, IH, IW] fp32 -> out: [N, C, OH, OW] fp32
-__global__ void resample_kernel(const float* __restrict__ in, float* __restrict__ out, int NC, int IH, int IW, int OH, int OW,
-                                ResampleTab t) {
-  const long total = (long)NC * OH * OW;
-  for (long idx = (long)blockIdx.x * blockDim.x + threadIdx.x; idx < total; idx += (long)gridDim.x * blockDim.x) {
-    const int ox = (int)(idx % OW);
-    const long r = idx / OW;
-    const int oy = (int)(r % OH);
-    const long nc = r / OH;
-    const float* src = in + nc * IH * IW;
-    const int ys = t.ystart[oy], yc = t.ycnt[oy], xs = t.xstart[ox], xc = t.xcnt[ox];
-    float acc = 0.f;
-    for (int j = 0; j < yc; ++j) {
-      const float* row = src + (long)(ys + j) * IW + xs;
-      float racc = 0.f;
-      for (int i = 0; i < xc; ++i) racc += t.xw[ox * t.maxt_x + i] * __ldg(row + i);
-      acc += t.yw[oy * t.maxt_y + j] * racc;
-    }
-    out[idx] = acc;
-  }
-}
+// (the kernel that consumes these tables is resize_sep_kernel in resize_blend.cuh)
 
 // ------------------------------------------------------------------------------------------------
 // K0: first U-Net layer.  imgs: [B, 3, H, W] fp32 RGB in [0,1] (H = W = processing size).  If yuv: x = 2*Y-1 with
@@ -178,97 +158,10 @@ __device__ __forceinline__ float jnd_from_lum(const float (*lum)[kBlendTW + 4 + 
   const float gx = (r1[1] - r1[-1]) + 2.f * (r2[1] - r2[-1]) + (r3[1] - r3[-1]);
   const float gy = (r1[-1] + 2.f * r1[0] + r1[1]) - (r3[-1] + 2.f * r3[0] + r3[1]);
   const float g2 = gx * gx + gy * gy;
-  const float g = sqrtf(g2);
-  const float cm = 0.117f * (16.f * powf(g, 2.4f) / (g2 + 676.f));
+  float pw;   // g^2.4 = (g^2)^1.2 on the SFU (lg2 / ex2, ~1e-6 relative); g2 == 0 -> lg2 = -inf -> 0
+  asm("{\n\t.reg .f32 t;\n\tlg2.approx.ftz.f32 t, %1;\n\tmul.f32 t, t, 0f3F99999A;\n\tex2.approx.ftz.f32 %0, t;\n\t}" : "=f"(pw) : "f"(g2));
+  const float cm = 0.117f * (16.f * pw / (g2 + 676.f));
   return fmaxf(la + cm - 0.3f * fminf(la, cm), 0.f) * (1.f / 255.f);
-}
-
-template <int VEC>
-__global__ void __launch_bounds__(256) jnd_blend_kernel(BlendParams p) {
-  __shared__ float lum[kBlendTH + 4][kBlendTW + 4 + 1];
-  const int f = blockIdx.z;
-  const int x0 = blockIdx.x * kBlendTW, y0 = blockIdx.y * kBlendTH;
-  const long plane = (long)p.H * p.W;
-  const float* img = p.imgs + (long)f * 3 * plane;
-  if (p.use_jnd) {
-    for (int i = threadIdx.x; i < (kBlendTH + 4) * (kBlendTW + 4); i += 256) {
-      const int ly = i / (kBlendTW + 4), lx = i - ly * (kBlendTW + 4);
-      const int gy = y0 + ly - 2, gx = x0 + lx - 2;
-      float v = 0.f;
-      if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) {
-        const long o = (long)gy * p.W + gx;
-        v = 0.299f * (255.f * __ldg(img + o)) + 0.587f * (255.f * __ldg(img + plane + o)) + 0.114f * (255.f * __ldg(img + 2 * plane + o));
-      }
-      lum[ly][lx] = v;
-    }
-    __syncthreads();
-  }
-  const int tx = (threadIdx.x & 31) * 4, ty = threadIdx.x >> 5;
-  const int gy = y0 + ty, gx = x0 + tx;
-  if (gy >= p.H || gx >= p.W) return;
-  const FrameKeys fk = frame_keys(f, p.F, p.step, p.alternate, p.interp_chunk);
-  const bool has_delta = fk.has;
-  const int nsrc = (fk.k1 != fk.k0 && fk.a != 1.f) ? 2 : 1;
-  float hm[4], d[3][4];
-  const int nvalid = min(4, p.W - gx);
-#pragma unroll
-  for (int q = 0; q < 4; ++q) {
-    hm[q] = 1.f;
-    if (p.use_jnd && q < nvalid) hm[q] = jnd_from_lum(lum, ty + 2, tx + q + 2);
-  }
-  for (int c = 0; c < p.CD; ++c) {
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float v = 0.f;
-      if (has_delta && q < nvalid) {
-        for (int s = 0; s < nsrc; ++s) {
-          const float* src = p.delta + ((long)(s ? fk.k1 : fk.k0) * p.CD + c) * p.PH * p.PW;
-          float vs = 0.f;
-          if (p.identity_resample) {
-            vs = __ldg(src + (long)gy * p.PW + gx + q);
-          } else {
-            const int ox = gx + q;
-            const int ys = p.tab.ystart[gy], yc = p.tab.ycnt[gy], xs = p.tab.xstart[ox], xc = p.tab.xcnt[ox];
-            for (int j = 0; j < yc; ++j) {
-              float racc = 0.f;
-              for (int i = 0; i < xc; ++i) racc += p.tab.xw[ox * p.tab.maxt_x + i] * __ldg(src + (long)(ys + j) * p.PW + xs + i);
-              vs += p.tab.yw[gy * p.tab.maxt_y + j] * racc;
-            }
-          }
-          v += (nsrc == 1 ? 1.f : (s ? 1.f - fk.a : fk.a)) * vs;
-        }
-      }
-      d[c][q] = v * hm[q];
-    }
-  }
-  const long o = (long)gy * p.W + gx;
-  if (p.preds_w != nullptr) {
-    for (int c = 0; c < p.CD; ++c) {
-      float* dst = p.preds_w + ((long)f * p.CD + c) * plane + o;
-      if (VEC == 4 && nvalid == 4) *reinterpret_cast<float4*>(dst) = make_float4(d[c][0], d[c][1], d[c][2], d[c][3]);
-      else for (int q = 0; q < nvalid; ++q) dst[q] = d[c][q];
-    }
-  }
-#pragma unroll
-  for (int c = 0; c < 3; ++c) {
-    const int dc = p.CD == 1 ? 0 : c;
-    float in[4], out[4];
-    if (VEC == 4 && nvalid == 4) {
-      const float4 t = __ldg(reinterpret_cast<const float4*>(img + c * plane + o));
-      in[0] = t.x; in[1] = t.y; in[2] = t.z; in[3] = t.w;
-    } else {
-      for (int q = 0; q < 4; ++q) in[q] = q < nvalid ? __ldg(img + c * plane + o + q) : 0.f;
-    }
-#pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      float v = p.scaling_i * in[q] + p.scaling_w * d[dc][q];
-      if (p.clamp) v = fminf(fmaxf(v, 0.f), 1.f);
-      out[q] = v;
-    }
-    float* dst = p.imgs_w + ((long)f * 3 + c) * plane + o;
-    if (VEC == 4 && nvalid == 4) *reinterpret_cast<float4*>(dst) = make_float4(out[0], out[1], out[2], out[3]);
-    else for (int q = 0; q < nvalid; ++q) dst[q] = out[q];
-  }
 }
 
 // low-resolution attenuation (wam.py:177-180): delta[k] *= hmap(imgs_res[k*step ... ]) is per FRAME in video mode, so this
@@ -304,8 +197,12 @@ __global__ void __launch_bounds__(256) jnd_lowres_kernel(const float* __restrict
       const long o = (long)gy * PW + gx;
       float dv = 0.f;
       if (fk.has) {
-        dv = delta[((long)fk.k0 * CD + c) * plane + o];
-        if (fk.k1 != fk.k0) dv = fk.a * dv + (1.f - fk.a) * delta[((long)fk.k1 * CD + c) * plane + o];
+        if (delta == nullptr) {
+          dv = 1.f;          // heat-map only
+        } else {
+          dv = delta[((long)fk.k0 * CD + c) * plane + o];
+          if (fk.k1 != fk.k0) dv = fk.a * dv + (1.f - fk.a) * delta[((long)fk.k1 * CD + c) * plane + o];
+        }
       }
       out[((long)f * CD + c) * plane + (long)gy * PW + gx] = hm * dv;
     }

@@ -16,17 +16,28 @@ static int fail(const std::exception& e, int code) {
   return code;
 }
 
+static_assert((int)kErrInvalid == (int)VSB_ERR_INVALID && (int)kErrUnsupported == (int)VSB_ERR_UNSUPPORTED && (int)kErrCuda == (int)VSB_ERR_CUDA &&
+                  (int)kErrState == (int)VSB_ERR_STATE,
+              "status codes of include/vsb200.h");
+
+// Every C entry point that touches the GPU runs on the model's device and restores the caller's current device afterwards (the
+// library must not change process-wide state under PyTorch), and holds the model's mutex: plans, scratch buffers, staging areas
+// and the launch / profile counters belong to the handle, so calls on ONE handle are serialised (use one handle per thread or
+// stream for concurrency; include/vsb200.h "Threading").
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(int dev) {
+    if (dev >= 0 && cudaGetDevice(&prev) == cudaSuccess && prev != dev) { VSB_CUDA(cudaSetDevice(dev)); } else { prev = -1; }
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+};
+#define VSB_MODEL_SCOPE(m) std::lock_guard<std::recursive_mutex> _lk((m)->impl.mu); DeviceGuard _dg((m)->impl.device)
+
 #define VSB_API_BEGIN try {
 #define VSB_API_END                                                                       \
   }                                                                                       \
-  catch (const vsb::Error& e) {                                                           \
-    const std::string w = e.what();                                                       \
-    int code = VSB_ERR_INVALID;                                                           \
-    if (w.find("CUDA error") != std::string::npos) code = VSB_ERR_CUDA;                   \
-    else if (w.find("unsupported") != std::string::npos || w.find("not implemented") != std::string::npos) code = VSB_ERR_UNSUPPORTED; \
-    else if (w.find("missing checkpoint") != std::string::npos || w.find("finalized") != std::string::npos) code = VSB_ERR_STATE;      \
-    return fail(e, code);                                                                 \
-  }                                                                                       \
+  catch (const vsb::Error& e) { return fail(e, e.code); }                                 \
+  catch (const std::bad_alloc& e) { return fail(e, VSB_ERR_CUDA); }                       \
   catch (const std::exception& e) { return fail(e, VSB_ERR_INVALID); }
 
 extern "C" {
@@ -45,7 +56,7 @@ int vsb_model_create(const vsb_model_desc* desc, vsb_model** out) {
 int vsb_model_set_tensor(vsb_model* m, const char* name, const float* data, const int64_t* shape, int32_t ndim) {
   VSB_API_BEGIN
   VSB_CHECK(m && name && data && (shape || ndim == 0) && ndim >= 0 && ndim <= 4, "bad tensor argument");
-  VSB_CHECK(!m->impl.finalized, "model already finalized");
+  if (m->impl.finalized) throw Error("model already finalized", kErrState);
   HostTensor t;
   t.shape.assign(shape, shape + ndim);
   t.data.assign(data, data + t.numel());
@@ -57,18 +68,24 @@ int vsb_model_set_tensor(vsb_model* m, const char* name, const float* data, cons
 int vsb_model_finalize(vsb_model* m, int32_t device) {
   VSB_API_BEGIN
   VSB_CHECK(m != nullptr, "null model");
+  std::lock_guard<std::recursive_mutex> lk(m->impl.mu);
+  DeviceGuard dg(device);
   m->impl.finalize(device);
   return VSB_OK;
   VSB_API_END
 }
 
-void vsb_model_destroy(vsb_model* m) { delete m; }
+void vsb_model_destroy(vsb_model* m) {
+  if (m == nullptr) return;
+  try { DeviceGuard dg(m->impl.device); delete m; } catch (...) {}
+}
 
 int vsb_embed(vsb_model* m, const float* imgs, const uint8_t* msgs, int32_t n_msgs, float* imgs_w, float* preds_w, int32_t F, int32_t H,
               int32_t W, int32_t step, int32_t video_mode, int32_t chunk_keys, float scaling_i, float scaling_w, int32_t flags,
               void* stream) {
   VSB_API_BEGIN
   VSB_CHECK(m && imgs && msgs && imgs_w, "null argument");
+  VSB_MODEL_SCOPE(m);
   m->impl.embed(imgs, msgs, n_msgs, imgs_w, preds_w, F, H, W, step, video_mode, chunk_keys, scaling_i, scaling_w, flags,
                 (cudaStream_t)stream);
   return VSB_OK;
@@ -78,6 +95,7 @@ int vsb_embed(vsb_model* m, const float* imgs, const uint8_t* msgs, int32_t n_ms
 int vsb_embedder_forward(vsb_model* m, const float* x, const uint8_t* msgs, int32_t n_msgs, float* delta, int32_t B, void* stream) {
   VSB_API_BEGIN
   VSB_CHECK(m && x && msgs && delta && B > 0, "null argument");
+  VSB_MODEL_SCOPE(m);
   m->impl.embedder_forward(x, msgs, n_msgs, delta, B, (cudaStream_t)stream);
   return VSB_OK;
   VSB_API_END
@@ -86,6 +104,7 @@ int vsb_embedder_forward(vsb_model* m, const float* x, const uint8_t* msgs, int3
 int vsb_detect(vsb_model* m, const float* imgs, float* logits, int32_t F, int32_t H, int32_t W, int32_t flags, void* stream) {
   VSB_API_BEGIN
   VSB_CHECK(m && imgs && logits, "null argument");
+  VSB_MODEL_SCOPE(m);
   m->impl.detect(imgs, logits, F, H, W, flags, (cudaStream_t)stream);
   return VSB_OK;
   VSB_API_END
@@ -94,6 +113,7 @@ int vsb_detect(vsb_model* m, const float* imgs, float* logits, int32_t F, int32_
 int vsb_jnd_heatmaps(vsb_model* m, const float* imgs, float* hmaps, int32_t F, int32_t H, int32_t W, void* stream) {
   VSB_API_BEGIN
   VSB_CHECK(m && imgs && hmaps, "null argument");
+  VSB_MODEL_SCOPE(m);
   m->impl.jnd_heatmaps(imgs, hmaps, F, H, W, (cudaStream_t)stream);
   return VSB_OK;
   VSB_API_END
@@ -104,8 +124,8 @@ int vsb_embed_host(vsb_model* m, const float* imgs_h, const uint8_t* msgs_h, int
                    int32_t flags) {
   VSB_API_BEGIN
   VSB_CHECK(m && imgs_h && msgs_h && imgs_w_h, "null argument");
+  VSB_MODEL_SCOPE(m);
   m->impl.check_ready();
-  VSB_CUDA(cudaSetDevice(m->impl.device));
   const size_t n = (size_t)F * 3 * H * W;
   const size_t np = (size_t)F * m->impl.d.unet_out_ch * H * W;
   float* imgs = (float*)m->impl.stage(0, n * sizeof(float));
@@ -126,8 +146,8 @@ int vsb_embed_host(vsb_model* m, const float* imgs_h, const uint8_t* msgs_h, int
 int vsb_detect_host(vsb_model* m, const float* imgs_h, float* logits_h, int32_t F, int32_t H, int32_t W, int32_t flags) {
   VSB_API_BEGIN
   VSB_CHECK(m && imgs_h && logits_h, "null argument");
+  VSB_MODEL_SCOPE(m);
   m->impl.check_ready();
-  VSB_CUDA(cudaSetDevice(m->impl.device));
   const size_t n = (size_t)F * 3 * H * W;
   const size_t nl = (size_t)F * (1 + m->impl.d.nbits);
   float* imgs = (float*)m->impl.stage(0, n * sizeof(float));
@@ -146,6 +166,7 @@ int vsb_embed_detect_host(vsb_model* m, const float* imgs_h, const uint8_t* msgs
                           float scaling_w, int32_t flags) {
   VSB_API_BEGIN
   VSB_CHECK(m && imgs_h && msgs_h && imgs_w_h && logits_h, "null argument");
+  VSB_MODEL_SCOPE(m);
   m->impl.embed_detect_host(imgs_h, msgs_h, n_msgs, imgs_w_h, logits_h, F, H, W, step, video_mode, chunk_keys, scaling_i, scaling_w,
                             flags);
   return VSB_OK;
@@ -157,6 +178,7 @@ int vsb_frames_host_u8(vsb_model* m, const uint8_t* frames_h, const uint8_t* msg
                        float scaling_w, int32_t flags) {
   VSB_API_BEGIN
   VSB_CHECK(m && frames_h && (frames_w_h || logits_h) && (msgs_h || !frames_w_h), "null argument");
+  VSB_MODEL_SCOPE(m);
   VSB_CHECK(F > 0 && H > 0 && W > 0 && step >= 1, "bad shape");
   m->impl.frames_host_u8(frames_h, msgs_h, n_msgs, frames_w_h, logits_h, F, H, W, step, video_mode, chunk_keys, scaling_i, scaling_w,
                          flags);
@@ -175,6 +197,7 @@ int64_t vsb_debug_get_tensor(vsb_model* m, const char* name, float* host_out, in
     VSB_CHECK(m && name && shape4, "null argument");
     Plan* pl = m->impl.last_plan;
     VSB_CHECK(pl != nullptr, "no plan has run yet");
+    VSB_MODEL_SCOPE(m);
     auto it = pl->dbg.find(name);
     if (it == pl->dbg.end()) throw Error(std::string("unknown debug tensor: ") + name);
     const DebugTensor& t = it->second;

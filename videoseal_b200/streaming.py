@@ -98,27 +98,45 @@ def iter_rawvideo_chunks(stream, width: int, height: int, chunk_size: int):
             return
 
 
+def _put(q: "queue.Queue", item, alive) -> bool:
+    """q.put that gives up when `alive()` turns false (the other side of the queue has died or left): a plain blocking put on
+    a full queue would wait forever for a consumer that no longer exists"""
+    while alive():
+        try:
+            q.put(item, timeout=0.1)
+            return True
+        except queue.Full:
+            continue
+    return False
+
+
 def _prefetched(it, depth: int):
-    """run iterator `it` in a thread, `depth` items ahead"""
+    """run iterator `it` in a thread, `depth` items ahead; the producer stops when the consumer goes away (generator closed or
+    garbage-collected, e.g. after an exception in the consumer's loop body)"""
     q: "queue.Queue" = queue.Queue(maxsize=max(1, depth))
     end = object()
+    stop = threading.Event()
 
     def work():
         try:
             for x in it:
-                q.put(x)
-            q.put(end)
+                if not _put(q, x, lambda: not stop.is_set()):
+                    return
+            _put(q, end, lambda: not stop.is_set())
         except BaseException as e:   # surfaced in the consumer
-            q.put(e)
+            _put(q, e, lambda: not stop.is_set())
 
     threading.Thread(target=work, daemon=True).start()
-    while True:
-        x = q.get()
-        if x is end:
-            return
-        if isinstance(x, BaseException):
-            raise x
-        yield x
+    try:
+        while True:
+            x = q.get()
+            if x is end:
+                return
+            if isinstance(x, BaseException):
+                raise x
+            yield x
+    finally:
+        stop.set()
 
 
 def embed_stream(model, src, dst, width: int, height: int, chunk_size: int, msgs: torch.Tensor = None, prefetch: int = 2,
@@ -143,13 +161,15 @@ def embed_stream(model, src, dst, width: int, height: int, chunk_size: int, msgs
 
     wt = threading.Thread(target=writer, daemon=True)
     wt.start()
+    chunks = _prefetched(iter_rawvideo_chunks(src, width, height, chunk_size), prefetch)
     try:
-        for chunk in _prefetched(iter_rawvideo_chunks(src, width, height, chunk_size), prefetch):
-            if err:
+        for chunk in chunks:
+            # a GPU faster than the encoder keeps out_q full: the put must notice a writer that died (BrokenPipe from ffmpeg)
+            if err or not _put(out_q, clip_fn(model, chunk, msgs), lambda: wt.is_alive() and not err):
                 break
-            out_q.put(clip_fn(model, chunk, msgs))
     finally:
-        out_q.put(None)
+        chunks.close()                                   # stops the reader thread
+        _put(out_q, None, lambda: wt.is_alive())         # sentinel, unless the writer is already gone
         wt.join()
     if err:
         raise err[0]
