@@ -95,3 +95,20 @@ def test_resample_tables_match_aten_interpolate(built_lib, n_in, n_out, aa):
     tol = 8e-6 if (aa and n_out > n_in) else 2e-6
     assert np.abs(op - ref).max() < tol
     assert np.allclose(op.sum(1), 1.0, atol=1e-5)
+
+
+def test_gelu_polynomial_constants_match_exact_erf_gelu():
+    """conv_gemm.cuh computes nn.GELU (exact erf, modules/convnext.py:33) as max(x,0) - 0.5|x| 2^Q(|x|) with ONE SFU op; the
+    constants are parsed from the header and the formula is evaluated in fp32 here against torch's exact GELU"""
+    import re
+    import torch
+    src = open(os.path.join(ROOT, "videoseal_b200", "csrc", "conv_gemm.cuh")).read()
+    q = [float(re.search(rf"kGeluQ{i} = (-?[0-9.eE+-]+)f", src).group(1)) for i in range(5)]
+    x = torch.linspace(-30, 30, 2_000_001, dtype=torch.float32)
+    ax = x.abs()
+    p = torch.full_like(ax, q[4])
+    for k in (3, 2, 1, 0):
+        p = p * ax + q[k]
+    got = x.clamp_min(0) - 0.5 * ax * torch.exp2(p * ax)
+    ref = torch.nn.functional.gelu(x.double()).float()
+    assert (got - ref).abs().max().item() <= 2e-6

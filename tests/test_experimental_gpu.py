@@ -1,4 +1,4 @@
-"""Opt-in checks of the experimental library build (videoseal_b200/libvsb200_pdl.so: -DVSB_PDL -DVSB_EXP, see __graft_entry__.py and
+"""Opt-in checks of the experimental library build (videoseal_b200/libvsb200_exp.so: -DVSB_EXP, see __graft_entry__.py and
 DESIGN.md section 8).  Skipped unless VSB_TEST_EXP=1: the default library is the product; this file is the first thing to run
 when the experimental kernels get GPU time:
 
@@ -15,7 +15,7 @@ import pytest
 
 pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-EXP_LIB = os.path.join(ROOT, "videoseal_b200", "libvsb200_pdl.so")
+EXP_LIB = os.path.join(ROOT, "videoseal_b200", "libvsb200_exp.so")
 
 
 def _walk(env_extra):

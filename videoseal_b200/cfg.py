@@ -116,11 +116,19 @@ def setup_model(card: dict, ckpt_path):
     spec = spec_from_card(card)
     if not os.path.exists(ckpt_path):
         raise FileNotFoundError(f"Checkpoint path does not exist: {ckpt_path}")
-    checkpoint = torch.load(ckpt_path, map_location="cpu", weights_only=True)
+    checkpoint = _safe_load(ckpt_path)
     model = Videoseal(spec)
     msg = model.load_state_dict(checkpoint["model"], strict=False)
     print(f"Model loaded successfully from {ckpt_path} with message: {msg}")
     return model
+
+
+def _safe_load(ckpt_path):
+    """torch.load with the safe unpickler only (weights_only=True, like utils/cfg.py:62,148 of the reference).  argparse.Namespace
+    -- how training scripts save `args` next to `model` -- is allow-listed for the duration of the load: a plain attribute bag."""
+    import argparse
+    with torch.serialization.safe_globals([argparse.Namespace]):
+        return torch.load(ckpt_path, map_location="cpu", weights_only=True)
 
 
 def _plain(o):
@@ -141,9 +149,7 @@ def get_config_from_checkpoint(ckpt_path) -> dict:
     # the safe unpickler only, like the reference (utils/cfg.py:62,148): a checkpoint is untrusted input.  Training scripts save
     # `args` as an argparse.Namespace, which is allow-listed for the duration of the load (a plain attribute bag, no code);
     # anything else the safe unpickler rejects (e.g. an OmegaConf container) is an error, never a silent full-pickle retry.
-    import argparse
-    with torch.serialization.safe_globals([argparse.Namespace]):
-        checkpoint = torch.load(ckpt_path, map_location="cpu", weights_only=True)
+    checkpoint = _safe_load(ckpt_path)
     if "args" not in checkpoint:
         raise KeyError(f"{ckpt_path} holds no 'args': not a training checkpoint (use a model card for released weights)")
     args = _plain(checkpoint["args"])

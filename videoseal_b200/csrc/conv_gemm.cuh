@@ -56,6 +56,9 @@ struct ConvGemmParams {
   uint32_t a_stage_bytes, b_stage_bytes, stage_bytes, idesc;
   int group;                      // consecutive M tiles that share one accumulator round (amortises per-tile handshakes for small N)
   int b_resident;                 // whole [block_n x K] weight slab lives in shared memory for the kernel's lifetime
+  int b_fixed_ntile;              // b_resident with several N tiles: this CTA only ever sees N tile blockIdx.x % n_tiles
+  int bias_global;                // epilogue reads the bias straight from global memory (warp-uniform 16-byte loads, L1 hits) instead
+                                  // of a shared copy: no per-tile barrier between the epilogue warps (whole tiles only)
   uint32_t bres_off;
   // ---- output-tile geometry: tile_mode 0: rows are consecutive GEMM rows; 1: tile_h x tile_w pixel patch of an H x W map
   int tile_mode, H, W, tile_w, tile_h, tiles_x, tiles_per_img;
@@ -87,43 +90,56 @@ struct ConvGemmParams {
   const float* ln_w; const float* ln_b; float ln_eps;     // EPI_LN (requires n_tiles == 1)
   const float* outc_w; const float* outc_b; float* delta; int n_out, hw, outc_tanh;  // fused 1x1 outc (+tanh)
   float* grn_stats;      // [num_samples, N] sum of squares of the epilogue output (GRN), or null
+  int grn_part;          // 1: grn_stats is [M / 32, N]: every epilogue warp STORES the column sums of its 32 rows (no atomics: the
+                         //    consumer adds the rows of a sample in a fixed order -> bit-reproducible logits); needs
+                         //    rows_per_sample % 32 == 0
 };
 
-// exact-erf GELU (nn.GELU default).  erf via Abramowitz-Stegun 7.1.26 (|abs err| <= 1.5e-7), branch-free.
+// exact-erf GELU (nn.GELU default) with ONE special-function op per element:
+//   gelu(x) = 0.5 x (1 + erf(x / sqrt2)) = max(x, 0) - 0.5 |x| erfc(|x| / sqrt2),   erfc(|x| / sqrt2) = 2^Q(|x|)
+// Q = degree-5 polynomial without constant term (erfc(0) = 1), weighted minimax fit of log2 erfc on [0, 3.3 sqrt2] (oracle-side
+// check in tests/test_cpu_library.py): |gelu - exact| <= 1.0e-6 for every fp32 x in [-30, 30] (the tail runs to 2^-88 -> 0 on its
+// own).  The version this replaces (Abramowitz-Stegun 7.1.25) needed rcp AND ex2 per element and was MUFU-bound in the pwconv1
+// epilogue (profiles/r1_cnx_kernels_ncu.md: MIO stalls 19 %); its error was 2.5e-5.
+constexpr float kGeluQ0 = -1.1510894298553467f, kGeluQ1 = -0.4592657685279846f, kGeluQ2 = -0.05254320427775383f,
+                kGeluQ3 = 0.007386638317257166f, kGeluQ4 = -0.0005183160537853837f;
 __device__ __forceinline__ float rcp_approx(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float ex2_approx(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float gelu_erf(float x) {
-  const float z = fabsf(x) * 0.70710678118654752f;
-  const float t = rcp_approx(fmaf(0.3275911f, z, 1.0f));   // argument in [1, inf): no range fix-ups needed
-  float poly = fmaf(1.061405429f, t, -1.453152027f);
-  poly = fmaf(poly, t, 1.421413741f);
-  poly = fmaf(poly, t, -0.284496736f);
-  poly = fmaf(poly, t, 0.254829592f);
-  const float ex = ex2_approx(z * (z * -1.4426950408889634f));   // exp(-z^2)
-  const float e = fmaf(-poly * t, ex, 1.0f);                  // erf(|x|/sqrt2) >= 0
-  const float h = 0.5f * x;
-  return fmaf(fabsf(h), e, h);                                // 0.5*x*(1 + sign(x)*e)
+  const float ax = fabsf(x);
+  float q = fmaf(kGeluQ4, ax, kGeluQ3);
+  q = fmaf(q, ax, kGeluQ2);
+  q = fmaf(q, ax, kGeluQ1);
+  q = fmaf(q, ax, kGeluQ0);
+  const float e = ex2_approx(q * ax);
+  return fmaf(-0.5f * ax, e, fmaxf(x, 0.f));
 }
 
 // two GELUs at once with Blackwell's packed fp32 arithmetic (fma/mul .f32x2): the polynomial costs half the issue slots
 __device__ __forceinline__ float2 f2fma(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }
 __device__ __forceinline__ float2 f2mul(float2 a, float2 b) { return __fmul2_rn(a, b); }
-// two elements at a time with packed fp32 ops.  erf from Abramowitz-Stegun 7.1.25 (three terms, |error| <= 2.5e-5, i.e.
-// <= 1.3e-5*|x| on the GELU: 40x below the fp16 rounding of the stored result):
-//   erf(z) = 1 - (a1 t + a2 t^2 + a3 t^3) exp(-z^2),  t = 1/(1 + p z),  z = |x|/sqrt(2)
-//   gelu(x) = 0.5 (x + |x| erf(z))
+// packed in, packed out; max(x, 0) as 0.5 (x + |x|) so that the tail is two packed FMAs: gelu = 0.5 x + 0.5 |x| (1 - e)
+__device__ __forceinline__ float2 gelu_erf_p(float2 x) {
+  const float2 ax = make_float2(fabsf(x.x), fabsf(x.y));
+  float2 q = f2fma(make_float2(kGeluQ4, kGeluQ4), ax, make_float2(kGeluQ3, kGeluQ3));
+  q = f2fma(q, ax, make_float2(kGeluQ2, kGeluQ2));
+  q = f2fma(q, ax, make_float2(kGeluQ1, kGeluQ1));
+  q = f2fma(q, ax, make_float2(kGeluQ0, kGeluQ0));
+  q = f2mul(q, ax);
+  const float2 e = make_float2(ex2_approx(q.x), ex2_approx(q.y));
+  const float2 hax = f2mul(ax, make_float2(0.5f, 0.5f));
+  const float2 t = f2fma(make_float2(-e.x, -e.y), hax, hax);            // 0.5 |x| (1 - e)
+  return f2fma(x, make_float2(0.5f, 0.5f), t);
+}
 __device__ __forceinline__ void gelu_erf2(float& x0, float& x1) {
-  const float2 x = make_float2(x0, x1);
   const float2 ax = make_float2(fabsf(x0), fabsf(x1));
-  const float2 dn = f2fma(ax, make_float2(0.47047f * 0.70710678118654752f, 0.47047f * 0.70710678118654752f), make_float2(1.f, 1.f));
-  const float2 t = make_float2(rcp_approx(dn.x), rcp_approx(dn.y));
-  float2 poly = f2fma(t, make_float2(-0.7478556f, -0.7478556f), make_float2(0.0958798f, 0.0958798f));
-  poly = f2fma(poly, t, make_float2(-0.3480242f, -0.3480242f));
-  poly = f2mul(poly, t);                                               // -(a1 t + a2 t^2 + a3 t^3)
-  const float2 ea = f2mul(f2mul(ax, make_float2(-0.72134752044448170f, -0.72134752044448170f)), ax);   // -z^2 * log2(e)
-  const float2 ex = make_float2(ex2_approx(ea.x), ex2_approx(ea.y));
-  const float2 e = f2fma(poly, ex, make_float2(1.f, 1.f));            // erf(|x|/sqrt2)
-  const float2 r = f2mul(f2fma(ax, e, x), make_float2(0.5f, 0.5f));
+  float2 q = f2fma(make_float2(kGeluQ4, kGeluQ4), ax, make_float2(kGeluQ3, kGeluQ3));
+  q = f2fma(q, ax, make_float2(kGeluQ2, kGeluQ2));
+  q = f2fma(q, ax, make_float2(kGeluQ1, kGeluQ1));
+  q = f2fma(q, ax, make_float2(kGeluQ0, kGeluQ0));
+  q = f2mul(q, ax);
+  const float2 e = make_float2(ex2_approx(q.x), ex2_approx(q.y));
+  const float2 r = f2fma(f2mul(ax, make_float2(-0.5f, -0.5f)), e, make_float2(fmaxf(x0, 0.f), fmaxf(x1, 0.f)));
   x0 = r.x; x1 = r.y;
 }
 
@@ -174,12 +190,13 @@ __device__ __forceinline__ void cp_async_wait_pending(int n) {   // wait until a
 template <int NT> __device__ __forceinline__ void epi_bar_sync() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
 __device__ __forceinline__ void bld_bar_sync() { asm volatile("bar.sync 2, 128;" ::: "memory"); }
 
-// epilogue warps: 16 for the pure-TMA kernel (its epilogues - GELU, GRN statistics - are issue-bound), 8 when 4 builder
-// warps also need registers
-template <int LOADER, int ACT> struct EpiCfg { static constexpr int kWarps = (LOADER == LD_TMA && ACT == ACT_GELU) ? 16 : 8; };
+// epilogue warps: 16 for the pure-TMA kernels (GELU / GRN statistics are issue-bound; the small-K affine epilogues are bound by
+// the TMEM-load -> math -> store chain of each warp, profiles/r2g_gemm_ncu.md: twice the warps hide twice the latency), 8 when 4
+// builder warps also need registers
+template <int LOADER, int ACT> struct EpiCfg { static constexpr int kWarps = (LOADER == LD_TMA) ? 16 : 8; };
 
 template <int LOADER, int ACT>
-__global__ void __launch_bounds__(LOADER == LD_TMA ? (ACT == ACT_GELU ? 640 : 384) : 512, 1)
+__global__ void __launch_bounds__(LOADER == LD_TMA ? 640 : 512, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
                  const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvGemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -264,7 +281,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       uint32_t hphase = 0;
       if (p.b_resident) {  // n_tiles == 1: the whole weight slab once
         mbar_arrive_expect_tx(bres_bar, (uint32_t)p.num_kb * p.b_stage_bytes);
-        for (int kb = 0; kb < p.num_kb; ++kb) tma_load_2d(&tmB, bres_bar, bres + (size_t)kb * p.b_stage_bytes, kb * p.kblk, 0);
+        const int brow0 = p.b_fixed_ntile ? ((int)blockIdx.x - p.fd_ntiles.div((int)blockIdx.x) * p.n_tiles) * p.block_n : 0;
+        for (int kb = 0; kb < p.num_kb; ++kb) tma_load_2d(&tmB, bres_bar, bres + (size_t)kb * p.b_stage_bytes, kb * p.kblk, brow0);
       }
       for (int tile = blockIdx.x; tile < p.num_tiles; tile += gridDim.x) {
        const int st = p.fd_ntiles.div(tile), n_tile = tile - st * p.n_tiles;
@@ -435,9 +453,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const int st = p.fd_ntiles.div(tile);
       const int n0 = (tile - st * p.n_tiles) * p.block_n;
       // ---- prologue, overlapped with the main loop: bias -> smem
-      float* sb = s_bias + bsel * 256;
-      if (et < p.block_n) sb[et] = (p.bias != nullptr && n0 + et < p.N) ? __ldg(p.bias + n0 + et) : 0.f;
-      epi_bar_sync<kEpiThreads>();  // bias visible to all epilogue warps (double-buffered across tiles)
+      const float* sb = s_bias + bsel * 256;
+      if (p.bias_global) {
+        sb = p.bias + n0;
+      } else {
+        if (et < p.block_n) s_bias[bsel * 256 + et] = (p.bias != nullptr && n0 + et < p.N) ? __ldg(p.bias + n0 + et) : 0.f;
+        epi_bar_sync<kEpiThreads>();  // bias visible to all epilogue warps (double-buffered across tiles)
+      }
      for (int g = 0; g < G; ++g, ++sq) {
       // residual of the sub-tile D-1 ahead -> ring (issued before waiting for this group's accumulators)
       {
@@ -529,7 +551,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             p.grn_stats != nullptr &&
             p.fd_rps.div(m_tile * kBlockM + q * 32) == p.fd_rps.div(m_tile * kBlockM + q * 32 + 31) &&
             (m_tile * kBlockM + q * 32 + 31) < p.M;
-        float* grn_row = grn_uniform ? p.grn_stats + (long)p.fd_rps.div(m_tile * kBlockM + q * 32) * p.N : nullptr;
+        float* grn_row = !grn_uniform ? nullptr
+                         : (p.grn_part ? p.grn_stats + (long)(m_tile * 4 + q) * p.N
+                                       : p.grn_stats + (long)p.fd_rps.div(m_tile * kBlockM + q * 32) * p.N);
         // whole tile, fp16 output only, no residual / fused 1x1, statistics (if any) uniform per warp
         const bool whole = (m_tile + 1) * kBlockM <= p.M && n0 + p.block_n <= p.N && p.out16 != nullptr && p.out32 == nullptr &&
                            p.outc_w == nullptr && (p.ld_out16 & 7) == 0;
@@ -540,69 +564,40 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                           : (whole && p.grn_stats == nullptr && (!has_res || (p.resid16 != nullptr && res_fast)));
         uint32_t vnext[16];
         if (half < nchunks) tmem_ld16_issue(trow + half * 16, vnext);
-        for (int ch = half; ch < nchunks; ch += kEpiSplit) {
-          const int c = ch * 16;
-          float v[16];
-          tmem_ld_wait(vnext);
-#pragma unroll
-          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(vnext[j]);
-          if (ch + kEpiSplit < nchunks) tmem_ld16_issue(trow + c + 16 * kEpiSplit, vnext);   // overlaps the math below
-          const int n = n0 + c;
-          if (ACT == ACT_GELU && lean) {
-            // pwconv1 on whole tiles (every shipped card): bias + GELU + fp16 store + GRN column statistics and nothing
-            // else.  The generic chunk body below costs ~490 instructions per 16 elements, 45 % of them guards and
-            // index arithmetic for tails, residuals and the other epilogue variants (profiles/r1_history.md).
+        if (ACT == ACT_GELU && lean) {
+          // pwconv1 on whole tiles (every shipped card): bias + GELU + fp16 store + GRN column statistics and nothing else, in packed
+          // fp32 arithmetic throughout.  The accumulators are consumed straight out of the TMEM load registers by the packed bias add,
+          // so the next chunk's load can be issued without a register copy; one saturating F2FP per output pair.
+          const __half* orow = p.out16 + m * p.ld_out16 + n0;
+          for (int ch = half; ch < nchunks; ch += kEpiSplit) {
+            const int c = ch * 16;
+            tmem_ld_wait(vnext);
             const float4* sb4 = reinterpret_cast<const float4*>(sb + c);
-#ifdef VSB_EXP
-            // experimental build: packed fp32 bias add, one saturating F2FP per pair instead of two FMNMX + F2FP, packed squares
-            // (profiles/r1_cnx_kernels_ncu.md: this epilogue is issue-bound at 26 thread instructions per element)
+            float2 w2[8];
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               const float4 bq = sb4[u];
-              const float2 a = __fadd2_rn(make_float2(v[4 * u + 0], v[4 * u + 1]), make_float2(bq.x, bq.y));
-              const float2 b = __fadd2_rn(make_float2(v[4 * u + 2], v[4 * u + 3]), make_float2(bq.z, bq.w));
-              v[4 * u + 0] = a.x; v[4 * u + 1] = a.y; v[4 * u + 2] = b.x; v[4 * u + 3] = b.y;
+              w2[2 * u] = __fadd2_rn(make_float2(__uint_as_float(vnext[4 * u]), __uint_as_float(vnext[4 * u + 1])), make_float2(bq.x, bq.y));
+              w2[2 * u + 1] = __fadd2_rn(make_float2(__uint_as_float(vnext[4 * u + 2]), __uint_as_float(vnext[4 * u + 3])), make_float2(bq.z, bq.w));
             }
+            if (ch + kEpiSplit < nchunks) tmem_ld16_issue(trow + c + 16 * kEpiSplit, vnext);   // overlaps the math below
 #pragma unroll
-            for (int j = 0; j < 16; j += 2) gelu_erf2(v[j], v[j + 1]);
+            for (int j = 0; j < 8; ++j) w2[j] = gelu_erf_p(w2[j]);
             {
               uint32_t h[8];
 #pragma unroll
-              for (int j = 0; j < 8; ++j)
-                asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[j]) : "f"(v[2 * j + 1]), "f"(v[2 * j]));   // {hi, lo}
-              uint4* o = reinterpret_cast<uint4*>(p.out16 + m * p.ld_out16 + n);
+              for (int j = 0; j < 8; ++j) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[j]) : "f"(w2[j].y), "f"(w2[j].x));   // {hi, lo}
+              uint4* o = reinterpret_cast<uint4*>(const_cast<__half*>(orow) + c);
               o[0] = make_uint4(h[0], h[1], h[2], h[3]);
               o[1] = make_uint4(h[4], h[5], h[6], h[7]);
             }
-#else
-#pragma unroll
-            for (int u = 0; u < 4; ++u) {
-              const float4 bq = sb4[u];
-              v[4 * u + 0] += bq.x; v[4 * u + 1] += bq.y; v[4 * u + 2] += bq.z; v[4 * u + 3] += bq.w;
-            }
-#pragma unroll
-            for (int j = 0; j < 16; j += 2) gelu_erf2(v[j], v[j + 1]);
-            {
-              __align__(16) __half2 h[8];
-#pragma unroll
-              for (int j = 0; j < 8; ++j) h[j] = __floats2half2_rn(fminf(v[2 * j], 65504.f), fminf(v[2 * j + 1], 65504.f));
-              uint4* o = reinterpret_cast<uint4*>(p.out16 + m * p.ld_out16 + n);
-              o[0] = reinterpret_cast<const uint4*>(h)[0];
-              o[1] = reinterpret_cast<const uint4*>(h)[1];
-            }
-#endif
             if (grn_row != nullptr) {
               float sq[16];
-#ifdef VSB_EXP
 #pragma unroll
-              for (int j = 0; j < 16; j += 2) {
-                const float2 t2 = __fmul2_rn(make_float2(v[j], v[j + 1]), make_float2(v[j], v[j + 1]));
-                sq[j] = t2.x; sq[j + 1] = t2.y;
+              for (int j = 0; j < 8; ++j) {
+                const float2 t2 = __fmul2_rn(w2[j], w2[j]);
+                sq[2 * j] = t2.x; sq[2 * j + 1] = t2.y;
               }
-#else
-#pragma unroll
-              for (int j = 0; j < 16; ++j) sq[j] = v[j] * v[j];
-#endif
 #pragma unroll
               for (int i = 0; i < 8; ++i) {
                 const float send = (lane & 16) ? sq[i] : sq[i + 8];
@@ -627,10 +622,21 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                 sq[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
               }
               sq[0] += __shfl_xor_sync(0xffffffffu, sq[0], 1);
-              if ((lane & 1) == 0) atomicAdd(grn_row + n + ((lane >> 1) & 15), sq[0]);
+              if ((lane & 1) == 0) {
+                if (p.grn_part) grn_row[n0 + c + ((lane >> 1) & 15)] = sq[0];
+                else atomicAdd(grn_row + n0 + c + ((lane >> 1) & 15), sq[0]);
+              }
             }
-            continue;
           }
+        } else
+        for (int ch = half; ch < nchunks; ch += kEpiSplit) {
+          const int c = ch * 16;
+          float v[16];
+          tmem_ld_wait(vnext);
+#pragma unroll
+          for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(vnext[j]);
+          if (ch + kEpiSplit < nchunks) tmem_ld16_issue(trow + c + 16 * kEpiSplit, vnext);   // overlaps the math below
+          const int n = n0 + c;
           if (ACT == ACT_NONE && lean32) {
             // pwconv2 on whole tiles: bias + fp32 residual stream from the prefetch ring, updated in place (+ fp16 copy)
             const float4* sb4 = reinterpret_cast<const float4*>(sb + c);
@@ -803,7 +809,10 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
               sq[0] += __shfl_xor_sync(0xffffffffu, sq[0], 1);
               const int col = (lane >> 1) & 15;
-              if ((lane & 1) == 0 && col < nval) atomicAdd(grn_row + n + col, sq[0]);
+              if ((lane & 1) == 0 && col < nval) {
+                if (p.grn_part) grn_row[n + col] = sq[0];
+                else atomicAdd(grn_row + n + col, sq[0]);
+              }
             } else if (mvalid) {
               float* gr = p.grn_stats + (long)p.fd_rps.div((int)m) * p.N + n;
 #pragma unroll

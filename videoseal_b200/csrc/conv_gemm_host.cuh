@@ -48,17 +48,18 @@ inline CUtensorMapSwizzle swizzle_for(int kblk) {
   return kblk == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : (kblk == 32 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
 }
 
-// fp16 tensor map, dims innermost-first; strides (bytes) for dims 1..rank-1
+// fp16 (or fp32: f32 = true, always unswizzled) tensor map, dims innermost-first; strides (bytes) for dims 1..rank-1
 inline void encode_map(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                       const uint32_t* box, int kblk, bool no_swizzle = false) {
+                       const uint32_t* box, int kblk, bool no_swizzle = false, bool f32 = false) {
   cuuint64_t gd[5], gs[4];
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
   for (int i = 0; i + 1 < rank; ++i) gs[i] = strides_bytes[i];
   VSB_CHECK((reinterpret_cast<uintptr_t>(base) & 15) == 0, "TMA base must be 16B aligned");
   for (int i = 0; i + 1 < rank; ++i) VSB_CHECK(gs[i] % 16 == 0, "TMA strides must be multiples of 16B");
-  CUresult r = get_encode_fn()(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gd, gs, bx, es,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, no_swizzle ? CU_TENSOR_MAP_SWIZZLE_NONE : swizzle_for(kblk),
+  CUresult r = get_encode_fn()(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank,
+                               const_cast<void*>(base), gd, gs, bx, es,
+                               CU_TENSOR_MAP_INTERLEAVE_NONE, (no_swizzle || f32) ? CU_TENSOR_MAP_SWIZZLE_NONE : swizzle_for(kblk),
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   VSB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
@@ -145,7 +146,16 @@ inline void finalize_op(ConvGemmOp& op, const __half* W, int N, int Kw, int ldw,
   // resident weights: one N tile, whole K slab <= 48 KB -> loaded once per CTA instead of once per tile
   const size_t bslab = (size_t)p.num_kb * p.b_stage_bytes;
   p.b_resident = (p.n_tiles == 1 && bslab <= 48 * 1024 && op.w_samples == 1) ? 1 : 0;
-  if (getenv("VSB_NO_BRES")) p.b_resident = 0;
+  // several N tiles: every CTA keeps ONE N tile for its whole life (grid a multiple of n_tiles, tile = blockIdx.x + k * gridDim.x),
+  // so its [block_n x K] weight slab can stay resident too when it fits beside >= 4 A stages.  Without this the slab is re-streamed
+  // from L2 for every M tile (res 1x1 384->384 @32^2: 151 MB of weight traffic per launch against 100 MB of activations: L2-bound).
+  p.b_fixed_ntile = 0;
+  if (!p.b_resident && p.n_tiles > 1 && p.n_tiles <= 8 && op.w_samples == 1 && op.loader == LD_TMA && !getenv("VSB_NO_BRES2") &&
+      kHeaderBytes + resid_bytes + bslab + 4 * (size_t)p.a_stage_bytes <= 225 * 1024 && p.num_tiles >= 2 * num_sms) {
+    p.b_resident = 1;
+    p.b_fixed_ntile = 1;
+  }
+  if (getenv("VSB_NO_BRES")) { p.b_resident = 0; p.b_fixed_ntile = 0; }
   const size_t bres_bytes = p.b_resident ? bslab : 0;
   if (p.b_resident) p.stage_bytes = p.a_stage_bytes;
   const size_t fixed = kHeaderBytes + resid_bytes + halo_total + u_bytes + bres_bytes;
@@ -172,8 +182,13 @@ inline void finalize_op(ConvGemmOp& op, const __half* W, int N, int Kw, int ldw,
   uint64_t strides[1] = {(uint64_t)ldw * 2};
   uint32_t box[2] = {(uint32_t)p.kblk, (uint32_t)p.block_n};
   encode_map(&op.tmB, W, 2, dims, strides, box, p.kblk);
+  // whole tiles and an aligned bias vector: the epilogue warps read it from global memory and never meet at a barrier (the fused
+  // 1x1 outc epilogue keeps its own barrier, so it keeps the shared copy)
+  p.bias_global = (p.bias != nullptr && N % p.block_n == 0 && p.epi == EPI_AFFINE && p.outc_w == nullptr &&
+                   (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0 && !getenv("VSB_NO_BIAS_GLOBAL")) ? 1 : 0;
   op.grid = p.num_tiles < num_sms ? p.num_tiles : num_sms;
-  op.threads = op.loader == LD_TMA ? (p.act == ACT_GELU ? 640 : 384) : 512;
+  if (p.b_fixed_ntile) op.grid = (num_sms / p.n_tiles) * p.n_tiles;
+  op.threads = op.loader == LD_TMA ? 640 : 512;
   VSB_CHECK((long)p.m_tiles * kBlockM < (1L << 31), "M too large for 32-bit row indices");
 }
 

@@ -14,6 +14,7 @@
 #include "conv3_direct_host.cuh"
 #include "pointwise.cuh"
 #include "resize_blend.cuh"
+#include "dwconv_ring.cuh"
 
 namespace vsb {
 
@@ -174,20 +175,64 @@ struct ResampleDev {
     ResampleHost y = make_resample(ih, oh, aa), x = make_resample(iw, ow, aa);
     tab.ystart = pool.upload(y.start); tab.ycnt = pool.upload(y.cnt); tab.yw = pool.upload(y.w); tab.maxt_y = y.maxt;
     tab.xstart = pool.upload(x.start); tab.xcnt = pool.upload(x.cnt); tab.xw = pool.upload(x.w); tab.maxt_x = x.maxt;
-    const int iwp = (iw + 3) & ~3;
-    gstage = std::max(1, std::min(8, (24 * 1024) / (iwp * 4)));
+    gstage = iw * 4 * 4 <= 16 * 1024 ? 4 : (iw * 4 * 2 <= 16 * 1024 ? 2 : 1);    // rows per cp.async round (two rounds in flight): 4, 2 or 1
     for (toy = 8; toy >= 1; toy >>= 1) {
       rin_max = 1;
       for (int o0 = 0; o0 < oh; o0 += toy) {
         const int o1 = std::min(oh, o0 + toy) - 1;
         rin_max = std::max(rin_max, y.start[o1] + y.cnt[o1] - y.start[o0]);
       }
-      smem = ((size_t)rin_max * ow + (size_t)gstage * iwp) * sizeof(float);
+      smem = ((((size_t)rin_max * ow + 3) & ~(size_t)3) + 2 * (((size_t)gstage * iw + 8 + 3) & ~(size_t)3)) * sizeof(float);
       if (smem <= 100 * 1024 || toy == 1) break;
     }
     if (smem > 200 * 1024) throw Error("resize: image too wide for the shared-memory resample kernel (not implemented)", kErrUnsupported);
   }
 };
+
+// K4 v3 launch (dwconv_ring.cuh): tensor map of the fp32 NHWC residual stream + geometry, built once per plan step
+struct DwRingOp {
+  CUtensorMap tm;
+  int C = 0, B = 0, H = 0, R = 0;
+  const float *dww = nullptr, *dwb = nullptr, *lnw = nullptr, *lnb = nullptr;
+  __half* out = nullptr;
+};
+template <int C, int NS, int SX, int NSLOT>
+inline void launch_dw_ring_t(const DwRingOp& op, cudaStream_t st) {
+  static bool attr = false;
+  constexpr size_t smem = dw_ring_smem<C, NS, SX, NSLOT>();
+  if (!attr) {
+    VSB_CUDA(cudaFuncSetAttribute(dwconv7_ln_ring_kernel<C, NS, SX, NSLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr = true;
+  }
+  const unsigned blocks = (unsigned)((long)op.B * (op.H / op.R) * (op.H / (NS * SX)));
+#ifdef VSB_PDL
+  launch_pdl(dwconv7_ln_ring_kernel<C, NS, SX, NSLOT>, dim3(blocks), dim3(NS * C / 2 + 32), smem, st, op.tm, op.B, op.H, op.H, op.dww, op.dwb, op.lnw,
+             op.lnb, op.out, op.R);
+#else
+  dwconv7_ln_ring_kernel<C, NS, SX, NSLOT><<<blocks, NS * C / 2 + 32, smem, st>>>(op.tm, op.B, op.H, op.H, op.dww, op.dwb, op.lnw, op.lnb, op.out, op.R);
+#endif
+  VSB_CUDA(cudaGetLastError());
+}
+inline bool dw_ring_ok(int C, int H, int ld) {
+  // (the 384-channel instantiation exists and is correct, but at 16 x 16 maps it measured 50 us against 33 us for the whole-row strip
+  //  kernel: one 192-thread block per SM with a 14-step prologue per 8 rows; profiles/r2_history.md)
+  static const bool all = getenv("VSB_DW_RING_384") != nullptr;
+  return ld == C && ((C == 96 && H % 16 == 0) || (C == 192 && H % 16 == 0) || (all && C == 384 && H % 8 == 0));
+}
+inline void setup_dw_ring(DwRingOp& op, const float* x, int B, int H, int C) {
+  op.C = C; op.B = B; op.H = H;
+  op.R = C == 384 ? 8 : (H % 32 == 0 ? 32 : 16);    // rows per block: 6 halo rows + the block prologue are amortised over R
+  const int BW = (C == 96 ? 8 : 4) + 6, CB = C <= 256 ? C : 192;
+  uint64_t dims[4] = {(uint64_t)C, (uint64_t)H, (uint64_t)H, (uint64_t)B};
+  uint64_t strides[3] = {(uint64_t)C * 4, (uint64_t)H * C * 4, (uint64_t)H * H * C * 4};
+  uint32_t box[4] = {(uint32_t)CB, (uint32_t)BW, 1u, 1u};
+  encode_map(&op.tm, x, 4, dims, strides, box, 0, true, /*f32=*/true);
+}
+inline void launch_dw_ring(const DwRingOp& op, cudaStream_t st) {
+  if (op.C == 96) launch_dw_ring_t<96, 2, 4, 8>(op, st);
+  else if (op.C == 192) launch_dw_ring_t<192, 1, 4, 8>(op, st);
+  else launch_dw_ring_t<384, 1, 4, 8>(op, st);
+}
 
 class Model {
  public:
@@ -834,8 +879,27 @@ class Model {
     float* stats_all = pl.pool.alloc_n<float>(2 * stats_n);
     float* stats_pp[2] = {stats_all, stats_all + stats_n};
     int blk_counter = 0;
-    pl.steps.push_back(Step{[=](cudaStream_t st) { VSB_CUDA(cudaMemsetAsync(stats_all, 0, 2 * stats_n * sizeof(float), st)); }, 0,
-                            "cnx.grn_clear"});
+    // Deterministic mode (every stage of the tiny trunk): rows per sample a multiple of 32 -> the pwconv1 epilogue
+    // warps STORE per-warp partial column sums ([M/32][4C]) and the GRN kernels add them in a fixed order: no atomics, no clearing,
+    // bit-reproducible logits.  Otherwise (chunkyseal's odd maps) float atomics into [B][4C] as before, cleared here and by the
+    // GRN kernels.
+    bool all_part = true;
+    size_t part_n = 0;
+    {
+      int h2 = hs;
+      for (int s = 0; s < 4; ++s) {
+        if (s > 0) h2 = (h2 - 2) / 2 + 1;
+        const long rps = (long)h2 * h2, Ms = (long)B * rps;
+        if (rps % 32 != 0) all_part = false;      // every epilogue warp (32 rows) then lies inside one sample, also in a ragged last tile
+        part_n = std::max(part_n, (size_t)((Ms + kBlockM - 1) / kBlockM * 4) * 4 * d.ext_dims[s]);
+      }
+    }
+    static const bool no_part = getenv("VSB_GRN_ATOMIC") != nullptr;
+    if (no_part) all_part = false;
+    float* part_buf = all_part ? pl.pool.alloc_n<float>(part_n) : nullptr;
+    if (!all_part)
+      pl.steps.push_back(Step{[=](cudaStream_t st) { VSB_CUDA(cudaMemsetAsync(stats_all, 0, 2 * stats_n * sizeof(float), st)); }, 0,
+                              "cnx.grn_clear"});
     __half* x16 = nullptr;
     for (int s = 0; s < 4; ++s) {
       if (s > 0) {
@@ -880,6 +944,15 @@ class Model {
           const int H = hs, Cc = C, ldc = Cp;
           const float* xin = x;
           float *dww = w.dww, *dwb = w.dwb, *lw = w.lnw, *lb = w.lnb;
+          static const bool no_ring = getenv("VSB_DW_NO_RING") != nullptr;
+          if (!no_ring && dw_ring_ok(Cc, H, ldc)) {
+            // TMA-ring register-rolling kernel (dwconv_ring.cuh) for the 96 / 192 / 384-channel stages of the tiny trunk
+            DwRingOp rop;
+            setup_dw_ring(rop, xin, B, H, Cc);
+            rop.dww = dww; rop.dwb = dwb; rop.lnw = lw; rop.lnb = lb; rop.out = a;
+            pl.steps.push_back(Step{[rop](cudaStream_t st) { launch_dw_ring(rop, st); }, 1,
+                                    "cnx.dwconv7_ln." + std::to_string(C) + "@" + std::to_string(hs)});
+          } else
           pl.steps.push_back(Step{[=](cudaStream_t st) {
 #ifdef VSB_EXP
             // experimental build only: register-rolling kernel (pointwise.cuh K4 v2), opt in with VSB_DW2=1
@@ -961,30 +1034,35 @@ class Model {
         {
           ConvGemmOp op; setup_tma_gemm(op, a, M, C, Cp);
           op.p.epi = EPI_AFFINE; op.p.act = ACT_GELU; op.p.bias = w.pw1.bias; op.p.out16 = g; op.p.ld_out16 = 4 * C;
-          float* stats = stats_pp[blk_counter & 1];
+          float* stats = all_part ? part_buf : stats_pp[blk_counter & 1];
           ++blk_counter;
-          op.p.grn_stats = stats; op.p.rows_per_sample = rows_per_sample;
+          op.p.grn_stats = stats; op.p.rows_per_sample = rows_per_sample; op.p.grn_part = all_part ? 1 : 0;
           add_conv(pl, op, w.pw1, "cnx.pwconv1." + std::to_string(C) + "@" + std::to_string(hs));
         }
         {
           const int K4 = 4 * C;
           float* gamma = w.gamma;
-          float* stats = stats_pp[(blk_counter - 1) & 1];
-          float* stats_next = stats_pp[blk_counter & 1];
+          float* stats = all_part ? part_buf : stats_pp[(blk_counter - 1) & 1];
+          float* stats_next = all_part ? nullptr : stats_pp[blk_counter & 1];
+          const int part_rows = all_part ? rows_per_sample / 32 : 0;
           if (wscale) {
             // GRN multiplier folded into per-sample copies of W2 (pointwise.cuh K2e): no pass over g at all
             const __half* w2 = w.pw2.w;
             __half* w2s_ = w2s;
             const int Nn = C;
             pl.steps.push_back(Step{[=](cudaStream_t st) {
-              grn_scale_weights_kernel<<<dim3(B, 4), 256, K4 * sizeof(float), st>>>(stats, stats_next, gamma, w2, w2s_, Nn, K4);
+              static bool attr = false;
+              if (!attr) { VSB_CUDA(cudaFuncSetAttribute(grn_scale_weights_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
+              grn_scale_weights_kernel<<<dim3(B, 4), 256, 2 * K4 * sizeof(float), st>>>(stats, stats_next, gamma, w2, w2s_, Nn, K4, part_rows);
               VSB_CUDA(cudaGetLastError());
             }, 1, "cnx.grn_wscale." + std::to_string(C) + "@" + std::to_string(hs)});
           } else {
           pl.steps.push_back(Step{[=](cudaStream_t st) {
             // enough row-slabs per sample to fill the GPU (~8 blocks per SM)
+            static bool attr = false;
+            if (!attr) { VSB_CUDA(cudaFuncSetAttribute(grn_apply_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
             int slabs = std::max(1, std::min(rows_per_sample, (148 * 8 + B - 1) / B));
-            grn_apply_kernel<<<B * slabs, 256, K4 * sizeof(float), st>>>(g, rows_per_sample, K4, K4, stats, stats_next, gamma, slabs);
+            grn_apply_kernel<<<B * slabs, 256, 2 * K4 * sizeof(float), st>>>(g, rows_per_sample, K4, K4, stats, stats_next, gamma, slabs, part_rows);
             VSB_CUDA(cudaGetLastError());
           }, 1, "cnx.grn_apply." + std::to_string(C) + "@" + std::to_string(hs)});
           }
@@ -1022,7 +1100,9 @@ class Model {
       float *lw = head_lnw, *lb = head_lnb, *hw = head_lw, *hb = head_lb;
       float* logits = pl.logits;
       pl.steps.push_back(Step{[=](cudaStream_t st) {
-        head_pool_kernel<<<B, 256, Cc * sizeof(float), st>>>(y, P, Cc, ldy, lw, lb, pooled);
+        static bool attr = false;
+        if (!attr) { VSB_CUDA(cudaFuncSetAttribute(head_pool_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr = true; }
+        head_pool_kernel<<<B, 256, (size_t)8 * Cc * sizeof(float), st>>>(y, P, Cc, ldy, lw, lb, pooled);
         const int grid = (int)(((long)B * NO + 7) / 8);
         head_linear_kernel<<<grid, 256, 0, st>>>(pooled, hw, hb, B, Cc, NO, logits);
         VSB_CUDA(cudaGetLastError());
@@ -1066,17 +1146,15 @@ class Model {
       return;
     }
     const dim3 grid((S + r->toy - 1) / r->toy, n * 3);
-    static bool attr = false;
-    if (!attr) {
-      VSB_CUDA(cudaFuncSetAttribute(resize_sep_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      VSB_CUDA(cudaFuncSetAttribute(resize_sep_kernel<8>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      VSB_CUDA(cudaFuncSetAttribute(resize_sep_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-      attr = true;
-    }
     prof_scope("pw.resize." + std::to_string(H) + "x" + std::to_string(W) + "@" + std::to_string(n), st, 1, [&] {
-      if (r->tab.maxt_x <= 2) resize_sep_kernel<2><<<grid, 256, r->smem, st>>>(src, frame_stride, dst, H, W, S, S, r->tab, r->toy, r->gstage, r->rin_max, vec);
-      else if (r->tab.maxt_x <= 8) resize_sep_kernel<8><<<grid, 256, r->smem, st>>>(src, frame_stride, dst, H, W, S, S, r->tab, r->toy, r->gstage, r->rin_max, vec);
-      else resize_sep_kernel<0><<<grid, 256, r->smem, st>>>(src, frame_stride, dst, H, W, S, S, r->tab, r->toy, r->gstage, r->rin_max, vec);
+      const int mt = r->tab.maxt_x <= 2 ? 2 : (r->tab.maxt_x <= 8 ? 8 : 0);
+#define VSB_RS(MT, GS) do { static bool attr_ = false; \
+        if (!attr_) { VSB_CUDA(cudaFuncSetAttribute(resize_sep_kernel<MT, GS>, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr_ = true; } \
+        resize_sep_kernel<MT, GS><<<grid, 256, r->smem, st>>>(src, frame_stride, dst, H, W, S, S, r->tab, r->toy, r->rin_max, vec); } while (0)
+      if (r->gstage == 4) { if (mt == 2) VSB_RS(2, 4); else if (mt == 8) VSB_RS(8, 4); else VSB_RS(0, 4); }
+      else if (r->gstage == 2) { if (mt == 2) VSB_RS(2, 2); else if (mt == 8) VSB_RS(8, 2); else VSB_RS(0, 2); }
+      else { if (mt == 2) VSB_RS(2, 1); else if (mt == 8) VSB_RS(8, 1); else VSB_RS(0, 1); }
+#undef VSB_RS
     });
     VSB_CUDA(cudaGetLastError());
   }
@@ -1306,19 +1384,19 @@ class Model {
     const bool vec = (bp.W % 4 == 0) && ((reinterpret_cast<uintptr_t>(bp.imgs) | reinterpret_cast<uintptr_t>(bp.imgs_w) |
                                           reinterpret_cast<uintptr_t>(bp.preds_w)) % 16 == 0);
     // delta read in place, or through <= 2 taps per axis (plain bilinear up-scale: every input at least as large as the processing size)
-    const bool fastup = bp.identity_resample || (bp.tab.maxt_x <= 2 && bp.tab.maxt_y <= 2);
-    static bool attr = false;
-    if (!attr) {
-      VSB_CUDA(cudaFuncSetAttribute(jnd_blend2_kernel<4, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kB2Smem));
-      VSB_CUDA(cudaFuncSetAttribute(jnd_blend2_kernel<4, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kB2Smem));
-      VSB_CUDA(cudaFuncSetAttribute(jnd_blend2_kernel<1, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kB2Smem));
-      VSB_CUDA(cudaFuncSetAttribute(jnd_blend2_kernel<1, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kB2Smem));
-      attr = true;
-    }
+    const bool fastup = bp.identity_resample || (bp.tab.maxt_x <= 2 && bp.tab.maxt_y <= 2 && bp.H >= bp.PH && bp.W >= bp.PW);
+    VSB_CHECK(bp.CD == 1 || bp.CD == 3, "delta must have 1 or 3 channels");
     prof_scope(std::string(bp.use_jnd ? "pw.jnd_blend." : "pw.blend.") + std::to_string(bp.H) + "x" + std::to_string(bp.W) + "@" + std::to_string(bp.F) +
                    (bp.preds_w ? "+preds" : ""), st, 1, [&] {
-      if (vec) { if (fastup) jnd_blend2_kernel<4, 1><<<grid, 256, kB2Smem, st>>>(bp); else jnd_blend2_kernel<4, 0><<<grid, 256, kB2Smem, st>>>(bp); }
-      else     { if (fastup) jnd_blend2_kernel<1, 1><<<grid, 256, kB2Smem, st>>>(bp); else jnd_blend2_kernel<1, 0><<<grid, 256, kB2Smem, st>>>(bp); }
+#define VSB_BL(V, FU, CDV) do { static bool attr_ = false; \
+        if (!attr_) { VSB_CUDA(cudaFuncSetAttribute(jnd_blend2_kernel<V, FU, CDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kB2Smem)); attr_ = true; } \
+        jnd_blend2_kernel<V, FU, CDV><<<grid, 256, kB2Smem, st>>>(bp); } while (0)
+      if (bp.CD == 1) {
+        if (vec) { if (fastup) VSB_BL(4, 1, 1); else VSB_BL(4, 0, 1); } else { if (fastup) VSB_BL(1, 1, 1); else VSB_BL(1, 0, 1); }
+      } else {
+        if (vec) { if (fastup) VSB_BL(4, 1, 3); else VSB_BL(4, 0, 3); } else { if (fastup) VSB_BL(1, 1, 3); else VSB_BL(1, 0, 3); }
+      }
+#undef VSB_BL
     });
     VSB_CUDA(cudaGetLastError());
   }

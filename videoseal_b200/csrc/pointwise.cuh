@@ -1091,16 +1091,58 @@ __global__ void __launch_bounds__(256) grn_scale_kernel(float* __restrict__ stat
 // One block per (sample, row-slab); the per-sample mean is recomputed by every block (K <= 3072 values).  `stats_next` (the
 // ping-pong buffer the NEXT block's pwconv1 accumulates into) is cleared here.  For all but the first stage g fits in the
 // 126 MB L2, so this pass mostly runs out of L2; pwconv2 is then a plain TMA-fed GEMM.
+// part_rows > 0: `stats` holds part_rows partial rows per sample ([B * part_rows][K], written by the pwconv1 epilogue warps without
+// atomics).  They are added here in a FIXED order (so the result does not depend on the order in which the tiles finished): 128-bit
+// loads, 8 rows in flight per thread, and two row groups per column when the block has the threads for it (combined lower rows first).
+// Fills sc[k] = sqrt(sum_rows) for all k; tmp is K floats of scratch.  Ends with a block barrier.
+__device__ __forceinline__ void grn_colnorms(const float* __restrict__ stats, int b, int K, int part_rows, float* sc, float* tmp) {
+  if (part_rows <= 0) {
+    for (int k = threadIdx.x; k < K; k += blockDim.x) sc[k] = sqrtf(stats[(long)b * K + k]);
+    __syncthreads();
+    return;
+  }
+  const int K4 = K >> 2;
+  const float4* base = reinterpret_cast<const float4*>(stats + (long)b * part_rows * K);
+  const bool two = (int)blockDim.x >= 2 * K4 && (part_rows & 1) == 0;
+  auto sum_rows = [&](int c4, int r0, int r1) {
+    float4 a = make_float4(0.f, 0.f, 0.f, 0.f);
+    int r = r0;
+    for (; r + 8 <= r1; r += 8) {
+      float4 v[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) v[u] = base[(long)(r + u) * K4 + c4];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { a.x += v[u].x; a.y += v[u].y; a.z += v[u].z; a.w += v[u].w; }
+    }
+    for (; r < r1; ++r) { const float4 v = base[(long)r * K4 + c4]; a.x += v.x; a.y += v.y; a.z += v.z; a.w += v.w; }
+    return a;
+  };
+  if (two) {
+    const int rg = threadIdx.x / K4, c4 = threadIdx.x - rg * K4, half = part_rows >> 1;
+    if (rg < 2) {
+      const float4 a = sum_rows(c4, rg * half, (rg + 1) * half);
+      *reinterpret_cast<float4*>((rg ? tmp : sc) + 4 * c4) = a;
+    }
+    __syncthreads();
+    for (int k = threadIdx.x; k < K; k += blockDim.x) sc[k] = sqrtf(sc[k] + tmp[k]);
+  } else {
+    for (int c4 = threadIdx.x; c4 < K4; c4 += blockDim.x) {
+      float4 a = sum_rows(c4, 0, part_rows);
+      *reinterpret_cast<float4*>(sc + 4 * c4) = make_float4(sqrtf(a.x), sqrtf(a.y), sqrtf(a.z), sqrtf(a.w));
+    }
+  }
+  __syncthreads();
+}
 __global__ void __launch_bounds__(256) grn_apply_kernel(__half* __restrict__ g, int rows_per_sample, int K, int ld,
                                                         const float* __restrict__ stats, float* __restrict__ stats_next,
-                                                        const float* __restrict__ gamma, int slabs) {
-  extern __shared__ float sc[];   // [K] multipliers of this sample
+                                                        const float* __restrict__ gamma, int slabs, int part_rows) {
+  extern __shared__ __align__(16) float sc[];   // [K] multipliers of this sample | [K] scratch
   __shared__ float red[8];
   __shared__ float mean_s;
   const int b = blockIdx.x / slabs, slab = blockIdx.x - b * slabs;
-  const float* st = stats + (long)b * K;
+  grn_colnorms(stats, b, K, part_rows, sc, sc + K);
   float sum = 0.f;
-  for (int k = threadIdx.x; k < K; k += blockDim.x) { const float gx = sqrtf(st[k]); sc[k] = gx; sum += gx; }
+  for (int k = threadIdx.x; k < K; k += blockDim.x) sum += sc[k];
 #pragma unroll
   for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
@@ -1113,7 +1155,7 @@ __global__ void __launch_bounds__(256) grn_apply_kernel(__half* __restrict__ g, 
   __syncthreads();
   const float inv = 1.0f / (mean_s + 1e-6f);
   for (int k = threadIdx.x; k < K; k += blockDim.x) sc[k] = __ldg(gamma + k) * (sc[k] * inv) + 1.0f;
-  if (slab == 0) for (int k = threadIdx.x; k < K; k += blockDim.x) stats_next[(long)b * K + k] = 0.f;
+  if (slab == 0 && stats_next != nullptr) for (int k = threadIdx.x; k < K; k += blockDim.x) stats_next[(long)b * K + k] = 0.f;
   __syncthreads();
   const int k8 = K >> 3;
   const int r0 = (int)(((long)rows_per_sample * slab) / slabs), r1 = (int)(((long)rows_per_sample * (slab + 1)) / slabs);
@@ -1145,14 +1187,14 @@ __global__ void __launch_bounds__(256) grn_apply_kernel(__half* __restrict__ g, 
 // re-read nor re-written.  grid (samples, splits); `stats_next` is cleared like grn_apply_kernel does.
 __global__ void __launch_bounds__(256) grn_scale_weights_kernel(const float* __restrict__ stats, float* __restrict__ stats_next,
                                                                 const float* __restrict__ gamma, const __half* __restrict__ w,
-                                                                __half* __restrict__ out, int N, int K) {
-  extern __shared__ float sc[];   // [K]
+                                                                __half* __restrict__ out, int N, int K, int part_rows) {
+  extern __shared__ __align__(16) float sc[];   // [K] | [K] scratch
   __shared__ float red[8];
   __shared__ float mean_s;
   const int b = blockIdx.x;
-  const float* st = stats + (long)b * K;
+  grn_colnorms(stats, b, K, part_rows, sc, sc + K);
   float sum = 0.f;
-  for (int k = threadIdx.x; k < K; k += blockDim.x) { const float gx = sqrtf(st[k]); sc[k] = gx; sum += gx; }
+  for (int k = threadIdx.x; k < K; k += blockDim.x) sum += sc[k];
 #pragma unroll
   for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = sum;
@@ -1165,7 +1207,7 @@ __global__ void __launch_bounds__(256) grn_scale_weights_kernel(const float* __r
   __syncthreads();
   const float inv = 1.0f / (mean_s + 1e-6f);
   for (int k = threadIdx.x; k < K; k += blockDim.x) sc[k] = __ldg(gamma + k) * (sc[k] * inv) + 1.0f;
-  if (blockIdx.y == 0) for (int k = threadIdx.x; k < K; k += blockDim.x) stats_next[(long)b * K + k] = 0.f;
+  if (blockIdx.y == 0 && stats_next != nullptr) for (int k = threadIdx.x; k < K; k += blockDim.x) stats_next[(long)b * K + k] = 0.f;
   __syncthreads();
   const int k8 = K >> 3;
   const int n0 = (int)(((long)N * blockIdx.y) / gridDim.y), n1 = (int)(((long)N * (blockIdx.y + 1)) / gridDim.y);
@@ -1219,10 +1261,13 @@ __global__ void __launch_bounds__(256) stem_im2col_kernel(const float* __restric
 // (pixel_decoder.py:44-55,77 with common.py:50-51).  y: [B*P, ld] fp32.  One block per sample, one warp per pixel (loop).
 __global__ void __launch_bounds__(256) head_pool_kernel(const float* __restrict__ y, int P, int C, int ld, const float* __restrict__ lnw,
                                                         const float* __restrict__ lnb, float* __restrict__ pooled) {
-  extern __shared__ float acc[];  // [C]
+  // acc [nw][C]: every warp adds its own pixels in a fixed order into its own row, the rows are added in warp order at the end:
+  // no atomics, bit-reproducible logits
+  extern __shared__ float acc_all[];
   const int b = blockIdx.x, warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int c = threadIdx.x; c < C; c += blockDim.x) acc[c] = 0.f;
-  __syncthreads();
+  float* acc = acc_all + warp * C;
+  for (int c = lane; c < C; c += 32) acc[c] = 0.f;
+  __syncwarp();
   for (int pix = warp; pix < P; pix += nw) {
     const float* r = y + ((long)b * P + pix) * ld;
     float sum = 0.f;
@@ -1237,11 +1282,15 @@ __global__ void __launch_bounds__(256) head_pool_kernel(const float* __restrict_
     const float rstd = 1.0f / sqrtf(var / (float)C + 1e-6f);
     for (int c = lane; c < C; c += 32) {
       const float v = (r[c] - mean) * rstd * __ldg(lnw + c) + __ldg(lnb + c);
-      atomicAdd(&acc[c], 0.5f * v * (1.0f + erff(v * 0.70710678118654752f)));
+      acc[c] += 0.5f * v * (1.0f + erff(v * 0.70710678118654752f));     // lane-private element of this warp's row
     }
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += blockDim.x) pooled[(long)b * C + c] = acc[c] / (float)P;
+  for (int c = threadIdx.x; c < C; c += blockDim.x) {
+    float t = 0.f;
+    for (int w = 0; w < nw; ++w) t += acc_all[w * C + c];
+    pooled[(long)b * C + c] = t / (float)P;
+  }
 }
 
 // K8b: logits[b, o] = bias[o] + sum_c pooled[b, c] * w[o, c]     (pixel_decoder.py:78).  One warp per output.

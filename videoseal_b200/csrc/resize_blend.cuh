@@ -11,21 +11,29 @@
 //                            Widths that are not multiples of 4 run the same kernel with lane-strided scalar accesses (still fully
 //                            coalesced) instead of falling back to a different kernel.
 #pragma once
+#include "conv_gemm.cuh"
 #include "pointwise.cuh"
 
 namespace vsb {
 
 // ------------------------------------------------------------------------------------------------ K5
+__device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
+}
 // in: planes [n][3][IH][IW] with frames `frame_stride` floats apart; out: [n*3][OH][OW] contiguous.
-// grid (ceil(OH / toy), n*3); block 256.  Shared: hbuf [rin_max][OW] | stage [gstage][IWp].
-template <int MAXT>   // x taps per output held in registers (2 or 8); 0 = any count, weights re-read from the table
+// grid (ceil(OH / toy), n*3); block 256.  Shared: hbuf [rin_max][OW] | stage [2][GST * IW + 8] (cp.async double buffer: the rows of
+// round r+1 are in flight while the horizontal pass of round r runs; consecutive input rows of a plane are contiguous in memory,
+// so a round is ONE flat asynchronous copy of GST * IW floats, 16 bytes per request when IW % 4 == 0).
+// The tap loops carry no predicates: taps beyond an output's support have weight 0 and read whatever FINITE value follows in the
+// staging buffer (the buffers are zero-filled once, an 8-float zero pad ends each of them) -- ncu of the first version showed
+// 33 % of its instructions were predicate bookkeeping (LOP3 / ISETP / P2R) and 17 % address IMADs against 8 % FFMA.
+template <int MAXT, int GST>   // MAXT: x taps per output held in registers (2 or 8); 0 = any count (weights from the table, predicated)
 __global__ void __launch_bounds__(256) resize_sep_kernel(const float* __restrict__ in, long frame_stride, float* __restrict__ out, int IH,
-                                                         int IW, int OH, int OW, ResampleTab t, int toy, int gstage, int rin_max,
-                                                         int vec) {
+                                                         int IW, int OH, int OW, ResampleTab t, int toy, int rin_max, int vec) {
   extern __shared__ __align__(16) float rs_smem[];
   float* hbuf = rs_smem;
-  float* stg = rs_smem + (size_t)rin_max * OW;
-  const int IWp = (IW + 3) & ~3;
+  const int stg_stride = (GST * IW + 8 + 3) & ~3;
+  float* stg = rs_smem + (((size_t)rin_max * OW + 3) & ~(size_t)3);
   const int pl = blockIdx.y;
   const int n = pl / 3, c = pl - n * 3;
   const float* src = in + (long)n * frame_stride + (long)c * IH * IW;
@@ -33,102 +41,149 @@ __global__ void __launch_bounds__(256) resize_sep_kernel(const float* __restrict
   const int r0 = __ldg(t.ystart + oy0);
   const int nr = __ldg(t.ystart + oy1 - 1) + __ldg(t.ycnt + oy1 - 1) - r0;   // <= rin_max (host-computed from the same table)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int g0 = 0; g0 < nr; g0 += gstage) {
-    const int ng = min(gstage, nr - g0);
-    for (int r = warp; r < ng; r += 8) {
-      const float* row = src + (long)(r0 + g0 + r) * IW;
-      float* d = stg + r * IWp;
-      if (vec) {
-        for (int i = lane; i < (IW >> 2); i += 32) reinterpret_cast<float4*>(d)[i] = __ldg(reinterpret_cast<const float4*>(row) + i);
-      } else {
-        for (int i = lane; i < IW; i += 32) d[i] = __ldg(row + i);
-      }
+  const int rounds = (nr + GST - 1) / GST;
+  for (int i = threadIdx.x * 4; i < 2 * stg_stride; i += 1024) *reinterpret_cast<float4*>(stg + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+  __syncthreads();
+  auto issue = [&](int rd) {
+    if (rd < rounds) {
+      const int g0 = rd * GST, nfl = min(GST, nr - g0) * IW;
+      const float* sp = src + (long)(r0 + g0) * IW;
+      float* d = stg + (rd & 1) * stg_stride;
+      if (vec) { for (int i = threadIdx.x * 4; i < nfl; i += 1024) cp_async16(d + i, sp + i); }
+      else     { for (int i = threadIdx.x; i < nfl; i += 256) cp_async4(d + i, sp + i); }
     }
+    cp_async_commit();
+  };
+  issue(0);
+  for (int rd = 0; rd < rounds; ++rd) {
+    issue(rd + 1);
+    cp_async_wait_pending(1);          // round rd has landed (this thread's part); the barrier makes it everybody's
     __syncthreads();
+    const int g0 = rd * GST, ng = min(GST, nr - g0);
+    const float* sb = stg + (rd & 1) * stg_stride;
     for (int ox = threadIdx.x; ox < OW; ox += 256) {
       const int xs = __ldg(t.xstart + ox), xc = __ldg(t.xcnt + ox);
       const float* wp = t.xw + (long)ox * t.maxt_x;
+      float* hb = hbuf + g0 * OW + ox;
       if (MAXT > 0) {
         float w[MAXT > 0 ? MAXT : 1];
 #pragma unroll
         for (int i = 0; i < MAXT; ++i) w[i] = i < xc ? __ldg(wp + i) : 0.f;
-        for (int r = 0; r < ng; ++r) {
-          const float* s = stg + r * IWp + xs;
-          float acc = w[0] * s[0];
+        const float* s = sb + xs;
 #pragma unroll
-          for (int i = 1; i < MAXT; ++i) acc = i < xc ? fmaf(w[i], s[i], acc) : acc;
-          hbuf[(g0 + r) * OW + ox] = acc;
+        for (int r = 0; r < GST; ++r) {
+          if (r < ng) {
+            float acc = w[0] * s[0];
+#pragma unroll
+            for (int i = 1; i < MAXT; ++i) acc = fmaf(w[i], s[i], acc);
+            hb[r * OW] = acc;
+          }
+          s += IW;
         }
       } else {
         for (int r = 0; r < ng; ++r) {
-          const float* s = stg + r * IWp + xs;
+          const float* s = sb + r * IW + xs;
           float acc = __ldg(wp) * s[0];
           for (int i = 1; i < xc; ++i) acc = fmaf(__ldg(wp + i), s[i], acc);
-          hbuf[(g0 + r) * OW + ox] = acc;
+          hb[r * OW] = acc;
         }
       }
     }
-    __syncthreads();
+    __syncthreads();                   // buffer (rd & 1) is rewritten by issue(rd + 2); hbuf complete after the last round
   }
   float* dst = out + (long)pl * OH * OW;
   for (int oy = oy0 + warp; oy < oy1; oy += 8) {          // one warp per output row: the y taps are warp-uniform
     const int ys = __ldg(t.ystart + oy) - r0, yc = __ldg(t.ycnt + oy);
     const float* wy = t.yw + (long)oy * t.maxt_y;
-    for (int ox = lane; ox < OW; ox += 32) {
-      const float* h = hbuf + ys * OW + ox;
-      float acc = __ldg(wy) * h[0];
-      for (int j = 1; j < yc; ++j) acc = fmaf(__ldg(wy + j), h[j * OW], acc);
-      dst[oy * OW + ox] = acc;
+    for (int oxb = 0; oxb < OW; oxb += 256) {              // 8 outputs per lane: accumulators in registers, one weight load per tap
+      const float* h = hbuf + ys * OW + oxb + lane;
+      float acc[8];
+      const float w0 = __ldg(wy);
+#pragma unroll
+      for (int k = 0; k < 8; ++k) acc[k] = (oxb + lane + 32 * k < OW) ? w0 * h[32 * k] : 0.f;
+      for (int j = 1; j < yc; ++j) {
+        const float wj = __ldg(wy + j);
+        const float* hj = h + j * OW;
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if (oxb + lane + 32 * k < OW) acc[k] = fmaf(wj, hj[32 * k], acc[k]);
+      }
+#pragma unroll
+      for (int k = 0; k < 8; ++k) if (oxb + lane + 32 * k < OW) dst[oy * OW + oxb + lane + 32 * k] = acc[k];
     }
   }
 }
 
 // ------------------------------------------------------------------------------------------------ K7
-constexpr int kB2TW = 128, kB2TH = 32, kB2LP = 136;   // tile, and the pitch of the luminance tile (image column x0 + j at index 4 + j)
-constexpr size_t kB2Smem = (size_t)((kB2TH + 4) * kB2LP + 3 * kB2TH * kB2TW) * sizeof(float);
+constexpr int kB2TW = 128, kB2TH = 16, kB2LP = 136;   // tile, and the pitch of the luminance tile (image column x0 + j at index 4 + j)
+constexpr int kB2DH = kB2TH + 2, kB2DW = kB2TW + 4;   // delta tile at processing resolution (up-scale: at most 1 source pixel per output pixel + 1)
+constexpr size_t kB2Smem = (size_t)((kB2TH + 4) * kB2LP + 3 * kB2TH * kB2TW + kB2DH * kB2DW) * sizeof(float);
 
 __device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float ex2_approx_f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float sqrt_approx(float x) { float y; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+__device__ __forceinline__ float rcp_approx_f(float x) { float y; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
+// L = 255 * Y with the factor folded into the weights (1 FMUL + 2 FFMA per pixel instead of 6 operations; differs from the
+// reference's (255 x) . w by one rounding, 1e-7 relative)
 __device__ __forceinline__ float lum255(float r, float g, float b) {
-  return 0.299f * (255.f * r) + 0.587f * (255.f * g) + 0.114f * (255.f * b);
+  return fmaf(0.114f * 255.f, b, fmaf(0.587f * 255.f, g, (0.299f * 255.f) * r));
 }
 // modules/jnd.py:63-108 on L = 255*Y: la = conv5x5(L)/32 -> piecewise; cm = .117 * 16 g^2.4 / (g^2 + 26^2), g = |Sobel|;
 // hmap = max(la + cm - .3 min(la, cm), 0) / 255.  la_sum = the 5x5 weighted sum (weights 1 / 2 / 0, jnd.py:37-43).
+// Transcendentals on the SFU (sqrt / lg2 / ex2 / rcp .approx, each <= 2 ulp-ish): 4 MUFU + ~16 FP32 instructions per pixel.
 __device__ __forceinline__ float jnd_value(float la_sum, float gx, float gy) {
-  float la = la_sum * (1.f / 32.f);
-  la = (la <= 127.f) ? 17.f * (1.f - sqrtf(la * (1.f / 127.f) + 1e-5f)) : (3.f / 128.f) * (la - 127.f) + 3.f;
-  const float g2 = gx * gx + gy * gy;
+  const float la0 = la_sum * (1.f / 32.f);
+  const float lo = fmaf(-17.f, sqrt_approx(fmaf(la0, 1.f / 127.f, 1e-5f)), 17.f);
+  const float hi = fmaf(3.f / 128.f, la0 - 127.f, 3.f);
+  const float la = (la0 <= 127.f) ? lo : hi;
+  const float g2 = fmaf(gx, gx, gy * gy);
   const float pw = ex2_approx_f(1.2f * lg2_approx(g2));    // g^2.4 = (g^2)^1.2;  g2 == 0 -> lg2 = -inf -> 0
-  const float cm = 0.117f * (16.f * pw / (g2 + 676.f));
+  const float cm = (0.117f * 16.f) * pw * rcp_approx_f(g2 + 676.f);
   return fmaxf(la + cm - 0.3f * fminf(la, cm), 0.f) * (1.f / 255.f);
-}
-// window rows r0..r4 are pointers to the element of the CENTRE column in five consecutive luminance rows
-__device__ __forceinline__ float jnd_window(const float* r0, const float* r1, const float* r2, const float* r3, const float* r4) {
-  const float la = (r0[-2] + r0[-1] + r0[0] + r0[1] + r0[2]) + (r1[-2] + r1[2]) + (r2[-2] + r2[2]) + (r3[-2] + r3[2]) +
-                   (r4[-2] + r4[-1] + r4[0] + r4[1] + r4[2]) + 2.f * (r1[-1] + r1[0] + r1[1] + r2[-1] + r2[1] + r3[-1] + r3[0] + r3[1]);
-  const float gx = (r1[1] - r1[-1]) + 2.f * (r2[1] - r2[-1]) + (r3[1] - r3[-1]);
-  const float gy = (r1[-1] + 2.f * r1[0] + r1[1]) - (r3[-1] + 2.f * r3[0] + r3[1]);
-  return jnd_value(la, gx, gy);
 }
 
 // VEC 4: W % 4 == 0 and 16-byte aligned tensors: thread = 4 consecutive pixels (128-bit global / shared accesses).
 // VEC 1: any W / alignment: thread = pixels lane, lane+32, lane+64, lane+96 of the tile row (32-bit accesses, fully coalesced).
-// FASTUP 1: the delta is read in place or through <= 2 taps per axis (plain bilinear up-scale); 0: generic separable tables.
-template <int VEC, int FASTUP>
-__global__ void __launch_bounds__(256, 2) jnd_blend2_kernel(const BlendParams p) {
+// FASTUP 1: the delta is read in place (identity) or up-scaled through <= 2 taps per axis from a tile staged in shared memory
+//           (every input at least as large as the processing size); 0: generic separable tables straight from global memory.
+// Thread = 2 rows x 4 pixels.  The 5x5 luminance filter and the Sobel pair are evaluated SEPARABLY while the six luminance rows
+// of the two output rows stream through registers (per row: 5- and 3-sums, the horizontal difference and the [1 2 1] smooth).
+// CD: delta channels (1 for the Y-channel cards, 3 for RGB U-Nets) as a compile-time constant: the per-channel loops and their
+// accumulators disappear from the single-channel instantiation.
+template <int VEC, int FASTUP, int CD>
+__global__ void __launch_bounds__(256, 3) jnd_blend2_kernel(const BlendParams p) {
   extern __shared__ __align__(16) float b2_smem[];
-  float* lum = b2_smem;                               // [TH + 4][LP]
-  float* rgb = b2_smem + (kB2TH + 4) * kB2LP;         // [3][TH][TW]
+  float* lum = b2_smem;                                   // [TH + 4][LP]
+  float* rgb = lum + (kB2TH + 4) * kB2LP;                 // [3][TH][TW]
+  float* dl = rgb + 3 * kB2TH * kB2TW;                    // [DH][DW]
   const int f = blockIdx.z, x0 = blockIdx.x * kB2TW, y0 = blockIdx.y * kB2TH;
   const long plane = (long)p.H * p.W;
   const float* img = p.imgs + (long)f * 3 * plane;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   auto col_of = [&](int q) { return VEC == 4 ? lane * 4 + q : lane + 32 * q; };
+  const FrameKeys fk = frame_keys(f, p.F, p.step, p.alternate, p.interp_chunk);
+  const bool has_delta = fk.has;
+  const int nsrc = (fk.k1 != fk.k0 && fk.a != 1.f) ? 2 : 1;
+  const bool staged = FASTUP && !p.identity_resample && has_delta;
 
-  // ---- phase 1: this thread's pixels (4 rows x 4 pixels x RGB) -> shared; luminance tile with a 2-pixel zero halo
+  // delta tile geometry (staged path): source rows / columns touched by this output tile
+  int sy0 = 0, sx0 = 0, dnr = 0, dnc = 0;
+  if (staged) {
+    const int ylast = min(y0 + kB2TH, p.H) - 1, xlast = min(x0 + kB2TW, p.W) - 1;
+    sy0 = __ldg(p.tab.ystart + y0);
+    sx0 = __ldg(p.tab.xstart + x0);
+    dnr = min(__ldg(p.tab.ystart + ylast) + __ldg(p.tab.ycnt + ylast), p.PH) - sy0;    // <= DH (host guarantees H >= PH, W >= PW)
+    dnc = min(__ldg(p.tab.xstart + xlast) + __ldg(p.tab.xcnt + xlast), p.PW) - sx0;    // <= DW
+  }
+  auto stage_delta = [&](int c, int s) {
+    const float* src = p.delta + ((long)(s ? fk.k1 : fk.k0) * CD + c) * p.PH * p.PW + (long)sy0 * p.PW + sx0;
+    for (int r = warp; r < dnr; r += 8)
+      for (int cc = lane; cc < dnc; cc += 32) dl[r * kB2DW + cc] = __ldg(src + (long)r * p.PW + cc);
+  };
+
+  // ---- phase 1: this thread's pixels (2 rows x 4 pixels x RGB) -> shared; luminance tile with a 2-pixel zero halo
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int yl = warp * 4 + k, gy = y0 + yl;
+  for (int k = 0; k < 2; ++k) {
+    const int yl = warp * 2 + k, gy = y0 + yl;
     if (VEC == 4) {
       const int gx = x0 + lane * 4;
       float4 v[3];
@@ -187,145 +242,218 @@ __global__ void __launch_bounds__(256, 2) jnd_blend2_kernel(const BlendParams p)
           lum[s * kB2LP + 4 + col] = l;
         }
       }
-    }
-    const int ht = (int)threadIdx.x - (256 - 4 * (kB2TH + 4));   // halo columns x0-2, x0-1, x0+TW, x0+TW+1 of all TH+4 rows
-    if (ht >= 0) {
-      const int s = ht >> 2, j = ht & 3;
-      const int col = j < 2 ? j - 2 : kB2TW + j - 2;
-      const int gy = y0 + s - 2, gx = x0 + col;
-      float l = 0.f;
-      if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) {
-        const float* sp = img + (long)gy * p.W + gx;
-        l = lum255(__ldg(sp), __ldg(sp + plane), __ldg(sp + 2 * plane));
+    } else {          // warps 4..7: halo columns x0-2, x0-1, x0+TW, x0+TW+1 of all TH+4 rows
+      const int ht = (int)threadIdx.x - 128;
+      if (ht < 4 * (kB2TH + 4)) {
+        const int s = ht >> 2, j = ht & 3;
+        const int col = j < 2 ? j - 2 : kB2TW + j - 2;
+        const int gy = y0 + s - 2, gx = x0 + col;
+        float l = 0.f;
+        if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) {
+          const float* sp = img + (long)gy * p.W + gx;
+          l = lum255(__ldg(sp), __ldg(sp + plane), __ldg(sp + 2 * plane));
+        }
+        lum[s * kB2LP + 4 + col] = l;
       }
-      lum[s * kB2LP + 4 + col] = l;
     }
   }
+  if (staged) stage_delta(0, 0);
   __syncthreads();
 
-  // ---- phase 2
-  const FrameKeys fk = frame_keys(f, p.F, p.step, p.alternate, p.interp_chunk);
-  const bool has_delta = fk.has;
-  const int nsrc = (fk.k1 != fk.k0 && fk.a != 1.f) ? 2 : 1;
-  // x taps of this thread's 4 pixels for the delta up-sample (FASTUP, not the identity)
-  int xs[4], xo[4];
-  float xw0[4], xw1[4];
-  if (FASTUP && !p.identity_resample) {
+  // ---- phase 2a: heat-map of this thread's 2 x 4 pixels.  VERTICAL sums first (they are shared by the pixels of a row segment):
+  //   output row j in {0, 1} sees luminance rows j .. j+4 of the six rows L0..L5 this thread reads; per column
+  //     V5_j = sum of its 5 rows, V3_j = sum of its 3 middle rows, VS_j = [1 2 1] smooth of the middle rows = V3_j + centre row,
+  //     VD_j = row j+1 - row j+3;
+  //   then per pixel  la = sum_5 V5 + sum_3 V3 - 2 centre,  gx = VS[x+1] - VS[x-1],  gy = VD[x-1] + 2 VD[x] + VD[x+1]
+  //   (the 5x5 kernel of modules/jnd.py:37-43 is ones(5,5) + ones(3,3) - 2 delta; Sobel pair jnd.py:44-53).
+  float hm[2][4];
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-      const int ox = min(x0 + col_of(q), p.W - 1);
-      xs[q] = __ldg(p.tab.xstart + ox);
-      const int xc = __ldg(p.tab.xcnt + ox);
-      xw0[q] = __ldg(p.tab.xw + (long)ox * p.tab.maxt_x);
-      xw1[q] = xc > 1 ? __ldg(p.tab.xw + (long)ox * p.tab.maxt_x + 1) : 0.f;
-      xo[q] = xc > 1 ? 1 : 0;
-    }
-  }
-  // rolling window of luminance rows (VEC 4): row i of the window = shared row warp*4 + k + i, 12 floats from shared column lane*4
-  float Lw[5][12];
-  if (VEC == 4 && p.use_jnd) {
+  for (int j = 0; j < 2; ++j)
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-      const float4* s4 = reinterpret_cast<const float4*>(lum + (warp * 4 + i) * kB2LP + lane * 4);
+    for (int q = 0; q < 4; ++q) hm[j][q] = 1.f;
+  if (p.use_jnd) {
+    if (VEC == 4) {
+      // segment columns 2..9 (V5) / 3..8 (the others) of the 12 floats at shared column lane*4; pixel q's centre = column 4 + q
+      float L[6][8];
+      {
 #pragma unroll
-      for (int u = 0; u < 3; ++u) {
-        const float4 t4 = s4[u];
-        Lw[i][4 * u] = t4.x; Lw[i][4 * u + 1] = t4.y; Lw[i][4 * u + 2] = t4.z; Lw[i][4 * u + 3] = t4.w;
-      }
-    }
-  }
-#pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    const int yl = warp * 4 + k, gy = y0 + yl;
-    float hm[4] = {1.f, 1.f, 1.f, 1.f};
-    if (p.use_jnd) {
-      if (VEC == 4) {
-        const float4* s4 = reinterpret_cast<const float4*>(lum + (yl + 4) * kB2LP + lane * 4);
-#pragma unroll
-        for (int u = 0; u < 3; ++u) {
-          const float4 t4 = s4[u];
-          Lw[4][4 * u] = t4.x; Lw[4][4 * u + 1] = t4.y; Lw[4][4 * u + 2] = t4.z; Lw[4][4 * u + 3] = t4.w;
+        for (int r = 0; r < 6; ++r) {
+          const float4* s4 = reinterpret_cast<const float4*>(lum + (warp * 2 + r) * kB2LP + lane * 4);
+          const float4 t0 = s4[0], t1 = s4[1], t2 = s4[2];
+          L[r][0] = t0.z; L[r][1] = t0.w; L[r][2] = t1.x; L[r][3] = t1.y; L[r][4] = t1.z; L[r][5] = t1.w; L[r][6] = t2.x; L[r][7] = t2.y;
         }
+      }
+      float V5[2][8], V3[2][6], VS[2][6], VD[2][6];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) hm[q] = jnd_window(&Lw[0][4 + q], &Lw[1][4 + q], &Lw[2][4 + q], &Lw[3][4 + q], &Lw[4][4 + q]);
+      for (int cidx = 0; cidx < 8; ++cidx) {
+        const float mid4 = (L[1][cidx] + L[2][cidx]) + (L[3][cidx] + L[4][cidx]);
+        V5[0][cidx] = mid4 + L[0][cidx];
+        V5[1][cidx] = mid4 + L[5][cidx];
+      }
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+      for (int cidx = 0; cidx < 6; ++cidx) {
+        const float c23 = L[2][cidx + 1] + L[3][cidx + 1];
+        V3[0][cidx] = c23 + L[1][cidx + 1];
+        V3[1][cidx] = c23 + L[4][cidx + 1];
+        VS[0][cidx] = V3[0][cidx] + L[2][cidx + 1];
+        VS[1][cidx] = V3[1][cidx] + L[3][cidx + 1];
+        VD[0][cidx] = L[1][cidx + 1] - L[3][cidx + 1];
+        VD[1][cidx] = L[2][cidx + 1] - L[4][cidx + 1];
+      }
 #pragma unroll
-          for (int j = 0; j < 12; ++j) Lw[i][j] = Lw[i + 1][j];
-      } else {
+      for (int j = 0; j < 2; ++j)
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
-          const float* cpt = lum + yl * kB2LP + 4 + lane + 32 * q;
-          hm[q] = jnd_window(cpt, cpt + kB2LP, cpt + 2 * kB2LP, cpt + 3 * kB2LP, cpt + 4 * kB2LP);
+          const float la = ((V5[j][q] + V5[j][q + 1]) + (V5[j][q + 2] + V5[j][q + 3])) + V5[j][q + 4] +
+                           (V3[j][q] + V3[j][q + 1] + V3[j][q + 2]);
+          const float lac = fmaf(-2.f, L[2 + j][q + 2], la);
+          const float gx = VS[j][q + 2] - VS[j][q];
+          const float gy = fmaf(2.f, VD[j][q + 1], VD[j][q] + VD[j][q + 2]);
+          hm[j][q] = jnd_value(lac, gx, gy);
+        }
+    } else {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float* cpt = lum + (warp * 2) * kB2LP + 4 + lane + 32 * q;      // row 0 of the window, centre column
+        float L[6][5];
+#pragma unroll
+        for (int r = 0; r < 6; ++r)
+#pragma unroll
+          for (int i = 0; i < 5; ++i) L[r][i] = cpt[r * kB2LP + i - 2];
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          float la = 0.f, gx = 0.f, gy = 0.f;
+#pragma unroll
+          for (int i = 0; i < 5; ++i) {
+            const float v5 = L[j][i] + L[j + 1][i] + L[j + 2][i] + L[j + 3][i] + L[j + 4][i];
+            la += v5;
+            if (i >= 1 && i <= 3) {
+              const float v3 = L[j + 1][i] + L[j + 2][i] + L[j + 3][i];
+              la += v3;
+              const float vs = v3 + L[j + 2][i], vd = L[j + 1][i] - L[j + 3][i];
+              if (i == 1) { gx -= vs; gy += vd; }
+              if (i == 2) gy = fmaf(2.f, vd, gy);
+              if (i == 3) { gx += vs; gy += vd; }
+            }
+          }
+          la = fmaf(-2.f, L[j + 2][2], la);
+          hm[j][q] = jnd_value(la, gx, gy);
         }
       }
     }
-    if (gy >= p.H) continue;                                   // uniform per warp
-    // ---- delta of this row (up-resampled from PH x PW) x heat-map
-    float d[3][4];
-    int ys = 0, yo = 0;
-    float yw0 = 1.f, yw1 = 0.f;
-    if (FASTUP && !p.identity_resample) {
-      ys = __ldg(p.tab.ystart + gy);
-      const int yc = __ldg(p.tab.ycnt + gy);
-      yw0 = __ldg(p.tab.yw + (long)gy * p.tab.maxt_y);
-      yw1 = yc > 1 ? __ldg(p.tab.yw + (long)gy * p.tab.maxt_y + 1) : 0.f;
-      yo = yc > 1 ? 1 : 0;
+  }
+
+  // ---- phase 2b: delta of the 2 x 4 pixels (up-resampled from PH x PW), x heat-map
+  float d[CD][2][4];
+#pragma unroll
+  for (int c = 0; c < CD; ++c)
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) d[c][j][q] = 0.f;
+  if (has_delta) {
+    int xr[4] = {0, 0, 0, 0}, xo[4] = {0, 0, 0, 0};
+    float xw0[4] = {1.f, 1.f, 1.f, 1.f}, xw1[4] = {0.f, 0.f, 0.f, 0.f};
+    int yr[2] = {0, 0}, yo[2] = {0, 0};
+    float yw0[2] = {1.f, 1.f}, yw1[2] = {0.f, 0.f};
+    if (staged) {
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const int ox = min(x0 + col_of(q), p.W - 1);
+        const int xc = __ldg(p.tab.xcnt + ox);
+        xr[q] = __ldg(p.tab.xstart + ox) - sx0;
+        xw0[q] = __ldg(p.tab.xw + (long)ox * p.tab.maxt_x);
+        xw1[q] = xc > 1 ? __ldg(p.tab.xw + (long)ox * p.tab.maxt_x + 1) : 0.f;
+        xo[q] = xc > 1 ? 1 : 0;
+      }
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+        const int oy = min(y0 + warp * 2 + j, p.H - 1);
+        const int yc = __ldg(p.tab.ycnt + oy);
+        yr[j] = __ldg(p.tab.ystart + oy) - sy0;
+        yw0[j] = __ldg(p.tab.yw + (long)oy * p.tab.maxt_y);
+        yw1[j] = yc > 1 ? __ldg(p.tab.yw + (long)oy * p.tab.maxt_y + 1) : 0.f;
+        yo[j] = yc > 1 ? 1 : 0;
+      }
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      if (c >= p.CD) break;
+      if (c >= CD) break;
+      for (int s = 0; s < nsrc; ++s) {
+        if (staged && (c | s) != 0) {      // the tile of the first (channel, key) was staged together with the image
+          __syncthreads();
+          stage_delta(c, s);
+          __syncthreads();
+        }
+        const float ws = nsrc == 1 ? 1.f : (s ? 1.f - fk.a : fk.a);
+        const bool same_rows = staged && yr[0] == yr[1] && yo[0] == yo[1];
+        float hra[4], hrb[4];
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        float v = 0.f;
-        const int gx = x0 + col_of(q);
-        if (has_delta && gx < p.W) {
-          for (int s = 0; s < nsrc; ++s) {
-            const float* src = p.delta + ((long)(s ? fk.k1 : fk.k0) * p.CD + c) * p.PH * p.PW;
-            float vs;
-            if (p.identity_resample) {
-              vs = __ldg(src + (long)gy * p.PW + gx);
-            } else if (FASTUP) {
-              const float* a = src + (long)ys * p.PW + xs[q];
-              const float* b = a + yo * p.PW;
-              const float ra = xw0[q] * __ldg(a) + xw1[q] * __ldg(a + xo[q]);
-              const float rb = xw0[q] * __ldg(b) + xw1[q] * __ldg(b + xo[q]);
-              vs = yw0 * ra + yw1 * rb;
-            } else {
-              const int ys2 = p.tab.ystart[gy], yc = p.tab.ycnt[gy], xs2 = p.tab.xstart[gx], xc = p.tab.xcnt[gx];
-              vs = 0.f;
-              for (int j = 0; j < yc; ++j) {
-                float racc = 0.f;
-                for (int i = 0; i < xc; ++i) racc += p.tab.xw[gx * p.tab.maxt_x + i] * __ldg(src + (long)(ys2 + j) * p.PW + xs2 + i);
-                vs += p.tab.yw[gy * p.tab.maxt_y + j] * racc;
+        for (int q = 0; q < 4; ++q) { hra[q] = 0.f; hrb[q] = 0.f; }
+        const float* src = p.delta + ((long)(s ? fk.k1 : fk.k0) * CD + c) * p.PH * p.PW;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int gy = y0 + warp * 2 + j;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const int gx = x0 + col_of(q);
+            float vs = 0.f;
+            if (gy < p.H && gx < p.W) {
+              if (p.identity_resample) {
+                vs = __ldg(src + (long)gy * p.PW + gx);
+              } else if (FASTUP) {
+                if (j == 0 || !same_rows) {     // (warp-uniform) at scale 3 two of three row pairs share both source rows
+                  const float* a0 = dl + yr[j] * kB2DW + xr[q];
+                  const float* b0 = a0 + yo[j] * kB2DW;
+                  hra[q] = xw0[q] * a0[0] + xw1[q] * a0[xo[q]];
+                  hrb[q] = xw0[q] * b0[0] + xw1[q] * b0[xo[q]];
+                }
+                vs = yw0[j] * hra[q] + yw1[j] * hrb[q];
+              } else {
+                const int ys2 = p.tab.ystart[gy], yc = p.tab.ycnt[gy], xs2 = p.tab.xstart[gx], xc = p.tab.xcnt[gx];
+                for (int jj = 0; jj < yc; ++jj) {
+                  float racc = 0.f;
+                  for (int i = 0; i < xc; ++i) racc += p.tab.xw[gx * p.tab.maxt_x + i] * __ldg(src + (long)(ys2 + jj) * p.PW + xs2 + i);
+                  vs += p.tab.yw[gy * p.tab.maxt_y + jj] * racc;
+                }
               }
             }
-            v += (nsrc == 1 ? 1.f : (s ? 1.f - fk.a : fk.a)) * vs;
+            d[c][j][q] = fmaf(ws, vs, d[c][j][q]);
           }
         }
-        d[c][q] = v * hm[q];
       }
     }
+#pragma unroll
+    for (int c = 0; c < CD; ++c)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) d[c][j][q] *= hm[j][q];
+  }
+
+  // ---- phase 2c: preds_w (optional) and the blend
+#pragma unroll
+  for (int j = 0; j < 2; ++j) {
+    const int yl = warp * 2 + j, gy = y0 + yl;
+    if (gy >= p.H) break;
     const long o = (long)gy * p.W + x0;
     const bool vfull = VEC == 4 && (x0 + lane * 4 < p.W);      // W % 4 == 0: a 4-pixel group is inside or outside as a whole
     if (p.preds_w != nullptr) {
 #pragma unroll
       for (int c = 0; c < 3; ++c) {
-        if (c >= p.CD) break;
-        float* dst = p.preds_w + ((long)f * p.CD + c) * plane + o;
+        if (c >= CD) break;
+        float* dst = p.preds_w + ((long)f * CD + c) * plane + o;
         if (VEC == 4) {
-          if (vfull) *reinterpret_cast<float4*>(dst + lane * 4) = make_float4(d[c][0], d[c][1], d[c][2], d[c][3]);
+          if (vfull) *reinterpret_cast<float4*>(dst + lane * 4) = make_float4(d[c][j][0], d[c][j][1], d[c][j][2], d[c][j][3]);
         } else {
 #pragma unroll
-          for (int q = 0; q < 4; ++q) if (x0 + lane + 32 * q < p.W) dst[lane + 32 * q] = d[c][q];
+          for (int q = 0; q < 4; ++q) if (x0 + lane + 32 * q < p.W) dst[lane + 32 * q] = d[c][j][q];
         }
       }
     }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
-      float in[4], out[4], dd[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) dd[q] = (p.CD == 1 || c == 0) ? d[0][q] : (c == 1 ? d[1][q] : d[2][q]);
+      float in[4], out[4];
       if (VEC == 4) {
         const float4 t4 = *reinterpret_cast<const float4*>(rgb + (c * kB2TH + yl) * kB2TW + lane * 4);
         in[0] = t4.x; in[1] = t4.y; in[2] = t4.z; in[3] = t4.w;
@@ -335,9 +463,9 @@ __global__ void __launch_bounds__(256, 2) jnd_blend2_kernel(const BlendParams p)
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        float v = p.scaling_i * in[q] + p.scaling_w * dd[q];
-        if (p.clamp) v = fminf(fmaxf(v, 0.f), 1.f);
-        out[q] = v;
+        const float dv = d[CD == 1 ? 0 : c][j][q];
+        const float v = fmaf(p.scaling_i, in[q], p.scaling_w * dv);
+        out[q] = p.clamp ? __saturatef(v) : v;
       }
       float* dst = p.imgs_w + ((long)f * 3 + c) * plane + o;
       if (VEC == 4) {
