@@ -282,6 +282,28 @@ def clip_leg(model, dev, world: int, rank: int, frames: int, size: int, steps: i
             ms = t.item()
         return ms / n
 
+    # sub-sharded variant: every rank owns TWO ranges (videoseal_b200.dist.subshard_bounds); the all-gather of the first half of the
+    # clip runs on NCCL's stream while the ranks embed their second range, the second one while they detect
+    sub = None
+    if world > 1 and frames % (world * 2 * step_size) == 0:
+        sb = vdist.subshard_bounds(frames, world, step_size, 2)[rank]
+        n_sub = sb[0][1] - sb[0][0]
+        seg = frames // 2
+
+        def step_sub(i):
+            x = local[i % 2]
+            outs, works = [], []
+            for sidx in range(2):
+                o = model.embed(x[sidx * n_sub:(sidx + 1) * n_sub], msgs, is_video=True)["imgs_w"]
+                works.append(dist.all_gather_into_tensor(gath_imgs[sidx * seg:(sidx + 1) * seg], o, async_op=True))
+                outs.append(o)
+            preds = model.detect(torch.cat(outs, dim=0), is_video=True)["preds"]
+            gather(gath_log, preds)
+            for w in works:
+                w.wait()
+            return preds
+        sub = step_sub
+
     res = {"frames": frames, "size": size, "frames_per_rank": n_loc, "step_size": step_size, "chunk_size": int(model.chunk_size),
            "scaling": "strong", "unit": "frames/s"}
     modes = ["none"] if world == 1 else ["none", "serial", "overlap"]
@@ -300,8 +322,18 @@ def clip_leg(model, dev, world: int, rank: int, frames: int, size: int, steps: i
         res["all_gather_imgs_w"] = {"collective": "ncclAllGather (torch.distributed all_gather_into_tensor)" if equal else "all_gather (ragged, padded)",
                                     "ms": ms, "bytes_received_per_rank": by, "bus_gbs": by / (ms * 1e-3) / 1e9,
                                     "limit": "inbound NVLink of every GPU: (N-1)/N of the clip's output per rank"}
-        res["value"] = res["gather_overlapped"]["value"]
-        res["ms_per_step"] = res["gather_overlapped"]["ms_per_step"]
+        best = "gather_overlapped"
+        if sub is not None:
+            for i in range(3):
+                sub(i)
+            ms = timed(sub, steps)
+            res["gather_overlapped_2_subshards"] = {"ms_per_step": ms, "value": frames / (ms / 1000.0),
+                                                    "note": "rank r owns frame ranges r and world+r of 2*world; gather of half 0 under embed of half 1, of half 1 under detect"}
+            if ms < res["gather_overlapped"]["ms_per_step"]:
+                best = "gather_overlapped_2_subshards"
+        res["value"] = res[best]["value"]
+        res["ms_per_step"] = res[best]["ms_per_step"]
+        res["value_mode"] = best
     else:
         res["value"] = res["sharded_outputs"]["value"]
         res["ms_per_step"] = res["sharded_outputs"]["ms_per_step"]

@@ -57,13 +57,13 @@ typedef struct vsb_model_desc {
   int32_t unet_levels;       /* len(z_channels_mults), <= 6 */
   int32_t unet_z[6];         /* z_channels * mult */
   int32_t unet_num_blocks;
-  int32_t unet_act;          /* 0 relu (only supported value) */
-  int32_t unet_norm;         /* 0 batch (only supported value) */
+  int32_t unet_act;          /* 0 relu (the only value the GPU path implements; 1 = silu is rejected by vsb_model_finalize) */
+  int32_t unet_norm;         /* 0 batch (the only value the GPU path implements; 1 = rms is rejected by vsb_model_finalize) */
   int32_t unet_last_tanh;
   int32_t ext_depths[4];
   int32_t ext_dims[4];       /* after proportional_dim scaling, extractor.py:193-198 */
   int32_t ext_stem_stride;
-  int32_t jnd_in_ch, jnd_out_ch; /* configs/attenuation.yaml entry; 0,0 = no attenuation */
+  int32_t jnd_in_ch, jnd_out_ch; /* configs/attenuation.yaml entry (jnd_1_1 / jnd_1_3 / jnd_3_1 / jnd_3_3); 0,0 = no attenuation */
 } vsb_model_desc;
 
 const char* vsb_last_error(void);
@@ -77,7 +77,8 @@ int vsb_model_finalize(vsb_model* m, int32_t device);
 void vsb_model_destroy(vsb_model* m);
 
 /* imgs_dev [F,3,H,W] fp32 in [0,1]; msgs_dev uint8 {0,1}: [F,nbits] (n_msgs == F) or [1,nbits] (n_msgs == 1);
- * imgs_w_dev [F,3,H,W]; preds_w_dev NULL or [F,unet_out_ch,H,W] (hmap * delta_up, before scaling_w);
+ * imgs_w_dev [F,3,H,W]; preds_w_dev NULL or [F,PC,H,W] (hmap * delta_up, before scaling_w; PC = max(unet_out_ch, jnd_out_ch) with
+ * attenuation on, the broadcast of `hmaps * preds_w` in wam.py:189-193, else unet_out_ch);
  * step = 1 for image mode, else frames share the key frame f/step (videoseal.py:292-340);
  * chunk_keys = the model's chunk_size (key frames per reference chunk, videoseal.py:300): it only changes the result in
  * video_mode 'interpolate', where neighbouring key frames of ONE chunk are mixed (videoseal.py:101-113); 1..64 there. */
@@ -94,7 +95,7 @@ int vsb_embedder_forward(vsb_model* m, const float* x_dev, const uint8_t* msgs_d
 int vsb_detect(vsb_model* m, const float* imgs_dev, float* logits_dev, int32_t F, int32_t H, int32_t W, int32_t flags,
                void* stream);
 
-/* imgs_dev [F,3,H,W] -> hmaps_dev [F,1,H,W] */
+/* imgs_dev [F,3,H,W] -> hmaps_dev [F,jnd_out_ch,H,W] */
 int vsb_jnd_heatmaps(vsb_model* m, const float* imgs_dev, float* hmaps_dev, int32_t F, int32_t H, int32_t W, void* stream);
 
 /* Host-buffer variants (pinned or pageable): copy in, run, copy out, synchronise. */

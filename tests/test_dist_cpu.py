@@ -86,3 +86,21 @@ def test_oracle_frame_sharding_invariance():
         d_whole = orc.detect(whole, is_video=True)["preds"]
         d_parts = torch.cat([orc.detect(whole[s0:e0], is_video=True)["preds"], orc.detect(whole[s1:e1], is_video=True)["preds"]])
         assert (d_whole - d_parts).abs().max().item() < 1e-5
+
+
+def test_subshard_bounds_cover_the_clip_in_frame_order():
+    from videoseal_b200.dist import subshard_bounds
+    F, world, step, S = 512, 8, 4, 2
+    b = subshard_bounds(F, world, step, S)
+    assert len(b) == world and all(len(x) == S for x in b)
+    # the all-gather of segment s concatenates rank 0..world-1 ranges: that must be a contiguous run of frames in order
+    pos = 0
+    for s in range(S):
+        for r in range(world):
+            a, e = b[r][s]
+            assert a == pos and (e - a) % step == 0 and e > a
+            pos = e
+    assert pos == F
+    import pytest
+    with pytest.raises(ValueError):
+        subshard_bounds(500, 8, 4, 2)

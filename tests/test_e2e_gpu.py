@@ -399,3 +399,30 @@ def test_structured_image_against_reference_golden(card, v1, px):
     det = model.detect(out["imgs_w"], is_video=False)["preds"].cpu()
     rel, flips, _ = logits_ok(det, c["preds"])
     assert rel <= LOGIT_RTOL and flips == 0, (rel, flips)
+
+
+@pytest.mark.parametrize("att", ["jnd_1_3", "jnd_3_1", "jnd_3_3"])
+def test_jnd_channel_variants(att):
+    """configs/attenuation.yaml: heat-maps from the luminance or per RGB channel, 1 or 3 output channels (modules/jnd.py:80-108);
+    preds_w = hmaps * delta broadcasts to max(channels) like wam.py:189-193"""
+    pair = make_model_pair("videoseal_1.0", tiny={"attenuation": att})
+    model, orc, spec = pair
+    assert model.attenuation.in_channels == int(att[4]) and model.attenuation.out_channels == int(att[6])
+    g = torch.Generator().manual_seed(41)
+    imgs = torch.rand(2, 3, 300, 340, generator=g)
+    with torch.no_grad():
+        h_ref = orc.heatmaps(imgs)
+    h = model.attenuation.heatmaps(imgs.cuda()).cpu()
+    assert h.shape == h_ref.shape and (h - h_ref).abs().max().item() <= 1e-5
+    out = _img_case(pair, 2, 300, 340, 42)
+    assert out["preds_w"].shape[1] == max(1, int(att[6]))
+    _img_case(pair, 1, 256, 256, 43)                    # identity resample
+    _img_case(pair, 1, 200, 333, 44)                    # scalar (W % 4 != 0) path, up-scaled input
+    msgs = torch.randint(0, 2, (2, spec["nbits"]), generator=g)
+    with torch.no_grad():
+        ref = orc.embed(imgs, msgs, is_video=False, lowres_attenuation=True)
+    got = model.embed(imgs.cuda(), msgs, is_video=False, lowres_attenuation=True)
+    assert (got["imgs_w"].cpu() - ref["imgs_w"]).abs().max().item() <= PIX_TOL
+    assert (got["preds_w"].cpu() - ref["preds_w"]).abs().max().item() <= 5 * PIX_TOL
+    del model
+    torch.cuda.empty_cache()

@@ -57,6 +57,8 @@ def apply_overrides(card: dict, o: dict) -> dict:
         card["args"]["nbits"] = o["nbits"]
     if "num_blocks" in o:
         card["embedder"]["params"]["unet"]["num_blocks"] = o["num_blocks"]
+    if "attenuation" in o:
+        card["args"]["attenuation"] = o["attenuation"]
     if "depths" in o:
         card["extractor"]["params"]["encoder"]["depths"] = o["depths"]
     return card

@@ -482,29 +482,35 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       const uint32_t trow = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * kAccStride + g * p.block_n);
 
       if (p.epi == EPI_LN) {
-        // channels-first LayerNorm over the full C_out row (biased variance), then activation; half-0 warps only
-        if (half == 0) {
+        // channels-first LayerNorm over the full C_out row (biased variance), then activation.  The kEpiSplit warps that share a
+        // TMEM lane quadrant split the 16-column chunks: pass 1 = per-warp partial (sum, sum of squares) of its chunks, exchanged
+        // through shared memory and added in a fixed order; pass 2 = normalise + store its chunks.  (The first version let one warp
+        // per quadrant walk the whole row three times: stem GEMM 124 us at 19 TF/s.)
+        {
           const int N = p.N;
-          float sum = 0.f;
-          for (int c = 0; c < p.block_n; c += 16) {
-            float v[16];
-            tmem_ld16(trow + c, v);
-#pragma unroll
-            for (int j = 0; j < 16; ++j) sum += (c + j < N) ? v[j] + sb[c + j] : 0.f;
-          }
-          const float mean = sum / (float)N;
-          float var = 0.f;
-          for (int c = 0; c < p.block_n; c += 16) {
+          float* s_part = s_dot;                                  // [kEpiSplit][128][2]
+          float sum = 0.f, sq = 0.f;
+          for (int ch = half; ch < nchunks; ch += kEpiSplit) {
+            const int c = ch * 16;
             float v[16];
             tmem_ld16(trow + c, v);
 #pragma unroll
             for (int j = 0; j < 16; ++j) {
-              const float d = v[j] + sb[c + j] - mean;
-              var += (c + j < N) ? d * d : 0.f;
+              const float x = (c + j < N) ? v[j] + sb[c + j] : 0.f;
+              sum += x;
+              sq = fmaf(x, x, sq);
             }
           }
-          const float rstd = 1.0f / sqrtf(var / (float)N + p.ln_eps);
-          for (int c = 0; c < p.block_n; c += 16) {
+          s_part[(half * 128 + row) * 2] = sum;
+          s_part[(half * 128 + row) * 2 + 1] = sq;
+          epi_bar_sync<kEpiThreads>();
+          sum = 0.f; sq = 0.f;
+#pragma unroll
+          for (int h2 = 0; h2 < kEpiSplit; ++h2) { sum += s_part[(h2 * 128 + row) * 2]; sq += s_part[(h2 * 128 + row) * 2 + 1]; }
+          const float mean = sum / (float)N;
+          const float rstd = 1.0f / sqrtf(fmaxf(sq / (float)N - mean * mean, 0.f) + p.ln_eps);
+          for (int ch = half; ch < nchunks; ch += kEpiSplit) {
+            const int c = ch * 16;
             float v[16];
             tmem_ld16(trow + c, v);
             if (c >= N) continue;
@@ -544,6 +550,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               }
             }
           }
+          epi_bar_sync<kEpiThreads>();     // s_part is rewritten by the next sub-tile
         }
       } else {
         float dot0 = 0.f, dot1 = 0.f, dot2 = 0.f;

@@ -487,7 +487,7 @@ class Model {
       bn_fold(P + "inc.double_conv.1", s, b);
       const HostTensor& w = get(P + "inc.double_conv.0.weight");
       VSB_CHECK((int)w.shape[0] == z[0] && (int)w.shape[1] == d.unet_in_ch, "inc conv shape");
-      VSB_CHECK(z[0] % 8 == 0, "z0 must be a multiple of 8");
+      VSB_CHECK(z[0] % 16 == 0, "z0 must be a multiple of 16");
       std::vector<float> w1(w.data);
       const size_t per = (size_t)d.unet_in_ch * 9;
       for (int n = 0; n < z[0]; ++n) for (size_t k = 0; k < per; ++k) w1[n * per + k] *= s[n];
@@ -688,7 +688,7 @@ class Model {
       const int Z = z[0], yuv = d.yuv, cin = d.unet_in_ch;
       float *w1 = first_w1, *b1 = first_b1, *wr = first_wr, *br = first_br;
       pl.steps.push_back(Step{[=](cudaStream_t st) {
-        dim3 grid((S + 15) / 16, (S + 15) / 16, B);
+        dim3 grid((S + 31) / 32, (S + 15) / 16, B);
         // frame stride lets image-size inputs be read in place (key frames of a video are `step` frames apart)
         const float* src = plp->in_imgs;
         if (plp->in_frame_stride != (long)3 * S * S) {
@@ -801,6 +801,24 @@ class Model {
         const int vpt = Cc <= 256 ? 1 : 2;            // 16-byte channel vectors per thread (chunkyseal's first up-conv: 512 channels)
         const int gthreads = Cc / (8 * vpt);          // threads per output pixel
         VSB_CHECK(Cc % (8 * vpt) == 0 && gthreads <= 32 && (gthreads & (gthreads - 1)) == 0, "up conv: C_out must be 8 * 2^k <= 512");
+        const size_t tsmem = (size_t)100 * 9 * Cc * sizeof(__half);
+        static const bool no_tiled = getenv("VSB_UPS_UNTILED") != nullptr;
+        if (!no_tiled && IH % 8 == 0 && tsmem <= 160 * 1024) {
+          // low-resolution taps of a 16 x 16 output tile staged in shared memory (ups_gather_ln_tiled_kernel)
+          pl.steps.push_back(Step{[=](cudaStream_t st) {
+            const unsigned blocks = (unsigned)((long)B * (IH / 8) * (IH / 8));
+            if (vpt == 1) {
+              static bool attr = false;
+              if (!attr) { VSB_CUDA(cudaFuncSetAttribute(ups_gather_ln_tiled_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr = true; }
+              ups_gather_ln_tiled_kernel<1><<<blocks, 256, tsmem, st>>>(ytap, B, IH, IH, Cc, lw, lb, 1e-6f, u, Cc);
+            } else {
+              static bool attr = false;
+              if (!attr) { VSB_CUDA(cudaFuncSetAttribute(ups_gather_ln_tiled_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, 160 * 1024)); attr = true; }
+              ups_gather_ln_tiled_kernel<2><<<blocks, 256, tsmem, st>>>(ytap, B, IH, IH, Cc, lw, lb, 1e-6f, u, Cc);
+            }
+            VSB_CUDA(cudaGetLastError());
+          }, 1, "unet.upgather." + std::to_string(Cout) + "@" + std::to_string(ho)});
+        } else
         pl.steps.push_back(Step{[=](cudaStream_t st) {
           const int ppb = 256 / gthreads;
           const long blocks = (Mo + ppb - 1) / ppb;
@@ -1320,7 +1338,10 @@ class Model {
     const bool same = (H == S && W == S);
     const bool aa = !(flags & VSB_FLAG_RESIZE_NO_AA);
     const bool use_jnd = !(flags & VSB_FLAG_NO_ATTENUATION) && d.jnd_in_ch != 0;
-    if (use_jnd && !(d.jnd_in_ch == 1 && d.jnd_out_ch == 1)) throw Error("only the jnd_1_1 attenuation is implemented on the GPU path", kErrUnsupported);
+    if (use_jnd && !((d.jnd_in_ch == 1 || d.jnd_in_ch == 3) && (d.jnd_out_ch == 1 || d.jnd_out_ch == 3)))
+      throw Error("JND attenuation: in_channels / out_channels must be 1 or 3 (configs/attenuation.yaml)", kErrUnsupported);
+    // channels of hmaps * preds_w (broadcast): what `preds_w` holds and what the low-resolution path hands to the blend
+    const int PC = use_jnd ? std::max(d.unet_out_ch, d.jnd_out_ch) : d.unet_out_ch;
     const bool lowres = use_jnd && (flags & VSB_FLAG_LOWRES_ATTN);
     const long fstride = (long)3 * H * W;
     const int nkeys = (F + step - 1) / step;
@@ -1356,21 +1377,22 @@ class Model {
       BlendParams bp;
       memset(&bp, 0, sizeof(bp));
       bp.imgs = imgs + (size_t)f0 * fstride; bp.imgs_w = imgs_w + (size_t)f0 * fstride;
-      bp.preds_w = preds_w ? preds_w + (size_t)f0 * d.unet_out_ch * H * W : nullptr;
+      bp.preds_w = preds_w ? preds_w + (size_t)f0 * PC * H * W : nullptr;
       bp.F = nf; bp.H = H; bp.W = W; bp.PH = S; bp.PW = S; bp.CD = d.unet_out_ch;
+      bp.jnd_in = d.jnd_in_ch ? d.jnd_in_ch : 1; bp.jnd_out = d.jnd_out_ch ? d.jnd_out_ch : 1;
       bp.clamp = (flags & VSB_FLAG_CLAMP) ? 1 : 0; bp.identity_resample = same ? 1 : 0;
       bp.scaling_i = scaling_i; bp.scaling_w = scaling_w;
       if (up) bp.tab = up->tab;
       if (lowres) {
         // per-frame attenuated delta at processing size: out[f] = hmap(frames_res[f]) * delta(keys of f); then a plain blend
-        float* lowres_buf = (float*)stage(7, (size_t)nf * d.unet_out_ch * S * S * sizeof(float));
+        float* lowres_buf = (float*)stage(7, (size_t)nf * PC * S * S * sizeof(float));
         VSB_CHECK(nf <= 65535, "too many frames per key-frame batch");
         dim3 grid((S + kBlendTW - 1) / kBlendTW, (S + kBlendTH - 1) / kBlendTH, nf);
         const int CD = d.unet_out_ch;
         prof_scope("pw.jnd_lowres@" + std::to_string(nf), st, 1,
-                   [&] { jnd_lowres_kernel<<<grid, 256, 0, st>>>(frames_res, delta, lowres_buf, S, S, CD, step, balt, bint); });
+                   [&] { jnd_lowres_kernel<<<grid, 256, 0, st>>>(frames_res, delta, lowres_buf, S, S, CD, step, balt, bint, bp.jnd_in, bp.jnd_out); });
         VSB_CUDA(cudaGetLastError());
-        bp.delta = lowres_buf; bp.step = 1; bp.alternate = 0; bp.interp_chunk = 0; bp.use_jnd = 0;
+        bp.delta = lowres_buf; bp.step = 1; bp.alternate = 0; bp.interp_chunk = 0; bp.use_jnd = 0; bp.CD = PC;
       } else {
         bp.delta = delta; bp.step = step; bp.alternate = balt; bp.interp_chunk = bint; bp.use_jnd = use_jnd ? 1 : 0;
       }
@@ -1388,24 +1410,26 @@ class Model {
     VSB_CHECK(bp.CD == 1 || bp.CD == 3, "delta must have 1 or 3 channels");
     prof_scope(std::string(bp.use_jnd ? "pw.jnd_blend." : "pw.blend.") + std::to_string(bp.H) + "x" + std::to_string(bp.W) + "@" + std::to_string(bp.F) +
                    (bp.preds_w ? "+preds" : ""), st, 1, [&] {
-#define VSB_BL(V, FU, CDV) do { static bool attr_ = false; \
-        if (!attr_) { VSB_CUDA(cudaFuncSetAttribute(jnd_blend2_kernel<V, FU, CDV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kB2Smem)); attr_ = true; } \
-        jnd_blend2_kernel<V, FU, CDV><<<grid, 256, kB2Smem, st>>>(bp); } while (0)
-      if (bp.CD == 1) {
-        if (vec) { if (fastup) VSB_BL(4, 1, 1); else VSB_BL(4, 0, 1); } else { if (fastup) VSB_BL(1, 1, 1); else VSB_BL(1, 0, 1); }
-      } else {
-        if (vec) { if (fastup) VSB_BL(4, 1, 3); else VSB_BL(4, 0, 3); } else { if (fastup) VSB_BL(1, 1, 3); else VSB_BL(1, 0, 3); }
-      }
+#define VSB_BL(V, FU, CDV, JI) do { static bool attr_ = false; \
+        if (!attr_) { VSB_CUDA(cudaFuncSetAttribute(jnd_blend2_kernel<V, FU, CDV, JI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b2_smem(JI))); attr_ = true; } \
+        jnd_blend2_kernel<V, FU, CDV, JI><<<grid, 256, b2_smem(JI), st>>>(bp); } while (0)
+#define VSB_BL2(CDV, JI) do { \
+        if (vec) { if (fastup) VSB_BL(4, 1, CDV, JI); else VSB_BL(4, 0, CDV, JI); } else { if (fastup) VSB_BL(1, 1, CDV, JI); else VSB_BL(1, 0, CDV, JI); } } while (0)
+      const bool j3 = bp.use_jnd && bp.jnd_in == 3;      // one heat-map per RGB channel (jnd_3_1 / jnd_3_3): rarely used, own instantiation
+      if (bp.CD == 1) { if (j3) VSB_BL2(1, 3); else VSB_BL2(1, 1); }
+      else            { if (j3) VSB_BL2(3, 3); else VSB_BL2(3, 1); }
+#undef VSB_BL2
 #undef VSB_BL
     });
     VSB_CUDA(cudaGetLastError());
   }
 
   void jnd_heatmaps(const float* imgs, float* hmaps, int F, int H, int W, cudaStream_t st) {
-    // heat-map only (operator seam, modules/jnd.py:80-108): jnd_lowres_kernel with delta == nullptr writes hmap * 1
+    // heat-map only (operator seam, modules/jnd.py:80-108): jnd_lowres_kernel with delta == nullptr writes hmap * 1; hmaps [F, jnd_out, H, W]
     VSB_CHECK(F <= 65535, "too many frames");
+    VSB_CHECK(d.jnd_in_ch != 0, "the card has no JND attenuation");
     dim3 grid((W + kBlendTW - 1) / kBlendTW, (H + kBlendTH - 1) / kBlendTH, F);
-    jnd_lowres_kernel<<<grid, 256, 0, st>>>(imgs, nullptr, hmaps, H, W, 1, 1, 0, 0);
+    jnd_lowres_kernel<<<grid, 256, 0, st>>>(imgs, nullptr, hmaps, H, W, 1, 1, 0, 0, d.jnd_in_ch, d.jnd_out_ch);
     g_launches += 1;
     VSB_CUDA(cudaGetLastError());
   }

@@ -10,6 +10,7 @@
 //   K8  head_pool_kernel / head_linear_kernel   LN + GELU + spatial mean, then Linear(C -> 1 + nbits)
 #pragma once
 #include <type_traits>
+#include "conv_gemm.cuh"
 #include "ptx.cuh"
 
 namespace vsb {
@@ -33,60 +34,86 @@ struct ResampleTab {
 // h1 = relu(conv3x3(x; w1') + b1')   (BN folded)      -> NHWC fp16 [B,H,W,Z]
 // r  = conv1x1(x; wr) + br                             -> NHWC fp16 [B,H,W,Z]
 // (modules/unet.py:24-39 for the `inc` block).  Zero padding applies to the preprocessed x.
+// Thread = 4 horizontally adjacent pixels x 8 of every 16 output channels (block = 16 rows x 32 columns; lane bit 0 picks the channel
+// half): every weight load feeds 4 FMAs, the 3 x 6 input window of the 4 pixels lives in registers, and the two lanes of a pair
+// store the two 16-byte halves of a pixel's 32-byte channel group in the SAME instruction (full sectors).  The first version (1 pixel
+// per thread, all channels) executed one weight load per FMA and was issue-bound at 152 us for a 64-frame batch against a 49 us HBM
+// bound (318 MB).  Z % 16 == 0.
 template <int CIN>
 __global__ void __launch_bounds__(256) unet_first_kernel(const float* __restrict__ imgs, int B, int H, int W, int Z,
                                                          const float* __restrict__ w1 /*[Z][CIN][3][3]*/, const float* __restrict__ b1,
                                                          const float* __restrict__ wr /*[Z][CIN]*/, const float* __restrict__ br,
                                                          __half* __restrict__ h1, __half* __restrict__ res, int yuv) {
-  __shared__ float tile[CIN][18][18 + 1];
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
-  const int x0 = blockIdx.x * 16, y0 = blockIdx.y * 16, b = blockIdx.z;
+  constexpr int NP = 4, TW = 8 * NP, TH = 16;
+  __shared__ float tile[CIN][TH + 2][TW + 2 + 2];
+  const int zh = threadIdx.x & 1, tx = (threadIdx.x >> 1) & 7, ty = threadIdx.x >> 4;
+  const int x0 = blockIdx.x * TW, y0 = blockIdx.y * TH, b = blockIdx.z;
   const float* img = imgs + (long)b * 3 * H * W;
-  for (int i = threadIdx.x; i < 18 * 18; i += 256) {
-    const int ly = i / 18, lx = i - ly * 18;
+  for (int i = threadIdx.x; i < (TH + 2) * (TW + 2); i += 256) {
+    const int ly = i / (TW + 2), lx = i - ly * (TW + 2);
     const int gy = y0 + ly - 1, gx = x0 + lx - 1;
     const bool in = gy >= 0 && gy < H && gx >= 0 && gx < W;
     if (CIN == 1) {
       float v = 0.f;
       if (in) {
         const long o = (long)gy * W + gx;
-        const float y = 0.299f * img[o] + 0.587f * img[(long)H * W + o] + 0.114f * img[2L * H * W + o];
+        const float y = 0.299f * __ldg(img + o) + 0.587f * __ldg(img + (long)H * W + o) + 0.114f * __ldg(img + 2L * H * W + o);
         v = 2.f * y - 1.f;
       }
       tile[0][ly][lx] = v;
     } else {
 #pragma unroll
-      for (int c = 0; c < CIN; ++c) tile[c][ly][lx] = in ? 2.f * img[(long)c * H * W + (long)gy * W + gx] - 1.f : 0.f;
+      for (int c = 0; c < CIN; ++c) tile[c][ly][lx] = in ? 2.f * __ldg(img + (long)c * H * W + (long)gy * W + gx) - 1.f : 0.f;
     }
   }
   __syncthreads();
-  const int gx = x0 + tx, gy = y0 + ty;
+  const int gx = x0 + tx * NP, gy = y0 + ty;
   if (gx >= W || gy >= H) return;
-  float xin[CIN * 9];
-#pragma unroll
-  for (int c = 0; c < CIN; ++c)
-#pragma unroll
-    for (int r = 0; r < 3; ++r)
-#pragma unroll
-      for (int s = 0; s < 3; ++s) xin[c * 9 + r * 3 + s] = tile[c][ty + r][tx + s];
   const long pix = ((long)b * H + gy) * W + gx;
-  for (int z0 = 0; z0 < Z; z0 += 8) {
-    __align__(16) __half ho[8];
-    __align__(16) __half ro[8];
+  const int npx = min(NP, W - gx);
+  for (int zb = 0; zb < Z; zb += 16) {
+    const int z0 = zb + 8 * zh;
+    float a[8][NP], rr[8][NP];
 #pragma unroll
     for (int q = 0; q < 8; ++q) {
-      const int z = z0 + q;
-      float a = __ldg(b1 + z);
+      const float bz = __ldg(b1 + z0 + q), brz = __ldg(br + z0 + q);
 #pragma unroll
-      for (int k = 0; k < CIN * 9; ++k) a += xin[k] * __ldg(w1 + z * CIN * 9 + k);
-      float rr = __ldg(br + z);
-#pragma unroll
-      for (int c = 0; c < CIN; ++c) rr += xin[c * 9 + 4] * __ldg(wr + z * CIN + c);
-      ho[q] = __float2half_rn(fmaxf(a, 0.f));
-      ro[q] = __float2half_rn(rr);
+      for (int p = 0; p < NP; ++p) { a[q][p] = bz; rr[q][p] = brz; }
     }
-    *reinterpret_cast<uint4*>(h1 + pix * Z + z0) = *reinterpret_cast<const uint4*>(ho);
-    *reinterpret_cast<uint4*>(res + pix * Z + z0) = *reinterpret_cast<const uint4*>(ro);
+#pragma unroll
+    for (int c = 0; c < CIN; ++c) {
+#pragma unroll
+      for (int r = 0; r < 3; ++r) {
+        float xr[NP + 2];
+#pragma unroll
+        for (int s = 0; s < NP + 2; ++s) xr[s] = tile[c][ty + r][tx * NP + s];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) {
+#pragma unroll
+          for (int s = 0; s < 3; ++s) {
+            const float wv = __ldg(w1 + ((z0 + q) * CIN + c) * 9 + r * 3 + s);
+#pragma unroll
+            for (int p = 0; p < NP; ++p) a[q][p] = fmaf(xr[p + s], wv, a[q][p]);
+          }
+          if (r == 1) {
+            const float wv = __ldg(wr + (z0 + q) * CIN + c);
+#pragma unroll
+            for (int p = 0; p < NP; ++p) rr[q][p] = fmaf(xr[p + 1], wv, rr[q][p]);
+          }
+        }
+      }
+    }
+#pragma unroll
+    for (int p = 0; p < NP; ++p) {
+      if (p < npx) {
+        __align__(16) __half ho[8];
+        __align__(16) __half ro[8];
+#pragma unroll
+        for (int q = 0; q < 8; ++q) { ho[q] = __float2half_rn(fmaxf(a[q][p], 0.f)); ro[q] = __float2half_rn(rr[q][p]); }
+        *reinterpret_cast<uint4*>(h1 + (pix + p) * Z + z0) = *reinterpret_cast<const uint4*>(ho);
+        *reinterpret_cast<uint4*>(res + (pix + p) * Z + z0) = *reinterpret_cast<const uint4*>(ro);
+      }
+    }
   }
 }
 
@@ -124,6 +151,7 @@ struct BlendParams {
   int F, H, W, PH, PW, CD, step, alternate;
   int interp_chunk;  // > 0: video_mode 'interpolate' with this many key frames per chunk (frame 0 starts a chunk)
   int use_jnd, clamp, identity_resample;
+  int jnd_in, jnd_out;   // configs/attenuation.yaml in_channels / out_channels (1 or 3 each); preds_w has max(CD, jnd_out) channels
   float scaling_i, scaling_w;
   ResampleTab tab;  // delta (PH x PW) -> (H x W); unused when identity_resample
 };
@@ -165,46 +193,63 @@ __device__ __forceinline__ float jnd_from_lum(const float (*lum)[kBlendTW + 4 + 
 }
 
 // low-resolution attenuation (wam.py:177-180): delta[k] *= hmap(imgs_res[k*step ... ]) is per FRAME in video mode, so this
-// kernel writes a per-frame attenuated delta:  out[f] = hmap(imgs_res[f]) * delta[f / step]   (all at PH x PW)
+// kernel writes a per-frame attenuated delta:  out[f] = hmap(imgs_res[f]) * delta[f / step]   (all at PH x PW).
+// JND configurations (configs/attenuation.yaml, modules/jnd.py:80-108): jin = 1: heat-map of the luminance; jin = 3: one heat-map per
+// RGB channel (255 * channel through the same filters); jout = 1 with jin = 3: their mean; jout = 3 with jin = 1: the luminance map
+// for all three channels.  Output channels PC = max(CD, jout): delta (CD = 1 or 3 channels) and heat-map broadcast against each
+// other like `hmaps * preds_w` does.  delta == nullptr: heat-maps only (jout channels).
 __global__ void __launch_bounds__(256) jnd_lowres_kernel(const float* __restrict__ imgs_res, const float* __restrict__ delta,
                                                          float* __restrict__ out, int PH, int PW, int CD, int step, int alternate,
-                                                         int interp_chunk) {
+                                                         int interp_chunk, int jin, int jout) {
   __shared__ float lum[kBlendTH + 4][kBlendTW + 4 + 1];
   const int f = blockIdx.z;
   const int x0 = blockIdx.x * kBlendTW, y0 = blockIdx.y * kBlendTH;
   const long plane = (long)PH * PW;
   const float* img = imgs_res + (long)f * 3 * plane;
-  for (int i = threadIdx.x; i < (kBlendTH + 4) * (kBlendTW + 4); i += 256) {
-    const int ly = i / (kBlendTW + 4), lx = i - ly * (kBlendTW + 4);
-    const int gy = y0 + ly - 2, gx = x0 + lx - 2;
-    float v = 0.f;
-    if (gy >= 0 && gy < PH && gx >= 0 && gx < PW) {
-      const long o = (long)gy * PW + gx;
-      v = 0.299f * (255.f * img[o]) + 0.587f * (255.f * img[plane + o]) + 0.114f * (255.f * img[2 * plane + o]);
-    }
-    lum[ly][lx] = v;
-  }
-  __syncthreads();
   const int tx = (threadIdx.x & 31) * 4, ty = threadIdx.x >> 5;
   const int gy = y0 + ty;
+  float hm[3][4];
+  for (int pass = 0; pass < jin; ++pass) {
+    if (pass) __syncthreads();
+    for (int i = threadIdx.x; i < (kBlendTH + 4) * (kBlendTW + 4); i += 256) {
+      const int ly = i / (kBlendTW + 4), lx = i - ly * (kBlendTW + 4);
+      const int yy = y0 + ly - 2, xx = x0 + lx - 2;
+      float v = 0.f;
+      if (yy >= 0 && yy < PH && xx >= 0 && xx < PW) {
+        const long o = (long)yy * PW + xx;
+        v = jin == 1 ? 0.299f * (255.f * img[o]) + 0.587f * (255.f * img[plane + o]) + 0.114f * (255.f * img[2 * plane + o])
+                     : 255.f * img[pass * plane + o];
+      }
+      lum[ly][lx] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) hm[pass][q] = (gy < PH && x0 + tx + q < PW) ? jnd_from_lum(lum, ty + 2, tx + q + 2) : 0.f;
+  }
   if (gy >= PH) return;
+  if (jin == 3 && jout == 1) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) hm[0][q] = hm[0][q] / 3.f + hm[1][q] / 3.f + hm[2][q] / 3.f;     // sum(hmaps / 3) / 255, jnd.py:101
+  }
   const FrameKeys fk = frame_keys(f, (int)gridDim.z, step, alternate, interp_chunk);
+  const int PC = delta == nullptr ? jout : max(CD, jout);
   for (int q = 0; q < 4; ++q) {
     const int gx = x0 + tx + q;
     if (gx >= PW) break;
-    const float hm = jnd_from_lum(lum, ty + 2, tx + q + 2);
-    for (int c = 0; c < CD; ++c) {
-      const long o = (long)gy * PW + gx;
+    const long o = (long)gy * PW + gx;
+    for (int c = 0; c < PC; ++c) {
+      const float h = (jin == 3 && jout == 3) ? hm[c][q] : hm[0][q];
       float dv = 0.f;
       if (fk.has) {
         if (delta == nullptr) {
           dv = 1.f;          // heat-map only
         } else {
-          dv = delta[((long)fk.k0 * CD + c) * plane + o];
-          if (fk.k1 != fk.k0) dv = fk.a * dv + (1.f - fk.a) * delta[((long)fk.k1 * CD + c) * plane + o];
+          const int dc = CD == 1 ? 0 : c;
+          dv = delta[((long)fk.k0 * CD + dc) * plane + o];
+          if (fk.k1 != fk.k0) dv = fk.a * dv + (1.f - fk.a) * delta[((long)fk.k1 * CD + dc) * plane + o];
         }
       }
-      out[((long)f * CD + c) * plane + (long)gy * PW + gx] = hm * dv;
+      out[((long)f * PC + c) * plane + o] = h * dv;
     }
   }
 }
@@ -307,6 +352,115 @@ __global__ void __launch_bounds__(256) ups_gather_ln_kernel(const __half* __rest
   }
 }
 
+// K3 (tiled): the same operation with the low-resolution taps staged in shared memory.  A block owns a 16 x 16 tile of OUTPUT pixels;
+// the (8 + 2) x (8 + 2) low-resolution pixels x 9C channels its 36 bilinear corners touch are copied once (16-byte cp.async, rows /
+// columns clamped at the image border), then every corner is a 128-bit shared load.  The untiled kernel above re-read each
+// low-resolution vector ~16 times through L1/L2 (2.4 GB of L1 traffic for 151 MB of input at 32@128: 203 us against a 34 us bound).
+// Requires IH, IW multiples of 8.  Dynamic shared memory: 100 * 9C halves.
+template <int VPT>
+__global__ void __launch_bounds__(256) ups_gather_ln_tiled_kernel(const __half* __restrict__ y, int B, int IH, int IW, int C,
+                                                                  const float* __restrict__ lnw, const float* __restrict__ lnb, float eps,
+                                                                  __half* __restrict__ out, int ld_out) {
+  extern __shared__ __align__(16) uint8_t ugt_smem[];
+  __half* tile = reinterpret_cast<__half*>(ugt_smem);       // [10][10][9C]
+  const int G = C / (8 * VPT);                // threads per pixel (power of two, <= 32)
+  const int OH = 2 * IH, OW = 2 * IW;
+  const int tiles_x = IW >> 3, tiles_y = IH >> 3;
+  int t = blockIdx.x;
+  const int tx = t % tiles_x; t /= tiles_x;
+  const int ty = t % tiles_y;
+  const int b = t / tiles_y;
+  const int I0 = ty * 8, J0 = tx * 8;          // low-resolution origin of the tile; the staged region starts at (I0 - 1, J0 - 1)
+  const int ldy = 9 * C, cpp = ldy >> 3;       // 16-byte chunks per low-resolution pixel
+  const __half* yb_ = y + (long)b * IH * IW * ldy;
+  for (int i = threadIdx.x; i < 100 * cpp; i += 256) {
+    const int px = i / cpp, ch = i - px * cpp;
+    const int ly = px / 10, lx = px - ly * 10;
+    const int gy = min(max(I0 - 1 + ly, 0), IH - 1), gx = min(max(J0 - 1 + lx, 0), IW - 1);
+    cp_async16(tile + (long)px * ldy + ch * 8, yb_ + ((long)gy * IW + gx) * ldy + ch * 8);
+  }
+  cp_async_commit();
+  cp_async_wait_pending(0);
+  __syncthreads();
+  const int lane_g = threadIdx.x % G;
+  const int ppb = 256 / G;
+  for (int lp = threadIdx.x / G; lp < 256; lp += ppb) {      // local output pixel of the 16 x 16 tile
+    const int loy = lp >> 4, lox = lp & 15;
+    const int oy = 2 * I0 + loy, ox = 2 * J0 + lox;
+    int ya[3], yb[3], xa[3], xb[3];
+    float wy[3], wx[3];
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+      int u = oy + r - 1;
+      if (u < 0) u = -u;
+      if (u >= OH) u = 2 * OH - 2 - u;
+      const int i = u >> 1;
+      if (u & 1) { ya[r] = i; yb[r] = min(i + 1, IH - 1); wy[r] = 0.75f; }
+      else       { ya[r] = max(i - 1, 0); yb[r] = i; wy[r] = 0.25f; }
+      ya[r] -= I0 - 1; yb[r] -= I0 - 1;           // tile rows (the clamped copies make the border rows valid)
+      int v = ox + r - 1;
+      if (v < 0) v = -v;
+      if (v >= OW) v = 2 * OW - 2 - v;
+      const int jx = v >> 1;
+      if (v & 1) { xa[r] = jx; xb[r] = min(jx + 1, IW - 1); wx[r] = 0.75f; }
+      else       { xa[r] = max(jx - 1, 0); xb[r] = jx; wx[r] = 0.25f; }
+      xa[r] -= J0 - 1; xb[r] -= J0 - 1;
+    }
+    float acc[8 * VPT];
+#pragma unroll
+    for (int k = 0; k < 8 * VPT; ++k) acc[k] = 0.f;
+    const __half* tb = tile + lane_g * 8;
+#pragma unroll
+    for (int r = 0; r < 3; ++r) {
+#pragma unroll
+      for (int s2 = 0; s2 < 3; ++s2) {
+        const __half2 w00 = __float2half2_rn(wy[r] * wx[s2]), w01 = __float2half2_rn(wy[r] * (1.f - wx[s2]));
+        const __half2 w10 = __float2half2_rn((1.f - wy[r]) * wx[s2]), w11 = __float2half2_rn((1.f - wy[r]) * (1.f - wx[s2]));
+#pragma unroll
+        for (int j = 0; j < VPT; ++j) {
+          const __half* base = tb + (r * 3 + s2) * C + j * G * 8;
+          const uint4 v00 = *reinterpret_cast<const uint4*>(base + (ya[r] * 10 + xa[s2]) * ldy);
+          const uint4 v01 = *reinterpret_cast<const uint4*>(base + (ya[r] * 10 + xb[s2]) * ldy);
+          const uint4 v10 = *reinterpret_cast<const uint4*>(base + (yb[r] * 10 + xa[s2]) * ldy);
+          const uint4 v11 = *reinterpret_cast<const uint4*>(base + (yb[r] * 10 + xb[s2]) * ldy);
+          const __half2* p00 = reinterpret_cast<const __half2*>(&v00);
+          const __half2* p01 = reinterpret_cast<const __half2*>(&v01);
+          const __half2* p10 = reinterpret_cast<const __half2*>(&v10);
+          const __half2* p11 = reinterpret_cast<const __half2*>(&v11);
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const __half2 tt = __hfma2(w00, p00[k], __hfma2(w01, p01[k], __hfma2(w10, p10[k], __hmul2(w11, p11[k]))));
+            const float2 f = __half22float2(tt);
+            acc[8 * j + 2 * k] += f.x;
+            acc[8 * j + 2 * k + 1] += f.y;
+          }
+        }
+      }
+    }
+    float sum = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8 * VPT; ++k) sum += acc[k];
+    for (int o = G >> 1; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+    const float mean = sum / (float)C;
+    float var = 0.f;
+#pragma unroll
+    for (int k = 0; k < 8 * VPT; ++k) { const float d = acc[k] - mean; var += d * d; }
+    for (int o = G >> 1; o; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
+    const float rstd = 1.0f / sqrtf(var / (float)C + eps);
+    const long pix = ((long)b * OH + oy) * OW + ox;
+#pragma unroll
+    for (int j = 0; j < VPT; ++j) {
+      __align__(16) __half h[8];
+#pragma unroll
+      for (int k = 0; k < 8; ++k) {
+        const int c = (lane_g + j * G) * 8 + k;
+        h[k] = __float2half_rn(fmaxf((acc[8 * j + k] - mean) * rstd * __ldg(lnw + c) + __ldg(lnb + c), 0.f));
+      }
+      *reinterpret_cast<uint4*>(out + pix * ld_out + (lane_g + j * G) * 8) = *reinterpret_cast<const uint4*>(h);
+    }
+  }
+}
+
 // K3b: exact border pixels of the UBlock up-conv for the phase-folded tensor-core path (conv3_direct_host.cuh,
 // setup_up_phase_direct): the outermost rows/columns of the 2H x 2W output see the reflect padding of the up-sampled map,
 // which breaks the per-phase weight pattern.  One block = 8 border pixels x 16 output channels; the 9 bilinear-sampled
@@ -341,6 +495,8 @@ __global__ void __launch_bounds__(256) up_border_fix_kernel(const __half* __rest
   // the block keeps its weights and walks over groups of PPB border pixels
   for (int q0 = (int)blockIdx.x * PPB; q0 < total; q0 += (int)gridDim.x * PPB) {
   __syncthreads();   // U of the previous group has been consumed (and Ws is complete on the first pass)
+  // (a two-pass variant that issues all 36 loads of a thread first was measured SLOWER, 232 vs 168 us: 178 registers -> one block per SM;
+  //  the kernel is bound by the shared-memory reads of its fp32 MAC loop, not by these loads - profiles/r2_history.md)
   for (int it = threadIdx.x; it < PPB * 9 * 16; it += 256) {
     const int g4 = it & 15, tap = (it >> 4) % 9, pp = it / 144;
     const int q = q0 + pp;

@@ -116,7 +116,7 @@ __global__ void __launch_bounds__(256) resize_sep_kernel(const float* __restrict
 // ------------------------------------------------------------------------------------------------ K7
 constexpr int kB2TW = 128, kB2TH = 16, kB2LP = 136;   // tile, and the pitch of the luminance tile (image column x0 + j at index 4 + j)
 constexpr int kB2DH = kB2TH + 2, kB2DW = kB2TW + 4;   // delta tile at processing resolution (up-scale: at most 1 source pixel per output pixel + 1)
-constexpr size_t kB2Smem = (size_t)((kB2TH + 4) * kB2LP + 3 * kB2TH * kB2TW + kB2DH * kB2DW) * sizeof(float);
+constexpr size_t b2_smem(int jin) { return (size_t)(jin * (kB2TH + 4) * kB2LP + 3 * kB2TH * kB2TW + kB2DH * kB2DW) * sizeof(float); }
 
 __device__ __forceinline__ float lg2_approx(float x) { float y; asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
 __device__ __forceinline__ float ex2_approx_f(float x) { float y; asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x)); return y; }
@@ -149,11 +149,13 @@ __device__ __forceinline__ float jnd_value(float la_sum, float gx, float gy) {
 // of the two output rows stream through registers (per row: 5- and 3-sums, the horizontal difference and the [1 2 1] smooth).
 // CD: delta channels (1 for the Y-channel cards, 3 for RGB U-Nets) as a compile-time constant: the per-channel loops and their
 // accumulators disappear from the single-channel instantiation.
-template <int VEC, int FASTUP, int CD>
+// JIN: heat-map inputs (1: luminance; 3: one map per RGB channel, configs/attenuation.yaml jnd_3_*), compile-time for the same reason.
+template <int VEC, int FASTUP, int CD, int JIN>
 __global__ void __launch_bounds__(256, 3) jnd_blend2_kernel(const BlendParams p) {
-  extern __shared__ __align__(16) float b2_smem[];
-  float* lum = b2_smem;                                   // [TH + 4][LP]
-  float* rgb = lum + (kB2TH + 4) * kB2LP;                 // [3][TH][TW]
+  extern __shared__ __align__(16) float b2_smem_[];
+  constexpr int LUMP = (kB2TH + 4) * kB2LP;               // floats per luminance plane
+  float* lum = b2_smem_;                                  // [JIN][TH + 4][LP]
+  float* rgb = lum + JIN * LUMP;                          // [3][TH][TW]
   float* dl = rgb + 3 * kB2TH * kB2TW;                    // [DH][DW]
   const int f = blockIdx.z, x0 = blockIdx.x * kB2TW, y0 = blockIdx.y * kB2TH;
   const long plane = (long)p.H * p.W;
@@ -195,10 +197,18 @@ __global__ void __launch_bounds__(256, 3) jnd_blend2_kernel(const BlendParams p)
       }
 #pragma unroll
       for (int c = 0; c < 3; ++c) *reinterpret_cast<float4*>(rgb + (c * kB2TH + yl) * kB2TW + lane * 4) = v[c];
-      if (p.use_jnd)
-        *reinterpret_cast<float4*>(lum + (yl + 2) * kB2LP + 4 + lane * 4) =
-            make_float4(lum255(v[0].x, v[1].x, v[2].x), lum255(v[0].y, v[1].y, v[2].y), lum255(v[0].z, v[1].z, v[2].z),
-                        lum255(v[0].w, v[1].w, v[2].w));
+      if (p.use_jnd) {
+        if (JIN == 1) {
+          *reinterpret_cast<float4*>(lum + (yl + 2) * kB2LP + 4 + lane * 4) =
+              make_float4(lum255(v[0].x, v[1].x, v[2].x), lum255(v[0].y, v[1].y, v[2].y), lum255(v[0].z, v[1].z, v[2].z),
+                          lum255(v[0].w, v[1].w, v[2].w));
+        } else {
+#pragma unroll
+          for (int c = 0; c < 3; ++c)
+            *reinterpret_cast<float4*>(lum + c * LUMP + (yl + 2) * kB2LP + 4 + lane * 4) =
+                make_float4(255.f * v[c].x, 255.f * v[c].y, 255.f * v[c].z, 255.f * v[c].w);
+        }
+      }
     } else {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -211,7 +221,13 @@ __global__ void __launch_bounds__(256, 3) jnd_blend2_kernel(const BlendParams p)
         }
 #pragma unroll
         for (int c = 0; c < 3; ++c) rgb[(c * kB2TH + yl) * kB2TW + col] = v[c];
-        if (p.use_jnd) lum[(yl + 2) * kB2LP + 4 + col] = lum255(v[0], v[1], v[2]);
+        if (p.use_jnd) {
+          if (JIN == 1) lum[(yl + 2) * kB2LP + 4 + col] = lum255(v[0], v[1], v[2]);
+          else {
+#pragma unroll
+            for (int c = 0; c < 3; ++c) lum[c * LUMP + (yl + 2) * kB2LP + 4 + col] = 255.f * v[c];
+          }
+        }
       }
     }
   }
@@ -228,18 +244,29 @@ __global__ void __launch_bounds__(256, 3) jnd_blend2_kernel(const BlendParams p)
           const float4 r = __ldg(reinterpret_cast<const float4*>(sp)), g = __ldg(reinterpret_cast<const float4*>(sp + plane)),
                        b = __ldg(reinterpret_cast<const float4*>(sp + 2 * plane));
           l4 = make_float4(lum255(r.x, g.x, b.x), lum255(r.y, g.y, b.y), lum255(r.z, g.z, b.z), lum255(r.w, g.w, b.w));
+          if (JIN == 3) {
+            *reinterpret_cast<float4*>(lum + 1 * LUMP + s * kB2LP + 4 + lane * 4) = make_float4(255.f * g.x, 255.f * g.y, 255.f * g.z, 255.f * g.w);
+            *reinterpret_cast<float4*>(lum + 2 * LUMP + s * kB2LP + 4 + lane * 4) = make_float4(255.f * b.x, 255.f * b.y, 255.f * b.z, 255.f * b.w);
+            l4 = make_float4(255.f * r.x, 255.f * r.y, 255.f * r.z, 255.f * r.w);
+          }
+        } else if (JIN == 3) {
+          *reinterpret_cast<float4*>(lum + 1 * LUMP + s * kB2LP + 4 + lane * 4) = l4;
+          *reinterpret_cast<float4*>(lum + 2 * LUMP + s * kB2LP + 4 + lane * 4) = l4;
         }
         *reinterpret_cast<float4*>(lum + s * kB2LP + 4 + lane * 4) = l4;
       } else {
 #pragma unroll
         for (int q = 0; q < 4; ++q) {
           const int col = lane + 32 * q, gx = x0 + col;
-          float l = 0.f;
+          float l3[3] = {0.f, 0.f, 0.f};
           if (rowok && gx < p.W) {
             const float* sp = img + (long)gy * p.W + gx;
-            l = lum255(__ldg(sp), __ldg(sp + plane), __ldg(sp + 2 * plane));
+            const float r = __ldg(sp), g = __ldg(sp + plane), bb = __ldg(sp + 2 * plane);
+            if (JIN == 1) l3[0] = lum255(r, g, bb);
+            else { l3[0] = 255.f * r; l3[1] = 255.f * g; l3[2] = 255.f * bb; }
           }
-          lum[s * kB2LP + 4 + col] = l;
+#pragma unroll
+          for (int c = 0; c < JIN; ++c) lum[c * LUMP + s * kB2LP + 4 + col] = l3[c];
         }
       }
     } else {          // warps 4..7: halo columns x0-2, x0-1, x0+TW, x0+TW+1 of all TH+4 rows
@@ -248,12 +275,15 @@ __global__ void __launch_bounds__(256, 3) jnd_blend2_kernel(const BlendParams p)
         const int s = ht >> 2, j = ht & 3;
         const int col = j < 2 ? j - 2 : kB2TW + j - 2;
         const int gy = y0 + s - 2, gx = x0 + col;
-        float l = 0.f;
+        float l3[3] = {0.f, 0.f, 0.f};
         if (gy >= 0 && gy < p.H && gx >= 0 && gx < p.W) {
           const float* sp = img + (long)gy * p.W + gx;
-          l = lum255(__ldg(sp), __ldg(sp + plane), __ldg(sp + 2 * plane));
+          const float r = __ldg(sp), g = __ldg(sp + plane), bb = __ldg(sp + 2 * plane);
+          if (JIN == 1) l3[0] = lum255(r, g, bb);
+          else { l3[0] = 255.f * r; l3[1] = 255.f * g; l3[2] = 255.f * bb; }
         }
-        lum[s * kB2LP + 4 + col] = l;
+#pragma unroll
+        for (int c = 0; c < JIN; ++c) lum[c * LUMP + s * kB2LP + 4 + col] = l3[c];
       }
     }
   }
@@ -266,19 +296,25 @@ __global__ void __launch_bounds__(256, 3) jnd_blend2_kernel(const BlendParams p)
   //     VD_j = row j+1 - row j+3;
   //   then per pixel  la = sum_5 V5 + sum_3 V3 - 2 centre,  gx = VS[x+1] - VS[x-1],  gy = VD[x-1] + 2 VD[x] + VD[x+1]
   //   (the 5x5 kernel of modules/jnd.py:37-43 is ones(5,5) + ones(3,3) - 2 delta; Sobel pair jnd.py:44-53).
-  float hm[2][4];
+  float hmc[JIN][2][4];
 #pragma unroll
-  for (int j = 0; j < 2; ++j)
+  for (int c = 0; c < JIN; ++c)
 #pragma unroll
-    for (int q = 0; q < 4; ++q) hm[j][q] = 1.f;
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int q = 0; q < 4; ++q) hmc[c][j][q] = 1.f;
   if (p.use_jnd) {
+#pragma unroll
+   for (int jc = 0; jc < JIN; ++jc) {
+    const float* lum_ = lum + jc * LUMP;
+    float (&hm)[2][4] = hmc[jc];
     if (VEC == 4) {
       // segment columns 2..9 (V5) / 3..8 (the others) of the 12 floats at shared column lane*4; pixel q's centre = column 4 + q
       float L[6][8];
       {
 #pragma unroll
         for (int r = 0; r < 6; ++r) {
-          const float4* s4 = reinterpret_cast<const float4*>(lum + (warp * 2 + r) * kB2LP + lane * 4);
+          const float4* s4 = reinterpret_cast<const float4*>(lum_ + (warp * 2 + r) * kB2LP + lane * 4);
           const float4 t0 = s4[0], t1 = s4[1], t2 = s4[2];
           L[r][0] = t0.z; L[r][1] = t0.w; L[r][2] = t1.x; L[r][3] = t1.y; L[r][4] = t1.z; L[r][5] = t1.w; L[r][6] = t2.x; L[r][7] = t2.y;
         }
@@ -314,7 +350,7 @@ __global__ void __launch_bounds__(256, 3) jnd_blend2_kernel(const BlendParams p)
     } else {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float* cpt = lum + (warp * 2) * kB2LP + 4 + lane + 32 * q;      // row 0 of the window, centre column
+        const float* cpt = lum_ + (warp * 2) * kB2LP + 4 + lane + 32 * q;      // row 0 of the window, centre column
         float L[6][5];
 #pragma unroll
         for (int r = 0; r < 6; ++r)
@@ -341,7 +377,15 @@ __global__ void __launch_bounds__(256, 3) jnd_blend2_kernel(const BlendParams p)
         }
       }
     }
+   }
+    if (JIN == 3 && p.jnd_out == 1) {      // hmaps = sum(hmaps / 3) over the channels (jnd.py:101); /255 is inside jnd_value
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) hmc[0][j][q] = hmc[0][j][q] / 3.f + hmc[JIN - 1 > 0 ? 1 : 0][j][q] / 3.f + hmc[JIN - 1][j][q] / 3.f;
+    }
   }
+  const bool hm_per_channel = JIN == 3 && p.jnd_out == 3;
 
   // ---- phase 2b: delta of the 2 x 4 pixels (up-resampled from PH x PW), x heat-map
   float d[CD][2][4];
@@ -423,36 +467,30 @@ __global__ void __launch_bounds__(256, 3) jnd_blend2_kernel(const BlendParams p)
         }
       }
     }
-#pragma unroll
-    for (int c = 0; c < CD; ++c)
-#pragma unroll
-      for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) d[c][j][q] *= hm[j][q];
   }
 
-  // ---- phase 2c: preds_w (optional) and the blend
+  // ---- phase 2c: preds_w = hmap * delta (optional output; max(CD, jnd_out) channels, broadcast like `hmaps * preds_w`) and the blend
+  const int PC = (p.use_jnd && p.jnd_out == 3) ? 3 : CD;
 #pragma unroll
   for (int j = 0; j < 2; ++j) {
     const int yl = warp * 2 + j, gy = y0 + yl;
     if (gy >= p.H) break;
     const long o = (long)gy * p.W + x0;
     const bool vfull = VEC == 4 && (x0 + lane * 4 < p.W);      // W % 4 == 0: a 4-pixel group is inside or outside as a whole
-    if (p.preds_w != nullptr) {
-#pragma unroll
-      for (int c = 0; c < 3; ++c) {
-        if (c >= CD) break;
-        float* dst = p.preds_w + ((long)f * CD + c) * plane + o;
-        if (VEC == 4) {
-          if (vfull) *reinterpret_cast<float4*>(dst + lane * 4) = make_float4(d[c][j][0], d[c][j][1], d[c][j][2], d[c][j][3]);
-        } else {
-#pragma unroll
-          for (int q = 0; q < 4; ++q) if (x0 + lane + 32 * q < p.W) dst[lane + 32 * q] = d[c][j][q];
-        }
-      }
-    }
 #pragma unroll
     for (int c = 0; c < 3; ++c) {
+      float pw[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) pw[q] = d[CD == 1 ? 0 : c][j][q] * (JIN == 3 ? (hm_per_channel ? hmc[JIN == 3 ? c : 0][j][q] : hmc[0][j][q]) : hmc[0][j][q]);
+      if (p.preds_w != nullptr && c < PC) {
+        float* dst = p.preds_w + ((long)f * PC + c) * plane + o;
+        if (VEC == 4) {
+          if (vfull) *reinterpret_cast<float4*>(dst + lane * 4) = make_float4(pw[0], pw[1], pw[2], pw[3]);
+        } else {
+#pragma unroll
+          for (int q = 0; q < 4; ++q) if (x0 + lane + 32 * q < p.W) dst[lane + 32 * q] = pw[q];
+        }
+      }
       float in[4], out[4];
       if (VEC == 4) {
         const float4 t4 = *reinterpret_cast<const float4*>(rgb + (c * kB2TH + yl) * kB2TW + lane * 4);
@@ -463,8 +501,7 @@ __global__ void __launch_bounds__(256, 3) jnd_blend2_kernel(const BlendParams p)
       }
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
-        const float dv = d[CD == 1 ? 0 : c][j][q];
-        const float v = fmaf(p.scaling_i, in[q], p.scaling_w * dv);
+        const float v = fmaf(p.scaling_i, in[q], p.scaling_w * pw[q]);
         out[q] = p.clamp ? __saturatef(v) : v;
       }
       float* dst = p.imgs_w + ((long)f * 3 + c) * plane + o;

@@ -127,7 +127,8 @@ int vsb_embed_host(vsb_model* m, const float* imgs_h, const uint8_t* msgs_h, int
   VSB_MODEL_SCOPE(m);
   m->impl.check_ready();
   const size_t n = (size_t)F * 3 * H * W;
-  const size_t np = (size_t)F * m->impl.d.unet_out_ch * H * W;
+  const bool use_jnd = !(flags & VSB_FLAG_NO_ATTENUATION) && m->impl.d.jnd_in_ch != 0;
+  const size_t np = (size_t)F * (use_jnd ? std::max(m->impl.d.unet_out_ch, m->impl.d.jnd_out_ch) : m->impl.d.unet_out_ch) * H * W;
   float* imgs = (float*)m->impl.stage(0, n * sizeof(float));
   float* out = (float*)m->impl.stage(1, n * sizeof(float));
   float* pw = preds_w_h ? (float*)m->impl.stage(2, np * sizeof(float)) : nullptr;

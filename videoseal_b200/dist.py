@@ -30,6 +30,19 @@ def shard_bounds(num_frames: int, world_size: int, step_size: int = 1) -> List[T
     return bounds
 
 
+def subshard_bounds(num_frames: int, world_size: int, step_size: int = 1, subshards: int = 2) -> List[List[Tuple[int, int]]]:
+    """Interleaved sharding for OVERLAPPED reassembly: the clip is cut into `subshards` contiguous segments and every segment into
+    `world_size` contiguous ranges (boundaries on multiples of `step_size`); rank r owns range r of every segment.  The all-gather of
+    segment s then reassembles frames [seg_start_s, seg_end_s) in frame order without any copy, and it can run (on NCCL's stream)
+    while the ranks are still computing segment s+1.  Returns bounds[rank][segment] = (start, end).
+    Requires equal ranges (num_frames a multiple of world_size * subshards * step_size)."""
+    unit = world_size * subshards * step_size
+    if num_frames % unit != 0:
+        raise ValueError(f"interleaved sub-shards need num_frames % (world_size * subshards * step_size) == 0, got {num_frames} % {unit}")
+    n = num_frames // (world_size * subshards)
+    return [[((s * world_size + r) * n, (s * world_size + r + 1) * n) for s in range(subshards)] for r in range(world_size)]
+
+
 def all_gather_ragged(local: torch.Tensor, sizes: List[int], group=None) -> torch.Tensor:
     """All-gather along dim 0 of per-rank tensors with different leading sizes (`sizes[r]` rows on rank r): each rank pads to
     the maximum, one `all_gather`, padding dropped.  Returns the concatenation in rank order on every rank."""

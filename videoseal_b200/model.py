@@ -41,7 +41,7 @@ class JND:
     def heatmaps(self, imgs: torch.Tensor) -> torch.Tensor:
         m = self._owner
         x = m._to_dev(imgs)
-        out = torch.empty((x.shape[0], 1, x.shape[2], x.shape[3]), device=x.device, dtype=torch.float32)
+        out = torch.empty((x.shape[0], self.out_channels, x.shape[2], x.shape[3]), device=x.device, dtype=torch.float32)
         _lib.check(_lib.lib().vsb_jnd_heatmaps(m._handle(), x.data_ptr(), out.data_ptr(), x.shape[0], x.shape[2], x.shape[3],
                                                m._stream()))
         return out.to(imgs.device)
@@ -226,7 +226,10 @@ class Videoseal(nn.Module):
         imgs_w = torch.empty_like(x)
         preds_w = None
         if not is_video:
-            preds_w = torch.empty((F_, self.spec["unet"]["out_channels"], H, W), device=x.device, dtype=torch.float32)
+            pc = self.spec["unet"]["out_channels"]
+            if self.attenuation is not None:       # hmaps * preds_w broadcasts to max(out_channels) channels (wam.py:189-193)
+                pc = max(pc, self.attenuation.out_channels)
+            preds_w = torch.empty((F_, pc, H, W), device=x.device, dtype=torch.float32)
         _lib.check(_lib.lib().vsb_embed(
             self._handle(), x.data_ptr(), mm.data_ptr(), mm.shape[0], imgs_w.data_ptr(),
             preds_w.data_ptr() if preds_w is not None else None, F_, H, W, step, _lib.VIDEO_MODES[self.video_mode],
