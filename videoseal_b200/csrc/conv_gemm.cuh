@@ -57,6 +57,9 @@ struct ConvGemmParams {
   int group;                      // consecutive M tiles that share one accumulator round (amortises per-tile handshakes for small N)
   int b_resident;                 // whole [block_n x K] weight slab lives in shared memory for the kernel's lifetime
   int b_fixed_ntile;              // b_resident with several N tiles: this CTA only ever sees N tile blockIdx.x % n_tiles
+  int tma_store;                  // fp16 output tiles leave through TMA stores: every epilogue warp stages its 32 rows x (cpw * 16) columns
+  int cpw;                        //   in shared memory (cpw = consecutive 16-column chunks per warp) and one lane issues the bulk store
+  uint32_t ostage_off, ostage_bytes;   // staging area: [epilogue warp][32 rows][cpw * 32 bytes]
   int bias_global;                // epilogue reads the bias straight from global memory (warp-uniform 16-byte loads, L1 hits) instead
                                   // of a shared copy: no per-tile barrier between the epilogue warps (whole tiles only)
   uint32_t bres_off;
@@ -198,7 +201,8 @@ template <int LOADER, int ACT> struct EpiCfg { static constexpr int kWarps = (LO
 template <int LOADER, int ACT>
 __global__ void __launch_bounds__(LOADER == LD_TMA ? 640 : 512, 1)
 conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmA2,
-                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ ConvGemmParams p) {
+                 const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmO,
+                 const __grid_constant__ ConvGemmParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   // header (kHeaderBytes): barriers | tmem ptr | s_bias[2][256] | s_lnw[256] s_lnb[256] s_oc2[256] | s_dot[128][3]
@@ -249,6 +253,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     if (LOADER == LD_TMA || kHalo) tma_prefetch_desc(&tmA);
     if (LOADER == LD_HALO_UPS || (LOADER == LD_TMA && p.c0_blocks != 0)) tma_prefetch_desc(&tmA2);
     tma_prefetch_desc(&tmB);
+    if (p.tma_store) tma_prefetch_desc(&tmO);
   }
   if (warp == 2) {
     tmem_alloc(tmem_ptr_smem, kTmemCols);
@@ -392,6 +397,12 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int row = q * 32 + lane;
     const int et = threadIdx.x - 128;  // 0..kEpiThreads-1
     const int nchunks = p.block_n >> 4;
+    // 16-column chunks of this warp: interleaved (half, half + kEpiSplit, ...) or, with TMA stores, cpw consecutive ones
+    const int c_beg = p.tma_store ? half * p.cpw : half;
+    const int c_end = p.tma_store ? c_beg + p.cpw : nchunks;
+    const int c_step = p.tma_store ? 1 : kEpiSplit;
+    uint8_t* ost = smem + p.ostage_off + (size_t)(warp - 4) * p.ostage_bytes;   // this warp's output staging tile
+    const uint32_t ost_row = (uint32_t)p.cpw * 32u;
     const int D = p.resid_depth;
     const bool has_res = (p.resid16 != nullptr) || (p.resid32 != nullptr);
 
@@ -426,13 +437,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             uint8_t* dst = rbuf + (size_t)slot * p.resid_stride;
             if (p.resid16 != nullptr) {
               const __half* r = p.resid16 + m * p.ld_res16 + n0;
-              for (int ch = half; ch < nchunks; ch += kEpiSplit) {
+              for (int ch = c_beg; ch < c_end; ch += c_step) {
                 cp_async16(dst + ((size_t)(2 * ch) * 128 + row) * 16, r + ch * 16);
                 cp_async16(dst + ((size_t)(2 * ch + 1) * 128 + row) * 16, r + ch * 16 + 8);
               }
             } else {
               const float* r = p.resid32 + m * p.ld_res32 + n0;
-              for (int ch = half; ch < nchunks; ch += kEpiSplit) {
+              for (int ch = c_beg; ch < c_end; ch += c_step) {
 #pragma unroll
                 for (int u = 0; u < 4; ++u) cp_async16(dst + ((size_t)(4 * ch + u) * 128 + row) * 16, r + ch * 16 + 4 * u);
               }
@@ -570,13 +581,18 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
         const bool lean = ACT == ACT_GELU ? (whole && !has_res && (p.grn_stats == nullptr || grn_uniform))
                                           : (whole && p.grn_stats == nullptr && (!has_res || (p.resid16 != nullptr && res_fast)));
         uint32_t vnext[16];
-        if (half < nchunks) tmem_ld16_issue(trow + half * 16, vnext);
+        if (c_beg < c_end) tmem_ld16_issue(trow + c_beg * 16, vnext);
+        const bool use_ts = p.tma_store && lean;       // this warp's part of the tile leaves through its staging tile + one TMA store
+        if (use_ts) {                                  // the previous store of this warp has finished reading the staging tile
+          if (lane == 0) bulk_wait_group_read0();
+          __syncwarp();
+        }
         if (ACT == ACT_GELU && lean) {
           // pwconv1 on whole tiles (every shipped card): bias + GELU + fp16 store + GRN column statistics and nothing else, in packed
           // fp32 arithmetic throughout.  The accumulators are consumed straight out of the TMEM load registers by the packed bias add,
           // so the next chunk's load can be issued without a register copy; one saturating F2FP per output pair.
           const __half* orow = p.out16 + m * p.ld_out16 + n0;
-          for (int ch = half; ch < nchunks; ch += kEpiSplit) {
+          for (int ch = c_beg; ch < c_end; ch += c_step) {
             const int c = ch * 16;
             tmem_ld_wait(vnext);
             const float4* sb4 = reinterpret_cast<const float4*>(sb + c);
@@ -587,14 +603,15 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               w2[2 * u] = __fadd2_rn(make_float2(__uint_as_float(vnext[4 * u]), __uint_as_float(vnext[4 * u + 1])), make_float2(bq.x, bq.y));
               w2[2 * u + 1] = __fadd2_rn(make_float2(__uint_as_float(vnext[4 * u + 2]), __uint_as_float(vnext[4 * u + 3])), make_float2(bq.z, bq.w));
             }
-            if (ch + kEpiSplit < nchunks) tmem_ld16_issue(trow + c + 16 * kEpiSplit, vnext);   // overlaps the math below
+            if (ch + c_step < c_end) tmem_ld16_issue(trow + c + 16 * c_step, vnext);   // overlaps the math below
 #pragma unroll
             for (int j = 0; j < 8; ++j) w2[j] = gelu_erf_p(w2[j]);
             {
               uint32_t h[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[j]) : "f"(w2[j].y), "f"(w2[j].x));   // {hi, lo}
-              uint4* o = reinterpret_cast<uint4*>(const_cast<__half*>(orow) + c);
+              uint4* o = use_ts ? reinterpret_cast<uint4*>(ost + lane * ost_row + (ch - c_beg) * 32)
+                                : reinterpret_cast<uint4*>(const_cast<__half*>(orow) + c);
               o[0] = make_uint4(h[0], h[1], h[2], h[3]);
               o[1] = make_uint4(h[4], h[5], h[6], h[7]);
             }
@@ -636,13 +653,13 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
         } else
-        for (int ch = half; ch < nchunks; ch += kEpiSplit) {
+        for (int ch = c_beg; ch < c_end; ch += c_step) {
           const int c = ch * 16;
           float v[16];
           tmem_ld_wait(vnext);
 #pragma unroll
           for (int j = 0; j < 16; ++j) v[j] = __uint_as_float(vnext[j]);
-          if (ch + kEpiSplit < nchunks) tmem_ld16_issue(trow + c + 16 * kEpiSplit, vnext);   // overlaps the math below
+          if (ch + c_step < c_end) tmem_ld16_issue(trow + c + 16 * c_step, vnext);   // overlaps the math below
           const int n = n0 + c;
           if (ACT == ACT_NONE && lean32) {
             // pwconv2 on whole tiles: bias + fp32 residual stream from the prefetch ring, updated in place (+ fp16 copy)
@@ -692,7 +709,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               if (ACT == ACT_NONE || has_res) { a = fmaxf(a, -65504.f); b2 = fmaxf(b2, -65504.f); }
               h2[j] = __floats2half2_rn(a, b2);
             }
-            uint4* o = reinterpret_cast<uint4*>(p.out16 + m * p.ld_out16 + n);
+            uint4* o = use_ts ? reinterpret_cast<uint4*>(ost + lane * ost_row + (ch - c_beg) * 32)
+                              : reinterpret_cast<uint4*>(p.out16 + m * p.ld_out16 + n);
             o[0] = reinterpret_cast<const uint4*>(h2)[0];
             o[1] = reinterpret_cast<const uint4*>(h2)[1];
             continue;
@@ -827,6 +845,17 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
         }
+        if (use_ts) {
+          // staging tile complete: make the generic-proxy writes visible to the async proxy, then ONE lane hands the 32 x (cpw * 16)
+          // tile to the TMA unit (full 32-byte sectors, no LSU tag traffic: the 16-byte-per-row register stores this replaces cost
+          // 32 tag cycles per warp instruction and were the bottleneck of every small-K layer)
+          fence_proxy_async_smem();
+          __syncwarp();
+          if (lane == 0) {
+            tma_store_2d(&tmO, ost, n0 + c_beg * 16, (int)(m - lane));
+            bulk_commit_group();
+          }
+        }
         if (p.outc_w != nullptr) {
           // the warps sharing a row each hold a partial dot product: combine through shared memory
           if (half != 0) {
@@ -860,6 +889,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       if (as == 0) aphase ^= 1u;
       bsel ^= 1;
     }
+    if (p.tma_store && lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");   // all stores of this warp have landed
   } else if (LOADER != LD_TMA && warp >= kBuilderWarp0) {
     // ===================================================================== A-tile builders (4 warps)
     const int gt = threadIdx.x - kBuilderWarp0 * 32;  // 0..127

@@ -79,12 +79,12 @@ inline FastDiv make_fastdiv(int d) {
 struct ConvGemmOp {
   int loader = LD_TMA;
   ConvGemmParams p;
-  CUtensorMap tmA, tmA2, tmB;
+  CUtensorMap tmA, tmA2, tmB, tmO;
   int grid = 0, threads = 0;
   int w_samples = 1;   // > 1: weights are [w_samples][N][K], sample = row / rows_per_sample (finalize_op)
   size_t smem = 0;
   const char* name = "";
-  ConvGemmOp() { memset(&p, 0, sizeof(p)); memset(&tmA, 0, sizeof(tmA)); memset(&tmA2, 0, sizeof(tmA2)); memset(&tmB, 0, sizeof(tmB)); }
+  ConvGemmOp() { memset(&p, 0, sizeof(p)); memset(&tmA, 0, sizeof(tmA)); memset(&tmA2, 0, sizeof(tmA2)); memset(&tmB, 0, sizeof(tmB)); memset(&tmO, 0, sizeof(tmO)); }
 };
 
 inline int pick_block_n(int N, int max_bn = 256) {
@@ -151,14 +151,28 @@ inline void finalize_op(ConvGemmOp& op, const __half* W, int N, int Kw, int ldw,
   // from L2 for every M tile (res 1x1 384->384 @32^2: 151 MB of weight traffic per launch against 100 MB of activations: L2-bound).
   p.b_fixed_ntile = 0;
   if (!p.b_resident && p.n_tiles > 1 && p.n_tiles <= 8 && op.w_samples == 1 && op.loader == LD_TMA && !getenv("VSB_NO_BRES2") &&
-      kHeaderBytes + resid_bytes + bslab + 4 * (size_t)p.a_stage_bytes <= 225 * 1024 && p.num_tiles >= 2 * num_sms) {
+      kHeaderBytes + resid_bytes + bslab + 4 * (size_t)p.a_stage_bytes + 64 * 1024 <= 225 * 1024 && p.num_tiles >= 2 * num_sms) {
     p.b_resident = 1;
     p.b_fixed_ntile = 1;
   }
   if (getenv("VSB_NO_BRES")) { p.b_resident = 0; p.b_fixed_ntile = 0; }
   const size_t bres_bytes = p.b_resident ? bslab : 0;
   if (p.b_resident) p.stage_bytes = p.a_stage_bytes;
-  const size_t fixed = kHeaderBytes + resid_bytes + halo_total + u_bytes + bres_bytes;
+  // TMA-store epilogue: fp16 output, whole tiles, every epilogue warp owns cpw consecutive chunks of its 32 rows
+  p.tma_store = 0; p.cpw = 0; p.ostage_bytes = 0;
+  {
+    const int nchunks = p.block_n / 16, epw = 4;     // 16 epilogue warps = 4 per TMEM lane quadrant
+    if (op.loader == LD_TMA && p.out16 != nullptr && p.out32 == nullptr && p.outc_w == nullptr && p.epi == EPI_AFFINE &&
+        (long)p.m_tiles * kBlockM == (long)p.M && N % p.block_n == 0 && nchunks % epw == 0 && (p.ld_out16 % 8) == 0 &&
+        (reinterpret_cast<uintptr_t>(p.out16) & 15) == 0 && p.num_kb <= 12 /* short main loops only: there the epilogue is the
+        critical path; long-K layers keep their shared memory for pipeline stages */ && !getenv("VSB_NO_TMA_STORE")) {
+      p.tma_store = 1;
+      p.cpw = nchunks / epw;
+      p.ostage_bytes = 32u * (uint32_t)p.cpw * 32u;
+    }
+  }
+  const size_t ostage_total = p.tma_store ? (size_t)16 * p.ostage_bytes : 0;
+  const size_t fixed = kHeaderBytes + resid_bytes + halo_total + u_bytes + bres_bytes + ostage_total;
   VSB_CHECK(fixed + 2 * (size_t)p.stage_bytes <= 225 * 1024, "tile does not fit in shared memory");
   int stages = (int)((225 * 1024 - fixed) / p.stage_bytes);
   if (stages > kMaxStages) stages = kMaxStages;
@@ -167,7 +181,14 @@ inline void finalize_op(ConvGemmOp& op, const __half* W, int N, int Kw, int ldw,
   p.u_off = (uint32_t)(p.halo_off + halo_total);
   p.bres_off = (uint32_t)(p.u_off + u_bytes);
   p.resid_off = (uint32_t)(p.bres_off + bres_bytes);
-  op.smem = 1024 /*align slack*/ + p.resid_off + resid_bytes;
+  p.ostage_off = (uint32_t)(p.resid_off + resid_bytes);
+  op.smem = 1024 /*align slack*/ + p.ostage_off + ostage_total;
+  if (p.tma_store) {   // output map: [M rows][N cols] fp16, box = one warp's staging tile (32 rows x cpw*16 columns), dense rows
+    uint64_t odims[2] = {(uint64_t)N, (uint64_t)p.M};
+    uint64_t ostrides[1] = {(uint64_t)p.ld_out16 * 2};
+    uint32_t obox[2] = {(uint32_t)(p.cpw * 16), 32u};
+    encode_map(&op.tmO, p.out16, 2, odims, ostrides, obox, 0, /*no_swizzle=*/true);
+  }
   // instruction descriptor (kind::f16): D=f32 (bit 4), A=B=f16 (0), K-major both, N>>3 at bit 17, M>>4 at bit 24
   p.idesc = (1u << 4) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
   if (p.epi == EPI_LN || p.outc_w) VSB_CHECK(p.n_tiles == 1 && N <= 256, "LN / fused-outc epilogues need the full row in one tile");
@@ -378,9 +399,9 @@ inline void launch_one(const ConvGemmOp& op, cudaStream_t st) {
     attr_set = true;
   }
 #ifdef VSB_PDL
-  launch_pdl(conv_gemm_kernel<LOADER, ACT>, dim3(op.grid), dim3(op.threads), op.smem, st, op.tmA, op.tmA2, op.tmB, op.p);
+  launch_pdl(conv_gemm_kernel<LOADER, ACT>, dim3(op.grid), dim3(op.threads), op.smem, st, op.tmA, op.tmA2, op.tmB, op.tmO, op.p);
 #else
-  conv_gemm_kernel<LOADER, ACT><<<op.grid, op.threads, op.smem, st>>>(op.tmA, op.tmA2, op.tmB, op.p);
+  conv_gemm_kernel<LOADER, ACT><<<op.grid, op.threads, op.smem, st>>>(op.tmA, op.tmA2, op.tmB, op.tmO, op.p);
 #endif
 }
 
