@@ -27,6 +27,9 @@ BIG = {
     "p_up_768_64":  dict(loader=cc.LD_GUPS, B=64, IH=32, IW=32, C0=384, C1=384, N=64, R=3, S=3, epi=1, act=1, out="f16"),
     "p_pw1_384":    dict(loader=cc.LD_TMA, B=1, IH=1, IW=64 * 256, C0=384, N=1536, R=1, S=1, bias=True, act=2, grn=True, rps=256, out="f16"),
     "p_pw2_384":    dict(loader=cc.LD_TMA, B=1, IH=1, IW=64 * 256, C0=1536, N=384, R=1, S=1, bias=True, resid32=True, out="f32"),
+    "p_pw2_96t":    dict(loader=cc.LD_TMA, B=1, IH=1, IW=64 * 4096, C0=384, N=96, R=1, S=1, bias=True, resid32=True, out="f32"),
+    "p_pw2_192t":   dict(loader=cc.LD_TMA, B=1, IH=1, IW=64 * 1024, C0=768, N=192, R=1, S=1, bias=True, resid32=True, out="f32"),
+    "p_uptap_128":  dict(loader=cc.LD_TMA, B=1, IH=1, IW=64 * 4096, C0=128, N=288, R=1, S=1, out="f16"),
     "p_down_16_32": dict(loader=cc.LD_GCONV, B=64, IH=256, IW=256, C0=16, N=32, R=3, S=3, stride=2, pad=1, bias=True, out="f16"),
 }
 cc.CASES.update(BIG)

@@ -57,9 +57,10 @@ struct ConvGemmParams {
   int group;                      // consecutive M tiles that share one accumulator round (amortises per-tile handshakes for small N)
   int b_resident;                 // whole [block_n x K] weight slab lives in shared memory for the kernel's lifetime
   int b_fixed_ntile;              // b_resident with several N tiles: this CTA only ever sees N tile blockIdx.x % n_tiles
-  int tma_store;                  // fp16 output tiles leave through TMA stores: every epilogue warp stages its 32 rows x (cpw * 16) columns
-  int cpw;                        //   in shared memory (cpw = consecutive 16-column chunks per warp) and one lane issues the bulk store
-  uint32_t ostage_off, ostage_bytes;   // staging area: [epilogue warp][32 rows][cpw * 32 bytes]
+  int tma_store;                  // 1: fp16, 2: fp32 output tiles leave through TMA stores: every epilogue warp stages its 16-column chunks
+  int cpw;                        //   ([32 rows][16 cols] boxes) in shared memory and one lane issues a bulk store per chunk; the warps of a
+                                  //   lane quadrant own consecutive chunks (cpw = the largest count; the split may be uneven)
+  uint32_t ostage_off, ostage_bytes;   // staging area: [epilogue warp][cpw][32 rows][16 cols]
   int bias_global;                // epilogue reads the bias straight from global memory (warp-uniform 16-byte loads, L1 hits) instead
                                   // of a shared copy: no per-tile barrier between the epilogue warps (whole tiles only)
   uint32_t bres_off;
@@ -398,11 +399,16 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     const int et = threadIdx.x - 128;  // 0..kEpiThreads-1
     const int nchunks = p.block_n >> 4;
     // 16-column chunks of this warp: interleaved (half, half + kEpiSplit, ...) or, with TMA stores, cpw consecutive ones
-    const int c_beg = p.tma_store ? half * p.cpw : half;
-    const int c_end = p.tma_store ? c_beg + p.cpw : nchunks;
-    const int c_step = p.tma_store ? 1 : kEpiSplit;
-    uint8_t* ost = smem + p.ostage_off + (size_t)(warp - 4) * p.ostage_bytes;   // this warp's output staging tile
-    const uint32_t ost_row = (uint32_t)p.cpw * 32u;
+    int c_beg = half, c_end = nchunks, c_step = kEpiSplit;
+    if (p.tma_store) {
+      const int base = nchunks / kEpiSplit, rem = nchunks - base * kEpiSplit;
+      c_beg = half * base + min(half, rem);
+      c_end = c_beg + base + (half < rem ? 1 : 0);
+      c_step = 1;
+    }
+    uint8_t* ost = smem + p.ostage_off + (size_t)(warp - 4) * p.ostage_bytes;   // this warp's output staging boxes
+    const uint32_t ost_row = p.tma_store == 2 ? 64u : 32u;                       // bytes per row of a box (16 columns)
+    const uint32_t ost_box = 32u * ost_row;
     const int D = p.resid_depth;
     const bool has_res = (p.resid16 != nullptr) || (p.resid32 != nullptr);
 
@@ -582,8 +588,9 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
                                           : (whole && p.grn_stats == nullptr && (!has_res || (p.resid16 != nullptr && res_fast)));
         uint32_t vnext[16];
         if (c_beg < c_end) tmem_ld16_issue(trow + c_beg * 16, vnext);
-        const bool use_ts = p.tma_store && lean;       // this warp's part of the tile leaves through its staging tile + one TMA store
-        if (use_ts) {                                  // the previous store of this warp has finished reading the staging tile
+        const bool use_ts = p.tma_store == 1 && lean;      // this warp's part of the tile leaves through its staging boxes + TMA stores
+        const bool use_ts32 = p.tma_store == 2 && lean32 && p.out16 == nullptr;
+        if (use_ts || use_ts32) {                          // the previous stores of this warp have finished reading the staging boxes
           if (lane == 0) bulk_wait_group_read0();
           __syncwarp();
         }
@@ -610,7 +617,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               uint32_t h[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[j]) : "f"(w2[j].y), "f"(w2[j].x));   // {hi, lo}
-              uint4* o = use_ts ? reinterpret_cast<uint4*>(ost + lane * ost_row + (ch - c_beg) * 32)
+              uint4* o = use_ts ? reinterpret_cast<uint4*>(ost + (ch - c_beg) * ost_box + lane * ost_row)
                                 : reinterpret_cast<uint4*>(const_cast<__half*>(orow) + c);
               o[0] = make_uint4(h[0], h[1], h[2], h[3]);
               o[1] = make_uint4(h[4], h[5], h[6], h[7]);
@@ -664,7 +671,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (ACT == ACT_NONE && lean32) {
             // pwconv2 on whole tiles: bias + fp32 residual stream from the prefetch ring, updated in place (+ fp16 copy)
             const float4* sb4 = reinterpret_cast<const float4*>(sb + c);
-            float4* o = reinterpret_cast<float4*>(p.out32 + m * p.ld_out32 + n);
+            float4* o = use_ts32 ? reinterpret_cast<float4*>(ost + (ch - c_beg) * ost_box + lane * ost_row)
+                                 : reinterpret_cast<float4*>(p.out32 + m * p.ld_out32 + n);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               const float4 bq = sb4[u];
@@ -709,7 +717,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               if (ACT == ACT_NONE || has_res) { a = fmaxf(a, -65504.f); b2 = fmaxf(b2, -65504.f); }
               h2[j] = __floats2half2_rn(a, b2);
             }
-            uint4* o = use_ts ? reinterpret_cast<uint4*>(ost + lane * ost_row + (ch - c_beg) * 32)
+            uint4* o = use_ts ? reinterpret_cast<uint4*>(ost + (ch - c_beg) * ost_box + lane * ost_row)
                               : reinterpret_cast<uint4*>(p.out16 + m * p.ld_out16 + n);
             o[0] = reinterpret_cast<const uint4*>(h2)[0];
             o[1] = reinterpret_cast<const uint4*>(h2)[1];
@@ -845,14 +853,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
           }
         }
-        if (use_ts) {
-          // staging tile complete: make the generic-proxy writes visible to the async proxy, then ONE lane hands the 32 x (cpw * 16)
-          // tile to the TMA unit (full 32-byte sectors, no LSU tag traffic: the 16-byte-per-row register stores this replaces cost
-          // 32 tag cycles per warp instruction and were the bottleneck of every small-K layer)
+        if (use_ts || use_ts32) {
+          // staging boxes complete: make the generic-proxy writes visible to the async proxy, then ONE lane hands the 32 x 16 boxes to
+          // the TMA unit (full 32-byte sectors, no LSU tag traffic: the 16-byte-per-row register stores this replaces cost 32 tag
+          // cycles per warp instruction and were the bottleneck of every short-K layer)
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            tma_store_2d(&tmO, ost, n0 + c_beg * 16, (int)(m - lane));
+            for (int k = 0; k < c_end - c_beg; ++k) tma_store_2d(&tmO, ost + k * ost_box, n0 + (c_beg + k) * 16, (int)(m - lane));
             bulk_commit_group();
           }
         }

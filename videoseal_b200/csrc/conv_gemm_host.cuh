@@ -158,17 +158,21 @@ inline void finalize_op(ConvGemmOp& op, const __half* W, int N, int Kw, int ldw,
   if (getenv("VSB_NO_BRES")) { p.b_resident = 0; p.b_fixed_ntile = 0; }
   const size_t bres_bytes = p.b_resident ? bslab : 0;
   if (p.b_resident) p.stage_bytes = p.a_stage_bytes;
-  // TMA-store epilogue: fp16 output, whole tiles, every epilogue warp owns cpw consecutive chunks of its 32 rows
+  // TMA-store epilogue (short main loops only: there the epilogue is the critical path; long-K layers keep their shared memory for
+  // pipeline stages): whole tiles, fp16 output (affine / GELU epilogues) or the in-place fp32 residual stream of pwconv2
   p.tma_store = 0; p.cpw = 0; p.ostage_bytes = 0;
   {
     const int nchunks = p.block_n / 16, epw = 4;     // 16 epilogue warps = 4 per TMEM lane quadrant
-    if (op.loader == LD_TMA && p.out16 != nullptr && p.out32 == nullptr && p.outc_w == nullptr && p.epi == EPI_AFFINE &&
-        (long)p.m_tiles * kBlockM == (long)p.M && N % p.block_n == 0 && nchunks % epw == 0 && (p.ld_out16 % 8) == 0 &&
-        (reinterpret_cast<uintptr_t>(p.out16) & 15) == 0 && p.num_kb <= 12 /* short main loops only: there the epilogue is the
-        critical path; long-K layers keep their shared memory for pipeline stages */ && !getenv("VSB_NO_TMA_STORE")) {
+    const bool common = op.loader == LD_TMA && p.outc_w == nullptr && p.epi == EPI_AFFINE && (long)p.m_tiles * kBlockM == (long)p.M &&
+                        N % p.block_n == 0 && p.num_kb <= 12 && !getenv("VSB_NO_TMA_STORE");
+    if (common && p.out16 != nullptr && p.out32 == nullptr && (p.ld_out16 % 8) == 0 && (reinterpret_cast<uintptr_t>(p.out16) & 15) == 0)
       p.tma_store = 1;
-      p.cpw = nchunks / epw;
-      p.ostage_bytes = 32u * (uint32_t)p.cpw * 32u;
+    else if (common && p.out32 != nullptr && p.out16 == nullptr && p.act == ACT_NONE && p.resid32 != nullptr && p.grn_stats == nullptr &&
+             (p.ld_out32 % 4) == 0 && (reinterpret_cast<uintptr_t>(p.out32) & 15) == 0 && !getenv("VSB_NO_TMA_STORE32"))
+      p.tma_store = 2;
+    if (p.tma_store) {
+      p.cpw = (nchunks + epw - 1) / epw;
+      p.ostage_bytes = (uint32_t)p.cpw * 32u * (p.tma_store == 2 ? 64u : 32u);
     }
   }
   const size_t ostage_total = p.tma_store ? (size_t)16 * p.ostage_bytes : 0;
@@ -183,11 +187,16 @@ inline void finalize_op(ConvGemmOp& op, const __half* W, int N, int Kw, int ldw,
   p.resid_off = (uint32_t)(p.bres_off + bres_bytes);
   p.ostage_off = (uint32_t)(p.resid_off + resid_bytes);
   op.smem = 1024 /*align slack*/ + p.ostage_off + ostage_total;
-  if (p.tma_store) {   // output map: [M rows][N cols] fp16, box = one warp's staging tile (32 rows x cpw*16 columns), dense rows
+  if (p.tma_store) {   // output map: [M rows][N cols], box = one staging box (32 rows x 16 columns), dense rows
     uint64_t odims[2] = {(uint64_t)N, (uint64_t)p.M};
-    uint64_t ostrides[1] = {(uint64_t)p.ld_out16 * 2};
-    uint32_t obox[2] = {(uint32_t)(p.cpw * 16), 32u};
-    encode_map(&op.tmO, p.out16, 2, odims, ostrides, obox, 0, /*no_swizzle=*/true);
+    uint32_t obox[2] = {16u, 32u};
+    if (p.tma_store == 1) {
+      uint64_t ostrides[1] = {(uint64_t)p.ld_out16 * 2};
+      encode_map(&op.tmO, p.out16, 2, odims, ostrides, obox, 0, /*no_swizzle=*/true);
+    } else {
+      uint64_t ostrides[1] = {(uint64_t)p.ld_out32 * 4};
+      encode_map(&op.tmO, p.out32, 2, odims, ostrides, obox, 0, /*no_swizzle=*/true, /*f32=*/true);
+    }
   }
   // instruction descriptor (kind::f16): D=f32 (bit 4), A=B=f16 (0), K-major both, N>>3 at bit 17, M>>4 at bit 24
   p.idesc = (1u << 4) | ((uint32_t)(p.block_n >> 3) << 17) | ((uint32_t)(kBlockM >> 4) << 24);
