@@ -60,7 +60,10 @@ struct ConvGemmParams {
   int tma_store;                  // 1: fp16, 2: fp32 output tiles leave through TMA stores: every epilogue warp stages its 16-column chunks
   int cpw;                        //   ([32 rows][16 cols] boxes) in shared memory and one lane issues a bulk store per chunk; the warps of a
                                   //   lane quadrant own consecutive chunks (cpw = the largest count; the split may be uneven)
-  uint32_t ostage_off, ostage_bytes;   // staging area: [epilogue warp][cpw][32 rows][16 cols]
+  uint32_t ostage_off, ostage_bytes;   // staging area: [epilogue warp][boxes][32 rows][ost_cpb * 16 cols]
+  int ost_cpb;                    //   chunks per staging box (cpw: one box per warp; 1: one box per chunk)
+  uint32_t ost_rowb;              //   bytes per box row
+  int ost_swz;                    //   0 linear, 1 / 2 / 3: 32 / 64 / 128-byte TMA swizzle of the box rows
   int bias_global;                // epilogue reads the bias straight from global memory (warp-uniform 16-byte loads, L1 hits) instead
                                   // of a shared copy: no per-tile barrier between the epilogue warps (whole tiles only)
   uint32_t bres_off;
@@ -407,8 +410,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
       c_step = 1;
     }
     uint8_t* ost = smem + p.ostage_off + (size_t)(warp - 4) * p.ostage_bytes;   // this warp's output staging boxes
-    const uint32_t ost_row = p.tma_store == 2 ? 64u : 32u;                       // bytes per row of a box (16 columns)
-    const uint32_t ost_box = 32u * ost_row;
+    const uint32_t ost_box = 32u * p.ost_rowb;
+    const uint32_t ost_upc = p.tma_store == 2 ? 4u : 2u;                         // 16-byte units per chunk
+    // 16-byte unit u of row r of a swizzled box lives at unit u ^ f(r) (CU_TENSOR_MAP_SWIZZLE_{32,64,128}B)
+    const uint32_t ost_x = p.ost_swz == 3 ? (uint32_t)(lane & 7) : (p.ost_swz == 2 ? (uint32_t)((lane >> 1) & 3) : (p.ost_swz == 1 ? (uint32_t)((lane >> 2) & 1) : 0u));
+    auto ost_ptr = [&](int k /*chunk of this warp*/, uint32_t t /*16-byte unit inside the chunk*/) -> uint4* {
+      const int box = p.ost_cpb == 1 ? k : 0, kin = p.ost_cpb == 1 ? 0 : k;
+      return reinterpret_cast<uint4*>(ost + (size_t)box * ost_box + (size_t)lane * p.ost_rowb + (((uint32_t)kin * ost_upc + t) ^ ost_x) * 16u);
+    };
     const int D = p.resid_depth;
     const bool has_res = (p.resid16 != nullptr) || (p.resid32 != nullptr);
 
@@ -617,10 +626,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               uint32_t h[8];
 #pragma unroll
               for (int j = 0; j < 8; ++j) asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[j]) : "f"(w2[j].y), "f"(w2[j].x));   // {hi, lo}
-              uint4* o = use_ts ? reinterpret_cast<uint4*>(ost + (ch - c_beg) * ost_box + lane * ost_row)
-                                : reinterpret_cast<uint4*>(const_cast<__half*>(orow) + c);
-              o[0] = make_uint4(h[0], h[1], h[2], h[3]);
-              o[1] = make_uint4(h[4], h[5], h[6], h[7]);
+              if (use_ts) {
+                *ost_ptr(ch - c_beg, 0) = make_uint4(h[0], h[1], h[2], h[3]);
+                *ost_ptr(ch - c_beg, 1) = make_uint4(h[4], h[5], h[6], h[7]);
+              } else {
+                uint4* o = reinterpret_cast<uint4*>(const_cast<__half*>(orow) + c);
+                o[0] = make_uint4(h[0], h[1], h[2], h[3]);
+                o[1] = make_uint4(h[4], h[5], h[6], h[7]);
+              }
             }
             if (grn_row != nullptr) {
               float sq[16];
@@ -671,14 +684,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           if (ACT == ACT_NONE && lean32) {
             // pwconv2 on whole tiles: bias + fp32 residual stream from the prefetch ring, updated in place (+ fp16 copy)
             const float4* sb4 = reinterpret_cast<const float4*>(sb + c);
-            float4* o = use_ts32 ? reinterpret_cast<float4*>(ost + (ch - c_beg) * ost_box + lane * ost_row)
-                                 : reinterpret_cast<float4*>(p.out32 + m * p.ld_out32 + n);
+            float4* o = reinterpret_cast<float4*>(p.out32 + m * p.ld_out32 + n);
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               const float4 bq = sb4[u];
               const float4 t = *reinterpret_cast<const float4*>(rb_ + ((size_t)(4 * ch + u) * 128 + row) * 16);
               v[4 * u + 0] += bq.x + t.x; v[4 * u + 1] += bq.y + t.y; v[4 * u + 2] += bq.z + t.z; v[4 * u + 3] += bq.w + t.w;
-              o[u] = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
+              float4* dst = use_ts32 ? reinterpret_cast<float4*>(ost_ptr(ch - c_beg, (uint32_t)u)) : o + u;
+              *dst = make_float4(v[4 * u], v[4 * u + 1], v[4 * u + 2], v[4 * u + 3]);
             }
             if (p.out16 != nullptr) {
               __align__(16) __half2 h2[8];
@@ -717,10 +730,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
               if (ACT == ACT_NONE || has_res) { a = fmaxf(a, -65504.f); b2 = fmaxf(b2, -65504.f); }
               h2[j] = __floats2half2_rn(a, b2);
             }
-            uint4* o = use_ts ? reinterpret_cast<uint4*>(ost + (ch - c_beg) * ost_box + lane * ost_row)
-                              : reinterpret_cast<uint4*>(p.out16 + m * p.ld_out16 + n);
-            o[0] = reinterpret_cast<const uint4*>(h2)[0];
-            o[1] = reinterpret_cast<const uint4*>(h2)[1];
+            if (use_ts) {
+              *ost_ptr(ch - c_beg, 0) = reinterpret_cast<const uint4*>(h2)[0];
+              *ost_ptr(ch - c_beg, 1) = reinterpret_cast<const uint4*>(h2)[1];
+            } else {
+              uint4* o = reinterpret_cast<uint4*>(p.out16 + m * p.ld_out16 + n);
+              o[0] = reinterpret_cast<const uint4*>(h2)[0];
+              o[1] = reinterpret_cast<const uint4*>(h2)[1];
+            }
             continue;
           }
           if (n >= p.N) continue;  // uniform across the warp
@@ -860,7 +877,8 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
           fence_proxy_async_smem();
           __syncwarp();
           if (lane == 0) {
-            for (int k = 0; k < c_end - c_beg; ++k) tma_store_2d(&tmO, ost + k * ost_box, n0 + (c_beg + k) * 16, (int)(m - lane));
+            for (int k = 0; k < c_end - c_beg; k += p.ost_cpb)
+              tma_store_2d(&tmO, ost + (size_t)(p.ost_cpb == 1 ? k : 0) * ost_box, n0 + (c_beg + k) * 16, (int)(m - lane));
             bulk_commit_group();
           }
         }

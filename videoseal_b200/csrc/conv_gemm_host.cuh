@@ -50,7 +50,7 @@ inline CUtensorMapSwizzle swizzle_for(int kblk) {
 
 // fp16 (or fp32: f32 = true, always unswizzled) tensor map, dims innermost-first; strides (bytes) for dims 1..rank-1
 inline void encode_map(CUtensorMap* tm, const void* base, int rank, const uint64_t* dims, const uint64_t* strides_bytes,
-                       const uint32_t* box, int kblk, bool no_swizzle = false, bool f32 = false) {
+                       const uint32_t* box, int kblk, bool no_swizzle = false, bool f32 = false, int swz_bytes = -1 /* >= 0: explicit 0/32/64/128 */) {
   cuuint64_t gd[5], gs[4];
   cuuint32_t bx[5], es[5];
   for (int i = 0; i < rank; ++i) { gd[i] = dims[i]; bx[i] = box[i]; es[i] = 1; }
@@ -59,7 +59,10 @@ inline void encode_map(CUtensorMap* tm, const void* base, int rank, const uint64
   for (int i = 0; i + 1 < rank; ++i) VSB_CHECK(gs[i] % 16 == 0, "TMA strides must be multiples of 16B");
   CUresult r = get_encode_fn()(tm, f32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16, (cuuint32_t)rank,
                                const_cast<void*>(base), gd, gs, bx, es,
-                               CU_TENSOR_MAP_INTERLEAVE_NONE, (no_swizzle || f32) ? CU_TENSOR_MAP_SWIZZLE_NONE : swizzle_for(kblk),
+                               CU_TENSOR_MAP_INTERLEAVE_NONE,
+                               swz_bytes >= 0 ? (swz_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B : swz_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B
+                                                 : swz_bytes == 32 ? CU_TENSOR_MAP_SWIZZLE_32B : CU_TENSOR_MAP_SWIZZLE_NONE)
+                                              : ((no_swizzle || f32) ? CU_TENSOR_MAP_SWIZZLE_NONE : swizzle_for(kblk)),
                                CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                                CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   VSB_CHECK(r == CUDA_SUCCESS, "cuTensorMapEncodeTiled failed (" + std::to_string((int)r) + ")");
@@ -172,10 +175,18 @@ inline void finalize_op(ConvGemmOp& op, const __half* W, int N, int Kw, int ldw,
       p.tma_store = 2;
     if (p.tma_store) {
       p.cpw = (nchunks + epw - 1) / epw;
-      p.ostage_bytes = (uint32_t)p.cpw * 32u * (p.tma_store == 2 ? 64u : 32u);
+      const uint32_t cb = p.tma_store == 2 ? 64u : 32u;          // bytes per row of one 16-column chunk
+      // staging boxes: all cpw chunks of a warp in one box when the split is even and the row is 32 / 64 / 96 / 128 bytes, else one box
+      // per chunk.  Rows of 32 / 64 / 128 bytes use the matching TMA swizzle so that the 16-byte register stores of the 32 lanes (one
+      // row each) are bank-conflict free; 96-byte rows stay linear (2-way conflicts).
+      p.ost_cpb = (nchunks % epw == 0 && p.cpw * cb <= 128u) ? p.cpw : 1;
+      p.ost_rowb = (uint32_t)p.ost_cpb * cb;
+      p.ost_swz = p.ost_rowb == 128u ? 3 : (p.ost_rowb == 64u ? 2 : (p.ost_rowb == 32u ? 1 : 0));
+      if (getenv("VSB_TMA_STORE_NOSWZ")) p.ost_swz = 0;
+      p.ostage_bytes = (uint32_t)p.cpw * 32u * cb;               // per warp: multiples of 1024 bytes (swizzle atoms stay aligned)
     }
   }
-  const size_t ostage_total = p.tma_store ? (size_t)16 * p.ostage_bytes : 0;
+  const size_t ostage_total = p.tma_store ? (size_t)16 * p.ostage_bytes + 1024 : 0;
   const size_t fixed = kHeaderBytes + resid_bytes + halo_total + u_bytes + bres_bytes + ostage_total;
   VSB_CHECK(fixed + 2 * (size_t)p.stage_bytes <= 225 * 1024, "tile does not fit in shared memory");
   int stages = (int)((225 * 1024 - fixed) / p.stage_bytes);
@@ -185,17 +196,18 @@ inline void finalize_op(ConvGemmOp& op, const __half* W, int N, int Kw, int ldw,
   p.u_off = (uint32_t)(p.halo_off + halo_total);
   p.bres_off = (uint32_t)(p.u_off + u_bytes);
   p.resid_off = (uint32_t)(p.bres_off + bres_bytes);
-  p.ostage_off = (uint32_t)(p.resid_off + resid_bytes);
+  p.ostage_off = (uint32_t)((p.resid_off + resid_bytes + 1023) & ~size_t(1023));   // swizzle atoms of the staging boxes need 1024-byte alignment
   op.smem = 1024 /*align slack*/ + p.ostage_off + ostage_total;
   if (p.tma_store) {   // output map: [M rows][N cols], box = one staging box (32 rows x 16 columns), dense rows
     uint64_t odims[2] = {(uint64_t)N, (uint64_t)p.M};
-    uint32_t obox[2] = {16u, 32u};
+    uint32_t obox[2] = {(uint32_t)(p.ost_cpb * 16), 32u};
+    const int swzb = p.ost_swz == 3 ? 128 : (p.ost_swz == 2 ? 64 : (p.ost_swz == 1 ? 32 : 0));
     if (p.tma_store == 1) {
       uint64_t ostrides[1] = {(uint64_t)p.ld_out16 * 2};
-      encode_map(&op.tmO, p.out16, 2, odims, ostrides, obox, 0, /*no_swizzle=*/true);
+      encode_map(&op.tmO, p.out16, 2, odims, ostrides, obox, 0, /*no_swizzle=*/true, false, swzb);
     } else {
       uint64_t ostrides[1] = {(uint64_t)p.ld_out32 * 4};
-      encode_map(&op.tmO, p.out32, 2, odims, ostrides, obox, 0, /*no_swizzle=*/true, /*f32=*/true);
+      encode_map(&op.tmO, p.out32, 2, odims, ostrides, obox, 0, /*no_swizzle=*/true, /*f32=*/true, swzb);
     }
   }
   // instruction descriptor (kind::f16): D=f32 (bit 4), A=B=f16 (0), K-major both, N>>3 at bit 17, M>>4 at bit 24

@@ -196,20 +196,20 @@ struct DwRingOp {
   const float *dww = nullptr, *dwb = nullptr, *lnw = nullptr, *lnb = nullptr;
   __half* out = nullptr;
 };
-template <int C, int NS, int SX, int NSLOT>
+template <int C, int NS, int SX, int NSLOT, bool WS = false>
 inline void launch_dw_ring_t(const DwRingOp& op, cudaStream_t st) {
   static bool attr = false;
-  constexpr size_t smem = dw_ring_smem<C, NS, SX, NSLOT>();
+  constexpr size_t smem = dw_ring_smem<C, NS, SX, NSLOT, WS>();
   if (!attr) {
-    VSB_CUDA(cudaFuncSetAttribute(dwconv7_ln_ring_kernel<C, NS, SX, NSLOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    VSB_CUDA(cudaFuncSetAttribute(dwconv7_ln_ring_kernel<C, NS, SX, NSLOT, WS>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr = true;
   }
   const unsigned blocks = (unsigned)((long)op.B * (op.H / op.R) * (op.H / (NS * SX)));
 #ifdef VSB_PDL
-  launch_pdl(dwconv7_ln_ring_kernel<C, NS, SX, NSLOT>, dim3(blocks), dim3(NS * C / 2 + 32), smem, st, op.tm, op.B, op.H, op.H, op.dww, op.dwb, op.lnw,
+  launch_pdl(dwconv7_ln_ring_kernel<C, NS, SX, NSLOT, WS>, dim3(blocks), dim3(NS * C / 2 + 32), smem, st, op.tm, op.B, op.H, op.H, op.dww, op.dwb, op.lnw,
              op.lnb, op.out, op.R);
 #else
-  dwconv7_ln_ring_kernel<C, NS, SX, NSLOT><<<blocks, NS * C / 2 + 32, smem, st>>>(op.tm, op.B, op.H, op.H, op.dww, op.dwb, op.lnw, op.lnb, op.out, op.R);
+  dwconv7_ln_ring_kernel<C, NS, SX, NSLOT, WS><<<blocks, NS * C / 2 + 32, smem, st>>>(op.tm, op.B, op.H, op.H, op.dww, op.dwb, op.lnw, op.lnb, op.out, op.R);
 #endif
   VSB_CUDA(cudaGetLastError());
 }
@@ -229,8 +229,9 @@ inline void setup_dw_ring(DwRingOp& op, const float* x, int B, int H, int C) {
   encode_map(&op.tm, x, 4, dims, strides, box, 0, true, /*f32=*/true);
 }
 inline void launch_dw_ring(const DwRingOp& op, cudaStream_t st) {
-  if (op.C == 96) launch_dw_ring_t<96, 2, 4, 8>(op, st);
-  else if (op.C == 192) launch_dw_ring_t<192, 1, 4, 8>(op, st);
+  static const bool ws = getenv("VSB_DW_WS") != nullptr;     // weights from shared memory (more blocks per SM): A/B switch
+  if (op.C == 96) { if (ws) launch_dw_ring_t<96, 2, 4, 6, true>(op, st); else launch_dw_ring_t<96, 2, 4, 8>(op, st); }
+  else if (op.C == 192) { if (ws) launch_dw_ring_t<192, 1, 4, 4, true>(op, st); else launch_dw_ring_t<192, 1, 4, 8>(op, st); }
   else launch_dw_ring_t<384, 1, 4, 8>(op, st);
 }
 
