@@ -28,7 +28,7 @@ def main(src: str, tag: str):
     rows = prof["table"]
     total = sum(r["ms_per_step"] for r in rows)
     with open(os.path.join(HERE, f"{tag}_step_profile.md"), "w") as f:
-        f.write(f"# Round 1 — per-kernel step profile (CUDA events around every plan step inside `bench.py`, batch {prof['batch']}, {prof['card']})\n\n")
+        f.write(f"# {tag} — per-kernel step profile (CUDA events around every plan step inside `bench.py`, batch {prof['batch']}, {prof['card']})\n\n")
         f.write(f"Step under events: {total:.2f} ms (timed step without events: {bench['ms_per_step']:.2f} ms = {bench['value']:.0f} frames/s). "
                 f"Source: `profiles/{tag}_step_profile.json` (bench.py --profile-out).\n\n")
         f.write("| plan step (shape tag = C_in-C_out@map) | ms/step | launches | avg µs | TFLOP/s | share |\n|---|---|---|---|---|---|\n")
@@ -44,6 +44,9 @@ def main(src: str, tag: str):
         per_step = bench.get("gpu_launches_per_step") or None
         steps_total = 5
         tail = ours[-(len(ours) * 2 // steps_total):] if not per_step else ours[-2 * per_step:]
+        ev = prof["table"]
+        ev_tot = sum(r["ms_per_step"] for r in ev)
+        ev_gemm = sum(r["ms_per_step"] for r in ev if r.get("tflops")) / ev_tot if ev_tot else 0
         agg = {}
         for r in tail:
             k = short(r["Kernel Name"])
@@ -52,8 +55,9 @@ def main(src: str, tag: str):
             a[1] += float(r["Metric Value"]) / 1e6
         tot = sum(a[1] for a in agg.values())
         with open(os.path.join(HERE, f"{tag}_launches_summary.md"), "w") as f:
-            f.write(f"# Round 1 - ncu launch list of `bench.py --steps 2 --warmup 3` (gpu__time_duration.sum, --clock-control none)\n\n")
+            f.write(f"# {tag} - ncu launch list of `bench.py --steps 2 --warmup 3` (gpu__time_duration.sum, --clock-control none)\n\n")
             f.write(f"{len(tail)} launches = the last 2/5 of the {len(ours)} captured (cold-cache, serialised: compare SHARES). Total {tot:.2f} ms.\n\n")
+            f.write(f"(event profile of the same command: the tensor-core conv / GEMM steps are {100 * ev_gemm:.1f} % of the step)\n\n")
             f.write("| kernel | launches | total ms | share |\n|---|---|---|---|\n")
             for k, a in sorted(agg.items(), key=lambda kv: -kv[1][1]):
                 f.write(f"| `{k}` | {a[0]} | {a[1]:.3f} | {100 * a[1] / tot:.1f}% |\n")

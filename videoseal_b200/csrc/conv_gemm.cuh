@@ -79,6 +79,8 @@ struct ConvGemmParams {
   // ---- residual prefetch ring (thread-private slots)
   uint32_t resid_off, resid_stride;
   int resid_depth;
+  int resid_direct;               // 1: no shared-memory ring, the epilogue reads the fp16 residual straight from global memory (long-K layers:
+                                  //    their epilogue is hidden behind the main loop, the 48 KB buy one more TMA pipeline stage)
   // ---- gather loaders (NHWC fp16 sources; K order = (r, s, c) with c over the virtual concat [src0 | src1])
   const __half* src0;
   const __half* src1;
@@ -439,7 +441,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
     // layout [16-byte chunk][row] = conflict-free)
     const int G = p.group;
     auto prefetch_resid = [&](int sq, int slot) {
-      if (has_res) {
+      if (has_res && !p.resid_direct) {
         const int it = p.fd_group.div(sq), g = sq - it * G;
         const int tile = (int)blockIdx.x + it * (int)gridDim.x;
         const int st = p.fd_ntiles.div(tile);
@@ -718,8 +720,14 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             }
             if (has_res) {
               __align__(16) __half h[16];
-              reinterpret_cast<uint4*>(h)[0] = *reinterpret_cast<const uint4*>(rb_ + ((size_t)(2 * ch) * 128 + row) * 16);
-              reinterpret_cast<uint4*>(h)[1] = *reinterpret_cast<const uint4*>(rb_ + ((size_t)(2 * ch + 1) * 128 + row) * 16);
+              if (p.resid_direct) {
+                const uint4* rg = reinterpret_cast<const uint4*>(p.resid16 + m * p.ld_res16 + n);
+                reinterpret_cast<uint4*>(h)[0] = __ldg(rg);
+                reinterpret_cast<uint4*>(h)[1] = __ldg(rg + 1);
+              } else {
+                reinterpret_cast<uint4*>(h)[0] = *reinterpret_cast<const uint4*>(rb_ + ((size_t)(2 * ch) * 128 + row) * 16);
+                reinterpret_cast<uint4*>(h)[1] = *reinterpret_cast<const uint4*>(rb_ + ((size_t)(2 * ch + 1) * 128 + row) * 16);
+              }
 #pragma unroll
               for (int j = 0; j < 16; ++j) v[j] += __half2float(h[j]);
             }
@@ -762,7 +770,7 @@ conv_gemm_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant_
             for (int j = 0; j < 16; ++j) if (j >= nval) v[j] = 0.f;   // ragged last chunk (chunky widths): keep the tail inert
           }
           if (has_res && mvalid) {
-            if (res_fast) {
+            if (res_fast && !p.resid_direct) {
               if (p.resid16 != nullptr) {
                 __align__(16) __half h[16];
                 reinterpret_cast<uint4*>(h)[0] = *reinterpret_cast<const uint4*>(rb_ + ((size_t)(2 * ch) * 128 + row) * 16);

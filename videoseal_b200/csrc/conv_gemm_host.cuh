@@ -133,7 +133,11 @@ inline void finalize_op(ConvGemmOp& op, const __half* W, int N, int Kw, int ldw,
   VSB_CHECK(p.a_stage_bytes % 1024 == 0, "A stage must be 1024B aligned");
   // shared memory: [header | stages x (A|B) | 2 halo tiles | upsampled halo | resident weights | residual ring]
   size_t resid_one = 0;
-  if (p.resid16) resid_one = (size_t)kBlockM * p.block_n * 2;
+  p.resid_direct = 0;
+  if (p.resid16 && op.loader == LD_TMA && p.num_kb >= 24 && (p.ld_res16 % 8) == 0 && N % p.block_n == 0 && (long)p.m_tiles * kBlockM == (long)p.M &&
+      p.out32 == nullptr && p.outc_w == nullptr && !getenv("VSB_RESID_RING"))
+    p.resid_direct = 1;     // whole tiles only (the lean affine path is the one that implements the direct read)
+  if (p.resid16 && !p.resid_direct) resid_one = (size_t)kBlockM * p.block_n * 2;
   if (p.resid32) resid_one = (size_t)kBlockM * p.block_n * 4;
   int depth = 1;
   if (resid_one) { depth = (int)(32768 / resid_one); if (depth > 4) depth = 4; if (depth < 1) depth = 1; }

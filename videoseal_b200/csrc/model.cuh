@@ -973,21 +973,6 @@ class Model {
                                     "cnx.dwconv7_ln." + std::to_string(C) + "@" + std::to_string(hs)});
           } else
           pl.steps.push_back(Step{[=](cudaStream_t st) {
-#ifdef VSB_EXP
-            // experimental build only: register-rolling kernel (pointwise.cuh K4 v2), opt in with VSB_DW2=1
-            static const bool dw2 = getenv("VSB_DW2") != nullptr;
-            if (dw2 && ldc == Cc && (Cc == 96 || Cc == 192)) {
-              const int R = (H >= 64 && H % 16 == 0) ? 16 : 8;
-              const int NS = Cc == 96 ? 2 : 1;
-              if (H % R == 0 && H % (4 * NS) == 0) {
-                const unsigned blocks = (unsigned)((long)B * (H / R) * (H / (4 * NS)));
-                if (Cc == 96) dwconv7_ln_roll_kernel<96, 2><<<blocks, 96, 0, st>>>(xin, B, H, H, dww, dwb, lw, lb, a, R);
-                else dwconv7_ln_roll_kernel<192, 1><<<blocks, 96, 0, st>>>(xin, B, H, H, dww, dwb, lw, lb, a, R);
-                VSB_CUDA(cudaGetLastError());
-                return;
-              }
-            }
-#endif
             if (!(Cc == 96 || Cc == 192 || Cc == 384 || Cc == 768) || getenv("VSB_DW_WIDE")) {
               // any even width / odd map size (chunkyseal's proportional trunk): threads loop over the channel pairs
               const long nstrips = (long)B * H * ((H + kDwStrip - 1) / kDwStrip);
@@ -1000,31 +985,15 @@ class Model {
               VSB_CUDA(cudaGetLastError());
               return;
             }
-            // experimental tiled kernel (input window staged in smem), VSB_DW_TILED=1: measured no faster than the strip kernel
-            // (both are latency-bound per block, profiles/r1_history.md), kept for round-2 work
-            const int TW = (H % 16 == 0) ? 16 : ((H % 8 == 0) ? 8 : 0);
-            const size_t smem_t = TW ? ((size_t)(kDwTH + 6) * (TW + 6) * kDwCC + (size_t)kDwTH * TW * Cc) * sizeof(float) : 0;
-            if (TW && H % kDwTH == 0 && Cc % kDwCC == 0 && smem_t <= 200 * 1024 && getenv("VSB_DW_TILED")) {
-              static bool attr = false;
-              if (!attr) { VSB_CUDA(cudaFuncSetAttribute(dwconv7_ln_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024)); attr = true; }
-              const int threads = (kDwCC / 2) * kDwTH * (TW / kDwStrip);
-              const int blocks = B * (H / kDwTH) * (H / TW);
-              dwconv7_ln_tiled_kernel<<<blocks, threads, smem_t, st>>>(xin, B, H, H, Cc, Cc, dww, dwb, lw, lb, a, Cc, TW);
-              VSB_CUDA(cudaGetLastError());
-              return;
-            }
             const int strips = (H + kDwStrip - 1) / kDwStrip;
             const long nstrips = (long)B * H * strips;
             const int C2 = Cc / 2;
             int spb = 1;
             for (int s2 = 1; s2 <= 4; s2 *= 2) if ((s2 * C2) % 32 == 0 && s2 * C2 <= 512) { spb = s2; break; }
             if (spb * C2 > 512) throw Error("dwconv7: C/2 > 512 threads is not implemented (unsupported chunky extractor width)", kErrUnsupported);
-            const long blocks = (nstrips + spb - 1) / spb;
-            const size_t smem_s = (size_t)spb * kDwStrip * Cc * sizeof(float);
-            static const bool generic_dw = getenv("VSB_DW_GENERIC") != nullptr;
 #define VSB_DWC(CC, ST, FR, SPB, NGR, RPB) dwconv7_ln_c_kernel<CC, ST, FR><<<(unsigned)(((NGR) + (SPB) - 1) / (SPB)), (SPB) * (CC) / 2, \
     (size_t)(SPB) * (ST) * (CC) * sizeof(float), st>>>(xin, B, H, H, dww, dwb, lw, lb, a, Cc, SPB, (int)(NGR), RPB)
-            if (!generic_dw && (Cc == 96 || Cc == 192 || Cc == 384 || Cc == 768)) {
+            {
               // rows per block: 1.  Walking 2-4 consecutive rows per block (L1 reuse of the 7-row input window) was measured
               // SLOWER (96@64: 148 -> 228 us, 192@32: 58 -> 87 us): the kernel is latency-bound and fewer, longer blocks with
               // two block barriers per row hide less of it; VSB_DW_RPB re-enables the experiment
@@ -1038,15 +1007,8 @@ class Model {
               else if (Cc == 192) VSB_DWC(192, 8, false, spb, nstrips / rpb, rpb);
               else if (Cc == 384) VSB_DWC(384, 8, false, spb, nstrips / rpb, rpb);
               else VSB_DWC(768, 8, false, spb, nstrips / rpb, rpb);
-              VSB_CUDA(cudaGetLastError());
-              return;
             }
 #undef VSB_DWC
-            const int kp = (Cc + 63) / 64;
-#define VSB_DW(KP) dwconv7_ln_kernel<KP><<<(unsigned)blocks, spb * C2, smem_s, st>>>(xin, B, H, H, Cc, Cc, dww, dwb, lw, lb, a, Cc, spb, nstrips)
-            if (kp <= 2) VSB_DW(2); else if (kp <= 3) VSB_DW(3); else if (kp <= 6) VSB_DW(6); else if (kp <= 12) VSB_DW(12);
-            else if (kp <= 16) VSB_DW(16); else throw Error("dwconv7: more than 1024 channels is not implemented", kErrUnsupported);
-#undef VSB_DW
             VSB_CUDA(cudaGetLastError());
           }, 1, "cnx.dwconv7_ln." + std::to_string(C) + "@" + std::to_string(hs)});
         }

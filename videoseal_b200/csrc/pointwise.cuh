@@ -643,100 +643,6 @@ __global__ void __launch_bounds__(256) stem_ln_kernel(const float* __restrict__ 
 // a channel pair and slides over the 7 x (strip+6) input window; pre-LN results go to smem, then LN per pixel by warps.
 constexpr int kDwStrip = 8;
 __device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) { return __ffma2_rn(a, b, c); }   // Blackwell packed fp32 FMA
-// blockDim.x = spb * C/2 threads: `spb` strips per block so that every warp is full.  KP = ceil(C / 64): channel pairs per
-// lane in the LayerNorm stage (values stay in registers between the mean and the variance pass).
-template <int KP>
-__global__ void __launch_bounds__(768) dwconv7_ln_kernel(const float* __restrict__ x, int B, int H, int W, int C, int ldx,
-                                                         const float* __restrict__ wdw /*[49][C]*/, const float* __restrict__ bdw,
-                                                         const float* __restrict__ lnw, const float* __restrict__ lnb,
-                                                         __half* __restrict__ out, int ld_out, int spb, long nstrips) {
-  extern __shared__ float pre[];  // [spb][kDwStrip][C]
-  const int strips_x = (W + kDwStrip - 1) / kDwStrip;
-  const int C2 = C >> 1;
-  const int ls = threadIdx.x / C2;                 // local strip
-  const int cp = threadIdx.x - ls * C2;            // channel pair
-  // (32-bit index math throughout: the 64-bit div/mod this replaced was ~30 % of the kernel's instructions)
-  const unsigned strip = blockIdx.x * (unsigned)spb + (unsigned)ls;
-  const bool active = (ls < spb) && (strip < (unsigned)nstrips);
-  int sx = 0, oy = 0, b = 0, ox0 = 0;
-  if (active) {
-    const unsigned t = strip / (unsigned)strips_x;
-    sx = (int)(strip - t * (unsigned)strips_x);
-    b = (int)(t / (unsigned)H); oy = (int)(t - (unsigned)b * (unsigned)H);
-    ox0 = sx * kDwStrip;
-    const int c = cp * 2;
-    float2 acc[kDwStrip];
-    const float2 bb = __ldg(reinterpret_cast<const float2*>(bdw + c));
-#pragma unroll
-    for (int i = 0; i < kDwStrip; ++i) acc[i] = bb;
-    for (int r = 0; r < 7; ++r) {
-      const int iy = oy + r - 3;
-      if (iy < 0 || iy >= H) continue;
-      float2 wr[7];
-#pragma unroll
-      for (int s2 = 0; s2 < 7; ++s2) wr[s2] = __ldg(reinterpret_cast<const float2*>(wdw + (r * 7 + s2) * C + c));
-      const float* rowp = x + (((long)b * H + iy) * W) * ldx + c;
-#pragma unroll
-      for (int u = 0; u < kDwStrip + 6; ++u) {
-        const int ix = ox0 + u - 3;
-        float2 v = make_float2(0.f, 0.f);
-        if (ix >= 0 && ix < W) v = __ldg(reinterpret_cast<const float2*>(rowp + (long)ix * ldx));
-#pragma unroll
-        for (int s2 = 0; s2 < 7; ++s2) {
-          const int i = u - s2;  // output pixel index within the strip
-          if (i >= 0 && i < kDwStrip) acc[i] = ffma2(v, wr[s2], acc[i]);
-        }
-      }
-    }
-    float* pr = pre + (size_t)ls * kDwStrip * C;
-#pragma unroll
-    for (int i = 0; i < kDwStrip; ++i) { pr[i * C + c] = acc[i].x; pr[i * C + c + 1] = acc[i].y; }
-  }
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int item = warp; item < spb * kDwStrip; item += nwarps) {
-    const int l2 = item / kDwStrip, i = item - l2 * kDwStrip;
-    const unsigned st2 = blockIdx.x * (unsigned)spb + (unsigned)l2;
-    if (st2 >= (unsigned)nstrips) continue;
-    const unsigned t2 = st2 / (unsigned)strips_x;
-    const int sx2 = (int)(st2 - t2 * (unsigned)strips_x);
-    const int b2 = (int)(t2 / (unsigned)H), oy2 = (int)(t2 - (unsigned)b2 * (unsigned)H);
-    const int ox = sx2 * kDwStrip + i;
-    if (ox >= W) continue;
-    const float2* pr2 = reinterpret_cast<const float2*>(pre + ((size_t)l2 * kDwStrip + i) * C);
-    float2 vv[KP];
-    float sum = 0.f;
-#pragma unroll
-    for (int k = 0; k < KP; ++k) {
-      const int c2 = lane + 32 * k;
-      vv[k] = c2 < C2 ? pr2[c2] : make_float2(0.f, 0.f);
-      sum += vv[k].x + vv[k].y;
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float mean = sum / (float)C;
-    float var = 0.f;
-#pragma unroll
-    for (int k = 0; k < KP; ++k) {
-      if (lane + 32 * k < C2) { const float dx = vv[k].x - mean, dy = vv[k].y - mean; var += dx * dx + dy * dy; }
-    }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
-    const float rstd = 1.0f / sqrtf(var / (float)C + 1e-6f);
-    __half* dst = out + (((long)b2 * H + oy2) * W + ox) * ld_out;
-#pragma unroll
-    for (int k = 0; k < KP; ++k) {
-      const int c2 = lane + 32 * k;
-      if (c2 < C2) {
-        const float2 g = __ldg(reinterpret_cast<const float2*>(lnw) + c2), bt = __ldg(reinterpret_cast<const float2*>(lnb) + c2);
-        const float a = (vv[k].x - mean) * rstd * g.x + bt.x;
-        const float bq = (vv[k].y - mean) * rstd * g.y + bt.y;
-        *reinterpret_cast<__half2*>(dst + 2 * c2) = __floats2half2_rn(a, bq);
-      }
-    }
-  }
-}
-
 // K4 for arbitrary (even) widths, used for the proportional chunkyseal trunk (362 / 724 / 1448 / 2896 channels on 127 / 63 / 31 /
 // 15 pixel maps): one block per strip of kDwStrip output pixels; the threads LOOP over the channel pairs (C/2 may exceed the
 // block size) and the LayerNorm stage re-reads the pre-LN strip from shared memory instead of holding it in registers.
@@ -940,259 +846,6 @@ __global__ void __launch_bounds__(768) dwconv7_ln_c_kernel(const float* __restri
   }  // rows of the block
 }
 
-// K4 (tiled): depthwise 7x7 + channels-last LayerNorm with the input staged in shared memory.
-// One block = a kDwTH x TW (4 x 16 or 4 x 8) tile of output pixels of one image.  The C channels are processed in chunks of
-// kDwCC = 96: the (4+6) x (TW+6) x 96 fp32 input window is loaded ONCE (coalesced, zero-filled outside the image) and every
-// thread (one channel pair x one 8-pixel strip) runs its 7 x 14 window out of shared memory with packed fp32 FMAs.  Pre-LN
-// results accumulate in a second shared buffer [pixel][C]; after the last chunk one warp per pixel normalises and stores fp16.
-// HBM/L2 traffic is (10*22)/(4*16) = 3.4x the input instead of the 12x of the strip kernel above.
-constexpr int kDwTH = 4, kDwCC = 96;
-__global__ void __launch_bounds__(384) dwconv7_ln_tiled_kernel(const float* __restrict__ x, int B, int H, int W, int C, int ldx,
-                                                               const float* __restrict__ wdw /*[49][C]*/, const float* __restrict__ bdw,
-                                                               const float* __restrict__ lnw, const float* __restrict__ lnb,
-                                                               __half* __restrict__ out, int ld_out, int TW) {
-  extern __shared__ __align__(16) float dsm[];
-  const int IW = TW + 6, IHt = kDwTH + 6;
-  float* in_s = dsm;                                  // [IHt][IW][kDwCC]
-  float* pre = dsm + (size_t)IHt * IW * kDwCC;        // [kDwTH*TW][C]
-  const int tiles_x = W / TW, tiles_y = H / kDwTH;
-  int t = blockIdx.x;
-  const int tx = t % tiles_x; t /= tiles_x;
-  const int ty = t % tiles_y;
-  const int b = t / tiles_y;
-  const int ox0 = tx * TW, oy0 = ty * kDwTH;
-  const int spr = TW / kDwStrip;                      // strips per tile row (2 or 1)
-  const int cp = threadIdx.x % (kDwCC / 2);           // channel pair inside the chunk
-  const int sidx = threadIdx.x / (kDwCC / 2);         // strip index 0 .. kDwTH*spr-1
-  const int sr = sidx / spr, sx0 = (sidx - sr * spr) * kDwStrip;
-  for (int c0 = 0; c0 < C; c0 += kDwCC) {
-    // ---- stage the input window of this channel chunk (float4 = 4 channels per load)
-    const int nvec = IHt * IW * (kDwCC / 4);
-    for (int i = threadIdx.x; i < nvec; i += blockDim.x) {
-      const int c4 = i % (kDwCC / 4);
-      const int pix = i / (kDwCC / 4);
-      const int iy = pix / IW, ix = pix - iy * IW;
-      const int gy = oy0 + iy - 3, gx = ox0 + ix - 3;
-      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (gy >= 0 && gy < H && gx >= 0 && gx < W)
-        v = __ldg(reinterpret_cast<const float4*>(x + (((long)b * H + gy) * W + gx) * ldx + c0 + c4 * 4));
-      reinterpret_cast<float4*>(in_s)[i] = v;
-    }
-    __syncthreads();
-    {
-      const int c = c0 + cp * 2;
-      float2 acc[kDwStrip];
-      const float2 bb = __ldg(reinterpret_cast<const float2*>(bdw + c));
-#pragma unroll
-      for (int i = 0; i < kDwStrip; ++i) acc[i] = bb;
-#pragma unroll 1
-      for (int r = 0; r < 7; ++r) {
-        float2 wr[7];
-#pragma unroll
-        for (int s2 = 0; s2 < 7; ++s2) wr[s2] = __ldg(reinterpret_cast<const float2*>(wdw + (r * 7 + s2) * C + c));
-        const float* rowp = in_s + ((size_t)(sr + r) * IW + sx0) * kDwCC + cp * 2;
-#pragma unroll
-        for (int u = 0; u < kDwStrip + 6; ++u) {
-          const float2 v = *reinterpret_cast<const float2*>(rowp + (size_t)u * kDwCC);
-#pragma unroll
-          for (int s2 = 0; s2 < 7; ++s2) {
-            const int i = u - s2;
-            if (i >= 0 && i < kDwStrip) acc[i] = ffma2(v, wr[s2], acc[i]);
-          }
-        }
-      }
-#pragma unroll
-      for (int i = 0; i < kDwStrip; ++i)
-        *reinterpret_cast<float2*>(pre + (size_t)(sr * TW + sx0 + i) * C + c) = acc[i];
-    }
-    __syncthreads();   // in_s is overwritten by the next chunk; pre complete after the last one
-  }
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nwarps = blockDim.x >> 5;
-  for (int pi = warp; pi < kDwTH * TW; pi += nwarps) {
-    const int oy = oy0 + pi / TW, ox = ox0 + pi % TW;
-    const float* pr = pre + (size_t)pi * C;
-    float sum = 0.f;
-    for (int c = lane; c < C; c += 32) sum += pr[c];
-#pragma unroll
-    for (int o = 16; o; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
-    const float mean = sum / (float)C;
-    float var = 0.f;
-    for (int c = lane; c < C; c += 32) { const float d = pr[c] - mean; var += d * d; }
-#pragma unroll
-    for (int o = 16; o; o >>= 1) var += __shfl_xor_sync(0xffffffffu, var, o);
-    const float rstd = 1.0f / sqrtf(var / (float)C + 1e-6f);
-    __half* dst = out + (((long)b * H + oy) * W + ox) * ld_out;
-    for (int c = lane * 2; c < C; c += 64) {
-      const float a = (pr[c] - mean) * rstd * __ldg(lnw + c) + __ldg(lnb + c);
-      const float bq = (pr[c + 1] - mean) * rstd * __ldg(lnw + c + 1) + __ldg(lnb + c + 1);
-      *reinterpret_cast<__half2*>(dst + c) = __floats2half2_rn(a, bq);
-    }
-  }
-}
-
-#ifdef VSB_EXP
-// K4 v2 (experimental build only, -DVSB_EXP; opt in at run time with VSB_DW2=1): depthwise 7x7 + LayerNorm with a REGISTER-ROLLING
-// walk down the rows.  Motivation (profiles/r1_cnx_kernels_ncu.md): the strip kernel above re-loads a 7 x 14 pixel window for
-// every 8-pixel strip (98 loads for 392 packed FMAs per thread), runs at 37 % occupancy with a long-scoreboard stall on 40 % of
-// the samples and executes 93 M warp instructions for 19 M FFMA2.  Here a thread owns one channel pair and a strip of 4 output
-// columns and walks R output rows: its 49 weights stay in registers, every input row (10 pixels) is loaded ONCE and feeds the 7
-// output rows it overlaps (7 x 4 accumulators in a statically rotated register ring: slot = (row phase + j + 1) mod 7), the next
-// row's pixels are prefetched while the current ones are used, and the LayerNorm statistics of a finished row are reduced with a
-// halving butterfly over 16-lane segments + one block barrier per row (double-buffered partial sums), one-pass variance.
-// Block = NS strips x C/2 channel pairs (C/2 is a multiple of 16, so a 16-lane segment never straddles two strips); grid =
-// B x (H/R) x (W/(4 NS)).  Requires H % R == 0, W % (4 NS) == 0, x and out dense (pixel pitch C).
-template <int C, int NS, bool EDGE>
-__device__ __forceinline__ void dw2_load_row(const float* __restrict__ rowp, int x0, int W, float2 (&v)[10]) {
-  // rowp -> channel pair of pixel (iy, x0 - 3); pixels outside the image read as zero (only strips at the left / right border)
-#pragma unroll
-  for (int u = 0; u < 10; ++u) {
-    if (!EDGE || (unsigned)(x0 - 3 + u) < (unsigned)W) v[u] = __ldg(reinterpret_cast<const float2*>(rowp + u * C));
-    else v[u] = make_float2(0.f, 0.f);
-  }
-}
-
-template <int C, int NS>
-__global__ void __launch_bounds__((C / 2) * NS, 2) dwconv7_ln_roll_kernel(const float* __restrict__ x, int B, int H, int W,
-                                                                          const float* __restrict__ wdw /*[49][C]*/,
-                                                                          const float* __restrict__ bdw, const float* __restrict__ lnw,
-                                                                          const float* __restrict__ lnb, __half* __restrict__ out, int R) {
-  constexpr int C2 = C / 2, KSEG = C2 / 16;          // 16-lane segments per strip
-  __shared__ __align__(16) float part[2][NS][KSEG][8];   // per-segment partial sums {sum, sumsq} x 4 pixels, double-buffered
-  const int s = threadIdx.x / C2, cp = threadIdx.x - s * C2, c = cp * 2;
-  const int lane = threadIdx.x & 31, seg = cp >> 4;
-  const int cgroups = W / (4 * NS), rgroups = H / R;
-  const int cg = blockIdx.x % cgroups;
-  const int t = blockIdx.x / cgroups;
-  const int rg = t % rgroups, b = t / rgroups;
-  const int x0 = (cg * NS + s) * 4, y0 = rg * R;
-  const bool edge = (x0 < 3) || (x0 + 7 > W);
-
-  float2 wt[49];
-#pragma unroll
-  for (int k = 0; k < 49; ++k) wt[k] = __ldg(reinterpret_cast<const float2*>(wdw + k * C + c));
-  const float2 bias = __ldg(reinterpret_cast<const float2*>(bdw + c));
-  const float2 lg = __ldg(reinterpret_cast<const float2*>(lnw + c)), lb = __ldg(reinterpret_cast<const float2*>(lnb + c));
-
-  float2 acc[7][4];
-  float2 cur[10], nxt[10];
-  const long rowpitch = (long)W * C;
-  // pixel (y0 - 3, x0 - 3): outside the image at the borders, only dereferenced where the row / column tests allow
-  const float* rowp = x + (((long)b * H + y0) * W + x0) * C + c - 3 * rowpitch - 3 * C;
-  const int nsteps = R + 6;                          // input rows y0 - 3 ... y0 + R + 2
-  int emitted = 0;                                   // rows emitted so far -> partial-sum buffer parity
-
-  // prefetch input row 0
-#pragma unroll
-  for (int u = 0; u < 10; ++u) nxt[u] = make_float2(0.f, 0.f);
-  if ((unsigned)(y0 - 3) < (unsigned)H) {
-    if (edge) dw2_load_row<C, NS, true>(rowp, x0, W, nxt); else dw2_load_row<C, NS, false>(rowp, x0, W, nxt);
-  }
-
-  // one step = one input row i (iy = y0 - 3 + i); PH = i mod 7 is a compile-time constant inside the 7-fold unrolled body so that
-  // every accumulator index below is static.  Output row o = i + j - 6 (kernel row 6 - j) lives in slot (PH + j + 1) % 7.
-  auto step = [&](auto ph_tag, int i) {
-    constexpr int PH = decltype(ph_tag)::value;
-    const int iy = y0 - 3 + i;
-    const bool rowok = (unsigned)iy < (unsigned)H;
-#pragma unroll
-    for (int u = 0; u < 10; ++u) cur[u] = nxt[u];
-    if (i + 1 < nsteps && (unsigned)(iy + 1) < (unsigned)H) {   // prefetch the next input row while this one is consumed
-      const float* np = rowp + (long)(i + 1) * rowpitch;
-      if (edge) dw2_load_row<C, NS, true>(np, x0, W, nxt); else dw2_load_row<C, NS, false>(np, x0, W, nxt);
-    }
-    {   // j = 6: output row o = i starts here (kernel row 0): initialise its slot
-      constexpr int SL = (PH + 7) % 7;
-      if (rowok && i < R) {
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-          acc[SL][p] = ffma2(cur[p], wt[0], bias);
-#pragma unroll
-          for (int q = 1; q < 7; ++q) acc[SL][p] = ffma2(cur[p + q], wt[q], acc[SL][p]);
-        }
-      } else {
-#pragma unroll
-        for (int p = 0; p < 4; ++p) acc[SL][p] = bias;
-      }
-    }
-    if (rowok) {
-#pragma unroll
-      for (int j = 0; j < 6; ++j) {                  // output rows o = i + j - 6, kernel row 6 - j
-        const int o = i + j - 6;
-        if (o >= 0 && o < R) {
-#pragma unroll
-          for (int p = 0; p < 4; ++p)
-#pragma unroll
-            for (int q = 0; q < 7; ++q) acc[(PH + j + 1) % 7][p] = ffma2(cur[p + q], wt[(6 - j) * 7 + q], acc[(PH + j + 1) % 7][p]);
-        }
-      }
-    }
-    const int o = i - 6;                             // j = 0: this output row has now seen its last input row
-    if (o >= 0) {
-      constexpr int SL = (PH + 1) % 7;
-      float v[8];
-#pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        const float2 a = acc[SL][p];
-        v[2 * p] = a.x + a.y;
-        v[2 * p + 1] = fmaf(a.x, a.x, a.y * a.y);
-      }
-      // halving butterfly over the 16 lanes of the segment: 8 values -> lane (l & 15) ends with value index
-      // ((l >> 3) & 1) * 4 + ((l >> 2) & 1) * 2 + ((l >> 1) & 1), summed over the 16 lanes
-#pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        const float send = (lane & 8) ? v[k] : v[k + 4];
-        const float keep = (lane & 8) ? v[k + 4] : v[k];
-        v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
-      }
-#pragma unroll
-      for (int k = 0; k < 2; ++k) {
-        const float send = (lane & 4) ? v[k] : v[k + 2];
-        const float keep = (lane & 4) ? v[k + 2] : v[k];
-        v[k] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
-      }
-      {
-        const float send = (lane & 2) ? v[0] : v[1];
-        const float keep = (lane & 2) ? v[1] : v[0];
-        v[0] = keep + __shfl_xor_sync(0xffffffffu, send, 2);
-      }
-      v[0] += __shfl_xor_sync(0xffffffffu, v[0], 1);
-      const int buf = emitted & 1;
-      if ((lane & 1) == 0) part[buf][s][seg][((lane >> 3) & 1) * 4 + ((lane >> 2) & 1) * 2 + ((lane >> 1) & 1)] = v[0];
-      __syncthreads();     // one barrier per emitted row: the other buffer is only rewritten after the NEXT barrier
-      float tot[8];
-#pragma unroll
-      for (int k = 0; k < 8; ++k) tot[k] = 0.f;
-#pragma unroll
-      for (int g = 0; g < KSEG; ++g) {
-        const float4 t0 = *reinterpret_cast<const float4*>(&part[buf][s][g][0]);
-        const float4 t1 = *reinterpret_cast<const float4*>(&part[buf][s][g][4]);
-        tot[0] += t0.x; tot[1] += t0.y; tot[2] += t0.z; tot[3] += t0.w;
-        tot[4] += t1.x; tot[5] += t1.y; tot[6] += t1.z; tot[7] += t1.w;
-      }
-      __half* dst = out + (((long)b * H + (y0 + o)) * W + x0) * C + c;
-#pragma unroll
-      for (int p = 0; p < 4; ++p) {
-        const float mean = tot[2 * p] * (1.0f / (float)C);
-        const float var = fmaxf(tot[2 * p + 1] * (1.0f / (float)C) - mean * mean, 0.f);
-        const float rstd = rsqrtf(var + 1e-6f);
-        const float sx = rstd * lg.x, sy = rstd * lg.y;
-        const float2 a = acc[SL][p];
-        *reinterpret_cast<__half2*>(dst + p * C) = __floats2half2_rn(fmaf(a.x, sx, fmaf(-mean, sx, lb.x)), fmaf(a.y, sy, fmaf(-mean, sy, lb.y)));
-      }
-      ++emitted;
-    }
-  };
-  for (int i0 = 0; i0 < nsteps; i0 += 7) {
-    if (i0 + 0 < nsteps) step(std::integral_constant<int, 0>{}, i0 + 0);
-    if (i0 + 1 < nsteps) step(std::integral_constant<int, 1>{}, i0 + 1);
-    if (i0 + 2 < nsteps) step(std::integral_constant<int, 2>{}, i0 + 2);
-    if (i0 + 3 < nsteps) step(std::integral_constant<int, 3>{}, i0 + 3);
-    if (i0 + 4 < nsteps) step(std::integral_constant<int, 4>{}, i0 + 4);
-    if (i0 + 5 < nsteps) step(std::integral_constant<int, 5>{}, i0 + 5);
-    if (i0 + 6 < nsteps) step(std::integral_constant<int, 6>{}, i0 + 6);
-  }
-}
-#endif  // VSB_EXP
 
 // K4b: per-row LayerNorm over C (biased variance, eps) of fp32 rows -> fp16 rows.  One warp per row.
 __global__ void __launch_bounds__(256) ln_rows_kernel(const float* __restrict__ x, long M, int C, int ldx, const float* __restrict__ w,
