@@ -1371,6 +1371,26 @@ class Model {
     // delta read in place, or through <= 2 taps per axis (plain bilinear up-scale: every input at least as large as the processing size)
     const bool fastup = bp.identity_resample || (bp.tab.maxt_x <= 2 && bp.tab.maxt_y <= 2 && bp.H >= bp.PH && bp.W >= bp.PW);
     VSB_CHECK(bp.CD == 1 || bp.CD == 3, "delta must have 1 or 3 channels");
+    // TMA-fed kernel (jnd_blend3_kernel): vector layout, delta in place or <= 2 taps per axis; the delta tile needs a TMA-legal row pitch
+    static const bool blend_old = getenv("VSB_BLEND_OLD") != nullptr;
+    const bool delta_tma = bp.identity_resample || (bp.PW % 4 == 0 && reinterpret_cast<uintptr_t>(bp.delta) % 16 == 0);
+    const bool tma = vec && fastup && delta_tma && !blend_old &&
+                     (!bp.identity_resample || (bp.PW % 4 == 0 && reinterpret_cast<uintptr_t>(bp.delta) % 16 == 0));
+    CUtensorMap tmI, tmD;
+    if (tma) {
+      const uint64_t idims[3] = {(uint64_t)bp.W, (uint64_t)bp.H, (uint64_t)bp.F * 3};
+      const uint64_t istr[2] = {(uint64_t)bp.W * 4, (uint64_t)bp.H * bp.W * 4};
+      const uint32_t ibox[3] = {(uint32_t)kB2LP, (uint32_t)(kB2TH + 4), 3};
+      encode_map(&tmI, bp.imgs, 3, idims, istr, ibox, 0, true, /*f32=*/true);
+      tmD = tmI;
+      if (!bp.identity_resample) {
+        const int nkeys = (bp.F + bp.step - 1) / bp.step;
+        const uint64_t ddims[3] = {(uint64_t)bp.PW, (uint64_t)bp.PH, (uint64_t)nkeys * bp.CD};
+        const uint64_t dstr[2] = {(uint64_t)bp.PW * 4, (uint64_t)bp.PH * bp.PW * 4};
+        const uint32_t dbox[3] = {(uint32_t)kB3DW, (uint32_t)kB2DH, 1};
+        encode_map(&tmD, bp.delta, 3, ddims, dstr, dbox, 0, true, /*f32=*/true);
+      }
+    }
     prof_scope(std::string(bp.use_jnd ? "pw.jnd_blend." : "pw.blend.") + std::to_string(bp.H) + "x" + std::to_string(bp.W) + "@" + std::to_string(bp.F) +
                    (bp.preds_w ? "+preds" : ""), st, 1, [&] {
 #define VSB_BL(V, FU, CDV, JI) do { static bool attr_ = false; \
@@ -1378,9 +1398,17 @@ class Model {
         jnd_blend2_kernel<V, FU, CDV, JI><<<grid, 256, b2_smem(JI), st>>>(bp); } while (0)
 #define VSB_BL2(CDV, JI) do { \
         if (vec) { if (fastup) VSB_BL(4, 1, CDV, JI); else VSB_BL(4, 0, CDV, JI); } else { if (fastup) VSB_BL(1, 1, CDV, JI); else VSB_BL(1, 0, CDV, JI); } } while (0)
+#define VSB_BL3(CDV, JI) do { static bool attr_ = false; \
+        if (!attr_) { VSB_CUDA(cudaFuncSetAttribute(jnd_blend3_kernel<CDV, JI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)b3_smem(JI))); attr_ = true; } \
+        jnd_blend3_kernel<CDV, JI><<<grid3, 256, b3_smem(JI), st>>>(bp, tmI, tmD); } while (0)
+      const dim3 grid3(grid.x, (bp.H + kB2TH * kB3NT - 1) / (kB2TH * kB3NT), bp.F);
       const bool j3 = bp.use_jnd && bp.jnd_in == 3;      // one heat-map per RGB channel (jnd_3_1 / jnd_3_3): rarely used, own instantiation
-      if (bp.CD == 1) { if (j3) VSB_BL2(1, 3); else VSB_BL2(1, 1); }
-      else            { if (j3) VSB_BL2(3, 3); else VSB_BL2(3, 1); }
+      if (tma) {
+        if (bp.CD == 1) { if (j3) VSB_BL3(1, 3); else VSB_BL3(1, 1); }
+        else            { if (j3) VSB_BL3(3, 3); else VSB_BL3(3, 1); }
+      } else if (bp.CD == 1) { if (j3) VSB_BL2(1, 3); else VSB_BL2(1, 1); }
+      else                   { if (j3) VSB_BL2(3, 3); else VSB_BL2(3, 1); }
+#undef VSB_BL3
 #undef VSB_BL2
 #undef VSB_BL
     });

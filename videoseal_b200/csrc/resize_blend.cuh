@@ -141,6 +141,78 @@ __device__ __forceinline__ float jnd_value(float la_sum, float gx, float gy) {
   return fmaxf(la + cm - 0.3f * fminf(la, cm), 0.f) * (1.f / 255.f);
 }
 
+// Heat-map of a thread's 2 rows x 4 consecutive pixels from a luminance tile with halo (pitch kB2LP; pixel (row yl, column j) of
+// the tile sits at [(yl + 2) * kB2LP + 4 + j]); thread = rows 2 warp, 2 warp + 1, columns 4 lane .. 4 lane + 3.
+// VERTICAL sums first (they are shared by the pixels of a row segment):
+//   output row j in {0, 1} sees luminance rows j .. j+4 of the six rows L0..L5 this thread reads; per column
+//     V5_j = sum of its 5 rows, V3_j = sum of its 3 middle rows, VS_j = [1 2 1] smooth of the middle rows = V3_j + centre row,
+//     VD_j = row j+1 - row j+3;
+//   then per pixel  la = sum_5 V5 + sum_3 V3 - 2 centre,  gx = VS[x+1] - VS[x-1],  gy = VD[x-1] + 2 VD[x] + VD[x+1]
+//   (the 5x5 kernel of modules/jnd.py:37-43 is ones(5,5) + ones(3,3) - 2 delta; Sobel pair jnd.py:44-53).
+__device__ __forceinline__ float2 f2add(float2 a, float2 b) { return __fadd2_rn(a, b); }
+__device__ __forceinline__ float2 f2sub(float2 a, float2 b) { return __ffma2_rn(b, make_float2(-1.f, -1.f), a); }
+__device__ __forceinline__ float2 f2s(float v) { return make_float2(v, v); }
+// jnd_value of two pixels with Blackwell's packed fp32 arithmetic (add / mul / fma .f32x2): 12 packed + 8 SFU + 8 scalar
+// instructions per pair instead of 2 x 26.  Same operations in the same order as jnd_value, except that hi's (la0 - 127) * 3/128 + 3
+// is one FMA with the constant folded (1 rounding less).
+__device__ __forceinline__ float2 jnd_value2(float2 la_sum, float2 gx, float2 gy) {
+  const float2 la0 = f2mul(la_sum, f2s(1.f / 32.f));
+  const float2 t = f2fma(la0, f2s(1.f / 127.f), f2s(1e-5f));
+  const float2 lo = f2fma(f2s(-17.f), make_float2(sqrt_approx(t.x), sqrt_approx(t.y)), f2s(17.f));
+  const float2 hi = f2fma(f2s(3.f / 128.f), la0, f2s(3.f - 127.f * 3.f / 128.f));
+  const float2 la = make_float2(la0.x <= 127.f ? lo.x : hi.x, la0.y <= 127.f ? lo.y : hi.y);
+  const float2 g2 = f2fma(gx, gx, f2mul(gy, gy));
+  const float2 e = f2mul(f2s(1.2f), make_float2(lg2_approx(g2.x), lg2_approx(g2.y)));     // g^2.4 = (g^2)^1.2;  g2 == 0 -> lg2 = -inf -> 0
+  const float2 den = f2add(g2, f2s(676.f));
+  const float2 cm = f2mul(f2mul(f2s(0.117f * 16.f), make_float2(ex2_approx_f(e.x), ex2_approx_f(e.y))),
+                          make_float2(rcp_approx_f(den.x), rcp_approx_f(den.y)));
+  const float2 r = f2fma(f2s(-0.3f), make_float2(fminf(la.x, cm.x), fminf(la.y, cm.y)), f2add(la, cm));
+  return f2mul(make_float2(fmaxf(r.x, 0.f), fmaxf(r.y, 0.f)), f2s(1.f / 255.f));
+}
+
+__device__ __forceinline__ void jnd_hm_vec4(const float* __restrict__ lum_, int warp, int lane, float (&hm)[2][4]) {
+  // columns 2..9 of the 12 floats at shared column lane*4, as the four aligned pairs the 128-bit loads deliver; pixel q's centre = column 2 + q of them
+  float2 L[6][4];
+#pragma unroll
+  for (int r = 0; r < 6; ++r) {
+    const float4* s4 = reinterpret_cast<const float4*>(lum_ + (warp * 2 + r) * kB2LP + lane * 4);
+    const float4 t0 = s4[0], t1 = s4[1], t2 = s4[2];
+    L[r][0] = make_float2(t0.z, t0.w); L[r][1] = make_float2(t1.x, t1.y); L[r][2] = make_float2(t1.z, t1.w); L[r][3] = make_float2(t2.x, t2.y);
+  }
+  float V5[2][8], V3[2][8], VS[2][8], VD[2][8];       // [output row][column 0..7]; V3 / VS / VD are used on columns 1..6 only
+#pragma unroll
+  for (int h = 0; h < 4; ++h) {
+    const float2 mid4 = f2add(f2add(L[1][h], L[2][h]), f2add(L[3][h], L[4][h]));
+    const float2 a0 = f2add(mid4, L[0][h]), a1 = f2add(mid4, L[5][h]);
+    const float2 c23 = f2add(L[2][h], L[3][h]);
+    const float2 b0 = f2add(c23, L[1][h]), b1 = f2add(c23, L[4][h]);
+    const float2 s0 = f2add(b0, L[2][h]), s1 = f2add(b1, L[3][h]);
+    const float2 d0 = f2sub(L[1][h], L[3][h]), d1 = f2sub(L[2][h], L[4][h]);
+    V5[0][2 * h] = a0.x; V5[0][2 * h + 1] = a0.y; V5[1][2 * h] = a1.x; V5[1][2 * h + 1] = a1.y;
+    V3[0][2 * h] = b0.x; V3[0][2 * h + 1] = b0.y; V3[1][2 * h] = b1.x; V3[1][2 * h + 1] = b1.y;
+    VS[0][2 * h] = s0.x; VS[0][2 * h + 1] = s0.y; VS[1][2 * h] = s1.x; VS[1][2 * h + 1] = s1.y;
+    VD[0][2 * h] = d0.x; VD[0][2 * h + 1] = d0.y; VD[1][2 * h] = d1.x; VD[1][2 * h + 1] = d1.y;
+  }
+#pragma unroll
+  for (int j = 0; j < 2; ++j)
+#pragma unroll
+    for (int q = 0; q < 4; q += 2) {
+      float lac[2], gx[2], gy[2];
+#pragma unroll
+      for (int u = 0; u < 2; ++u) {
+        const int x = q + u;                                   // centre column x + 2
+        const float la = ((V5[j][x] + V5[j][x + 1]) + (V5[j][x + 2] + V5[j][x + 3])) + V5[j][x + 4] +
+                         (V3[j][x + 1] + V3[j][x + 2] + V3[j][x + 3]);
+        const float ctr = (x & 1) ? L[2 + j][(x + 2) >> 1].y : L[2 + j][(x + 2) >> 1].x;
+        lac[u] = fmaf(-2.f, ctr, la);
+        gx[u] = VS[j][x + 3] - VS[j][x + 1];
+        gy[u] = fmaf(2.f, VD[j][x + 2], VD[j][x + 1] + VD[j][x + 3]);
+      }
+      const float2 v = jnd_value2(make_float2(lac[0], lac[1]), make_float2(gx[0], gx[1]), make_float2(gy[0], gy[1]));
+      hm[j][q] = v.x; hm[j][q + 1] = v.y;
+    }
+}
+
 // VEC 4: W % 4 == 0 and 16-byte aligned tensors: thread = 4 consecutive pixels (128-bit global / shared accesses).
 // VEC 1: any W / alignment: thread = pixels lane, lane+32, lane+64, lane+96 of the tile row (32-bit accesses, fully coalesced).
 // FASTUP 1: the delta is read in place (identity) or up-scaled through <= 2 taps per axis from a tile staged in shared memory
@@ -309,44 +381,7 @@ __global__ void __launch_bounds__(256, 3) jnd_blend2_kernel(const BlendParams p)
     const float* lum_ = lum + jc * LUMP;
     float (&hm)[2][4] = hmc[jc];
     if (VEC == 4) {
-      // segment columns 2..9 (V5) / 3..8 (the others) of the 12 floats at shared column lane*4; pixel q's centre = column 4 + q
-      float L[6][8];
-      {
-#pragma unroll
-        for (int r = 0; r < 6; ++r) {
-          const float4* s4 = reinterpret_cast<const float4*>(lum_ + (warp * 2 + r) * kB2LP + lane * 4);
-          const float4 t0 = s4[0], t1 = s4[1], t2 = s4[2];
-          L[r][0] = t0.z; L[r][1] = t0.w; L[r][2] = t1.x; L[r][3] = t1.y; L[r][4] = t1.z; L[r][5] = t1.w; L[r][6] = t2.x; L[r][7] = t2.y;
-        }
-      }
-      float V5[2][8], V3[2][6], VS[2][6], VD[2][6];
-#pragma unroll
-      for (int cidx = 0; cidx < 8; ++cidx) {
-        const float mid4 = (L[1][cidx] + L[2][cidx]) + (L[3][cidx] + L[4][cidx]);
-        V5[0][cidx] = mid4 + L[0][cidx];
-        V5[1][cidx] = mid4 + L[5][cidx];
-      }
-#pragma unroll
-      for (int cidx = 0; cidx < 6; ++cidx) {
-        const float c23 = L[2][cidx + 1] + L[3][cidx + 1];
-        V3[0][cidx] = c23 + L[1][cidx + 1];
-        V3[1][cidx] = c23 + L[4][cidx + 1];
-        VS[0][cidx] = V3[0][cidx] + L[2][cidx + 1];
-        VS[1][cidx] = V3[1][cidx] + L[3][cidx + 1];
-        VD[0][cidx] = L[1][cidx + 1] - L[3][cidx + 1];
-        VD[1][cidx] = L[2][cidx + 1] - L[4][cidx + 1];
-      }
-#pragma unroll
-      for (int j = 0; j < 2; ++j)
-#pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float la = ((V5[j][q] + V5[j][q + 1]) + (V5[j][q + 2] + V5[j][q + 3])) + V5[j][q + 4] +
-                           (V3[j][q] + V3[j][q + 1] + V3[j][q + 2]);
-          const float lac = fmaf(-2.f, L[2 + j][q + 2], la);
-          const float gx = VS[j][q + 2] - VS[j][q];
-          const float gy = fmaf(2.f, VD[j][q + 1], VD[j][q] + VD[j][q + 2]);
-          hm[j][q] = jnd_value(lac, gx, gy);
-        }
+      jnd_hm_vec4(lum_, warp, lane, hm);
     } else {
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
@@ -499,10 +534,12 @@ __global__ void __launch_bounds__(256, 3) jnd_blend2_kernel(const BlendParams p)
 #pragma unroll
         for (int q = 0; q < 4; ++q) in[q] = rgb[(c * kB2TH + yl) * kB2TW + lane + 32 * q];
       }
+      if (p.clamp) {       // FFMA.SAT
 #pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float v = fmaf(p.scaling_i, in[q], p.scaling_w * pw[q]);
-        out[q] = p.clamp ? __saturatef(v) : v;
+        for (int q = 0; q < 4; ++q) out[q] = __saturatef(fmaf(p.scaling_i, in[q], p.scaling_w * pw[q]));
+      } else {
+#pragma unroll
+        for (int q = 0; q < 4; ++q) out[q] = fmaf(p.scaling_i, in[q], p.scaling_w * pw[q]);
       }
       float* dst = p.imgs_w + ((long)f * 3 + c) * plane + o;
       if (VEC == 4) {
@@ -512,6 +549,218 @@ __global__ void __launch_bounds__(256, 3) jnd_blend2_kernel(const BlendParams p)
         for (int q = 0; q < 4; ++q) if (x0 + lane + 32 * q < p.W) dst[lane + 32 * q] = out[q];
       }
     }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------ K7, TMA-fed
+// The same blend for the common layout (W % 4 == 0, 16-byte aligned tensors, delta read in place or up-scaled through <= 2 taps per
+// axis): a block walks kB3NT vertically adjacent 128 x 16 tiles.  ONE TMA box per tile brings the raw RGB tile with its 2-pixel
+// halo ([3][20][136] floats at (x0 - 4, y0 - 2); the engine zero-fills what lies outside the image, which is exactly the zero padding of
+// the reference's conv2d), a second one the delta tile at processing resolution; both land in the other half of a double buffer while
+// the current tile is computed.  ncu of the load-then-compute kernel above (profiles/r2q): 1316 warp instructions per warp, of which
+// 291 were the predicated halo / image loads and 142 per-block set-up, 53 % issue utilisation with 22 % of the samples at the barrier
+// behind the loads; here the loads cost one instruction per tile and the set-up is amortised over kB3NT tiles.
+constexpr int kB3NT = 4;
+constexpr int kB3RAW = 3 * (kB2TH + 4) * kB2LP;             // floats of one raw tile (32 640 B, a multiple of 128)
+constexpr int kB3DW = kB2DW + 4;                            // delta tile pitch: the box starts at a 16-byte aligned source column (TMA faults otherwise)
+constexpr int kB3DL = 2464;                                 // floats reserved per delta tile (kB2DH * kB3DW = 2448, rounded to 128 B)
+constexpr size_t b3_smem(int jin) {
+  return (size_t)(2 * kB3RAW + 2 * kB3DL + jin * (kB2TH + 4) * kB2LP) * sizeof(float) + 2 * sizeof(uint64_t) + 128;
+}
+
+template <int CD, int JIN>
+__global__ void __launch_bounds__(256, 2) jnd_blend3_kernel(const BlendParams p, const __grid_constant__ CUtensorMap tmI,
+                                                            const __grid_constant__ CUtensorMap tmD) {
+  extern __shared__ uint8_t b3_smem_[];
+  constexpr int LUMP = (kB2TH + 4) * kB2LP;
+  float* raw = reinterpret_cast<float*>(b3_smem_ + ((128u - (smem_u32(b3_smem_) & 127u)) & 127u));   // [2][3][TH + 4][LP], 128-byte aligned
+  float* dlb = raw + 2 * kB3RAW;                          // [2][DH][kB3DW]
+  float* lum = dlb + 2 * kB3DL;                           // [JIN][TH + 4][LP]
+  uint64_t* full = reinterpret_cast<uint64_t*>(lum + JIN * LUMP);
+  const int f = blockIdx.z, x0 = blockIdx.x * kB2TW, Y0 = blockIdx.y * (kB3NT * kB2TH);
+  const int plane = p.H * p.W;                            // < 2^31 (host-checked)
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const FrameKeys fk = frame_keys(f, p.F, p.step, p.alternate, p.interp_chunk);
+  const bool has_delta = fk.has;
+  const int nsrc = (fk.k1 != fk.k0 && fk.a != 1.f) ? 2 : 1;
+  const bool staged = !p.identity_resample && has_delta;
+  const int ntl = min(kB3NT, (p.H - Y0 + kB2TH - 1) / kB2TH);
+  const int sx0 = staged ? (__ldg(p.tab.xstart + x0) & ~3) : 0;      // first source column of the delta tile, rounded down to 16 bytes
+  const uint32_t tx_bytes = (uint32_t)(kB3RAW * sizeof(float)) + (staged ? (uint32_t)(kB2DH * kB3DW * sizeof(float)) : 0u);
+
+  auto issue = [&](int t) {                               // thread 0: both boxes of tile t
+    const int buf = t & 1, y0 = Y0 + t * kB2TH;
+    fence_proxy_async_smem();                             // the buffer was last touched through the generic proxy
+    mbar_arrive_expect_tx(&full[buf], tx_bytes);
+    tma_load_3d(&tmI, &full[buf], raw + buf * kB3RAW, x0 - 4, y0 - 2, f * 3);
+    if (staged) tma_load_3d(&tmD, &full[buf], dlb + buf * kB3DL, sx0, __ldg(p.tab.ystart + y0), fk.k0 * CD);
+  };
+  if (threadIdx.x == 0) {
+    mbar_init(&full[0], 1);
+    mbar_init(&full[1], 1);
+    fence_barrier_init();
+    issue(0);
+  }
+  // x taps of this thread's 4 pixels for the delta up-sample (the same for every tile of the block)
+  int xr[4] = {0, 0, 0, 0}, xo[4] = {0, 0, 0, 0};
+  float xw0[4] = {1.f, 1.f, 1.f, 1.f}, xw1[4] = {0.f, 0.f, 0.f, 0.f};
+  if (staged) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      const int ox = min(x0 + lane * 4 + q, p.W - 1);
+      const int xc = __ldg(p.tab.xcnt + ox);
+      xr[q] = __ldg(p.tab.xstart + ox) - sx0;
+      xw0[q] = __ldg(p.tab.xw + ox * p.tab.maxt_x);
+      xw1[q] = xc > 1 ? __ldg(p.tab.xw + ox * p.tab.maxt_x + 1) : 0.f;
+      xo[q] = xc > 1 ? 1 : 0;
+    }
+  }
+  const bool vfull = x0 + lane * 4 < p.W;                 // W % 4 == 0: a 4-pixel group is inside or outside as a whole
+  const int PC = (p.use_jnd && p.jnd_out == 3) ? 3 : CD;
+  const bool hm_per_channel = JIN == 3 && p.jnd_out == 3;
+  __syncthreads();                                        // barrier initialisation visible to every waiter
+
+  for (int t = 0; t < ntl; ++t) {
+    const int y0 = Y0 + t * kB2TH, buf = t & 1;
+    const float* rawb = raw + buf * kB3RAW;
+    float* dl = dlb + buf * kB3DL;
+    if (t + 1 < ntl && threadIdx.x == 0) issue(t + 1);    // buffer buf^1 was released by the barrier that ended tile t - 1
+    mbar_wait(&full[buf], (t >> 1) & 1);
+
+    // ---- luminance planes (with halo) from the raw tile
+    if (p.use_jnd) {
+      for (int i = threadIdx.x; i < (kB2TH + 4) * (kB2LP / 4); i += 256) {
+        const float4 r = *reinterpret_cast<const float4*>(rawb + i * 4), g = *reinterpret_cast<const float4*>(rawb + LUMP + i * 4),
+                     bq = *reinterpret_cast<const float4*>(rawb + 2 * LUMP + i * 4);
+        if (JIN == 1) {
+          *reinterpret_cast<float4*>(lum + i * 4) =
+              make_float4(lum255(r.x, g.x, bq.x), lum255(r.y, g.y, bq.y), lum255(r.z, g.z, bq.z), lum255(r.w, g.w, bq.w));
+        } else {
+          *reinterpret_cast<float4*>(lum + i * 4) = make_float4(255.f * r.x, 255.f * r.y, 255.f * r.z, 255.f * r.w);
+          *reinterpret_cast<float4*>(lum + (JIN > 1 ? LUMP : 0) + i * 4) = make_float4(255.f * g.x, 255.f * g.y, 255.f * g.z, 255.f * g.w);
+          *reinterpret_cast<float4*>(lum + (JIN > 2 ? 2 * LUMP : 0) + i * 4) = make_float4(255.f * bq.x, 255.f * bq.y, 255.f * bq.z, 255.f * bq.w);
+        }
+      }
+      __syncthreads();
+    }
+
+    // ---- heat-map of this thread's 2 x 4 pixels
+    float hmc[JIN][2][4];
+#pragma unroll
+    for (int c = 0; c < JIN; ++c)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) hmc[c][j][q] = 1.f;
+    if (p.use_jnd) {
+#pragma unroll
+      for (int jc = 0; jc < JIN; ++jc) jnd_hm_vec4(lum + jc * LUMP, warp, lane, hmc[jc]);
+      if (JIN == 3 && p.jnd_out == 1) {      // hmaps = sum(hmaps / 3) over the channels (jnd.py:101); /255 is inside jnd_value
+#pragma unroll
+        for (int j = 0; j < 2; ++j)
+#pragma unroll
+          for (int q = 0; q < 4; ++q) hmc[0][j][q] = hmc[0][j][q] / 3.f + hmc[JIN - 1 > 0 ? 1 : 0][j][q] / 3.f + hmc[JIN - 1][j][q] / 3.f;
+      }
+    }
+
+    // ---- delta of the 2 x 4 pixels (read in place, or up-sampled from the staged PH x PW tile)
+    float d[CD][2][4];
+#pragma unroll
+    for (int c = 0; c < CD; ++c)
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int q = 0; q < 4; ++q) d[c][j][q] = 0.f;
+    if (has_delta) {
+      int yr[2] = {0, 0}, yo[2] = {0, 0};
+      float yw0[2] = {1.f, 1.f}, yw1[2] = {0.f, 0.f};
+      int sy0 = 0, dnr = 0, dnc = 0;
+      if (staged) {
+        sy0 = __ldg(p.tab.ystart + y0);
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+          const int oy = min(y0 + warp * 2 + j, p.H - 1);
+          const int yc = __ldg(p.tab.ycnt + oy);
+          yr[j] = __ldg(p.tab.ystart + oy) - sy0;
+          yw0[j] = __ldg(p.tab.yw + oy * p.tab.maxt_y);
+          yw1[j] = yc > 1 ? __ldg(p.tab.yw + oy * p.tab.maxt_y + 1) : 0.f;
+          yo[j] = yc > 1 ? 1 : 0;
+        }
+        if (CD * nsrc > 1) {                 // geometry of the tiles staged by hand below
+          const int ylast = min(y0 + kB2TH, p.H) - 1, xlast = min(x0 + kB2TW, p.W) - 1;
+          dnr = min(__ldg(p.tab.ystart + ylast) + __ldg(p.tab.ycnt + ylast), p.PH) - sy0;
+          dnc = min(__ldg(p.tab.xstart + xlast) + __ldg(p.tab.xcnt + xlast), p.PW) - sx0;
+        }
+      }
+      const bool same_rows = staged && yr[0] == yr[1] && yo[0] == yo[1];
+#pragma unroll
+      for (int c = 0; c < 3; ++c) {
+        if (c >= CD) break;
+        for (int s = 0; s < nsrc; ++s) {
+          const float* src = p.delta + ((long)(s ? fk.k1 : fk.k0) * CD + c) * p.PH * p.PW;
+          if (staged && (c | s) != 0) {      // the tile of the first (channel, key) arrived with the image tile; the others are staged here
+            __syncthreads();
+            for (int r = warp; r < dnr; r += 8)
+              for (int cc = lane; cc < dnc; cc += 32) dl[r * kB3DW + cc] = __ldg(src + (long)(sy0 + r) * p.PW + sx0 + cc);
+            __syncthreads();
+          }
+          const float ws = nsrc == 1 ? 1.f : (s ? 1.f - fk.a : fk.a);
+          float hra[4] = {0.f, 0.f, 0.f, 0.f}, hrb[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const int gy = y0 + warp * 2 + j;
+            float vs[4] = {0.f, 0.f, 0.f, 0.f};
+            if (gy < p.H && vfull) {
+              if (p.identity_resample) {
+                const float4 v4 = __ldg(reinterpret_cast<const float4*>(src + (long)gy * p.PW + x0 + lane * 4));
+                vs[0] = v4.x; vs[1] = v4.y; vs[2] = v4.z; vs[3] = v4.w;
+              } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                  if (j == 0 || !same_rows) {     // (warp-uniform) at scale 3 two of three row pairs share both source rows
+                    const float* a0 = dl + yr[j] * kB3DW + xr[q];
+                    const float* b0 = a0 + yo[j] * kB3DW;
+                    hra[q] = xw0[q] * a0[0] + xw1[q] * a0[xo[q]];
+                    hrb[q] = xw0[q] * b0[0] + xw1[q] * b0[xo[q]];
+                  }
+                  vs[q] = yw0[j] * hra[q] + yw1[j] * hrb[q];
+                }
+              }
+            }
+#pragma unroll
+            for (int q = 0; q < 4; ++q) d[c][j][q] = fmaf(ws, vs[q], d[c][j][q]);
+          }
+        }
+      }
+    }
+
+    // ---- preds_w = hmap * delta (optional output; max(CD, jnd_out) channels, broadcast like `hmaps * preds_w`) and the blend
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const int yl = warp * 2 + j, gy = y0 + yl;
+      if (gy < p.H && vfull) {
+        const int o = gy * p.W + x0 + lane * 4;
+#pragma unroll
+        for (int c = 0; c < 3; ++c) {
+          float pw[4], out[4];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) pw[q] = d[CD == 1 ? 0 : c][j][q] * (hm_per_channel ? hmc[JIN == 3 ? c : 0][j][q] : hmc[0][j][q]);
+          if (p.preds_w != nullptr && c < PC)
+            *reinterpret_cast<float4*>(p.preds_w + ((long)f * PC + c) * plane + o) = make_float4(pw[0], pw[1], pw[2], pw[3]);
+          const float4 t4 = *reinterpret_cast<const float4*>(rawb + (c * (kB2TH + 4) + yl + 2) * kB2LP + 4 + lane * 4);
+          const float in[4] = {t4.x, t4.y, t4.z, t4.w};
+          if (p.clamp) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) out[q] = __saturatef(fmaf(p.scaling_i, in[q], p.scaling_w * pw[q]));
+          } else {
+#pragma unroll
+            for (int q = 0; q < 4; ++q) out[q] = fmaf(p.scaling_i, in[q], p.scaling_w * pw[q]);
+          }
+          *reinterpret_cast<float4*>(p.imgs_w + ((long)f * 3 + c) * plane + o) = make_float4(out[0], out[1], out[2], out[3]);
+        }
+      }
+    }
+    __syncthreads();       // every read of raw[buf] / lum / dl[buf] is done: the next iteration may refill them
   }
 }
 
