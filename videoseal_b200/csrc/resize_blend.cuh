@@ -54,6 +54,19 @@ __global__ void __launch_bounds__(256) resize_sep_kernel(const float* __restrict
     }
     cp_async_commit();
   };
+  // OW <= 256 (every card: processing size 256): a thread owns ONE output column for the whole block, so its taps are loaded once
+  // (ncu of the per-round version, profiles/r2t: 2116 warp instructions per warp of which 534 were LDS + FFMA; 81 LDG of the same
+  // weights every round, 214 ISETP + 117 BRA of row / column predicates, 310 IMAD of addresses)
+  const bool single = MAXT > 0 && OW <= 256;
+  const bool act = (int)threadIdx.x < OW;
+  int xs1 = 0;
+  float w1[MAXT > 0 ? MAXT : 1];
+  if (single && act) {
+    const int xc = __ldg(t.xcnt + threadIdx.x);
+    xs1 = __ldg(t.xstart + threadIdx.x);
+#pragma unroll
+    for (int i = 0; i < MAXT; ++i) w1[i] = i < xc ? __ldg(t.xw + threadIdx.x * t.maxt_x + i) : 0.f;
+  }
   issue(0);
   for (int rd = 0; rd < rounds; ++rd) {
     issue(rd + 1);
@@ -61,54 +74,93 @@ __global__ void __launch_bounds__(256) resize_sep_kernel(const float* __restrict
     __syncthreads();
     const int g0 = rd * GST, ng = min(GST, nr - g0);
     const float* sb = stg + (rd & 1) * stg_stride;
-    for (int ox = threadIdx.x; ox < OW; ox += 256) {
-      const int xs = __ldg(t.xstart + ox), xc = __ldg(t.xcnt + ox);
-      const float* wp = t.xw + (long)ox * t.maxt_x;
-      float* hb = hbuf + g0 * OW + ox;
-      if (MAXT > 0) {
-        float w[MAXT > 0 ? MAXT : 1];
+    if (single) {
+      if (act) {
+        const float* s = sb + xs1;
+        float* hb = hbuf + g0 * OW + threadIdx.x;
+        if (ng == GST) {
 #pragma unroll
-        for (int i = 0; i < MAXT; ++i) w[i] = i < xc ? __ldg(wp + i) : 0.f;
-        const float* s = sb + xs;
+          for (int r = 0; r < GST; ++r) {
+            float acc = w1[0] * s[0];
 #pragma unroll
-        for (int r = 0; r < GST; ++r) {
-          if (r < ng) {
-            float acc = w[0] * s[0];
+            for (int i = 1; i < MAXT; ++i) acc = fmaf(w1[i], s[i], acc);
+            hb[r * OW] = acc;
+            s += IW;
+          }
+        } else {
+          for (int r = 0; r < ng; ++r) {
+            float acc = w1[0] * s[0];
 #pragma unroll
-            for (int i = 1; i < MAXT; ++i) acc = fmaf(w[i], s[i], acc);
+            for (int i = 1; i < MAXT; ++i) acc = fmaf(w1[i], s[i], acc);
+            hb[r * OW] = acc;
+            s += IW;
+          }
+        }
+      }
+    } else {
+      for (int ox = threadIdx.x; ox < OW; ox += 256) {
+        const int xs = __ldg(t.xstart + ox), xc = __ldg(t.xcnt + ox);
+        const float* wp = t.xw + (long)ox * t.maxt_x;
+        float* hb = hbuf + g0 * OW + ox;
+        if (MAXT > 0) {
+          float w[MAXT > 0 ? MAXT : 1];
+#pragma unroll
+          for (int i = 0; i < MAXT; ++i) w[i] = i < xc ? __ldg(wp + i) : 0.f;
+          const float* s = sb + xs;
+#pragma unroll
+          for (int r = 0; r < GST; ++r) {
+            if (r < ng) {
+              float acc = w[0] * s[0];
+#pragma unroll
+              for (int i = 1; i < MAXT; ++i) acc = fmaf(w[i], s[i], acc);
+              hb[r * OW] = acc;
+            }
+            s += IW;
+          }
+        } else {
+          for (int r = 0; r < ng; ++r) {
+            const float* s = sb + r * IW + xs;
+            float acc = __ldg(wp) * s[0];
+            for (int i = 1; i < xc; ++i) acc = fmaf(__ldg(wp + i), s[i], acc);
             hb[r * OW] = acc;
           }
-          s += IW;
-        }
-      } else {
-        for (int r = 0; r < ng; ++r) {
-          const float* s = sb + r * IW + xs;
-          float acc = __ldg(wp) * s[0];
-          for (int i = 1; i < xc; ++i) acc = fmaf(__ldg(wp + i), s[i], acc);
-          hb[r * OW] = acc;
         }
       }
     }
     __syncthreads();                   // buffer (rd & 1) is rewritten by issue(rd + 2); hbuf complete after the last round
   }
   float* dst = out + (long)pl * OH * OW;
+  const bool ow_full = (OW & 255) == 0;                    // no column predicates in the vertical pass
   for (int oy = oy0 + warp; oy < oy1; oy += 8) {          // one warp per output row: the y taps are warp-uniform
     const int ys = __ldg(t.ystart + oy) - r0, yc = __ldg(t.ycnt + oy);
-    const float* wy = t.yw + (long)oy * t.maxt_y;
+    const float* wy = t.yw + oy * t.maxt_y;
     for (int oxb = 0; oxb < OW; oxb += 256) {              // 8 outputs per lane: accumulators in registers, one weight load per tap
       const float* h = hbuf + ys * OW + oxb + lane;
       float acc[8];
       const float w0 = __ldg(wy);
+      if (ow_full) {
 #pragma unroll
-      for (int k = 0; k < 8; ++k) acc[k] = (oxb + lane + 32 * k < OW) ? w0 * h[32 * k] : 0.f;
-      for (int j = 1; j < yc; ++j) {
-        const float wj = __ldg(wy + j);
-        const float* hj = h + j * OW;
+        for (int k = 0; k < 8; ++k) acc[k] = w0 * h[32 * k];
+        for (int j = 1; j < yc; ++j) {
+          const float wj = __ldg(wy + j);
+          const float* hj = h + j * OW;
 #pragma unroll
-        for (int k = 0; k < 8; ++k) if (oxb + lane + 32 * k < OW) acc[k] = fmaf(wj, hj[32 * k], acc[k]);
+          for (int k = 0; k < 8; ++k) acc[k] = fmaf(wj, hj[32 * k], acc[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) dst[oy * OW + oxb + lane + 32 * k] = acc[k];
+      } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) acc[k] = (oxb + lane + 32 * k < OW) ? w0 * h[32 * k] : 0.f;
+        for (int j = 1; j < yc; ++j) {
+          const float wj = __ldg(wy + j);
+          const float* hj = h + j * OW;
+#pragma unroll
+          for (int k = 0; k < 8; ++k) if (oxb + lane + 32 * k < OW) acc[k] = fmaf(wj, hj[32 * k], acc[k]);
+        }
+#pragma unroll
+        for (int k = 0; k < 8; ++k) if (oxb + lane + 32 * k < OW) dst[oy * OW + oxb + lane + 32 * k] = acc[k];
       }
-#pragma unroll
-      for (int k = 0; k < 8; ++k) if (oxb + lane + 32 * k < OW) dst[oy * OW + oxb + lane + 32 * k] = acc[k];
     }
   }
 }
