@@ -175,14 +175,14 @@ struct ResampleDev {
     ResampleHost y = make_resample(ih, oh, aa), x = make_resample(iw, ow, aa);
     tab.ystart = pool.upload(y.start); tab.ycnt = pool.upload(y.cnt); tab.yw = pool.upload(y.w); tab.maxt_y = y.maxt;
     tab.xstart = pool.upload(x.start); tab.xcnt = pool.upload(x.cnt); tab.xw = pool.upload(x.w); tab.maxt_x = x.maxt;
-    gstage = iw * 4 * 4 <= 16 * 1024 ? 4 : (iw * 4 * 2 <= 16 * 1024 ? 2 : 1);    // rows per cp.async round (two rounds in flight): 4, 2 or 1
+    gstage = iw * 4 * 4 <= 16 * 1024 ? 4 : (iw * 4 * 2 <= 16 * 1024 ? 2 : 1);    // rows per staging round (kRsStages - 1 rounds in flight): 4, 2 or 1
     for (toy = 8; toy >= 1; toy >>= 1) {
       rin_max = 1;
       for (int o0 = 0; o0 < oh; o0 += toy) {
         const int o1 = std::min(oh, o0 + toy) - 1;
         rin_max = std::max(rin_max, y.start[o1] + y.cnt[o1] - y.start[o0]);
       }
-      smem = ((((size_t)rin_max * ow + 3) & ~(size_t)3) + 2 * (((size_t)gstage * iw + 8 + 3) & ~(size_t)3)) * sizeof(float);
+      smem = ((((size_t)rin_max * ow + 3) & ~(size_t)3) + kRsStages * (((size_t)gstage * iw + 8 + 3) & ~(size_t)3)) * sizeof(float);
       if (smem <= 100 * 1024 || toy == 1) break;
     }
     if (smem > 200 * 1024) throw Error("resize: image too wide for the shared-memory resample kernel (not implemented)", kErrUnsupported);

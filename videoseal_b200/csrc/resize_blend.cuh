@@ -21,12 +21,13 @@ __device__ __forceinline__ void cp_async4(void* smem_dst, const void* gsrc) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gsrc) : "memory");
 }
 // in: planes [n][3][IH][IW] with frames `frame_stride` floats apart; out: [n*3][OH][OW] contiguous.
-// grid (ceil(OH / toy), n*3); block 256.  Shared: hbuf [rin_max][OW] | stage [2][GST * IW + 8] (cp.async double buffer: the rows of
+// grid (ceil(OH / toy), n*3); block 256.  Shared: hbuf [rin_max][OW] | stage [kRsStages][GST * IW + 8] (ring of staging rounds: the rows of
 // round r+1 are in flight while the horizontal pass of round r runs; consecutive input rows of a plane are contiguous in memory,
 // so a round is ONE flat asynchronous copy of GST * IW floats, 16 bytes per request when IW % 4 == 0).
 // The tap loops carry no predicates: taps beyond an output's support have weight 0 and read whatever FINITE value follows in the
 // staging buffer (the buffers are zero-filled once, an 8-float zero pad ends each of them) -- ncu of the first version showed
 // 33 % of its instructions were predicate bookkeeping (LOP3 / ISETP / P2R) and 17 % address IMADs against 8 % FFMA.
+constexpr int kRsStages = 3;
 template <int MAXT, int GST>   // MAXT: x taps per output held in registers (2 or 8); 0 = any count (weights from the table, predicated)
 __global__ void __launch_bounds__(256) resize_sep_kernel(const float* __restrict__ in, long frame_stride, float* __restrict__ out, int IH,
                                                          int IW, int OH, int OW, ResampleTab t, int toy, int rin_max, int vec) {
@@ -42,17 +43,36 @@ __global__ void __launch_bounds__(256) resize_sep_kernel(const float* __restrict
   const int nr = __ldg(t.ystart + oy1 - 1) + __ldg(t.ycnt + oy1 - 1) - r0;   // <= rin_max (host-computed from the same table)
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rounds = (nr + GST - 1) / GST;
-  for (int i = threadIdx.x * 4; i < 2 * stg_stride; i += 1024) *reinterpret_cast<float4*>(stg + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int i = threadIdx.x * 4; i < kRsStages * stg_stride; i += 1024) *reinterpret_cast<float4*>(stg + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+  __shared__ uint64_t rs_full[kRsStages];
+  if (vec && threadIdx.x == 0) {
+    for (int i = 0; i < kRsStages; ++i) mbar_init(&rs_full[i], 1);
+    fence_barrier_init();
+  }
   __syncthreads();
+  // vec (IW % 4 == 0, 16-byte aligned planes): a round is ONE bulk copy issued by thread 0 (the first version's cp.async loop cost
+  // ~70 instructions per thread and round for three 16-byte requests: profiles/r2_final pointwise capture), kRsStages - 1 rounds in flight.
+  // otherwise: 4-byte cp.async by every thread, one round in flight.
+  const int depth = vec ? kRsStages - 1 : 1;
   auto issue = [&](int rd) {
-    if (rd < rounds) {
-      const int g0 = rd * GST, nfl = min(GST, nr - g0) * IW;
-      const float* sp = src + (long)(r0 + g0) * IW;
-      float* d = stg + (rd & 1) * stg_stride;
-      if (vec) { for (int i = threadIdx.x * 4; i < nfl; i += 1024) cp_async16(d + i, sp + i); }
-      else     { for (int i = threadIdx.x; i < nfl; i += 256) cp_async4(d + i, sp + i); }
+    if (vec) {
+      if (rd < rounds && threadIdx.x == 0) {
+        const int g0 = rd * GST;
+        const uint32_t bytes = (uint32_t)(min(GST, nr - g0) * IW) * 4u;
+        const int b = rd % kRsStages;
+        fence_proxy_async_smem();            // the buffer was zero-filled / read through the generic proxy
+        mbar_arrive_expect_tx(&rs_full[b], bytes);
+        bulk_load_1d(stg + b * stg_stride, src + (long)(r0 + g0) * IW, bytes, &rs_full[b]);
+      }
+    } else {
+      if (rd < rounds) {
+        const int g0 = rd * GST, nfl = min(GST, nr - g0) * IW;
+        const float* sp = src + (long)(r0 + g0) * IW;
+        float* d = stg + (rd & 1) * stg_stride;
+        for (int i = threadIdx.x; i < nfl; i += 256) cp_async4(d + i, sp + i);
+      }
+      cp_async_commit();
     }
-    cp_async_commit();
   };
   // OW <= 256 (every card: processing size 256): a thread owns ONE output column for the whole block, so its taps are loaded once
   // (ncu of the per-round version, profiles/r2t: 2116 warp instructions per warp of which 534 were LDS + FFMA; 81 LDG of the same
@@ -67,13 +87,17 @@ __global__ void __launch_bounds__(256) resize_sep_kernel(const float* __restrict
 #pragma unroll
     for (int i = 0; i < MAXT; ++i) w1[i] = i < xc ? __ldg(t.xw + threadIdx.x * t.maxt_x + i) : 0.f;
   }
-  issue(0);
+  for (int rd = 0; rd < depth; ++rd) issue(rd);
   for (int rd = 0; rd < rounds; ++rd) {
-    issue(rd + 1);
-    cp_async_wait_pending(1);          // round rd has landed (this thread's part); the barrier makes it everybody's
-    __syncthreads();
+    issue(rd + depth);                 // its buffer was released by the barrier that ended round rd - 1
+    if (vec) {
+      mbar_wait(&rs_full[rd % kRsStages], (rd / kRsStages) & 1);
+    } else {
+      cp_async_wait_pending(1);        // round rd has landed (this thread's part); the barrier makes it everybody's
+      __syncthreads();
+    }
     const int g0 = rd * GST, ng = min(GST, nr - g0);
-    const float* sb = stg + (rd & 1) * stg_stride;
+    const float* sb = stg + (vec ? rd % kRsStages : (rd & 1)) * stg_stride;
     if (single) {
       if (act) {
         const float* s = sb + xs1;
@@ -127,7 +151,7 @@ __global__ void __launch_bounds__(256) resize_sep_kernel(const float* __restrict
         }
       }
     }
-    __syncthreads();                   // buffer (rd & 1) is rewritten by issue(rd + 2); hbuf complete after the last round
+    __syncthreads();                   // this round's buffer may be refilled; hbuf complete after the last round
   }
   float* dst = out + (long)pl * OH * OW;
   const bool ow_full = (OW & 255) == 0;                    // no column predicates in the vertical pass
