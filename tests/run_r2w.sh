@@ -1,0 +1,8 @@
+# round 2, call w: CTA-pair (cta_group::2) kernel for the long-K bottleneck convs
+mkdir -p gpurun_out
+timeout 300 python tests/prof_cases.py --time p_conv3_bott 2>&1 | tail -4
+VSB_NO_PAIR=1 timeout 300 python tests/prof_cases.py --time p_conv3_bott 2>&1 | tail -2
+timeout 900 python -m pytest tests/test_conv_gemm_gpu.py tests/test_e2e_gpu.py tests/test_config_size_gpu.py -m gpu -q -x -k "not chunky" 2>&1 | tail -4
+timeout 600 python bench.py --steps 20 --warmup 3 --no-clip-leg --no-cpu-baseline --no-e2e --no-hbm-leg --profile-out gpurun_out/r2w_step_profile.json > gpurun_out/r2w_bench.json 2> gpurun_out/r2w_bench_err.log; python -c "
+import json; b=json.load(open('gpurun_out/r2w_bench.json')); print(b['value'], b['ms_per_step'])
+for r in b['top_kernels'][:3]: print(r['name'], r['avg_us'], r['launches_per_step'], r.get('tflops'))"

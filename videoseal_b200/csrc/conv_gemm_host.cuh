@@ -6,6 +6,7 @@
 #include <string>
 
 #include "conv_gemm.cuh"
+#include "conv_pair.cuh"
 
 namespace vsb {
 
@@ -85,9 +86,13 @@ struct ConvGemmOp {
   CUtensorMap tmA, tmA2, tmB, tmO;
   int grid = 0, threads = 0;
   int w_samples = 1;   // > 1: weights are [w_samples][N][K], sample = row / rows_per_sample (finalize_op)
+  bool pair = false;   // long-K conv on whole 128-pixel row tiles: CTA-pair kernel (conv_pair.cuh), parameters in pp, weights map in tmB
+  ConvPairParams pp;
+  size_t pair_smem = 0;
+  int pair_grid = 0;
   size_t smem = 0;
   const char* name = "";
-  ConvGemmOp() { memset(&p, 0, sizeof(p)); memset(&tmA, 0, sizeof(tmA)); memset(&tmA2, 0, sizeof(tmA2)); memset(&tmB, 0, sizeof(tmB)); memset(&tmO, 0, sizeof(tmO)); }
+  ConvGemmOp() { memset(&pp, 0, sizeof(pp)); memset(&p, 0, sizeof(p)); memset(&tmA, 0, sizeof(tmA)); memset(&tmA2, 0, sizeof(tmA2)); memset(&tmB, 0, sizeof(tmB)); memset(&tmO, 0, sizeof(tmO)); }
 };
 
 inline int pick_block_n(int N, int max_bn = 256) {
@@ -236,6 +241,33 @@ inline void finalize_op(ConvGemmOp& op, const __half* W, int N, int Kw, int ldw,
   if (p.b_fixed_ntile) op.grid = (num_sms / p.n_tiles) * p.n_tiles;
   op.threads = op.loader == LD_TMA ? 640 : 512;
   VSB_CHECK((long)p.m_tiles * kBlockM < (1L << 31), "M too large for 32-bit row indices");
+  // CTA-pair kernel for the long-K convs on whole row tiles (the 16 bottleneck convs of the U-Net): plain bias / ReLU / fp16 residual epilogue
+  static const bool no_pair = getenv("VSB_NO_PAIR") != nullptr;
+  if (!no_pair && op.loader == LD_TMA && p.a_is_conv && p.kblk == 64 && p.num_kb >= 24 && p.tile_w == p.W && p.m_tiles % 2 == 0 &&
+      p.epi == EPI_AFFINE && (p.act == ACT_NONE || p.act == ACT_RELU) && p.out16 != nullptr && p.out32 == nullptr && p.resid32 == nullptr &&
+      p.outc_w == nullptr && p.grn_stats == nullptr && op.w_samples == 1 && p.bias != nullptr && (reinterpret_cast<uintptr_t>(p.bias) & 15) == 0 &&
+      (p.ld_out16 % 8) == 0 && (p.resid16 == nullptr || p.ld_res16 % 8 == 0) && num_sms >= 2) {
+    int bn = 0;
+    for (int cand : {256, 192, 128}) if (N % cand == 0) { bn = cand; break; }
+    if (const char* e = getenv("VSB_PAIR_BN")) { const int v = atoi(e); if (v >= 32 && v <= 256 && v % 32 == 0 && N % v == 0) bn = v; }
+    if (bn) {
+      ConvPairParams& q = op.pp;
+      q.M = p.M; q.N = N; q.num_kb = p.num_kb; q.c_blocks = p.c_blocks; q.S = p.S; q.pad = p.pad;
+      q.tile_h = p.tile_h; q.tiles_per_img = p.tiles_per_img;
+      q.m_pairs = p.m_tiles / 2; q.n_tiles = N / bn; q.num_work = q.m_pairs * q.n_tiles;
+      q.block_n = bn; q.a_bytes = 128 * 64 * 2; q.b_bytes = (uint32_t)(bn / 2) * 64 * 2;
+      q.stages = (int)std::min<size_t>(kPairMaxStages, (size_t)(200 * 1024) / (q.a_bytes + q.b_bytes));
+      if (const char* e = getenv("VSB_PAIR_STAGES")) { const int v = atoi(e); if (v >= 2 && v <= q.stages) q.stages = v; }
+      q.idesc = (1u << 4) | ((uint32_t)(bn >> 3) << 17) | ((uint32_t)(256 >> 4) << 24);
+      q.relu = p.act == ACT_RELU ? 1 : 0;
+      q.bias = p.bias; q.resid = p.resid16; q.ld_res = p.ld_res16; q.out = p.out16; q.ld_out = p.ld_out16;
+      uint32_t pbox[2] = {64u, (uint32_t)(bn / 2)};
+      encode_map(&op.tmB, W, 2, dims, strides, pbox, 64);      // each CTA of the pair stages half of the tile's weight rows
+      op.pair_smem = (size_t)q.stages * (q.a_bytes + q.b_bytes) + (2 * kPairMaxStages + 4) * sizeof(uint64_t) + 16 + 1024;
+      op.pair_grid = 2 * std::min(num_sms / 2, q.num_work);
+      op.pair = true;
+    }
+  }
 }
 
 // A = NHWC fp16 activation [B, H, W, C] (pixel pitch ld elements); conv RxS stride 1, zero padding `pad`
@@ -431,7 +463,21 @@ inline void launch_one(const ConvGemmOp& op, cudaStream_t st) {
 }
 
 // instantiated (loader, activation) pairs: only what the networks need, to bound compile time
+inline void launch_pair(const ConvGemmOp& op, cudaStream_t st) {
+  static bool attr_set = false;
+  if (!attr_set) {
+    VSB_CUDA(cudaFuncSetAttribute(conv_pair_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024));
+    attr_set = true;
+  }
+#ifdef VSB_PDL
+  launch_pdl(conv_pair_kernel, dim3(op.pair_grid), dim3(kPairThreads), op.pair_smem, st, op.tmA, op.tmB, op.pp);
+#else
+  conv_pair_kernel<<<op.pair_grid, kPairThreads, op.pair_smem, st>>>(op.tmA, op.tmB, op.pp);
+#endif
+}
+
 inline void launch(const ConvGemmOp& op, cudaStream_t st) {
+  if (op.pair) { launch_pair(op, st); VSB_CUDA(cudaGetLastError()); return; }
   const int a = op.p.act;
   switch (op.loader) {
     case LD_TMA:
