@@ -14,6 +14,7 @@ modules) on the host cores; the unmodified reference itself needs packages that 
 import argparse
 import json
 import os
+import re
 import subprocess
 import sys
 import threading
@@ -529,7 +530,11 @@ def run_ours(args):
         if dom:
             # the kernel is event-timed launch by launch at full clock (clocks line: 1965 MHz, no power cap inside these 3 steps),
             # so the denominator is the BURST cuBLAS figure; the sustained one is reported next to it
-            roofline = {"bound": "tensor", "kernel": "conv_gemm_kernel<LD_TMA> " + dom["name"], "achieved": dom["tflops"],
+            # finalize_op (conv_gemm_host.cuh) sends 3x3 TMA convs with >= 24 K blocks (C_in >= 192) on whole-row tiles to the CTA-pair kernel
+            mm = re.match(r"unet\.conv3x3\.(\d+)-", dom["name"])
+            pair = bool(mm) and int(mm.group(1)) >= 192 and not os.environ.get("VSB_NO_PAIR")
+            roofline = {"bound": "tensor", "kernel": ("conv_pair_kernel (tcgen05 cta_group::2) " if pair else "conv_gemm_kernel<LD_TMA> ") + dom["name"],
+                        "achieved": dom["tflops"],
                         "peak": peaks["tf_burst"], "unit": "TFLOP/s", "frac": dom["tflops"] / peaks["tf_burst"],
                         "peak_source": peaks["src"] + " bf16 cuBLAS, burst (kernel event-timed per launch at full clock)",
                         "frac_of_sustained_peak": dom["tflops"] / peaks["tf_sustained"],
@@ -575,7 +580,8 @@ def run_ours(args):
             by = pointwise_bytes(name, model.spec["img_size"])
             gbs = by / (tms / cnt * 1e-3) / 1e9 if by else None
             rows.append({"name": name, "avg_us": 1000 * tms / cnt, "launches_per_step": cnt // 3, "algorithmic_bytes": by,
-                         "gbs": gbs, "frac": gbs / peaks["hbm_gbs"] if gbs else None})
+                         "gbs": gbs, "frac": gbs / peaks["hbm_gbs"] if gbs else None,
+                         "traffic": ncu_traffic(f"{args.card}:{name}")})
             tot_b += by * cnt / 3
             tot_ms += tms / 3
         rows.sort(key=lambda r: -r["avg_us"] * r["launches_per_step"])

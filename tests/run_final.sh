@@ -9,5 +9,5 @@ timeout 600 python bench.py --steps 5 --warmup 3 --no-cpu-baseline --no-e2e --no
 for f in pixelseal768 v1_video768 chunky; do python -c "
 import json; b=json.load(open('gpurun_out/bench_$f.json')); print('$f', round(b['value']), round(b['ms_per_step'],2))"; done
 timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file gpurun_out/launches.csv python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-e2e --no-clip-leg --no-hbm-leg > gpurun_out/ncu_bench.log 2>&1; wc -l gpurun_out/launches.csv
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:conv_gemm -c 1 -o gpurun_out/final_dominant python tests/prof_cases.py p_conv3_bott > gpurun_out/ncu_dom.log 2>&1; tail -1 gpurun_out/ncu_dom.log
-timeout 400 ncu --set full --clock-control none --import-source on -k regex:"jnd_blend3|resize_sep" --launch-skip 3 --launch-count 3 -o gpurun_out/final_pointwise python tests/prof_pointwise.py > gpurun_out/ncu_pw.log 2>&1; tail -1 gpurun_out/ncu_pw.log
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:conv_pair -c 1 -f -o gpurun_out/final_dominant python tests/prof_cases.py p_conv3_bott > gpurun_out/ncu_dom.log 2>&1; tail -1 gpurun_out/ncu_dom.log
+timeout 400 ncu --set full --clock-control none --import-source on -k regex:"jnd_blend3|resize_sep" --launch-skip 3 --launch-count 3 -f -o gpurun_out/final_pointwise python tests/prof_pointwise.py > gpurun_out/ncu_pw.log 2>&1; tail -1 gpurun_out/ncu_pw.log
