@@ -426,3 +426,45 @@ def test_jnd_channel_variants(att):
     assert (got["preds_w"].cpu() - ref["preds_w"]).abs().max().item() <= 5 * PIX_TOL
     del model
     torch.cuda.empty_cache()
+
+
+def test_plan_cache_is_bounded_and_rebuilds(monkeypatch):
+    """one activation arena per distinct batch size is cached; the cache is an LRU of VSB_MAX_PLANS entries and
+    an evicted batch size is rebuilt with identical results"""
+    monkeypatch.setenv("VSB_MAX_PLANS", "2")
+    model, orc, spec = make_model_pair("videoseal_1.0", tiny={"num_blocks": 1, "depths": [1, 1, 1, 1]})
+    g = torch.Generator().manual_seed(5)
+    imgs = torch.rand(5, 3, 256, 256, generator=g).cuda()
+    msgs = torch.randint(0, 2, (5, spec["nbits"]), generator=g)
+    first = {}
+    for b in (1, 2, 3, 4, 5, 1, 2, 3):          # 5 sizes through a 2-entry cache: every revisit hits an evicted plan
+        out = model.embed(imgs[:b], msgs[:b], is_video=False)
+        det = model.detect(out["imgs_w"], is_video=False)["preds"]
+        if b in first:
+            assert torch.equal(first[b][0], out["imgs_w"]) and torch.equal(first[b][1], det)
+        else:
+            first[b] = (out["imgs_w"].clone(), det.clone())
+    # frames are independent units: the single frame equals the first frame of the larger batches
+    assert torch.equal(first[1][0][0], first[4][0][0])
+
+
+def test_img_size_property_rebuilds_the_native_model():
+    """model.img_size (wam.py:147) is baked into the native handle: assigning it must change the processing size, like the reference"""
+    model, orc, spec = make_model_pair("videoseal_1.0", tiny={"num_blocks": 1, "depths": [1, 1, 1, 1]})
+    g = torch.Generator().manual_seed(6)
+    imgs = torch.rand(2, 3, 600, 520, generator=g)
+    msgs = torch.randint(0, 2, (2, spec["nbits"]), generator=g)
+    try:
+        model.img_size = 512
+        orc.img_size = 512
+        with torch.no_grad():
+            ref = orc.embed(imgs, msgs, is_video=False)
+            ref_det = orc.detect(ref["imgs_w"], is_video=False)["preds"]
+        out = model.embed(imgs.cuda(), msgs, is_video=False)
+        assert (out["imgs_w"].cpu() - ref["imgs_w"]).abs().max().item() <= PIX_TOL
+        rel, flips, _ = logits_ok(model.detect(out["imgs_w"], is_video=False)["preds"].cpu(), ref_det)
+        assert rel <= LOGIT_RTOL and flips == 0
+        with pytest.raises(ValueError):
+            model.img_size = 300
+    finally:
+        orc.img_size = spec["img_size"]

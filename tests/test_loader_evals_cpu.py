@@ -275,3 +275,45 @@ def test_embed_stream_surfaces_a_dead_writer_instead_of_deadlocking():
     t.join(timeout=20)
     assert not t.is_alive(), "embed_stream deadlocked on a full queue with a dead writer"
     assert isinstance(done.get("err"), BrokenPipeError)
+
+
+def test_baked_in_attributes_are_live_properties():
+    """img_size / embedder.yuv / attenuation are baked into the native handle; assigning them must
+    rebuild it (or raise), never be a silent no-op (wam.py:147-149,196 mutate them freely in the reference)"""
+    import videoseal_b200
+    from videoseal_b200.model import JND
+    from tests.util import synthetic_card_on_disk
+    cpath, spec, _ = synthetic_card_on_disk("videoseal_1.0", tiny={"num_blocks": 1, "depths": [1, 1, 1, 1]})
+    m = videoseal_b200.load(cpath).eval()
+    assert m.img_size == spec["img_size"] == 256 and m.embedder.yuv is True
+    m._native = None
+    m.img_size = 384                                   # rebuilt lazily with the new processing size
+    assert m.img_size == 384 and m.spec["img_size"] == 384 and m._native is None
+    for bad in (0, 200, -128):
+        with pytest.raises(ValueError):
+            m.img_size = bad
+    assert m.img_size == 384
+    # attenuation: None switches it off; a JND with another channel layout re-specs the handle (jnd_1_1 -> jnd_3_3)
+    assert m.attenuation is not None and tuple(m.spec["jnd"]) == (1, 1)
+    keep = m.attenuation
+    m.attenuation = None
+    assert m.attenuation is None and tuple(m.spec["jnd"]) == (1, 1)
+    m.attenuation = keep
+    assert m.attenuation is keep
+
+    class RefJND:                                      # duck-typed like the reference's modules/jnd.py object
+        in_channels, out_channels = 3, 3
+    m.attenuation = RefJND()
+    assert isinstance(m.attenuation, JND) and tuple(m.spec["jnd"]) == (3, 3)
+    with pytest.raises(ValueError):
+        m.attenuation = object()
+    # the Y-channel U-Net of this card cannot run on RGB input
+    with pytest.raises(ValueError):
+        m.embedder.yuv = False
+    m.embedder.yuv = True
+    # the tensor-API facade forwards to the same properties
+    from videoseal_b200 import jit
+    t = jit.TensorAPI(m) if hasattr(jit, "TensorAPI") else None
+    if t is not None:
+        t.img_size = 256
+        assert m.img_size == 256

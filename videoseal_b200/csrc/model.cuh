@@ -85,6 +85,7 @@ static Profile g_profile;
 
 struct Plan {
   DevicePool pool;
+  uint64_t last_use = 0;    // LRU stamp of the plan cache
   std::vector<Step> steps;
   std::map<std::string, DebugTensor> dbg;
   // embed plan I/O
@@ -671,9 +672,26 @@ class Model {
     return out;
   }
 
+  // Plan cache: one activation arena per distinct batch size, at most `max_plans` per kind (VSB_MAX_PLANS, default 8): a service that sees
+  // many different clip / tail lengths would otherwise accumulate up to 64 arenas of up to 2.3 GB each.  The least recently used plan
+  // is dropped (its cudaFree calls synchronise the device, so work still in flight on it completes first).
+  uint64_t plan_clock = 0;
+  int max_plans = [] { const char* e = getenv("VSB_MAX_PLANS"); const int v = e ? atoi(e) : 8; return v < 2 ? 2 : v; }();
+  void evict_plans(std::map<int, std::unique_ptr<Plan>>& m, const Plan* keep) {
+    while ((int)m.size() > max_plans) {
+      auto victim = m.end();
+      for (auto it = m.begin(); it != m.end(); ++it)
+        if (it->second.get() != keep && (victim == m.end() || it->second->last_use < victim->second->last_use)) victim = it;
+      if (victim == m.end()) break;
+      if (victim->second.get() == last_plan) last_plan = nullptr;
+      m.erase(victim);
+    }
+  }
+  size_t cached_plans() const { return embed_plans.size() + detect_plans.size(); }
+
   Plan* get_embed_plan(int B) {
     auto it = embed_plans.find(B);
-    if (it != embed_plans.end()) return it->second.get();
+    if (it != embed_plans.end()) { it->second->last_use = ++plan_clock; return it->second.get(); }
     std::unique_ptr<Plan> up(new Plan());
     Plan& pl = *up;
     const int S = d.img_size, L = d.unet_levels;
@@ -836,13 +854,15 @@ class Model {
     }
     dbg(pl, "delta", pl.delta, 0, B, d.unet_out_ch, S, S, S);
     Plan* ret = up.get();
+    ret->last_use = ++plan_clock;
     embed_plans[B] = std::move(up);
+    evict_plans(embed_plans, ret);
     return ret;
   }
 
   Plan* get_detect_plan(int B) {
     auto it = detect_plans.find(B);
-    if (it != detect_plans.end()) return it->second.get();
+    if (it != detect_plans.end()) { it->second->last_use = ++plan_clock; return it->second.get(); }
     std::unique_ptr<Plan> up(new Plan());
     Plan& pl = *up;
     Plan* plp = &pl;
@@ -1090,7 +1110,9 @@ class Model {
       }, 2, "cnx.head_tail"});
     }
     Plan* ret = up.get();
+    ret->last_use = ++plan_clock;
     detect_plans[B] = std::move(up);
+    evict_plans(detect_plans, ret);
     return ret;
   }
 

@@ -52,7 +52,21 @@ class _Embedder:
 
     def __init__(self, owner: "Videoseal"):
         self._owner = owner
-        self.yuv = owner.spec["yuv"]
+
+    # the colour handling is baked into the native first layer (RGB -> Y fused): changing it rebuilds the native handle
+    @property
+    def yuv(self) -> bool:
+        return bool(self._owner.spec["yuv"])
+
+    @yuv.setter
+    def yuv(self, v: bool):
+        m = self._owner
+        if bool(v) != bool(m.spec["yuv"]):
+            want = 1 if v else 3
+            if m.spec["unet"]["in_channels"] != want:
+                raise ValueError(f"embedder.yuv={bool(v)} needs a U-Net with {want} input channel(s); this checkpoint has "
+                                 f"{m.spec['unet']['in_channels']}")
+            m._respec(yuv=bool(v))
 
     def get_random_msg(self, bsz: int = 1, nb_repetitions: int = 1) -> torch.Tensor:
         nbits = self._owner.spec["nbits"]
@@ -93,15 +107,50 @@ class Videoseal(nn.Module):
         self._native = None          # (device_index, ctypes handle)
         self._dev = torch.device("cpu")
         self._anchor = nn.Parameter(torch.zeros(1), requires_grad=False)  # lets `.to()` / `.device` behave like a module
-        self.img_size = spec["img_size"]
         self.blender = Blender(spec["scaling_i"], spec["scaling_w"])
-        self.attenuation: Optional[JND] = JND(self, *spec["jnd"]) if spec["jnd"][0] else None
+        self._attenuation: Optional[JND] = JND(self, *spec["jnd"]) if spec["jnd"][0] else None
         self.clamp = True
         self.chunk_size, self.step_size = spec["chunk_size"], spec["step_size"]
         self.video_mode = "repeat"
         self.lowres_attenuation = False
         self.embedder = _Embedder(self)
         self.detector = _Detector(self)
+
+    # ------------------------------------------------------------------ attributes the native handle bakes in
+    # (ModelDesc of vsb_model_create): assigning them rebuilds the handle on the next call instead of being a silent no-op
+    def _respec(self, **changes):
+        self.spec = {**self.spec, **changes}
+        self._release()
+
+    @property
+    def img_size(self) -> int:
+        return self.spec["img_size"]
+
+    @img_size.setter
+    def img_size(self, v: int):
+        v = int(v)
+        if v != self.spec["img_size"]:
+            if v <= 0 or v % 128 != 0:
+                raise ValueError(f"img_size={v}: the native path needs a processing size that is a positive multiple of 128")
+            self._respec(img_size=v)
+
+    @property
+    def attenuation(self) -> Optional[JND]:
+        return self._attenuation
+
+    @attenuation.setter
+    def attenuation(self, jnd):
+        """None switches the attenuation off (wam.py:196); a JND (ours or the reference's modules/jnd.py object: anything with
+        in_channels / out_channels in {1, 3}) switches it on with that channel configuration"""
+        if jnd is None:
+            self._attenuation = None
+            return
+        cin, cout = int(getattr(jnd, "in_channels", 0)), int(getattr(jnd, "out_channels", 0))
+        if cin not in (1, 3) or cout not in (1, 3):
+            raise ValueError("attenuation must be None or a JND with in_channels / out_channels in {1, 3}")
+        if (cin, cout) != tuple(self.spec["jnd"]):
+            self._respec(jnd=(cin, cout))
+        self._attenuation = jnd if isinstance(jnd, JND) and jnd._owner is self else JND(self, cin, cout)
 
     # ------------------------------------------------------------------ nn.Module plumbing
     @property
