@@ -236,7 +236,8 @@ class Videoseal(nn.Module):
     def _msgs_u8(self, msgs: torch.Tensor) -> torch.Tensor:
         if msgs.dim() != 2 or msgs.shape[1] != self.spec["nbits"]:
             raise ValueError(f"msgs must be [B, {self.spec['nbits']}], got {tuple(msgs.shape)}")
-        return (msgs.to(self.device) > 0.5).to(torch.uint8).contiguous()
+        # thresholded on the side the tensor lives on: a host tensor (the usual case) costs one small H2D copy and no device kernel
+        return (msgs > 0.5).to(torch.uint8).contiguous().to(self.device)
 
     def _flags(self, interpolation: dict, lowres: bool = False) -> int:
         if interpolation.get("mode", "bilinear") != "bilinear" or interpolation.get("align_corners", False):
