@@ -475,9 +475,9 @@ def run_ours(args):
             e_ms = t.item()
         e2e = {"value": world * B * n_e2e / (e_ms / 1000.0), "unit": "frames/s",
                "h2d_bytes_per_step": B * 3 * S * S * 4 + B * K, "d2h_bytes_per_step": B * 3 * S * S * 4 + B * (1 + K) * 4,
-               "path": "vsb_embed_detect_host: pinned host frames in, watermarked frames + logits out; H2D in 32-frame slices, embed per "
-                       "slice, D2H of a slice under the following compute, detect per 64-frame group (3 streams); timed by host wall "
-                       "clock around the synchronous calls"}
+               "path": "vsb_embed_detect_host: pinned host frames in, watermarked frames + logits out; H2D in slices (16 frames, then 48), "
+                       "embed per slice, D2H of a slice under the following compute, detect per 64 accumulated frames (3 streams); timed by "
+                       "host wall clock around the synchronous calls"}
         # the streaming caller's RGB24 form of the same call (inference_streaming.py): uint8 HWC frames over PCIe,
         # conversions on the GPU; the detector sees the re-quantised frames.  Reported next to the fp32-API number, not instead.
         u_in = [torch.randint(0, 256, (B, S, S, 3), dtype=torch.uint8, generator=g).pin_memory() for _ in range(2)]

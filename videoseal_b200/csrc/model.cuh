@@ -1181,15 +1181,29 @@ class Model {
     float* out = (float*)stage(1, (size_t)F * fpx * sizeof(float));
     float* lg = (float*)stage(2, (size_t)F * NO * sizeof(float));
     uint8_t* msgs = (uint8_t*)stage(3, (size_t)n_msgs * d.nbits + 256);
-    // Pipeline (three streams): frames travel in SLICES of ~32 (multiples of `step`, and of whole reference chunks in
+    // Pipeline (three streams): frames travel in SLICES (a short first one, then ~48; multiples of `step`, and of whole reference chunks in
     // 'interpolate' mode where neighbouring keys of one chunk are mixed, so that key-frame groups stay whole); embed() runs per
     // slice as soon as its copy has landed, the D2H of a slice's watermarked frames starts as soon as its embed() is done and
-    // runs under the following compute; detect() runs once per GROUP of two slices (64 frames: full-size extractor batches).
+    // runs under the following compute; detect() runs once 64 frames have accumulated (full-size extractor batches) and on the tail.
     // Exposed copies: the first slice in and the last group's logits out.
-    int sl = 32;
+    // Slice sizes: the FIRST slice's copy is the exposed one, so it may be shorter than the rest (VSB_E2E_SL0 / VSB_E2E_SL1, read per
+    // call so that one process can compare settings).  Measured at 64 x 3x256x256 (tests/e2e_ab.py, results bit-identical for every
+    // setting): 32/32 7 165 f/s, 24/40 7 207, 16/48 7 317, 8/56 7 310, 16/24 7 020 -> defaults 16 / 48.
     const int unit = (video_mode == VSB_VIDEO_INTERPOLATE && step > 1) ? step * std::max(1, chunk_keys) : step;
-    if (sl % unit) sl = ((sl + unit - 1) / unit) * unit;
-    const int nsl = (F + sl - 1) / sl;
+    auto knob = [&](const char* name, int dflt) {
+      const char* e = getenv(name);
+      int v = e ? atoi(e) : dflt;
+      if (v < 1 || v > kMaxBatch) v = dflt;
+      return ((v + unit - 1) / unit) * unit;
+    };
+    const int sl0 = knob("VSB_E2E_SL0", 16), sl1 = knob("VSB_E2E_SL1", 48);
+    std::vector<std::pair<int, int>> slices;   // (first frame, frames)
+    for (int f0 = 0; f0 < F;) {
+      const int n = std::min(slices.empty() ? sl0 : sl1, F - f0);
+      slices.push_back({f0, n});
+      f0 += n;
+    }
+    const int nsl = (int)slices.size();
     while ((int)ev_in.size() < nsl + 1) {
       cudaEvent_t a, b;
       VSB_CUDA(cudaEventCreateWithFlags(&a, cudaEventDisableTiming));
@@ -1198,12 +1212,13 @@ class Model {
     }
     VSB_CUDA(cudaMemcpyAsync(msgs, msgs_h, (size_t)n_msgs * d.nbits, cudaMemcpyHostToDevice, s_in));
     for (int k = 0; k < nsl; ++k) {       // all input copies are queued up front: s_in runs ahead of the compute
-      const int f0 = k * sl, n = std::min(sl, F - f0);
+      const int f0 = slices[k].first, n = slices[k].second;
       VSB_CUDA(cudaMemcpyAsync(imgs + (size_t)f0 * fpx, imgs_h + (size_t)f0 * fpx, (size_t)n * fpx * sizeof(float), cudaMemcpyHostToDevice, s_in));
       VSB_CUDA(cudaEventRecord(ev_in[k], s_in));
     }
+    int g0 = 0;                           // first frame not yet detected
     for (int k = 0; k < nsl; ++k) {
-      const int f0 = k * sl, n = std::min(sl, F - f0);
+      const int f0 = slices[k].first, n = slices[k].second;
       VSB_CUDA(cudaStreamWaitEvent(s_cmp, ev_in[k], 0));
       const uint8_t* mk = msgs + (n_msgs == 1 ? 0 : (size_t)f0 * d.nbits);
       embed(imgs + (size_t)f0 * fpx, mk, n_msgs == 1 ? 1 : n, out + (size_t)f0 * fpx, nullptr, n, H, W, step, video_mode, chunk_keys, scaling_i,
@@ -1211,12 +1226,13 @@ class Model {
       VSB_CUDA(cudaEventRecord(ev_cmp[k], s_cmp));
       VSB_CUDA(cudaStreamWaitEvent(s_out, ev_cmp[k], 0));
       VSB_CUDA(cudaMemcpyAsync(imgs_w_h + (size_t)f0 * fpx, out + (size_t)f0 * fpx, (size_t)n * fpx * sizeof(float), cudaMemcpyDeviceToHost, s_out));
-      if ((k & 1) == 1 || k == nsl - 1) {   // a group is complete: detect its frames in one batch
-        const int g0 = (k & ~1) * sl, gn = std::min(F, (k + 1) * sl) - g0;
+      if (f0 + n - g0 >= kMaxBatch || k == nsl - 1) {   // a full extractor batch (or the tail) is complete: detect its frames
+        const int gn = f0 + n - g0;
         detect(out + (size_t)g0 * fpx, lg + (size_t)g0 * NO, gn, H, W, flags & VSB_FLAG_RESIZE_NO_AA, s_cmp);
         VSB_CUDA(cudaEventRecord(ev_cmp[nsl], s_cmp));
         VSB_CUDA(cudaStreamWaitEvent(s_out, ev_cmp[nsl], 0));
         VSB_CUDA(cudaMemcpyAsync(logits_h + (size_t)g0 * NO, lg + (size_t)g0 * NO, (size_t)gn * NO * sizeof(float), cudaMemcpyDeviceToHost, s_out));
+        g0 = f0 + n;
       }
     }
     VSB_CUDA(cudaStreamSynchronize(s_out));
