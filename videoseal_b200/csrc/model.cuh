@@ -1412,7 +1412,9 @@ class Model {
     // TMA-fed kernel (jnd_blend3_kernel): vector layout, delta in place or <= 2 taps per axis; the delta tile needs a TMA-legal row pitch
     static const bool blend_old = getenv("VSB_BLEND_OLD") != nullptr;
     const bool delta_tma = bp.identity_resample || (bp.PW % 4 == 0 && reinterpret_cast<uintptr_t>(bp.delta) % 16 == 0);
-    const bool tma = vec && fastup && delta_tma && !blend_old &&
+    // (boxes never exceed the tensor they are cut from: tiny frames / processing sizes take the load-then-compute kernel)
+    const bool tma = vec && fastup && delta_tma && !blend_old && bp.W >= kB2LP && bp.H >= kB2TH + 4 &&
+                     (bp.identity_resample || (bp.PW >= kB3DW && bp.PH >= kB2DH)) &&
                      (!bp.identity_resample || (bp.PW % 4 == 0 && reinterpret_cast<uintptr_t>(bp.delta) % 16 == 0));
     CUtensorMap tmI, tmD;
     if (tma) {
