@@ -44,6 +44,7 @@ __global__ void __launch_bounds__(256) resize_sep_kernel(const float* __restrict
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int rounds = (nr + GST - 1) / GST;
   for (int i = threadIdx.x * 4; i < kRsStages * stg_stride; i += 1024) *reinterpret_cast<float4*>(stg + i) = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (vec) fence_proxy_async_smem();     // every writer orders its zero fill before the bulk copies (async proxy) into the same buffers
   __shared__ uint64_t rs_full[kRsStages];
   if (vec && threadIdx.x == 0) {
     for (int i = 0; i < kRsStages; ++i) mbar_init(&rs_full[i], 1);
@@ -836,6 +837,7 @@ __global__ void __launch_bounds__(256, 2) jnd_blend3_kernel(const BlendParams p,
         }
       }
     }
+    if (CD * nsrc > 1) fence_proxy_async_smem();   // hand-staged delta tiles (generic proxy) before the next TMA box into the same buffer
     __syncthreads();       // every read of raw[buf] / lum / dl[buf] is done: the next iteration may refill them
   }
 }
