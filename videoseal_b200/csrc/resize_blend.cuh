@@ -1,15 +1,18 @@
-// HBM-bound full-resolution stage of the path, second generation (round 2):
-//   K5  resize_sep_kernel    F.interpolate(bilinear, align_corners=False, antialias on/off) as a SEPARABLE resample: input rows are
-//                            staged in shared memory with 128-bit coalesced loads, the horizontal pass runs out of shared memory
-//                            with the taps in registers, the vertical pass out of a second shared buffer.  One launch handles key
-//                            frames that are `frame_stride` apart (video mode).  Replaces the scalar per-output-pixel gather
-//                            (49 global loads per output at 768 -> 256).  (models/wam.py:161-164,222-226; videoseal.py:303-310)
-//   K7  jnd_blend2_kernel    JND heat-map x up-resampled delta, additive blend, clamp (modules/jnd.py:63-108, wam.py:183-201,
-//                            blender.py:61-68, videoseal.py:80-118): 128 x 32 pixel tiles, every input pixel is read from HBM once
-//                            (128-bit loads) and kept in shared memory, luminance halo 16 % instead of 55 %, 5x5 / Sobel windows
-//                            read as 128-bit shared loads into a rolling register window, g^2.4 as ex2(1.2 lg2 g^2) on the SFU.
-//                            Widths that are not multiples of 4 run the same kernel with lane-strided scalar accesses (still fully
-//                            coalesced) instead of falling back to a different kernel.
+// HBM-bound full-resolution stage of the path (round 2):
+//   K5  resize_sep_kernel    F.interpolate(bilinear, align_corners=False, antialias on/off) as a SEPARABLE resample: groups of input
+//                            rows arrive in shared memory as single bulk copies on an mbarrier ring, the horizontal pass runs out of
+//                            shared memory with the thread's taps in registers, the vertical pass out of a second shared buffer.  One
+//                            launch handles key frames that are `frame_stride` apart (video mode).  Replaces the scalar per-output-pixel
+//                            gather of round 1 (49 global loads per output at 768 -> 256).
+//                            (models/wam.py:161-164,222-226; videoseal.py:303-310)
+//   K7  jnd_blend3_kernel    JND heat-map x up-resampled delta, additive blend, clamp (modules/jnd.py:63-108, wam.py:183-201,
+//                            blender.py:61-68, videoseal.py:80-118), TMA-fed: one box per 128 x 16 tile brings the RGB tile with its
+//                            2-pixel halo (out-of-image = zero fill = the conv padding), a second one the delta tile; double buffer
+//                            over 4 tiles per block; separable 5x5 / Sobel sums and jnd_value in packed fp32, SFU transcendentals.
+//       jnd_blend2_kernel    the same arithmetic with per-thread loads: widths that are not multiples of 4, unaligned tensors,
+//                            anti-aliased delta down-scale, frames smaller than a TMA box.
+// Measured (B200, 32 x 3x768x768, profiles/r2_pointwise_ncu.md): resize 63 us = 0.61, blend + preds_w 119 us = 0.69 of the measured
+// HBM copy bandwidth; DRAM traffic = algorithmic bytes.
 #pragma once
 #include "conv_gemm.cuh"
 #include "pointwise.cuh"
